@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — read-pairs/s of the BWA-MEM candidate-generation path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the whole hot path (seeding -> SA -> chaining -> extension -> dedup + mate rescue -> CIGARs)
+over one batch of barcode-sorted synthetic read pairs.  Workload at N=1: BASELINE.json configs[1] — synthetic 100 Mb
+reference with 5 % segmental duplications, 1 M read pairs / 10 k barcodes, 50 kb molecules (`--config c2`).
+  value : whole-job read-pairs/s with the reads already resident in HBM (lc_batch_run only)
+  e2e   : the same through the C-ABI call a Lariat shim makes (lc_align_packed: pinned host reads -> H2D -> kernels -> D2H results)
+  roofline : dominant kernel (smem_kernel) algorithmic FM-index bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline : the reference's own CPU path (oracle/_ref/replay_ref, else the oracle port) on a bounded sample, all host cores
+N>1 (torchrun, one rank per GPU): barcode groups shard across ranks, index replicated per GPU, no data-path collective (weak scaling).
+`--impl reference` times only the CPU reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from lariat_b200 import iofmt, synth  # noqa: E402
+
+CACHE = os.path.join(ROOT, "data", "cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def config_sizes(name, scale):
+    g, r = synth.config_specs(name)
+    if scale != 1.0:
+        g.total_bp = int(g.total_bp * scale)
+        r.n_pairs = max(2000, int(r.n_pairs * scale))
+        r.n_barcodes = max(20, int(r.n_barcodes * scale))
+    return g, r
+
+
+def prepare_data(name, scale, rank_seed=0, need_index=True, device="cuda"):
+    """Genome + index (own GPU builder, byte-identical to `bwa index`) + read pairs; cached under data/cache."""
+    g, r = config_sizes(name, scale)
+    r.seed += 1000 * rank_seed
+    tag = f"{name}_s{scale:g}"
+    d = os.path.join(CACHE, tag)
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, f"{name}.fa")
+    pairs = os.path.join(d, f"{name}.r{rank_seed}.pairs")
+    contigs = loci = None
+    if need_index and not all(os.path.exists(fa + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
+        t = time.time()
+        contigs, loci = synth.make_genome(g)
+        from lariat_b200 import index_build
+        index_build.build_index(fa, contigs, device)
+        log(f"[bench] built index for {g.total_bp} bp in {time.time() - t:.1f}s")
+    if not os.path.exists(pairs):
+        t = time.time()
+        if contigs is None:
+            contigs, loci = synth.make_genome(g)
+        sim = synth.simulate_pairs(contigs, loci, r)
+        iofmt.write_pairs(pairs, sim["r1"], sim["r2"])
+        log(f"[bench] simulated {r.n_pairs} pairs in {time.time() - t:.1f}s")
+    return fa, pairs, g, r
+
+
+def load_pairs(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    n = int(raw[4:8].view("<i4")[0])
+    lens = raw[8:8 + 8 * n].view("<i4")
+    off = np.zeros(2 * n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    bases = raw[8 + 8 * n:8 + 8 * n + int(off[-1])]
+    return n, bases, off
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, idx):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.stop_flag = idx, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append([x.strip() for x in o])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = [x for x in self.samples if len(x) >= 6 and x[0].isdigit()]
+        if not s:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for x in s for i in range(4) if x[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median([int(x[0]) for x in s])), "sm_max_mhz": float(s[0][1]), "reasons": reasons, "samples": len(s)}
+
+
+def cpu_reference(fa, pairs, sample_pairs, threads, repeat=1):
+    """Times the reference CPU implementation (unmodified libbwa driven by oracle/replay.c) or, if it was not built here, the oracle port."""
+    exe, kind = os.path.join(ROOT, "oracle", "_ref", "replay_ref"), "reference"
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+        exe, kind = os.path.join(ROOT, "oracle", "replay_port"), "port"
+    out = subprocess.run([exe, fa, pairs, "-", "-t", str(threads), "-n", str(sample_pairs), "-r", str(repeat)],
+                         capture_output=True, text=True, check=True).stderr.strip().splitlines()[-1]
+    j = json.loads(out)
+    return kind, j
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("LARIAT_BENCH_SCALE", "1.0")))
+    ap.add_argument("--cpu-sample", type=int, default=40000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    workload = {"c1": "synthetic 10 Mb reference, 20k 2x150 pairs / 200 barcodes",
+                "c2": "synthetic 100 Mb reference with 5% segmental duplications, 1M 2x150 read pairs / 10k barcodes, 50 kb molecules"}.get(args.config, args.config)
+    cfg = {"workload": workload, "config": args.config, "scale": args.scale, "reads": "2x150", "batch": "one launch sequence per step over all barcode groups of the rank",
+           "l2_policy": "inputs (index 175 MB + per-step pools > 1 GB) exceed the 126 MB L2", "sharding": f"barcode groups split over {world} rank(s), index replicated"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        fa, pairs, g, r = prepare_data(args.config, args.scale, 0, need_index=True, device="cuda" if _has_cuda() else "cpu")
+        sample = min(r.n_pairs, args.cpu_sample)
+        vals = []
+        for _ in range(args.warmup):
+            cpu_reference(fa, pairs, min(sample, 2000), ncores)
+        t0 = time.time()
+        for _ in range(args.steps):
+            kind, j = cpu_reference(fa, pairs, sample, ncores)
+            vals.append(j["pairs_per_s"])
+        v = float(np.mean(vals))
+        print(json.dumps({"metric": "read-pairs/s aligned (bit-exact vs BWA)", "value": v, "unit": "read-pairs/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample / v, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg, "impl": "reference",
+                          "cpu_baseline": {"value": v, "unit": "read-pairs/s", "cores": ncores, "kind": kind,
+                                           "sample": f"first {sample} pairs of the workload per step, index preloaded, {ncores} threads"},
+                          "e2e": {"value": v, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lariat_b200 import gobwa
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl cuda needs a GPU: libcuda_lariat has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # data: rank 0 builds the shared index, every rank simulates its own shard of barcode groups (weak scaling)
+    if rank == 0:
+        prepare_data(args.config, args.scale, 0, device=f"cuda:{local}")
+    if world > 1:
+        dist.barrier()
+    fa, pairs, g, r = prepare_data(args.config, args.scale, rank, device=f"cuda:{local}")
+    n_pairs, bases, off = load_pairs(pairs)
+    lib = gobwa.load_library()
+    t0 = time.time()
+    ref = gobwa.GoBwaLoadReference(fa, device=local)
+    if ref is None:
+        raise SystemExit("index load failed: " + gobwa.last_error())
+    log(f"[bench] rank {rank}: index resident in HBM after {time.time() - t0:.1f}s; {n_pairs} pairs")
+    # pinned host staging for the e2e arm
+    hb = torch.from_numpy(bases.copy()).pin_memory()
+    ho = torch.from_numpy(off).pin_memory()
+    ctx = ref.BWTData
+    res = C.POINTER(gobwa.lc_result_t)()
+
+    def check(rc):
+        if rc != 0:
+            raise SystemExit(f"libcuda_lariat error {rc}: {gobwa.last_error()}")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- one counted pass (outside the timed region) for the algorithmic-work figures
+    lib.lc_set_counting(ctx, 1)
+    check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+    counters = gobwa.BatchResult(res.contents, copy=False).counters
+    n_cand = int(res.contents.n_regs)
+    lib.lc_set_counting(ctx, 0)
+
+    # ---- device-resident arm: value
+    check(lib.lc_batch_upload(ctx, n_pairs, hb.data_ptr(), ho.data_ptr()))
+    for _ in range(args.warmup):
+        check(lib.lc_batch_run(ctx, 25))
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    stage = np.zeros(10)
+    launches = 0
+    for _ in range(args.steps):
+        check(lib.lc_batch_run(ctx, 25))
+    sync_all()
+    dt = time.perf_counter() - t0
+    sampler.stop_flag = True
+    # per-stage CUDA-event times of the last timed step (events are recorded on the library's own stream)
+    check(lib.lc_batch_fetch(ctx, C.byref(res)))
+    rr = res.contents
+    stage_ms = {k: float(getattr(rr, k)) for k in ("ms_seed", "ms_sa", "ms_chain", "ms_extend", "ms_pair", "ms_cigar", "ms_total")}
+    launches = int(rr.gpu_launches)
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt_max = float(tt.item())
+    value = world * n_pairs * args.steps / dt_max
+
+    # ---- end-to-end arm: host buffers in, host results out, every step
+    for _ in range(max(1, args.warmup - 1)):
+        check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+    sync_all()
+    dte = time.perf_counter() - t0
+    tt = torch.tensor([dte], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = world * n_pairs * args.steps / float(tt.item())
+    rr = res.contents
+    h2d = int(bases.nbytes + off.nbytes)
+    d2h = int(rr.n_regs * (88 + 32) + rr.n_cigar_words * 4 + (rr.n_reads + 1) * 8)
+    e2e_ms = {k: float(getattr(rr, k)) for k in ("ms_h2d", "ms_d2h", "ms_total")}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (smem_kernel): algorithmic FM-index bytes the reference would touch / CUDA-event time
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    fm_bytes = 64.0 * counters["occ_blocks"]
+    ach = fm_bytes / (stage_ms["ms_seed"] * 1e-3) / 1e9 if stage_ms["ms_seed"] > 0 else 0.0
+    roof = {"kernel": "smem_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes_per_launch": fm_bytes, "kernel_ms": stage_ms["ms_seed"],
+            "sa_lookup_kernel": {"algorithmic_bytes": 64.0 * counters["lf_steps"] + 8.0 * counters["sa_calls"], "ms": stage_ms["ms_sa"],
+                                 "achieved": (64.0 * counters["lf_steps"] + 8.0 * counters["sa_calls"]) / max(stage_ms["ms_sa"], 1e-9) / 1e6},
+            "extend_kernel": {"cells": counters["ext_cells"], "ms": stage_ms["ms_extend"],
+                              "gcups": counters["ext_cells"] / max(stage_ms["ms_extend"], 1e-9) / 1e6}}
+    cpu = None
+    if not args.no_cpu:
+        sample = min(n_pairs, args.cpu_sample)
+        kind, j = cpu_reference(fa, pairs, sample, ncores)
+        cpu = {"value": j["pairs_per_s"], "unit": "read-pairs/s", "cores": ncores, "kind": kind,
+               "sample": f"first {sample} pairs of the workload, index preloaded, {ncores} threads, wall clock {j['seconds']:.2f}s"}
+    out = {"metric": "read-pairs/s aligned (bit-exact vs BWA)", "value": value, "unit": "read-pairs/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt_max / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic (seeded numpy genome + simulated linked reads; index built on the GPU, byte-identical to bwa index)",
+           "config": cfg, "pairs_per_step_per_gpu": n_pairs, "candidates_per_step": n_cand,
+           "e2e": {"value": e2e, "unit": "read-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "stage_ms": e2e_ms},
+           "gpu_launches": launches * args.steps, "stage_ms_last_step": stage_ms, "counters_per_step": counters,
+           "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary()}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+/* cuda_lariat.h — C ABI of libcuda_lariat.so: B200-native BWA-MEM candidate generation for Lariat.
+ *
+ * This is the drop-in boundary for the ONE hot path of 10XGenomics/lariat that is rebuilt here:
+ * everything Lariat's cgo bridge (go/src/gobwa/gobwa.go, go/src/gobwa/bwa_bridge.h) asks of BWA while it
+ * generates candidate alignments for the read pairs of a barcode group.  Plain C, plain pointers and sizes,
+ * no torch / CUDA types.  Each entry point names the reference interface it replaces ("G/" =
+ * go/src/gobwa/, "B/" = go/src/gobwa/bwa/ in the reference tree).  See INTEGRATION.md for the cgo stub.
+ *
+ * Threading: an lc_ctx is bound to one GPU; calls on one lc_ctx are serialised internally.  Use one lc_ctx
+ * per GPU (lc_init per device) and any number of host threads.
+ * Errors: functions return 0 on success, a negative LC_E* code otherwise; lc_last_error() gives the text.
+ * Nothing here ever calls exit() (the reference does: B/malloc_wrap.c, B/utils.c).
+ * There is NO CPU fallback: without a CUDA device lc_init fails with LC_ENODEV.
+ */
+#ifndef CUDA_LARIAT_H
+#define CUDA_LARIAT_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_OK        0
+#define LC_ENODEV   -1   /* no CUDA device / CUDA runtime error at init */
+#define LC_EINDEX   -2   /* index files missing or inconsistent (reference: bwa_idx_load returns NULL, G/gobwa.go:130-135) */
+#define LC_EARG     -3   /* bad argument (e.g. read longer than LC_MAX_READ_LEN) */
+#define LC_ECUDA    -4   /* CUDA error while running */
+#define LC_ENOMEM   -5
+
+#define LC_MAX_READ_LEN 700  /* B/bwamem.c:598-602: the per-seed SW screen is a no-op below ~725 bp; longer reads are out of scope */
+
+/* ---- options: layout-identical to mem_opt_t (B/bwamem.h:25-57); defaults = mem_opt_init (B/bwamem.c:48-84) ---- */
+typedef struct {
+	int a, b;
+	int o_del, e_del;
+	int o_ins, e_ins;
+	int pen_unpaired;
+	int pen_clip5, pen_clip3;
+	int w;
+	int zdrop;
+	uint64_t max_mem_intv;
+	int T;
+	int flag;
+	int min_seed_len;
+	int min_chain_weight;
+	int max_chain_extend;
+	float split_factor;
+	int split_width;
+	int max_occ;
+	int max_chain_gap;
+	int n_threads;
+	int chunk_size;
+	float mask_level;
+	float drop_ratio;
+	float XA_drop_ratio;
+	float mask_level_redun;
+	float mapQ_coef_len;
+	int mapQ_coef_fac;
+	int max_ins;
+	int max_matesw;
+	int max_XA_hits, max_XA_hits_alt;
+	int8_t mat[25];
+} lc_opt_t;
+
+/* ---- candidate region: layout-identical to mem_alnreg_t (B/bwamem.h:59-77; sizeof == 88) ---- */
+typedef struct {
+	int64_t rb, re;
+	int qb, qe;
+	int rid;
+	int score;
+	int truesc;
+	int sub;
+	int alt_sc;
+	int csub;
+	int sub_n;
+	int w;
+	int seedcov;
+	int secondary;
+	int secondary_all;
+	int seedlen0;
+	int n_comp:30, is_alt:2;
+	float frac_rep;
+	uint64_t hash;
+} lc_alnreg_t;
+
+/* ---- final alignment of one candidate: the fields of mem_aln_t Lariat reads (G/gobwa.go:449-487) ---- */
+typedef struct {
+	int64_t pos;        /* 0-based leftmost forward-strand position on contig `rid` (mem_aln_t.pos) */
+	int32_t rid;
+	int32_t is_rev;
+	int32_t NM;
+	int32_t n_cigar;
+	uint32_t cigar_off; /* index of the first op in lc_result.cigars; BAM encoding len<<4|op, MIDSH = 01234 */
+	int32_t n_mismatch; /* number of mismatching aligned bases (== NM - gap bases), for GetAlignments (I/lariat.go:1633) */
+} lc_aln_t;
+
+/* ---- insert-size model: mem_pestat_t (B/bwamem.h:81-85). Lariat hard-codes FR, low=-35, high=500 (G/gobwa.go:229-237) ---- */
+typedef struct { int low, high, failed; double avg, std; } lc_pestat_t;
+
+/* ---- contig table: replaces the struct peeking of G/gobwa.go:27-40,136-145,435-447 ---- */
+typedef struct {
+	int32_t n_seqs;
+	int64_t l_pac;
+	const char *const *names;
+	const int32_t *lens;
+	const int64_t *offsets;
+} lc_contigs_t;
+
+/* ---- result of one batched call.  Read end e of pair p has index r = 2*p + e.
+ * Its candidates are regs[reg_off[r] .. reg_off[r+1]) in exactly the order the reference's
+ * GoBwaMemMateSW returns them; aln[i] is mem_reg2aln of regs[i] (what GetAlignments computes per candidate). */
+typedef struct {
+	int32_t n_reads;              /* 2 * n_pairs */
+	int64_t n_regs;
+	const int64_t *reg_off;       /* [n_reads + 1] */
+	const lc_alnreg_t *regs;      /* [n_regs] */
+	const lc_aln_t *aln;          /* [n_regs] */
+	const uint32_t *cigars;
+	int64_t n_cigar_words;
+	/* device-side stage timings of this call, CUDA events on the library's stream (ms) */
+	float ms_h2d, ms_seed, ms_sa, ms_chain, ms_extend, ms_dedup, ms_pair, ms_cigar, ms_d2h, ms_total;
+	int64_t gpu_launches;         /* kernels of this library launched for the call */
+	/* algorithmic work counters, filled when lc_set_counting(ctx, 1) */
+	uint64_t cnt_occ_blocks, cnt_extend_calls, cnt_sa_calls, cnt_lf_steps;
+	uint64_t cnt_ext_calls, cnt_ext_cells, cnt_sw_calls, cnt_sw_cells, cnt_glb_calls, cnt_glb_cells;
+} lc_result_t;
+
+typedef struct lc_ctx lc_ctx;
+
+/* mem_opt_init (B/bwamem.c:48-84) — fills *opt with BWA-MEM defaults; what GoBwaAllocSettings returns (G/gobwa.go:149-153) */
+void lc_opt_init(lc_opt_t *opt);
+
+/* bwa_idx_load(prefix, BWA_IDX_ALL) (B/bwa.c:262-294; G/gobwa.go:128-147) + upload to HBM of device `device`.
+ * opt == NULL means defaults.  Returns NULL on failure (see lc_last_error). */
+lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt);
+void lc_destroy(lc_ctx *ctx);
+const char *lc_last_error(void);
+
+/* contig names / lengths / offsets (GetReferenceContigsInfo, EnumerateContigs: G/gobwa.go:27-40,435-447) */
+const lc_contigs_t *lc_contigs(const lc_ctx *ctx);
+
+/* GoBwaMemMateSW (G/gobwa.go:226-337) for every pair of one or more barcode groups, followed by
+ * GoBwaSmithWaterman / mem_reg2aln (G/gobwa.go:400-415) on every candidate — one call, a fixed number of launches.
+ * seq1[p]/seq2[p]: ASCII bases (ACGTacgt, anything else = N) of length len1[p]/len2[p]; a zero length end is
+ * skipped exactly as the Go code does (G/gobwa.go:243,252,287,311).  score_delta: Lariat passes 25 (I/lariat.go:475).
+ * *out stays valid until the next call on ctx that produces a result, or lc_free_result. */
+int lc_align_pairs(lc_ctx *ctx, int n_pairs, const uint8_t *const *seq1, const int32_t *len1,
+                   const uint8_t *const *seq2, const int32_t *len2, int score_delta, lc_result_t **out);
+
+/* Same, from one packed buffer: bases of read r at bases[off[r] .. off[r+1]), r = 2*pair + end (no per-read pointers). */
+int lc_align_packed(lc_ctx *ctx, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out);
+
+/* Split form used by bench.py to time the device-resident path: upload (H2D), run (kernels only, inputs already in HBM),
+ * fetch (D2H + result assembly).  lc_align_packed == upload + run + fetch. */
+int lc_batch_upload(lc_ctx *ctx, int n_pairs, const uint8_t *bases, const int64_t *off);
+int lc_batch_run(lc_ctx *ctx, int score_delta);
+int lc_batch_fetch(lc_ctx *ctx, lc_result_t **out);
+void lc_free_result(lc_ctx *ctx, lc_result_t *res);
+
+/* bns_fetch_seq as used by GoBwaReference.GetSeq (G/gobwa.go:50-80): 2-bit codes of contig `rid`, [start,end) on the
+ * forward strand, clamped to the contig like the reference; returns the number of codes written to out (<= end-start). */
+int64_t lc_fetch_seq(const lc_ctx *ctx, int rid, int64_t start, int64_t end, uint8_t *out);
+
+/* ---- source-compatible single-read forms (slow: one tiny batch each; for tests and for a strictly call-by-call port
+ * of the Go bridge).  Returned arrays are malloc'd; the caller frees them with free(), as the Go Arena does (G/gobwa.go:107-126). */
+typedef struct { size_t n, m; lc_alnreg_t *a; } lc_alnreg_v;
+/* mem_align1_core (B/bwamem.c:1048-1084; G/gobwa.go:181,244,253): seq = 2-bit codes (0..3, >=4 ambiguous) */
+int lc_mem_align1_core(lc_ctx *ctx, int l_seq, const uint8_t *seq, lc_alnreg_v *out);
+/* mem_matesw (B/bwamem_pair.c:111-180; G/gobwa.go:291,315): returns the number of SW performed, <0 on error */
+int lc_mem_matesw(lc_ctx *ctx, const lc_pestat_t pes[4], const lc_alnreg_t *a, int l_ms, const uint8_t *ms, lc_alnreg_v *ma);
+/* mem_reg2aln (B/bwamem.c:1086-1156; G/gobwa.go:404): *cigar is malloc'd (n_cigar words) */
+int lc_mem_reg2aln(lc_ctx *ctx, int l_query, const uint8_t *query, const lc_alnreg_t *ar, lc_aln_t *aln, uint32_t **cigar);
+
+/* ---- kernel-level entry points for the microbenchmark config (BASELINE.json configs[4]) and parity tests ---- */
+/* ksw_extend2 (B/ksw.c:380-479) on n independent jobs; job j: query = q[qoff[j]..qoff[j+1]), target = t[toff[j]..toff[j+1]).
+ * out[j*6..] = {score, qle, tle, gtle, gscore, max_off}.  *ms = device time of the kernel, *cells = sum over rows of (end-beg). */
+int lc_ksw_extend_batch(lc_ctx *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                        const int32_t *h0, int w, int end_bonus, int zdrop, int32_t *out, float *ms, uint64_t *cells);
+/* ksw_align2 with mem_matesw's flags (B/bwamem_pair.c:150-151): out[j*7..] = {score, te, qe, score2, te2, tb, qb} */
+int lc_ksw_align_batch(lc_ctx *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                       int32_t *out, float *ms, uint64_t *cells);
+/* mem_collect_intv (B/bwamem.c:114-162): SMEM + re-seeding + LAST-like seeds of each read, sorted by info.
+ * out_off[n+1], out = {x0, x1, x2, info} x total (caller gives capacity in intervals; returns total or <0) */
+int64_t lc_collect_intv_batch(lc_ctx *ctx, int n, const uint8_t *codes, const int64_t *off, int64_t *out_off,
+                              uint64_t *out, int64_t out_cap, float *ms);
+/* bwt_sa (B/bwt.c:86-96) for n BWT rows */
+int lc_sa_batch(lc_ctx *ctx, int64_t n, const uint64_t *rows, uint64_t *out, float *ms);
+
+void lc_set_counting(lc_ctx *ctx, int on);
+/* library build info: "sm_100a", version */
+const char *lc_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

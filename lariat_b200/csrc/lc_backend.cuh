@@ -1,0 +1,51 @@
+// lc_backend.cuh — CUDA backend of LcPipeline: device memory, one stream, CUDA events, kernel launches.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "lc_pipeline.hpp"
+
+#define LC_N_EVENTS 16
+
+struct LcExtJobs {      // batch of independent ksw_extend2 jobs (microbenchmark / parity entry point)
+	int n; const uint8_t *q; const int64_t *qoff; const uint8_t *t; const int64_t *toff; const int32_t *h0;
+	int w, end_bonus, zdrop; LcScore sc; int32_t *out; int *w_int; int w_int_n; LcCounters *cnt;
+};
+struct LcSwJobs {       // batch of independent ksw_align2 jobs with mem_matesw's flags
+	int n; const uint8_t *q; const int64_t *qoff; const uint8_t *t; const int64_t *toff;
+	LcScore sc; int min_seed_len; int32_t *out; int *w_int; int w_int_n; unsigned long long *w_u64; int w_u64_n; LcCounters *cnt;
+};
+
+struct LcCudaBackend {
+	int device, n_sm = 0, workers = 0;
+	cudaStream_t stream = 0;
+	cudaEvent_t ev[LC_N_EVENTS];
+	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+
+	explicit LcCudaBackend(int device_);
+	~LcCudaBackend();
+	int n_workers() const { return workers; }
+	void *dmalloc(size_t n);
+	void dfree(void *p);
+	void dzero(void *p, size_t n);
+	void dzero_words(unsigned long long *p, size_t n);
+	void h2d(void *d, const void *s, size_t n);
+	void d2h(void *d, const void *s, size_t n);
+	void d2d(void *d, const void *s, size_t n);
+	void sync();
+	void ev_record(int i);
+	float ev_ms(int a, int b);
+	int grid_for(unsigned long long items, int tpb, int ctas_per_sm) const;
+	void k_convert(uint8_t *p, unsigned long long n, bool ascii);
+	void k_seed(const LcBatch &b);
+	void k_sa(const LcBatch &b, unsigned long long n);
+	void k_chain(const LcBatch &b);
+	void k_extend(const LcBatch &b);
+	void k_pair(const LcBatch &b, int n_pairs);
+	void k_cigar(const LcBatch &b, unsigned long long n);
+	void k_pack(const LcBatch &b, const LcPackArgs &pa);
+	void scan_exclusive(const int32_t *in, int64_t *out, int n);
+	void k_ksw_extend(const LcExtJobs &j);
+	void k_ksw_align(const LcSwJobs &j);
+	void k_sa_batch(const LcIndex &ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt);
+	int check(std::string &err);
+};

@@ -1,0 +1,193 @@
+// lc_kernels.cu — the CUDA kernels of libcuda_lariat.so (sm_100a) and the backend that launches them.
+//
+// One kernel per pipeline stage (SURVEY.md §2 "kernels the new framework must write"):
+//   convert_kernel      ASCII -> 2-bit codes                                   (G/gobwa.go:159-167)
+//   smem_kernel         mem_collect_intv: SMEM / re-seed / LAST-like seeding   (B/bwamem.c:114-162, B/bwt.c:262-379)
+//   sa_lookup_kernel    bwt_sa for every scheduled occurrence                  (B/bwt.c:53-59,86-129; B/bwamem.c:283)
+//   chain_kernel        mem_chain tree insert/merge + mem_chain_flt            (B/bwamem.c:190-385)
+//   extend_kernel       mem_chain2aln -> ksw_extend2                           (B/bwamem.c:632-786, B/ksw.c:380-479)
+//   matesw_kernel       mem_sort_dedup_patch + the two rescue phases + mem_matesw/ksw_align2
+//                                                                              (B/bwamem.c:437-489, G/gobwa.go:264-324, B/bwamem_pair.c:111-180)
+//   global_cigar_kernel mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2           (B/bwamem.c:1086-1156, B/bwa.c:121-207, B/ksw.c:504-606)
+//   pack_kernel         dense result arrays in barcode/read order
+// All are integer/byte kernels; grids are sized in multiples of the SM count and stride over the batch.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include "lc_backend.cuh"
+
+#define LC_TPB 128
+
+__global__ void __launch_bounds__(256) convert_kernel(uint8_t *p, unsigned long long n, int is_ascii)
+{
+	// 16 bytes per thread per step
+	unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 16, stride = (unsigned long long)gridDim.x * blockDim.x * 16;
+	for (; i < n; i += stride) {
+		if (i + 16 <= n && (((size_t)(p + i)) & 15) == 0) {
+			uint4 v = *(const uint4 *)(p + i);
+			unsigned w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				unsigned o = 0;
+#pragma unroll
+				for (int s = 0; s < 32; s += 8) o |= (unsigned)lc_nt4((uint8_t)(w[k] >> s), is_ascii) << s;
+				w[k] = o;
+			}
+			*(uint4 *)(p + i) = make_uint4(w[0], w[1], w[2], w[3]);
+		} else {
+			for (unsigned long long j = i; j < n && j < i + 16; ++j) p[j] = lc_nt4(p[j], is_ascii);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(LC_TPB) smem_kernel(const LcBatch b)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	for (int r = worker; r < b.n_reads; r += stride) lc_stage_seed(b, r, worker);
+}
+
+__global__ void __launch_bounds__(256) sa_lookup_kernel(const LcBatch b, unsigned long long n)
+{
+	unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (; g < n; g += stride) lc_stage_sa(b, g);
+}
+
+__global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	for (int r = worker; r < b.n_reads; r += stride) lc_stage_chain(b, r);
+}
+
+__global__ void __launch_bounds__(LC_TPB) extend_kernel(const LcBatch b)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	for (int r = worker; r < b.n_reads; r += stride) lc_stage_extend(b, r, worker);
+}
+
+__global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, int n_pairs)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	for (int p = worker; p < n_pairs; p += stride) lc_stage_pair(b, p, worker);
+}
+
+__global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, unsigned long long n)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (unsigned long long c = worker; c < n; c += stride) lc_stage_cigar(b, c, worker);
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const LcBatch b, const LcPackArgs pa)
+{
+	const int stride = gridDim.x * blockDim.x;
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += stride) lc_stage_pack(b, pa, r);
+}
+
+// ---- microbenchmark kernels (BASELINE.json configs[4]) -------------------------------------------------------
+__global__ void __launch_bounds__(LC_TPB) ksw_extend_kernel(const LcExtJobs j)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	int *H = j.w_int + (size_t)worker * j.w_int_n, *E = H + (j.w_int_n >> 1);
+	for (int i = worker; i < j.n; i += stride) {
+		LcSeqFwd qf = { j.q + j.qoff[i] };
+		LcSeqFwd tf = { j.t + j.toff[i] };
+		LcExtResult r = lc_extend2((int)(j.qoff[i + 1] - j.qoff[i]), qf, (int)(j.toff[i + 1] - j.toff[i]), tf, j.sc, j.w, j.end_bonus, j.zdrop,
+								   j.h0[i], H, E, j.cnt);
+		int32_t *o = j.out + 6 * (size_t)i;
+		o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
+	}
+}
+
+__global__ void __launch_bounds__(LC_TPB) ksw_align_kernel(const LcSwJobs j)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	int *H = j.w_int + (size_t)worker * j.w_int_n, *E = H + j.w_int_n / 3, *Hmax = H + 2 * (j.w_int_n / 3);
+	unsigned long long *bl = j.w_u64 + (size_t)worker * j.w_u64_n;
+	for (int i = worker; i < j.n; i += stride) {
+		const int ql = (int)(j.qoff[i + 1] - j.qoff[i]), tl = (int)(j.toff[i + 1] - j.toff[i]);
+		LcSeqFwd qf = { j.q + j.qoff[i] };
+		LcSeqFwd tf = { j.t + j.toff[i] };
+		const int xtra = LC_XSUBO | LC_XSTART | (ql * j.sc.a < 250 ? LC_XBYTE : 0) | (j.min_seed_len * j.sc.a);
+		LcSwResult r = lc_sw_align2(ql, qf, tl, tf, j.sc, xtra, H, E, Hmax, bl, j.cnt);
+		int32_t *o = j.out + 7 * (size_t)i;
+		o[0] = r.score; o[1] = r.te; o[2] = r.qe; o[3] = r.score2; o[4] = r.te2; o[5] = r.tb; o[6] = r.qb;
+	}
+}
+
+__global__ void __launch_bounds__(256) sa_batch_kernel(const LcIndex ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt)
+{
+	long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+	for (; g < n; g += stride) out[g] = lc_sa(ix, rows[g], cnt);
+}
+
+// ---- backend -------------------------------------------------------------------------------------------------
+struct LcCastI64 { __host__ __device__ int64_t operator()(const int32_t &x) const { return (int64_t)x; } };
+
+LcCudaBackend::LcCudaBackend(int device_) : device(device_)
+{
+	cudaSetDevice(device);
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	n_sm = prop.multiProcessorCount;
+	cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventCreate(&ev[i]);
+	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
+}
+LcCudaBackend::~LcCudaBackend()
+{
+	cudaSetDevice(device);
+	if (scan_tmp) cudaFree(scan_tmp);
+	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventDestroy(ev[i]);
+	cudaStreamDestroy(stream);
+}
+void *LcCudaBackend::dmalloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
+void LcCudaBackend::dfree(void *p) { cudaStreamSynchronize(stream); cudaFree(p); }
+void LcCudaBackend::dzero(void *p, size_t n) { cudaMemsetAsync(p, 0, n, stream); }
+void LcCudaBackend::dzero_words(unsigned long long *p, size_t n) { cudaMemsetAsync(p, 0, 8 * n, stream); }
+void LcCudaBackend::h2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream); }
+void LcCudaBackend::d2h(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); }
+void LcCudaBackend::d2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream); }
+void LcCudaBackend::sync() { cudaStreamSynchronize(stream); }
+void LcCudaBackend::ev_record(int i) { cudaEventRecord(ev[i], stream); }
+float LcCudaBackend::ev_ms(int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0; } return ms; }
+int LcCudaBackend::grid_for(unsigned long long items, int tpb, int ctas_per_sm) const
+{
+	unsigned long long need = (items + tpb - 1) / tpb;
+	unsigned long long cap = (unsigned long long)n_sm * ctas_per_sm;
+	if (need >= cap) return (int)cap;
+	// round up to a multiple of the SM count when the batch is big enough, else just what is needed
+	return (int)(need ? need : 1);
+}
+void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
+{
+	if (!n) return;
+	convert_kernel<<<grid_for((n + 15) / 16, 256, 8), 256, 0, stream>>>(p, n, ascii ? 1 : 0);
+}
+void LcCudaBackend::k_seed(const LcBatch &b) { smem_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
+void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
+void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
+void LcCudaBackend::k_extend(const LcBatch &b) { extend_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
+void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs) { matesw_kernel<<<grid_for(n_pairs, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_pairs); }
+void LcCudaBackend::k_cigar(const LcBatch &b, unsigned long long n) { global_cigar_kernel<<<grid_for(n, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n); }
+void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for(b.n_reads, 256, 8), 256, 0, stream>>>(b, pa); }
+void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
+{
+	cub::TransformInputIterator<int64_t, LcCastI64, const int32_t *> it(in, LcCastI64());
+	size_t need = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, need, it, out, n, stream);
+	if (need > scan_tmp_bytes) { if (scan_tmp) { cudaStreamSynchronize(stream); cudaFree(scan_tmp); } cudaMalloc(&scan_tmp, need + 256); scan_tmp_bytes = need + 256; }
+	cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, out, n, stream);
+}
+void LcCudaBackend::k_ksw_extend(const LcExtJobs &j) { ksw_extend_kernel<<<grid_for(j.n, LC_TPB, 4), LC_TPB, 0, stream>>>(j); }
+void LcCudaBackend::k_ksw_align(const LcSwJobs &j) { ksw_align_kernel<<<grid_for(j.n, LC_TPB, 4), LC_TPB, 0, stream>>>(j); }
+void LcCudaBackend::k_sa_batch(const LcIndex &ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt)
+{
+	sa_batch_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, rows, out, n, cnt);
+}
+int LcCudaBackend::check(std::string &err)
+{
+	cudaError_t e = cudaStreamSynchronize(stream);
+	if (e == cudaSuccess) e = cudaGetLastError();
+	if (e != cudaSuccess) { err = std::string("CUDA error: ") + cudaGetErrorString(e); return -1; }
+	return 0;
+}

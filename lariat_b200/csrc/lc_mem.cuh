@@ -1,0 +1,870 @@
+// lc_mem.cuh — per-read / per-pair stage bodies of the batched BWA-MEM pipeline.
+//
+// One call of a stage body = the work of one read (or pair, or candidate); the CUDA kernels in lc_kernels.cu
+// run them for a whole batch of barcode groups.  All inter-stage data lives in HBM pools described by LcBatch;
+// variable-size outputs are carved from bump pools (one atomicAdd per read), and a stage that would overrun
+// its pool raises `overflow` so the host enlarges the pool and reruns the batch — there is no CPU path.
+// Reference lines: "B/" = go/src/gobwa/bwa/, "G/" = go/src/gobwa/.
+#pragma once
+#include "../../include/cuda_lariat.h"
+#include "lc_fmindex.cuh"
+#include "lc_sort.cuh"
+#include "lc_sw.cuh"
+
+struct LcIntvOut { uint64_t x0, x2; uint32_t qbeg, qend; uint32_t soff, step; };   // 32 B: one seeding interval of a read
+struct LcSeed { int64_t rbeg; int32_t qbeg, len; };                                 // mem_seed_t (B/bwamem.c:168-172); score == len here
+struct LcChainOut { int32_t rid, n; int64_t seed_off; uint32_t w; int32_t is_alt; }; // a kept chain; seeds in cseed[seed_off..+n)
+struct LcChainRec { int64_t pos; int32_t rid, n, head, tail; uint32_t w; int32_t kept, first, is_alt; };
+#define LC_BT_T 5
+#define LC_BT_MAXK (2 * LC_BT_T - 1)
+struct LcBtNode { int32_t n, internal; int32_t key[LC_BT_MAXK]; int32_t child[LC_BT_MAXK + 1]; };
+
+enum { LC_OVF_INTV = 1, LC_OVF_SEED = 2, LC_OVF_SCRATCH = 4, LC_OVF_CSEED = 8, LC_OVF_REG = 16, LC_OVF_FINAL = 32,
+	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512 };
+
+struct LcBatch {
+	// ---- inputs
+	int32_t n_reads;
+	const uint8_t *seq;            // 2-bit codes, 4 = ambiguous
+	const int64_t *off;            // [n_reads + 1]
+	LcIndex ix;
+	lc_opt_t opt;
+	LcScore sc;
+	int32_t score_delta, pes_low, pes_high, max_anchors;
+	LcCounters *cnt;               // null = off
+	uint32_t *overflow;            // OR of LC_OVF_* raised by any thread
+	int32_t lmax;                  // longest read of the batch
+	// ---- per-worker scratch (n_workers slots)
+	int32_t n_workers;
+	LcIntv *w_intv;                // per worker: 3 * (lmax + 1) + memcap
+	int32_t memcap;
+	int32_t *w_int;                // per worker: w_int_n ints (SW rows)
+	int32_t w_int_n;
+	unsigned long long *w_u64;     // per worker: w_u64_n (sub-optimal row list of the local SW)
+	int32_t w_u64_n;
+	// ---- stage 1: seeding
+	LcIntvOut *intv; unsigned long long intv_cap, *intv_cur;
+	uint64_t *seed_row;            // BWT rows, overwritten by their SA values in stage 2
+	unsigned long long seed_cap, *seed_cur;
+	int64_t *r_intv_off; int32_t *r_n_intv; int64_t *r_seed_off; int32_t *r_n_seed;
+	// ---- stage 3: chaining (scratch pool in bytes) -> kept chains with compacted seeds
+	uint8_t *scratch; unsigned long long scratch_cap, *scratch_cur;
+	LcChainOut *chain; unsigned long long chain_cap, *chain_cur;
+	LcSeed *cseed; unsigned long long cseed_cap, *cseed_cur;
+	int64_t *r_chain_off; int32_t *r_n_chain; float *r_frac_rep; int32_t *r_n_cseed;
+	// ---- stage 4: extension -> regions
+	lc_alnreg_t *reg; unsigned long long reg_cap, *reg_cur, *reg_total;   // reg_total = number of regions produced
+	int64_t *r_reg_off; int32_t *r_n_reg;
+	// ---- stage 5: per pair dedup + mate rescue -> final candidate lists
+	lc_alnreg_t *fin; unsigned long long fin_cap, *fin_cur;
+	int64_t *r_fin_off; int32_t *r_n_fin;
+	uint64_t *cand; unsigned long long *cand_cur;   // flat list of (read << 32 | idx) for stage 6
+	// ---- stage 6: CIGARs
+	lc_aln_t *aln;                 // parallel to fin
+	uint32_t *cigar; unsigned long long cigar_cap, *cigar_cur;
+	uint8_t *zpool; unsigned long long z_cap, *z_cur;   // traceback matrices too large for the per-worker scratch
+	uint8_t *w_z; int32_t w_z_n;                         // per worker: w_z_n bytes of traceback scratch
+};
+
+LC_HD void lc_raise(const LcBatch &b, uint32_t flag)
+{
+#ifdef __CUDA_ARCH__
+	atomicOr(b.overflow, flag);
+#else
+	*b.overflow |= flag;
+#endif
+}
+// carve `n` elements from a bump pool; returns the offset, or (u64)-1 after raising `flag`
+LC_HD unsigned long long lc_carve(const LcBatch &b, unsigned long long *cur, unsigned long long cap, unsigned long long n, uint32_t flag)
+{
+	unsigned long long o = lc_atomic_add(cur, n);
+	if (o + n > cap) { lc_raise(b, flag); return (unsigned long long)-1; }
+	return o;
+}
+
+// ============================================================================================================
+// Stage 1 — seeding: mem_collect_intv (B/bwamem.c:114-162) and the occurrence schedule of mem_chain (B/bwamem.c:273-279)
+// ============================================================================================================
+// mem_collect_intv (B/bwamem.c:114-162): returns the number of intervals written to mem[] (sorted by info), or -1 if memcap is too small.
+// prev/curr/m1 are scratch lists of len + 1 entries.
+LC_HDN int lc_collect_intv(const LcIndex &ix, const lc_opt_t &opt, int len, const uint8_t *q, LcIntv *prev, LcIntv *curr, LcIntv *m1,
+						   LcIntv *mem, int memcap, LcCounters *cnt)
+{
+	int n = 0, n1, x;
+	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
+	for (x = 0; x < len;) {                                                // pass 1: all SMEMs
+		if (q[x] > 3) { ++x; continue; }
+		x = lc_smem1(ix, len, q, x, 1, m1, n1, prev, curr, cnt);
+		for (int i = 0; i < n1; ++i) {
+			int slen = (int)((uint32_t)m1[i].info - (uint32_t)(m1[i].info >> 32));
+			if (slen >= opt.min_seed_len) { if (n == memcap) return -1; mem[n++] = m1[i]; }
+		}
+	}
+	const int old_n = n;
+	for (int k = 0; k < old_n; ++k) {                                      // pass 2: re-seed inside long near-unique SMEMs
+		const LcIntv p = mem[k];
+		int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
+		if (end - start < split_len || p.x2 > (uint64_t)opt.split_width) continue;
+		lc_smem1(ix, len, q, (start + end) >> 1, (int)p.x2 + 1, m1, n1, prev, curr, cnt);
+		for (int i = 0; i < n1; ++i)
+			if ((int)((uint32_t)m1[i].info - (uint32_t)(m1[i].info >> 32)) >= opt.min_seed_len) {
+				if (n == memcap) return -1;
+				mem[n++] = m1[i];
+			}
+	}
+	if (opt.max_mem_intv > 0)                                              // pass 3: LAST-like seeds
+		for (x = 0; x < len;) {
+			if (q[x] > 3) { ++x; continue; }
+			LcIntv m;
+			x = lc_seed_strategy1(ix, len, q, x, opt.min_seed_len, (int)opt.max_mem_intv, m, cnt);
+			if (m.x2 > 0) { if (n == memcap) return -1; mem[n++] = m; }
+		}
+	// elements with equal `info` are identical (same substring => same interval), so any correct sort reproduces B/bwamem.c:161
+	lc_introsort(mem, (long)n, [](const LcIntv &a, const LcIntv &c) { return a.info < c.info; });
+	return n;
+}
+
+LC_HDN void lc_stage_seed(const LcBatch &b, int r, int worker)
+{
+	const lc_opt_t &opt = b.opt;
+	const int len = (int)(b.off[r + 1] - b.off[r]);
+	const uint8_t *q = b.seq + b.off[r];
+	b.r_n_intv[r] = 0; b.r_n_seed[r] = 0; b.r_intv_off[r] = 0; b.r_seed_off[r] = 0;
+	if (len < opt.min_seed_len) return;                                    // B/bwamem.c:260
+	LcIntv *base = b.w_intv + (size_t)worker * (3 * (size_t)(b.lmax + 1) + b.memcap);
+	LcIntv *prev = base, *curr = base + (b.lmax + 1), *m1 = base + 2 * (size_t)(b.lmax + 1), *mem = base + 3 * (size_t)(b.lmax + 1);
+	const int n = lc_collect_intv(b.ix, opt, len, q, prev, curr, m1, mem, b.memcap, b.cnt);
+	if (n < 0) { lc_raise(b, LC_OVF_MEMLIST); return; }
+	// occurrence schedule: at most max_occ rows per interval, evenly strided (B/bwamem.c:278-279)
+	unsigned long long S = 0;
+	for (int i = 0; i < n; ++i) {
+		uint64_t step = mem[i].x2 > (uint64_t)opt.max_occ ? mem[i].x2 / opt.max_occ : 1;
+		uint64_t cnt = (mem[i].x2 + step - 1) / step;
+		if (cnt > (uint64_t)opt.max_occ) cnt = opt.max_occ;
+		mem[i].x1 = cnt;          // x1 is not needed past seeding; reuse it for the count
+		S += cnt;
+	}
+	unsigned long long io = lc_carve(b, b.intv_cur, b.intv_cap, n, LC_OVF_INTV);
+	unsigned long long so = lc_carve(b, b.seed_cur, b.seed_cap, S, LC_OVF_SEED);
+	if (io == (unsigned long long)-1 || so == (unsigned long long)-1) return;
+	unsigned long long s = 0;
+	for (int i = 0; i < n; ++i) {
+		uint64_t step = mem[i].x2 > (uint64_t)opt.max_occ ? mem[i].x2 / opt.max_occ : 1;
+		LcIntvOut o;
+		o.x0 = mem[i].x0; o.x2 = mem[i].x2; o.qbeg = (uint32_t)(mem[i].info >> 32); o.qend = (uint32_t)mem[i].info;
+		o.soff = (uint32_t)s; o.step = (uint32_t)step;
+		b.intv[io + i] = o;
+		for (uint64_t t = 0; t < mem[i].x1; ++t) b.seed_row[so + s + t] = mem[i].x0 + t * step;
+		s += mem[i].x1;
+	}
+	b.r_intv_off[r] = (int64_t)io; b.r_n_intv[r] = n; b.r_seed_off[r] = (int64_t)so; b.r_n_seed[r] = (int32_t)S;
+}
+
+// ============================================================================================================
+// Stage 2 — suffix-array lookups, one BWT row each (bwt_sa inside mem_chain, B/bwamem.c:283)
+// ============================================================================================================
+LC_HD void lc_stage_sa(const LcBatch &b, unsigned long long g)
+{
+	b.seed_row[g] = lc_sa(b.ix, b.seed_row[g], b.cnt);
+}
+
+// ============================================================================================================
+// Stage 3 — chaining and chain filtering: mem_chain (B/bwamem.c:251-315), mem_chain_flt (B/bwamem.c:327-385)
+// ============================================================================================================
+struct LcChainer {
+	LcChainRec *ch; int n_ch;
+	LcBtNode *nd; int n_nd, root, n_keys;
+	int64_t *s_rbeg; int32_t *s_q, *s_len, *s_next;
+
+	LC_HD int cmp(int64_t pos, int key) const { int64_t kp = ch[key].pos; return (kp < pos) - (pos < kp); }   // chain_cmp (B/bwamem.c:186)
+	LC_HD int new_node(int internal)
+	{
+		LcBtNode &x = nd[n_nd];
+		x.n = 0; x.internal = internal;
+		return n_nd++;
+	}
+	// __kb_getp_aux (B/kbtree.h:117-131)
+	LC_HD int find(const LcBtNode &x, int64_t pos, int *r) const
+	{
+		int lo = 0, hi = x.n;
+		if (x.n == 0) return -1;
+		while (lo < hi) { int mid = (lo + hi) >> 1; if (cmp(pos, x.key[mid]) > 0) lo = mid + 1; else hi = mid; }
+		if (lo == x.n) { if (r) *r = 1; return x.n - 1; }
+		int rr = cmp(pos, x.key[lo]);
+		if (r) *r = rr;
+		return rr < 0 ? lo - 1 : lo;
+	}
+	// kb_intervalp, lower neighbour only (B/kbtree.h:151-168)
+	LC_HD int lower(int64_t pos) const
+	{
+		int x = root, low = -1;
+		for (;;) {
+			const LcBtNode &n = nd[x];
+			int r = 0, i = find(n, pos, &r);
+			if (i >= 0 && r == 0) return n.key[i];
+			if (i >= 0) low = n.key[i];
+			if (!n.internal) return low;
+			x = n.child[i + 1];
+		}
+	}
+	// __kb_split (B/kbtree.h:176-191)
+	LC_HD void split(int xi, int i, int yi)
+	{
+		int zi = new_node(nd[yi].internal);
+		LcBtNode &x = nd[xi], &y = nd[yi], &z = nd[zi];
+		z.n = LC_BT_T - 1;
+		for (int t = 0; t < LC_BT_T - 1; ++t) z.key[t] = y.key[t + LC_BT_T];
+		if (y.internal) for (int t = 0; t < LC_BT_T; ++t) z.child[t] = y.child[t + LC_BT_T];
+		y.n = LC_BT_T - 1;
+		for (int t = x.n; t > i; --t) x.child[t + 1] = x.child[t];
+		x.child[i + 1] = zi;
+		for (int t = x.n; t > i; --t) x.key[t] = x.key[t - 1];
+		x.key[i] = y.key[LC_BT_T - 1];
+		++x.n;
+	}
+	// kb_putp / __kb_putp_aux (B/kbtree.h:192-224)
+	LC_HD void put(int key)
+	{
+		const int64_t pos = ch[key].pos;
+		++n_keys;
+		if (nd[root].n == LC_BT_MAXK) {
+			int s = new_node(1);
+			nd[s].child[0] = root;
+			split(s, 0, root);
+			root = s;
+		}
+		int xi = root;
+		for (;;) {
+			LcBtNode &x = nd[xi];
+			int i = find(x, pos, 0);
+			if (!x.internal) {
+				for (int t = x.n - 1; t > i; --t) x.key[t + 1] = x.key[t];
+				x.key[i + 1] = key;
+				++x.n;
+				return;
+			}
+			++i;
+			if (nd[x.child[i]].n == LC_BT_MAXK) {
+				split(xi, i, x.child[i]);
+				if (cmp(pos, x.key[i]) > 0) ++i;
+			}
+			xi = x.child[i];
+		}
+	}
+	// test_and_merge (B/bwamem.c:190-211) for seed `si` against chain `ci`
+	LC_HD bool merge(const lc_opt_t &opt, int64_t l_pac, int ci, int si, int rid)
+	{
+		LcChainRec &c = ch[ci];
+		const int64_t p_r = s_rbeg[si]; const int p_q = s_q[si], p_l = s_len[si];
+		const int64_t f_r = s_rbeg[c.head], l_r = s_rbeg[c.tail]; const int f_q = s_q[c.head], l_q = s_q[c.tail], l_l = s_len[c.tail];
+		const int64_t qend = l_q + l_l, rend = l_r + l_l;
+		if (rid != c.rid) return false;
+		if (p_q >= f_q && p_q + p_l <= qend && p_r >= f_r && p_r + p_l <= rend) return true;   // contained: dropped
+		if ((l_r < l_pac || f_r < l_pac) && p_r >= l_pac) return false;
+		const int64_t x = p_q - l_q, y = p_r - l_r;
+		if (y >= 0 && x - y <= opt.w && y - x <= opt.w && x - l_l < opt.max_chain_gap && y - l_l < opt.max_chain_gap) {
+			s_next[c.tail] = si; c.tail = si; ++c.n;
+			return true;
+		}
+		return false;
+	}
+	// mem_chain_weight (B/bwamem.c:213-232)
+	LC_HD int weight(int ci) const
+	{
+		int64_t end = 0; int wq = 0, wr = 0;
+		for (int s = ch[ci].head; s >= 0; s = s_next[s]) {
+			if (s_q[s] >= end) wq += s_len[s];
+			else if (s_q[s] + s_len[s] > end) wq += (int)(s_q[s] + s_len[s] - end);
+			end = lc_max(end, (int64_t)s_q[s] + s_len[s]);
+		}
+		end = 0;
+		for (int s = ch[ci].head; s >= 0; s = s_next[s]) {
+			if (s_rbeg[s] >= end) wr += s_len[s];
+			else if (s_rbeg[s] + s_len[s] > end) wr += (int)(s_rbeg[s] + s_len[s] - end);
+			end = lc_max(end, s_rbeg[s] + s_len[s]);
+		}
+		wq = lc_min(wq, wr);
+		return wq < 1 << 30 ? wq : (1 << 30) - 1;
+	}
+};
+
+LC_HD size_t lc_align8(size_t x) { return (x + 7) & ~(size_t)7; }
+LC_HD size_t lc_chain_scratch_bytes(int S)
+{
+	return lc_align8(sizeof(LcChainRec) * (size_t)S) + lc_align8(sizeof(LcBtNode) * ((size_t)S / (LC_BT_T - 1) + 2)) +
+		   lc_align8(4 * (size_t)S) * 6 /* s_q, s_len, s_next, order, srt, kept_idx */ + 64;
+}
+
+LC_HDN void lc_stage_chain(const LcBatch &b, int r)
+{
+	const lc_opt_t &opt = b.opt;
+	const int S = b.r_n_seed[r], NI = b.r_n_intv[r];
+	const int len = (int)(b.off[r + 1] - b.off[r]);
+	b.r_n_chain[r] = 0; b.r_chain_off[r] = 0; b.r_frac_rep[r] = 0.f; b.r_n_cseed[r] = 0;
+	if (S == 0 && NI == 0) return;
+	const LcIntvOut *iv = b.intv + b.r_intv_off[r];
+	// frac_rep: span covered by intervals more frequent than max_occ (B/bwamem.c:265-272,310)
+	int rb = 0, re = 0, l_rep = 0;
+	for (int i = 0; i < NI; ++i) {
+		int sb = (int)iv[i].qbeg, se = (int)iv[i].qend;
+		if (iv[i].x2 <= (uint64_t)opt.max_occ) continue;
+		if (sb > re) { l_rep += re - rb; rb = sb; re = se; } else re = lc_max(re, se);
+	}
+	l_rep += re - rb;
+	const float frac_rep = (float)l_rep / len;
+	b.r_frac_rep[r] = frac_rep;
+	if (S == 0) return;
+	unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, lc_chain_scratch_bytes(S), LC_OVF_SCRATCH);
+	if (so == (unsigned long long)-1) return;
+	uint8_t *p = b.scratch + so;
+	p = (uint8_t *)lc_align8((size_t)p);
+	LcChainer c;
+	c.ch = (LcChainRec *)p; p += lc_align8(sizeof(LcChainRec) * (size_t)S);
+	c.nd = (LcBtNode *)p; p += lc_align8(sizeof(LcBtNode) * ((size_t)S / (LC_BT_T - 1) + 2));
+	c.s_q = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+	c.s_len = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+	c.s_next = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+	int32_t *order = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+	int32_t *srt = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+	int32_t *kept_idx = (int32_t *)p;
+	c.s_rbeg = (int64_t *)(b.seed_row + b.r_seed_off[r]);
+	c.n_ch = 0; c.n_nd = 0; c.n_keys = 0;
+	c.root = c.new_node(0);
+	for (int i = 0; i < NI; ++i) {
+		const int slen = (int)(iv[i].qend - iv[i].qbeg);
+		const int cnt = (i + 1 < NI ? (int)iv[i + 1].soff : S) - (int)iv[i].soff;
+		for (int t = 0; t < cnt; ++t) {
+			const int si = (int)iv[i].soff + t;
+			c.s_q[si] = (int)iv[i].qbeg; c.s_len[si] = slen; c.s_next[si] = -1;
+			const int64_t rbeg = c.s_rbeg[si];
+			const int rid = lc_intv2rid(b.ix, rbeg, rbeg + slen);
+			if (rid < 0) continue;                       // spans contigs or the strand boundary (B/bwamem.c:286-287)
+			bool add = true;
+			if (c.n_keys) {
+				int low = c.lower(rbeg);
+				if (low >= 0 && c.merge(opt, b.ix.l_pac, low, si, rid)) add = false;
+			}
+			if (add) {
+				LcChainRec &n = c.ch[c.n_ch];
+				n.pos = rbeg; n.rid = rid; n.n = 1; n.head = n.tail = si; n.w = 0; n.kept = 0; n.first = -1;
+				n.is_alt = b.ix.anns[rid].is_alt ? 1 : 0;
+				c.put(c.n_ch++);
+			}
+		}
+	}
+	int n = 0;
+	{   // in-order walk (__kb_traverse, B/kbtree.h:336-358) with an explicit stack; step t of an internal node:
+		// even t = descend into child t/2, odd t = emit key t/2
+		int st_node[24], st_t[24], top = 0;
+		st_node[0] = c.root; st_t[0] = 0;
+		while (top >= 0) {
+			const LcBtNode &x = c.nd[st_node[top]];
+			if (!x.internal) { for (int i = 0; i < x.n; ++i) order[n++] = x.key[i]; --top; continue; }
+			const int t = st_t[top]++;
+			if (t > 2 * x.n) { --top; continue; }
+			if (t & 1) order[n++] = x.key[t >> 1];
+			else { ++top; st_node[top] = x.child[t >> 1]; st_t[top] = 0; }
+		}
+	}
+	// ---- mem_chain_flt
+	int k = 0;
+	for (int i = 0; i < n; ++i) {
+		LcChainRec &cc = c.ch[order[i]];
+		cc.first = -1; cc.kept = 0;
+		cc.w = (uint32_t)c.weight(order[i]);
+		if ((int)cc.w >= opt.min_chain_weight) srt[k++] = order[i];
+	}
+	n = k;
+	if (n == 0) return;
+	{
+		const LcChainRec *ch = c.ch;
+		lc_introsort(srt, (long)n, [ch](int a, int d) { return ch[a].w > ch[d].w; });      // flt_lt (B/bwamem.c:324-325,341)
+	}
+#define LC_CBEG(id) (c.s_q[c.ch[id].head])
+#define LC_CEND(id) (c.s_q[c.ch[id].tail] + c.s_len[c.ch[id].tail])
+	int n_kept = 0;
+	c.ch[srt[0]].kept = 3; kept_idx[n_kept++] = 0;
+	for (int i = 1; i < n; ++i) {
+		const int ai = srt[i];
+		int large_ovlp = 0;
+		for (k = 0; k < n_kept; ++k) {
+			const int j = kept_idx[k], aj = srt[j];
+			int b_max = lc_max(LC_CBEG(aj), LC_CBEG(ai)), e_min = lc_min(LC_CEND(aj), LC_CEND(ai));
+			if (e_min > b_max && (!c.ch[aj].is_alt || c.ch[ai].is_alt)) {
+				int li = LC_CEND(ai) - LC_CBEG(ai), lj = LC_CEND(aj) - LC_CBEG(aj), min_l = lc_min(li, lj);
+				if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+					large_ovlp = 1;
+					if (c.ch[aj].first < 0) c.ch[aj].first = i;
+					if ((int)c.ch[ai].w < (int)c.ch[aj].w * opt.drop_ratio && (int)c.ch[aj].w - (int)c.ch[ai].w >= opt.min_seed_len << 1) break;
+				}
+			}
+		}
+		if (k == n_kept) { kept_idx[n_kept++] = i; c.ch[ai].kept = large_ovlp ? 2 : 3; }
+	}
+	for (int i = 0; i < n_kept; ++i) { const LcChainRec &cc = c.ch[srt[kept_idx[i]]]; if (cc.first >= 0) c.ch[srt[cc.first]].kept = 1; }
+	{
+		int i;
+		for (i = k = 0; i < n; ++i) {
+			int kp = c.ch[srt[i]].kept;
+			if (kp == 0 || kp == 3) continue;
+			if (++k >= opt.max_chain_extend) break;
+		}
+		for (; i < n; ++i) if (c.ch[srt[i]].kept < 3) c.ch[srt[i]].kept = 0;
+	}
+	// ---- emit kept chains in filter order with their seeds compacted
+	int nk = 0; unsigned long long ns = 0;
+	for (int i = 0; i < n; ++i) if (c.ch[srt[i]].kept) { ++nk; ns += c.ch[srt[i]].n; }
+	unsigned long long co = lc_carve(b, b.chain_cur, b.chain_cap, nk, LC_OVF_CHAIN);
+	unsigned long long eo = lc_carve(b, b.cseed_cur, b.cseed_cap, ns, LC_OVF_CSEED);
+	if (co == (unsigned long long)-1 || eo == (unsigned long long)-1) return;
+	nk = 0; ns = 0;
+	for (int i = 0; i < n; ++i) {
+		const LcChainRec &cc = c.ch[srt[i]];
+		if (!cc.kept) continue;
+		LcChainOut o; o.rid = cc.rid; o.n = cc.n; o.seed_off = (int64_t)(eo + ns); o.w = cc.w; o.is_alt = cc.is_alt;
+		b.chain[co + nk++] = o;
+		for (int s = cc.head; s >= 0; s = c.s_next[s]) { LcSeed sd; sd.rbeg = c.s_rbeg[s]; sd.qbeg = c.s_q[s]; sd.len = c.s_len[s]; b.cseed[eo + ns++] = sd; }
+	}
+	b.r_chain_off[r] = (int64_t)co; b.r_n_chain[r] = nk; b.r_n_cseed[r] = (int32_t)ns;
+}
+
+// ============================================================================================================
+// Stage 4 — extension: mem_chain2aln (B/bwamem.c:632-786) for every kept chain of a read
+// ============================================================================================================
+LC_HD int lc_cal_max_gap(const lc_opt_t &opt, int qlen)          // B/bwamem.c:621-628
+{
+	int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
+	int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+	int l = lc_max(l_del, l_ins);
+	l = lc_max(l, 1);
+	return lc_min(l, opt.w << 1);
+}
+
+LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
+{
+	const lc_opt_t &opt = b.opt;
+	const int l_query = (int)(b.off[r + 1] - b.off[r]);
+	const uint8_t *query = b.seq + b.off[r];
+	const int NC = b.r_n_chain[r], T = b.r_n_cseed[r];
+	b.r_n_reg[r] = 0; b.r_reg_off[r] = 0;
+	if (NC == 0) return;
+	unsigned long long ro = lc_carve(b, b.reg_cur, b.reg_cap, T, LC_OVF_REG);
+	unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * T + 8, LC_OVF_SCRATCH);
+	if (ro == (unsigned long long)-1 || so == (unsigned long long)-1) return;
+	lc_alnreg_t *av = b.reg + ro;
+	uint64_t *srt = (uint64_t *)lc_align8((size_t)(b.scratch + so));
+	int *H = b.w_int + (size_t)worker * b.w_int_n, *E = H + (b.lmax + 2);
+	const int64_t l_pac = b.ix.l_pac;
+	int n_av = 0;
+	for (int ci = 0; ci < NC; ++ci) {
+		const LcChainOut &c = b.chain[b.r_chain_off[r] + ci];
+		const LcSeed *seeds = b.cseed + c.seed_off;
+		if (c.n == 0) continue;
+		int64_t r0 = l_pac << 1, r1 = 0;
+		for (int i = 0; i < c.n; ++i) {                     // widest window any seed may extend into (B/bwamem.c:642-657)
+			const LcSeed &t = seeds[i];
+			int64_t bb = t.rbeg - (t.qbeg + lc_cal_max_gap(opt, t.qbeg));
+			int tail = l_query - t.qbeg - t.len;
+			int64_t ee = t.rbeg + t.len + (tail + lc_cal_max_gap(opt, tail));
+			r0 = lc_min(r0, bb); r1 = lc_max(r1, ee);
+		}
+		r0 = lc_max(r0, (int64_t)0); r1 = lc_min(r1, l_pac << 1);
+		if (r0 < l_pac && l_pac < r1) { if (seeds[0].rbeg < l_pac) r1 = l_pac; else r0 = l_pac; }
+		lc_fetch_clamp(b.ix, r0, seeds[0].rbeg, r1);        // bns_fetch_seq clamps to the contig (B/bwamem.c:659)
+		for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;   // score == len (B/bwamem.c:663-665)
+		lc_introsort(srt, (long)c.n, [](uint64_t x, uint64_t y) { return x < y; });
+		for (int k = c.n - 1; k >= 0; --k) {
+			const LcSeed s = seeds[(uint32_t)srt[k]];
+			int i;
+			for (i = 0; i < n_av; ++i) {                    // seed already explained by an earlier region? (B/bwamem.c:671-687)
+				const lc_alnreg_t &p = av[i];
+				int64_t rd; int qd, w, g;
+				if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+				if (s.len - p.seedlen0 > .1 * l_query) continue;
+				qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
+				g = lc_cal_max_gap(opt, qd < rd ? qd : (int)rd); w = lc_min(g, p.w);
+				if (qd - rd < w && rd - qd < w) break;
+				qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+				g = lc_cal_max_gap(opt, qd < rd ? qd : (int)rd); w = lc_min(g, p.w);
+				if (qd - rd < w && rd - qd < w) break;
+			}
+			if (i < n_av) {                                 // contained: extend only if an overlapping off-diagonal seed exists (B/bwamem.c:688-706)
+				for (i = k + 1; i < c.n; ++i) {
+					if (srt[i] == 0) continue;
+					const LcSeed &t = seeds[(uint32_t)srt[i]];
+					if (t.len < s.len * .95) continue;
+					if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+					if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+				}
+				if (i == c.n) { srt[k] = 0; continue; }
+			}
+			lc_alnreg_t a;
+			memset(&a, 0, sizeof(a));
+			int aw0 = opt.w, aw1 = opt.w;
+			a.w = opt.w; a.score = a.truesc = -1; a.rid = c.rid;
+			if (s.qbeg) {                                   // left extension on reversed sequences (B/bwamem.c:715-744)
+				LcSeqRev qf = { query + s.qbeg - 1 };
+				LcRefRev tf = { &b.ix, s.rbeg - 1 };
+				LcExtResult x = { 0, 0, 0, 0, 0, 0 };
+				for (i = 0; i < 2; ++i) {
+					int prev = a.score;
+					aw0 = opt.w << i;
+					x = lc_extend2(s.qbeg, qf, (int)(s.rbeg - r0), tf, b.sc, aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, H, E, b.cnt);
+					a.score = x.score;
+					if (a.score == prev || x.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
+				}
+				if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip5) { a.qb = s.qbeg - x.qle; a.rb = s.rbeg - x.tle; a.truesc = a.score; }
+				else { a.qb = 0; a.rb = s.rbeg - x.gtle; a.truesc = x.gscore; }
+			} else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+			if (s.qbeg + s.len != l_query) {                // right extension (B/bwamem.c:746-771)
+				const int qe = s.qbeg + s.len, sc0 = a.score;
+				const int64_t re = s.rbeg + s.len;
+				LcSeqFwd qf = { query + qe };
+				LcRefFwd tf = { &b.ix, re };
+				LcExtResult x = { 0, 0, 0, 0, 0, 0 };
+				for (i = 0; i < 2; ++i) {
+					int prev = a.score;
+					aw1 = opt.w << i;
+					x = lc_extend2(l_query - qe, qf, (int)(r1 - re), tf, b.sc, aw1, opt.pen_clip3, opt.zdrop, sc0, H, E, b.cnt);
+					a.score = x.score;
+					if (a.score == prev || x.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
+				}
+				if (x.gscore <= 0 || x.gscore <= a.score - opt.pen_clip3) { a.qe = qe + x.qle; a.re = re + x.tle; a.truesc += a.score - sc0; }
+				else { a.qe = l_query; a.re = re + x.gtle; a.truesc += x.gscore - sc0; }
+			} else { a.qe = l_query; a.re = s.rbeg + s.len; }
+			a.seedcov = 0;
+			for (i = 0; i < c.n; ++i) {
+				const LcSeed &t = seeds[i];
+				if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+			}
+			a.w = lc_max(aw0, aw1);
+			a.seedlen0 = s.len;
+			a.frac_rep = b.r_frac_rep[r];
+			av[n_av++] = a;
+		}
+	}
+	b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av;
+	if (n_av) lc_atomic_add(b.reg_total, (unsigned long long)n_av);
+}
+
+// ============================================================================================================
+// Stage 5 — per pair: mem_sort_dedup_patch (B/bwamem.c:437-489) on each end, then the two mate-rescue phases of
+// GoBwaMemMateSW (G/gobwa.go:264-324) with mem_matesw (B/bwamem_pair.c:111-180)
+// ============================================================================================================
+struct LcSwScratch { int *H, *E, *Hmax; unsigned long long *b; uint8_t *z_unused; };
+
+// bwa_gen_cigar2, score only (B/bwa.c:121-207) — used by mem_patch_reg
+LC_HDN int lc_global_score(const LcBatch &b, int w_, int l_query, const uint8_t *query, int64_t rb, int64_t re, int *H, int *E, bool &ok)
+{
+	const int64_t l_pac = b.ix.l_pac;
+	ok = false;
+	if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return 0;
+	if (re > l_pac << 1 || rb < 0) return 0;               // bns_get_seq would return a shorter sequence (B/bwa.c:134)
+	const int rlen = (int)(re - rb);
+	ok = true;
+	const bool rev = rb >= l_pac;
+	if (l_query == rlen && w_ == 0) {
+		int s = 0;
+		for (int i = 0; i < l_query; ++i) s += b.sc.sub(lc_ref_base(b.ix, rb + i), query[i]);   // order-independent sum
+		return s;
+	}
+	int mi = (int)((double)(((l_query + 1) >> 1) * b.sc.a - b.sc.o_ins) / b.sc.e_ins + 1.);
+	int md = (int)((double)(((l_query + 1) >> 1) * b.sc.a - b.sc.o_del) / b.sc.e_del + 1.);
+	int mg = lc_max(lc_max(mi, md), 1), dl = rlen > l_query ? rlen - l_query : l_query - rlen;
+	int w = (mg + dl + 1) >> 1;
+	w = lc_min(w, w_);
+	w = lc_max(w, dl + 3);
+	if (rev) {   // both sequences reversed so gaps are left-aligned on the forward strand (B/bwa.c:135-140)
+		LcSeqRev qf = { query + l_query - 1 }; LcRefRev tf = { &b.ix, re - 1 };
+		return lc_global2(l_query, qf, rlen, tf, b.sc, w, H, E, (uint8_t *)0, (uint32_t *)0, 0, (int *)0, b.cnt);
+	}
+	LcSeqFwd qf = { query }; LcRefFwd tf = { &b.ix, rb };
+	return lc_global2(l_query, qf, rlen, tf, b.sc, w, H, E, (uint8_t *)0, (uint32_t *)0, 0, (int *)0, b.cnt);
+}
+
+// mem_patch_reg (B/bwamem.c:406-435)
+LC_HDN int lc_patch_reg(const LcBatch &b, const uint8_t *query, const lc_alnreg_t &a, const lc_alnreg_t &p, int *H, int *E, int &w_out)
+{
+	const lc_opt_t &opt = b.opt;
+	if (a.rb < b.ix.l_pac && p.rb >= b.ix.l_pac) return 0;
+	if (a.qb >= p.qb || a.qe >= p.qe || a.re >= p.re) return 0;
+	int w = (int)((a.re - p.rb) - (a.qe - p.qb));
+	w = w > 0 ? w : -w;
+	double r = (double)(a.re - p.rb) / (p.re - a.rb) - (double)(a.qe - p.qb) / (p.qe - a.qb);
+	r = r > 0. ? r : -r;
+	if (a.re < p.rb || a.qe < p.qb) { if (w > opt.w << 1 || r >= 0.05f) return 0; }
+	else if (w > opt.w << 2 || r >= 0.05f * 2) return 0;
+	w += a.w + p.w;
+	w = lc_min(w, opt.w << 2);
+	bool ok;
+	int score = lc_global_score(b, w, p.qe - a.qb, query + a.qb, a.rb, p.re, H, E, ok);
+	// when bwa_gen_cigar2 rejects the span it leaves `score` unset (B/bwa.c:132,134 / B/bwamem.c:408,428); that cannot
+	// happen for two colinear same-strand regions inside one contig, which is all that reaches this point
+	int q_s = (int)((double)(p.qe - a.qb) / ((p.qe - p.qb) + (a.qe - a.qb)) * (p.score + a.score) + .499);
+	int r_s = (int)((double)(p.re - a.rb) / ((p.re - p.rb) + (a.re - a.rb)) * (p.score + a.score) + .499);
+	if ((double)score / lc_max(q_s, r_s) < 0.90f) return 0;
+	w_out = w;
+	return score;
+}
+
+// mem_sort_dedup_patch (B/bwamem.c:437-489); query == null disables patching (the call from mem_matesw, B/bwamem_pair.c:175)
+LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E)
+{
+	const lc_opt_t &opt = b.opt;
+	int m, i, j;
+	if (n <= 1) return n;
+	lc_introsort(a, (long)n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; });
+	for (i = 0; i < n; ++i) a[i].n_comp = 1;
+	for (i = 1; i < n; ++i) {
+		lc_alnreg_t &p = a[i];
+		if (p.rid != a[i - 1].rid || p.rb >= a[i - 1].re + opt.max_chain_gap) continue;
+		for (j = i - 1; j >= 0 && p.rid == a[j].rid && p.rb < a[j].re + opt.max_chain_gap; --j) {
+			lc_alnreg_t &q = a[j];
+			int64_t orr, oq, mr, mq;
+			int score, w;
+			if (q.qe == q.qb) continue;
+			orr = q.re - p.rb;
+			oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+			mr = lc_min(q.re - q.rb, p.re - p.rb);
+			mq = lc_min(q.qe - q.qb, p.qe - p.qb);
+			if (orr > opt.mask_level_redun * mr && oq > opt.mask_level_redun * mq) {
+				if (p.score < q.score) { p.qe = p.qb; break; }
+				else q.qe = q.qb;
+			} else if (query && q.rb < p.rb && (score = lc_patch_reg(b, query, q, p, H, E, w)) > 0) {
+				p.n_comp += q.n_comp + 1;
+				p.seedcov = lc_max(p.seedcov, q.seedcov);
+				p.sub = lc_max(p.sub, q.sub);
+				p.csub = lc_max(p.csub, q.csub);
+				p.qb = q.qb; p.rb = q.rb;
+				p.truesc = p.score = score;
+				p.w = w;
+				q.qb = q.qe;
+			}
+		}
+	}
+	for (i = 0, m = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+	n = m;
+	lc_introsort(a, (long)n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
+		return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb))); });
+	for (i = 1; i < n; ++i)
+		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+	for (i = 1, m = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+	return m;
+}
+
+LC_HD int lc_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t &dist)   // mem_infer_dir (B/bwamem_pair.c:23-30)
+{
+	int r1 = b1 >= l_pac, r2 = b2 >= l_pac;
+	int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;
+	dist = p2 > b1 ? p2 - b1 : b1 - p2;
+	return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
+}
+
+// mem_matesw (B/bwamem_pair.c:111-180) with Lariat's insert model: only orientation FR (index 1) is enabled
+// (G/gobwa.go:229-237), so at most one SW is run and at most one region is added per call.
+LC_HDN int lc_matesw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const LcSwScratch &ws)
+{
+	const lc_opt_t &opt = b.opt;
+	const int64_t l_pac = b.ix.l_pac;
+	const int low = b.pes_low, high = b.pes_high;
+	for (int i = 0; i < n_ma; ++i) {                       // an existing mate hit in range satisfies the orientation (:118-124)
+		int64_t dist;
+		int r = lc_infer_dir(l_pac, a.rb, ma[i].rb, dist);
+		if (r == 1 && dist >= low && dist <= high) return 0;
+	}
+	// r = 1: is_rev = 1 (mate is reverse-complemented), is_larger = 1 (:130-143)
+	int64_t rb = a.rb + low - l_ms, re = a.rb + high;
+	if (rb < 0) rb = 0;
+	if (re > l_pac << 1) re = l_pac << 1;
+	int rid = -1;
+	if (rb < re) rid = lc_fetch_clamp(b.ix, rb, (rb + re) >> 1, re);
+	// (when rb >= re the reference compares against an uninitialised rid, :147; treated as "no window")
+	if (a.rid != rid || re - rb < opt.min_seed_len) return 0;
+	const int xtra = LC_XSUBO | LC_XSTART | (l_ms * opt.a < 250 ? LC_XBYTE : 0) | (opt.min_seed_len * opt.a);
+	LcSeqRevComp qf = { ms, l_ms };
+	LcRefFwd tf = { &b.ix, rb };
+	LcSwResult aln = lc_sw_align2(l_ms, qf, (int)(re - rb), tf, b.sc, xtra, ws.H, ws.E, ws.Hmax, ws.b, b.cnt);
+	if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
+		lc_alnreg_t nb;
+		memset(&nb, 0, sizeof(nb));
+		nb.rid = a.rid;
+		nb.is_alt = a.is_alt;
+		nb.qb = l_ms - (aln.qe + 1);
+		nb.qe = l_ms - aln.qb;
+		nb.rb = (l_pac << 1) - (rb + aln.te + 1);
+		nb.re = (l_pac << 1) - (rb + aln.tb);
+		nb.score = aln.score;
+		nb.csub = aln.score2;
+		nb.secondary = -1;
+		nb.seedcov = (int)((nb.re - nb.rb < nb.qe - nb.qb ? nb.re - nb.rb : nb.qe - nb.qb) >> 1);
+		int at;
+		++n_ma;
+		for (at = 0; at < n_ma - 1; ++at) if (ma[at].score < nb.score) break;     // keep sorted by score (:165-171)
+		for (int i = n_ma - 1; i > at; --i) ma[i] = ma[i - 1];
+		ma[at] = nb;
+	}
+	n_ma = lc_sort_dedup_patch(b, (const uint8_t *)0, n_ma, ma, ws.H, ws.E);       // :175 (n == 1 here)
+	return 1;
+}
+
+LC_HDN void lc_stage_pair(const LcBatch &b, int p, int worker)
+{
+	const lc_opt_t &opt = b.opt;
+	int *wi = b.w_int + (size_t)worker * b.w_int_n;
+	LcSwScratch ws;
+	ws.H = wi; ws.E = wi + (b.lmax + 18); ws.Hmax = wi + 2 * (b.lmax + 18);
+	ws.b = b.w_u64 + (size_t)worker * b.w_u64_n; ws.z_unused = 0;
+	int n[2], len[2], best[2] = { 0, 0 };
+	const uint8_t *q[2];
+	lc_alnreg_t *src[2];
+	for (int e = 0; e < 2; ++e) {
+		const int r = 2 * p + e;
+		len[e] = (int)(b.off[r + 1] - b.off[r]); q[e] = b.seq + b.off[r];
+		src[e] = b.reg + b.r_reg_off[r];
+		n[e] = lc_sort_dedup_patch(b, q[e], b.r_n_reg[r], src[e], ws.H, ws.E);      // tail of mem_align1_core (B/bwamem.c:1070)
+		for (int i = 0; i < n[e]; ++i) {
+			if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
+			best[e] = lc_max(best[e], src[e][i].score);                                         // G/gobwa.go:264-283
+		}
+	}
+	// capacity of the final lists: every rescue call adds at most one region
+	int a2 = 0;
+	if (len[0] > 0) for (int i = 0; i < n[1] && a2 < b.max_anchors; ++i) if (src[1][i].score >= best[1] - b.score_delta) ++a2;
+	const int cap0 = n[0] + a2;
+	const int cap1 = n[1] + (len[1] > 0 ? lc_min(b.max_anchors, cap0) : 0);
+	unsigned long long fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
+	b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
+	if (fo == (unsigned long long)-1) return;
+	lc_alnreg_t *f0 = b.fin + fo, *f1 = b.fin + fo + cap0;
+	for (int i = 0; i < n[0]; ++i) f0[i] = src[0][i];
+	for (int i = 0; i < n[1]; ++i) f1[i] = src[1][i];
+	int n0 = n[0], n1 = n[1], num = 0;
+	// phase 1: rescue read 1 from read 2's hits (G/gobwa.go:286-300). read 2's list is not touched in this phase.
+	for (int i = 0; i < n1 && num < b.max_anchors && len[0] > 0; ++i)
+		if (f1[i].score >= best[1] - b.score_delta) { ++num; lc_matesw(b, f1[i], len[0], q[0], f0, n0, ws); }
+	// phase 2: rescue read 2 from read 1's post-rescue list, gated by the pre-rescue best (G/gobwa.go:302-324)
+	num = 0;
+	for (int i = 0; i < n0 && num < b.max_anchors && len[1] > 0; ++i)
+		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw(b, f0[i], len[1], q[1], f1, n1, ws); }
+	b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n0;
+	b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n1;
+	unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));   // candidate list for stage 6 (sized like fin)
+	for (int i = 0; i < n0; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
+	for (int i = 0; i < n1; ++i) b.cand[co + n0 + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
+}
+
+// ============================================================================================================
+// Stage 6 — final alignment of one candidate: mem_reg2aln (B/bwamem.c:1086-1156) -> bwa_gen_cigar2 (B/bwa.c:121-207)
+// ============================================================================================================
+LC_HD int lc_infer_bw(int l1, int l2, int score, int a, int q, int r)   // B/bwamem.c:792-799
+{
+	if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+	int w = (int)(((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.));
+	int d = l1 > l2 ? l1 - l2 : l2 - l1;
+	return w < d ? d : w;
+}
+
+LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
+{
+	const lc_opt_t &opt = b.opt;
+	const uint64_t cd = b.cand[ci];
+	const int r = (int)(cd >> 32), idx = (int)(uint32_t)cd;
+	const int l_query = (int)(b.off[r + 1] - b.off[r]);
+	const uint8_t *query = b.seq + b.off[r];
+	const size_t slot = (size_t)b.r_fin_off[r] + idx;
+	const lc_alnreg_t &ar = b.fin[slot];
+	lc_aln_t out;
+	memset(&out, 0, sizeof(out));
+	if (ar.rb < 0 || ar.re < 0) { out.rid = -1; out.pos = -1; b.aln[slot] = out; return; }
+	int *H = b.w_int + (size_t)worker * b.w_int_n, *E = H + (b.lmax + 2);
+	const int64_t l_pac = b.ix.l_pac, rb = ar.rb, re = ar.re;
+	const int qb = ar.qb, qe = ar.qe, lq = qe - qb, rlen = (int)(re - rb);
+	const bool rev = rb >= l_pac;
+	int tmp = lc_infer_bw(lq, rlen, ar.truesc, opt.a, opt.o_del, opt.e_del);
+	int w2 = lc_infer_bw(lq, rlen, ar.truesc, opt.a, opt.o_ins, opt.e_ins);
+	w2 = lc_max(w2, tmp);
+	if (w2 > opt.w) w2 = lc_min(w2, ar.w);
+	// the CIGAR is built in a per-worker buffer (an alignment of lq x rlen has at most 2*min(lq,rlen)+1 merged ops) and
+	// only its final ops are carved from the output pool
+	const int cig_cap = 2 * b.lmax + 8;
+	uint32_t *cig = (uint32_t *)(E + (b.lmax + 2));
+	int n_cigar = 0, score = 0, last_sc = -(1 << 30), i = 0;
+	const bool bad = lq <= 0 || rb >= re || (rb < l_pac && re > l_pac) || re > l_pac << 1;
+	do {
+		w2 = lc_min(w2, opt.w << 2);
+		n_cigar = 0;
+		if (bad) { score = 0; break; }                       // bwa_gen_cigar2 returns no CIGAR (B/bwa.c:132-134)
+		if (lq == rlen && w2 == 0) {                         // gap-free (B/bwa.c:141-149)
+			cig[0] = (uint32_t)lq << 4; n_cigar = 1;
+			score = 0;
+			for (int k = 0; k < lq; ++k) score += b.sc.sub(lc_ref_base(b.ix, rb + k), query[qb + k]);
+		} else {
+			int mi = (int)((double)(((lq + 1) >> 1) * b.sc.a - b.sc.o_ins) / b.sc.e_ins + 1.);
+			int md = (int)((double)(((lq + 1) >> 1) * b.sc.a - b.sc.o_del) / b.sc.e_del + 1.);
+			int mg = lc_max(lc_max(mi, md), 1), dl = rlen > lq ? rlen - lq : lq - rlen;
+			int w = (mg + dl + 1) >> 1;
+			w = lc_min(w, w2);
+			w = lc_max(w, dl + 3);
+			const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
+			const unsigned long long zneed = (unsigned long long)n_col * rlen + 8;
+			uint8_t *z;
+			if (zneed <= (unsigned long long)b.w_z_n) z = b.w_z + (size_t)worker * b.w_z_n;   // common case: per-worker traceback scratch
+			else {
+				unsigned long long zo = lc_carve(b, b.z_cur, b.z_cap, zneed, LC_OVF_Z);
+				if (zo == (unsigned long long)-1) return;
+				z = b.zpool + zo;
+			}
+			if (rev) {
+				LcSeqRev qf = { query + qe - 1 }; LcRefRev tf = { &b.ix, re - 1 };
+				score = lc_global2(lq, qf, rlen, tf, b.sc, w, H, E, z, cig, cig_cap, &n_cigar, b.cnt);
+			} else {
+				LcSeqFwd qf = { query + qb }; LcRefFwd tf = { &b.ix, rb };
+				score = lc_global2(lq, qf, rlen, tf, b.sc, w, H, E, z, cig, cig_cap, &n_cigar, b.cnt);
+			}
+		}
+		if (score == last_sc || w2 == opt.w << 2) break;
+		last_sc = score;
+		w2 <<= 1;
+	} while (++i < 3 && score < ar.truesc - opt.a);
+	// NM = mismatches + gap bases, skipping a leading/trailing deletion (B/bwa.c:169-199)
+	int NM = -1, n_mm = 0;
+	if (!bad) {
+		int x = 0, y = 0, n_gap = 0;
+		for (int k = 0; k < n_cigar; ++k) {
+			const int op = cig[k] & 0xf, len = (int)(cig[k] >> 4);
+			if (op == 0) {
+				for (int t = 0; t < len; ++t) {
+					int qc = rev ? query[qe - 1 - (x + t)] : query[qb + x + t];
+					int rc = rev ? lc_ref_base(b.ix, re - 1 - (y + t)) : lc_ref_base(b.ix, rb + y + t);
+					n_mm += qc != rc;
+				}
+				x += len; y += len;
+			} else if (op == 2) { if (k > 0 && k < n_cigar - 1) n_gap += len; y += len; }
+			else if (op == 1) { x += len; n_gap += len; }
+		}
+		NM = n_mm + n_gap;
+	}
+	int64_t pos = rev ? (l_pac << 1) - 1 - (re - 1) : rb;       // bns_depos (B/bwamem.c:1122)
+	if (n_cigar < 0) { lc_raise(b, LC_OVF_CIGAR); return; }
+	int cs = 0, ce = n_cigar;
+	if (n_cigar > 0) {                                       // squeeze out a leading or trailing deletion (B/bwamem.c:1124-1133)
+		if ((cig[0] & 0xf) == 2) { pos += cig[0] >> 4; cs = 1; }
+		else if ((cig[ce - 1] & 0xf) == 2) --ce;
+	}
+	const bool clipped = qb != 0 || qe != l_query;          // soft clips (B/bwamem.c:1134-1148)
+	const int clip5 = clipped ? (rev ? l_query - qe : qb) : 0, clip3 = clipped ? (rev ? qb : l_query - qe) : 0;
+	const int o = (clip5 ? 1 : 0) + (ce - cs) + (clip3 ? 1 : 0);
+	unsigned long long co = lc_carve(b, b.cigar_cur, b.cigar_cap, (unsigned long long)o, LC_OVF_CIGAR);
+	if (co == (unsigned long long)-1) return;
+	{
+		uint32_t *dst = b.cigar + co;
+		int k = 0;
+		if (clip5) dst[k++] = (uint32_t)clip5 << 4 | 3;
+		for (int t = cs; t < ce; ++t) dst[k++] = cig[t];
+		if (clip3) dst[k++] = (uint32_t)clip3 << 4 | 3;
+	}
+	out.pos = pos; out.is_rev = rev ? 1 : 0; out.NM = NM; out.n_cigar = o; out.cigar_off = (uint32_t)co; out.n_mismatch = n_mm;
+	out.rid = lc_pos2rid(b.ix, pos);
+	if (out.rid >= 0) out.pos = pos - b.ix.anns[out.rid].offset;
+	b.aln[slot] = out;
+}

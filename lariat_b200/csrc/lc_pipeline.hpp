@@ -1,0 +1,400 @@
+// lc_pipeline.hpp — host-side orchestration of one batch: pool sizing, stage sequence, overflow/regrow, result packing.
+//
+// Templated on a Backend that owns memory and launches.  The product instantiates it with the CUDA backend
+// (lc_api.cu: cudaMalloc + the __global__ kernels of lc_kernels.cu).  tests/hostsim instantiates it with a
+// serial loop backend to check the orchestration logic on a machine without a GPU; that backend is test code
+// and is never compiled into libcuda_lariat.so.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "lc_mem.cuh"
+
+struct LcHostIndex {
+	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0;
+	std::vector<uint32_t> bwt;          // 64-byte occ blocks, as in the .bwt file after its 40-byte header
+	std::vector<uint64_t> sa;
+	int sa_intv = 0;
+	std::vector<uint8_t> pac;
+	int64_t l_pac = 0;
+	std::vector<LcAnn> anns;
+	std::vector<std::string> names;
+};
+
+static inline bool lc_slurp(const std::string &fn, std::vector<uint8_t> &out)
+{
+	FILE *f = fopen(fn.c_str(), "rb");
+	if (!f) return false;
+	fseek(f, 0, SEEK_END);
+	long n = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	out.resize((size_t)n);
+	bool ok = n == 0 || fread(out.data(), 1, (size_t)n, f) == (size_t)n;
+	fclose(f);
+	return ok;
+}
+
+// Reads <prefix>.bwt/.sa/.ann/.pac(/.alt) — the files `bwa index` writes and bwa_idx_load reads
+// (B/bwt.c:421-462, B/bntseq.c:98-206, B/bwa.c:262-289).
+static inline bool lc_load_index(const char *prefix, LcHostIndex &ix, std::string &err)
+{
+	std::vector<uint8_t> raw;
+	std::string p(prefix);
+	if (!lc_slurp(p + ".bwt", raw) || raw.size() < 40 + 64) { err = "cannot read " + p + ".bwt"; return false; }
+	memcpy(&ix.primary, raw.data(), 8);
+	memcpy(&ix.L2[1], raw.data() + 8, 32);
+	ix.L2[0] = 0;
+	ix.seq_len = ix.L2[4];
+	size_t nw = (raw.size() - 40) / 4;
+	ix.bwt.assign(((nw + 15) / 16) * 16 + 16, 0);   // padded to whole 64-byte blocks
+	memcpy(ix.bwt.data(), raw.data() + 40, nw * 4);
+	if (!lc_slurp(p + ".sa", raw) || raw.size() < 56) { err = "cannot read " + p + ".sa"; return false; }
+	uint64_t h[7];
+	memcpy(h, raw.data(), 56);
+	if (h[0] != ix.primary || h[6] != ix.seq_len) { err = "SA-BWT inconsistency in " + p; return false; }
+	ix.sa_intv = (int)h[5];
+	if (ix.sa_intv <= 0 || (ix.sa_intv & (ix.sa_intv - 1))) { err = "SA interval is not a power of two"; return false; }
+	size_t n_sa = (size_t)((ix.seq_len + ix.sa_intv) / ix.sa_intv);
+	if (raw.size() < 56 + (n_sa - 1) * 8) { err = "truncated " + p + ".sa"; return false; }
+	ix.sa.resize(n_sa);
+	ix.sa[0] = (uint64_t)-1;
+	memcpy(ix.sa.data() + 1, raw.data() + 56, (n_sa - 1) * 8);
+	FILE *f = fopen((p + ".ann").c_str(), "r");
+	if (!f) { err = "cannot read " + p + ".ann"; return false; }
+	long long lp; int n_seqs; unsigned seed;
+	if (fscanf(f, "%lld%d%u", &lp, &n_seqs, &seed) != 3) { fclose(f); err = "bad .ann header"; return false; }
+	ix.l_pac = lp;
+	ix.anns.resize(n_seqs);
+	ix.names.resize(n_seqs);
+	for (int i = 0; i < n_seqs; ++i) {
+		unsigned gi; char name[8192], rest[8192];
+		long long off; int len, n_ambs;
+		if (fscanf(f, "%u%8191s", &gi, name) != 2 || !fgets(rest, sizeof rest, f) || fscanf(f, "%lld%d%d", &off, &len, &n_ambs) != 3) {
+			fclose(f); err = "bad .ann record"; return false;
+		}
+		ix.names[i] = name;
+		ix.anns[i].offset = off; ix.anns[i].len = len; ix.anns[i].is_alt = 0;
+	}
+	fclose(f);
+	if ((f = fopen((p + ".alt").c_str(), "r")) != 0) {      // ALT contig list (B/bntseq.c:179-204)
+		char line[8192];
+		while (fgets(line, sizeof line, f)) {
+			if (line[0] == '@') continue;
+			line[strcspn(line, "\t\r\n")] = 0;
+			for (int i = 0; i < n_seqs; ++i) if (ix.names[i] == line) ix.anns[i].is_alt = 1;
+		}
+		fclose(f);
+	}
+	if (!lc_slurp(p + ".pac", raw)) { err = "cannot read " + p + ".pac"; return false; }
+	ix.pac.assign((size_t)(ix.l_pac / 4 + 2) + 16, 0);
+	memcpy(ix.pac.data(), raw.data(), std::min(raw.size(), (size_t)(ix.l_pac / 4 + 1)));
+	if (ix.seq_len != (uint64_t)ix.l_pac * 2) { err = "index does not hold forward+reverse text (seq_len != 2*l_pac)"; return false; }
+	return true;
+}
+
+static inline void lc_default_opt(lc_opt_t *o)    // mem_opt_init (B/bwamem.c:48-84)
+{
+	memset(o, 0, sizeof(*o));
+	o->a = 1; o->b = 4; o->o_del = o->o_ins = 6; o->e_del = o->e_ins = 1;
+	o->w = 100; o->T = 30; o->zdrop = 100; o->pen_unpaired = 17; o->pen_clip5 = o->pen_clip3 = 5;
+	o->max_mem_intv = 20; o->min_seed_len = 19; o->split_width = 10; o->max_occ = 500; o->max_chain_gap = 10000;
+	o->max_ins = 10000; o->mask_level = 0.50f; o->drop_ratio = 0.50f; o->XA_drop_ratio = 0.80f; o->split_factor = 1.5f;
+	o->chunk_size = 10000000; o->n_threads = 1; o->max_XA_hits = 5; o->max_XA_hits_alt = 200; o->max_matesw = 50;
+	o->mask_level_redun = 0.95f; o->min_chain_weight = 0; o->max_chain_extend = 1 << 30;
+	o->mapQ_coef_len = 50; o->mapQ_coef_fac = 3;    // (int)log(50)
+	for (int i = 0, k = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) o->mat[k++] = (i == 4 || j == 4) ? -1 : (i == j ? o->a : -o->b);
+}
+
+// ASCII base or raw code -> 2-bit code; restates nst_nt4_table (B/bntseq.c:47-64) — '-' (5 there) folds to 4 like every consumer does
+LC_HD uint8_t lc_nt4(uint8_t c, bool is_ascii)
+{
+	if (!is_ascii) return c > 4 ? 4 : c;
+	switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+
+struct LcPackArgs {            // stage 7: dense result arrays
+	const int64_t *out_off;    // [n_reads+1] exclusive scan of r_n_fin
+	lc_alnreg_t *out_reg; lc_aln_t *out_aln;
+};
+
+LC_HD void lc_stage_pack(const LcBatch &b, const LcPackArgs &pa, int r)
+{
+	const int n = b.r_n_fin[r];
+	const int64_t src = b.r_fin_off[r], dst = pa.out_off[r];
+	for (int i = 0; i < n; ++i) { pa.out_reg[dst + i] = b.fin[src + i]; pa.out_aln[dst + i] = b.aln[src + i]; }
+}
+
+struct LcHostResult {
+	std::vector<int64_t> reg_off;
+	std::vector<lc_alnreg_t> regs;
+	std::vector<lc_aln_t> aln;
+	std::vector<uint32_t> cigars;
+	float ms[10] = {0};        // h2d, seed, sa, chain, extend, (dedup: folded into pair), pair, cigar, d2h, total
+	int64_t launches = 0;
+	LcCounters counters;
+};
+
+// A growable device buffer
+template <class BE> struct LcBuf {
+	void *p = nullptr; size_t cap = 0;
+	bool ensure(BE &be, size_t bytes, bool keep = false)
+	{
+		if (bytes <= cap) return true;
+		size_t want = bytes + bytes / 4 + 256;
+		void *np = be.dmalloc(want);
+		if (!np) return false;
+		if (keep && p && cap) be.d2d(np, p, cap);
+		if (p) be.dfree(p);
+		p = np; cap = want;
+		return true;
+	}
+	void release(BE &be) { if (p) be.dfree(p); p = nullptr; cap = 0; }
+};
+
+template <class BE> class LcPipeline {
+public:
+	BE &be;
+	LcBatch b;
+	std::string err;
+	int n_pairs = 0;
+	bool counting = false;
+	// tunables (bytes / elements per read); grown on overflow
+	double intv_per_read = 24, seed_per_read = 48, cigar_per_cand = 6;
+	size_t z_pool_bytes = 64u << 20;
+	int memcap = 256;
+
+	explicit LcPipeline(BE &be_) : be(be_) { memset(&b, 0, sizeof(b)); }
+	~LcPipeline() { release(); }
+
+	void set_index(const LcIndex &ix, const lc_opt_t &opt)
+	{
+		b.ix = ix; b.opt = opt;
+		b.sc.a = opt.a; b.sc.b = opt.b; b.sc.o_del = opt.o_del; b.sc.e_del = opt.e_del; b.sc.o_ins = opt.o_ins; b.sc.e_ins = opt.e_ins;
+		b.pes_low = -35; b.pes_high = 500; b.max_anchors = 50;     // G/gobwa.go:229-237,287,311
+	}
+
+	// ---- upload: bases are ASCII or codes (is_ascii), off[2*n_pairs+1]
+	int upload(int n_pairs_, const uint8_t *bases, const int64_t *off, bool is_ascii)
+	{
+		n_pairs = n_pairs_;
+		const int R = 2 * n_pairs;
+		const int64_t total = off[R];
+		int lmax = 1;
+		for (int r = 0; r < R; ++r) lmax = std::max<int>(lmax, (int)(off[r + 1] - off[r]));
+		if (lmax > LC_MAX_READ_LEN) { err = "read longer than LC_MAX_READ_LEN"; return LC_EARG; }
+		be.ev_record(0);
+		if (!d_seq.ensure(be, (size_t)total + 16) || !d_off.ensure(be, sizeof(int64_t) * (R + 1))) return nomem();
+		if (total) be.h2d(d_seq.p, bases, (size_t)total);
+		be.h2d(d_off.p, off, sizeof(int64_t) * (R + 1));
+		be.k_convert((uint8_t *)d_seq.p, (unsigned long long)total, is_ascii);   // ASCII -> 2-bit codes on the device (G/gobwa.go:159-167)
+		be.ev_record(1);
+		b.n_reads = R; b.seq = (const uint8_t *)d_seq.p; b.off = (const int64_t *)d_off.p; b.lmax = lmax;
+		return LC_OK;
+	}
+
+	// per-read arrays, control block (cursors, overflow word, counters), per-worker scratch
+	int setup()
+	{
+		const int R = b.n_reads;
+		launches = 0;
+		if (!d_perread.ensure(be, (size_t)R * (8 * 5 + 4 * 7) + 256) || !d_nfin.ensure(be, 4 * ((size_t)R + 1))) return nomem();
+		b.r_n_fin = (int32_t *)d_nfin.p;
+		be.dzero(d_nfin.p, 4 * ((size_t)R + 1));
+		{
+			uint8_t *p = (uint8_t *)d_perread.p;
+			b.r_intv_off = (int64_t *)p; p += 8 * (size_t)R;
+			b.r_seed_off = (int64_t *)p; p += 8 * (size_t)R;
+			b.r_chain_off = (int64_t *)p; p += 8 * (size_t)R;
+			b.r_reg_off = (int64_t *)p; p += 8 * (size_t)R;
+			b.r_fin_off = (int64_t *)p; p += 8 * (size_t)R;
+			b.r_n_intv = (int32_t *)p; p += 4 * (size_t)R;
+			b.r_n_seed = (int32_t *)p; p += 4 * (size_t)R;
+			b.r_n_chain = (int32_t *)p; p += 4 * (size_t)R;
+			b.r_n_cseed = (int32_t *)p; p += 4 * (size_t)R;
+			b.r_n_reg = (int32_t *)p; p += 4 * (size_t)R;
+			b.r_frac_rep = (float *)p;
+		}
+		if (!d_ctl.ensure(be, 4096)) return nomem();
+		{
+			unsigned long long *c = (unsigned long long *)d_ctl.p;
+			b.intv_cur = c + 0; b.seed_cur = c + 1; b.scratch_cur = c + 2; b.chain_cur = c + 3; b.cseed_cur = c + 4;
+			b.reg_cur = c + 5; b.fin_cur = c + 6; b.cand_cur = c + 7; b.cigar_cur = c + 8; b.z_cur = c + 9;
+			b.reg_total = c + 10;
+			b.overflow = (uint32_t *)(c + 16);
+			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
+		}
+		be.dzero(d_ctl.p, 4096);
+		b.n_workers = be.n_workers();
+		b.memcap = memcap;
+		b.w_int_n = std::max(3 * (b.lmax + 18), 2 * (b.lmax + 2) + 2 * b.lmax + 8) + 8;
+		b.w_u64_n = (b.pes_high - b.pes_low + b.lmax) / 2 + 8;
+		b.w_z_n = 8192;
+		if (!d_wintv.ensure(be, sizeof(LcIntv) * (size_t)b.n_workers * (3 * (size_t)(b.lmax + 1) + b.memcap)) ||
+			!d_wint.ensure(be, 4 * (size_t)b.n_workers * b.w_int_n) || !d_wu64.ensure(be, 8 * (size_t)b.n_workers * b.w_u64_n) ||
+			!d_wz.ensure(be, (size_t)b.n_workers * b.w_z_n)) return nomem();
+		b.w_intv = (LcIntv *)d_wintv.p; b.w_int = (int32_t *)d_wint.p; b.w_u64 = (unsigned long long *)d_wu64.p; b.w_z = (uint8_t *)d_wz.p;
+		return LC_OK;
+	}
+	int prepare_scratch() { return setup(); }
+
+	// stage 1 with regrow + rerun on overflow
+	int stage_seed()
+	{
+		const int R = b.n_reads;
+		be.ev_record(2);
+		for (int attempt = 0;; ++attempt) {
+			b.intv_cap = (unsigned long long)(intv_per_read * R) + 1024;
+			b.seed_cap = (unsigned long long)(seed_per_read * R) + 4096;
+			if (!d_intv.ensure(be, sizeof(LcIntvOut) * b.intv_cap) || !d_seed.ensure(be, 8 * b.seed_cap)) return nomem();
+			b.intv = (LcIntvOut *)d_intv.p; b.seed_row = (uint64_t *)d_seed.p;
+			be.k_seed(b); ++launches;
+			read_ctl();
+			if (!(h_ctl_ovf & (LC_OVF_INTV | LC_OVF_SEED | LC_OVF_MEMLIST))) break;
+			if (attempt > 12) { err = "seeding pools keep overflowing"; return LC_ENOMEM; }
+			if (h_ctl_ovf & LC_OVF_INTV) intv_per_read = std::max(intv_per_read * 2, (double)h_ctl[0] / R * 1.25);
+			if (h_ctl_ovf & LC_OVF_SEED) seed_per_read = std::max(seed_per_read * 2, (double)h_ctl[1] / R * 1.25);
+			if (h_ctl_ovf & LC_OVF_MEMLIST) {
+				memcap *= 4; b.memcap = memcap;
+				if (!d_wintv.ensure(be, sizeof(LcIntv) * (size_t)b.n_workers * (3 * (size_t)(b.lmax + 1) + b.memcap))) return nomem();
+				b.w_intv = (LcIntv *)d_wintv.p;
+			}
+			be.dzero(d_ctl.p, 4096);
+		}
+		be.ev_record(3);
+		return LC_OK;
+	}
+	int run_seed_only() { int rc = setup(); if (!rc) rc = stage_seed(); return rc; }
+	unsigned long long seed_intv_used() const { return h_ctl[0]; }
+
+	// mem_reg2aln of one region against read 0 of the uploaded batch (source-compatible single-read form)
+	int run_single_cigar(const lc_alnreg_t &ar, LcHostResult &res)
+	{
+		int rc = setup();
+		if (rc) return rc;
+		b.fin_cap = 4;
+		if (!d_fin.ensure(be, sizeof(lc_alnreg_t) * 4) || !d_aln.ensure(be, sizeof(lc_aln_t) * 4) || !d_cand.ensure(be, 32)) return nomem();
+		b.fin = (lc_alnreg_t *)d_fin.p; b.aln = (lc_aln_t *)d_aln.p; b.cand = (uint64_t *)d_cand.p;
+		be.dzero(d_perread.p, (size_t)b.n_reads * (8 * 5 + 4 * 7));
+		be.dzero(d_cand.p, 32);
+		be.h2d(d_fin.p, &ar, sizeof(ar));
+		const unsigned long long need = (unsigned long long)(b.lmax + 2) * (unsigned long long)(ar.re > ar.rb ? ar.re - ar.rb : 1) + 4096;
+		b.cigar_cap = 4 * (unsigned long long)b.lmax + 64; b.z_cap = need;
+		if (!d_cigar.ensure(be, 4 * b.cigar_cap) || !d_z.ensure(be, b.z_cap)) return nomem();
+		b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p;
+		be.k_cigar(b, 1); ++launches;
+		read_ctl();
+		if (h_ctl_ovf) { err = "overflow in single cigar"; return LC_ENOMEM; }
+		res.aln.resize(1); res.cigars.resize((size_t)h_ctl[8]);
+		be.d2h(res.aln.data(), d_aln.p, sizeof(lc_aln_t));
+		if (h_ctl[8]) be.d2h(res.cigars.data(), d_cigar.p, 4 * (size_t)h_ctl[8]);
+		be.sync();
+		return LC_OK;
+	}
+
+	int run(int score_delta)
+	{
+		const int R = b.n_reads;
+		b.score_delta = score_delta;
+		int rc0 = setup();
+		if (rc0) return rc0;
+		rc0 = stage_seed();
+		if (rc0) return rc0;
+		const unsigned long long S = h_ctl[1];
+		// ---- stage 2-4 pools, sized exactly from the seed count
+		b.scratch_cap = 96ull * S + 320ull * R + 4096;     // chain scratch (<= 85 B/seed + 280 B/read) + extension sort keys (8 B/seed + 16 B/read)
+		b.chain_cap = S + 16; b.cseed_cap = S + 16; b.reg_cap = S + 16;
+		if (!d_scratch.ensure(be, b.scratch_cap) || !d_chain.ensure(be, sizeof(LcChainOut) * b.chain_cap) ||
+			!d_cseed.ensure(be, sizeof(LcSeed) * b.cseed_cap) || !d_reg.ensure(be, sizeof(lc_alnreg_t) * b.reg_cap)) return nomem();
+		b.scratch = (uint8_t *)d_scratch.p; b.chain = (LcChainOut *)d_chain.p; b.cseed = (LcSeed *)d_cseed.p; b.reg = (lc_alnreg_t *)d_reg.p;
+		if (S) { be.k_sa(b, S); ++launches; }
+		be.ev_record(4);
+		be.k_chain(b); ++launches;
+		be.ev_record(5);
+		be.k_extend(b); ++launches;
+		be.ev_record(6);
+		read_ctl();
+		if (h_ctl_ovf) { err = "internal pool overflow in chain/extend (flags " + std::to_string(h_ctl_ovf) + ")"; return LC_ENOMEM; }
+		const unsigned long long NREG = h_ctl[10];
+		// ---- stage 5: per-pair dedup + rescue. every rescue call adds at most one region: sum of caps <= 3 * regions
+		b.fin_cap = 3 * NREG + 64;
+		if (!d_fin.ensure(be, sizeof(lc_alnreg_t) * b.fin_cap) || !d_aln.ensure(be, sizeof(lc_aln_t) * b.fin_cap) ||
+			!d_cand.ensure(be, 8 * b.fin_cap)) return nomem();
+		b.fin = (lc_alnreg_t *)d_fin.p; b.aln = (lc_aln_t *)d_aln.p; b.cand = (uint64_t *)d_cand.p;
+		be.k_pair(b, n_pairs); ++launches;
+		be.ev_record(7);
+		read_ctl();
+		if (h_ctl_ovf) { err = "internal pool overflow in pair stage"; return LC_ENOMEM; }
+		const unsigned long long NC = h_ctl[7];
+		// ---- stage 6: CIGARs (regrow + rerun on overflow)
+		for (int attempt = 0;; ++attempt) {
+			b.cigar_cap = (unsigned long long)(cigar_per_cand * NC) + 1024;
+			b.z_cap = z_pool_bytes;
+			if (!d_cigar.ensure(be, 4 * b.cigar_cap) || !d_z.ensure(be, b.z_cap)) return nomem();
+			b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p;
+			if (NC) { be.k_cigar(b, NC); ++launches; }
+			read_ctl();
+			if (!h_ctl_ovf) break;
+			if (attempt > 12) { err = "cigar pools keep overflowing"; return LC_ENOMEM; }
+			if (h_ctl_ovf & LC_OVF_CIGAR) cigar_per_cand = std::max(cigar_per_cand * 2, (double)h_ctl[8] / std::max<double>(NC, 1) * 1.25);
+			if (h_ctl_ovf & LC_OVF_Z) z_pool_bytes = std::max<size_t>(z_pool_bytes * 2, (size_t)(h_ctl[9] * 1.25));
+			be.dzero_words(b.cigar_cur, 1); be.dzero_words(b.z_cur, 1); be.dzero_words((unsigned long long *)b.overflow, 1);
+		}
+		be.ev_record(8);
+		n_cand = NC; n_cigar_words = h_ctl[8];
+		// ---- stage 7: pack into dense arrays
+		if (!d_outoff.ensure(be, 8 * ((size_t)R + 1)) || !d_outreg.ensure(be, sizeof(lc_alnreg_t) * (NC + 1)) ||
+			!d_outaln.ensure(be, sizeof(lc_aln_t) * (NC + 1))) return nomem();
+		be.scan_exclusive(b.r_n_fin, (int64_t *)d_outoff.p, R + 1); ++launches;   // r_n_fin[R] == 0, so out[R] = total
+		LcPackArgs pa; pa.out_off = (const int64_t *)d_outoff.p; pa.out_reg = (lc_alnreg_t *)d_outreg.p; pa.out_aln = (lc_aln_t *)d_outaln.p;
+		be.k_pack(b, pa); ++launches;
+		be.ev_record(9);
+		return LC_OK;
+	}
+
+	int fetch(LcHostResult &res)
+	{
+		const int R = b.n_reads;
+		res.reg_off.resize(R + 1);
+		res.regs.resize(n_cand); res.aln.resize(n_cand); res.cigars.resize(n_cigar_words);
+		be.d2h(res.reg_off.data(), d_outoff.p, 8 * ((size_t)R + 1));
+		if (n_cand) { be.d2h(res.regs.data(), d_outreg.p, sizeof(lc_alnreg_t) * n_cand); be.d2h(res.aln.data(), d_outaln.p, sizeof(lc_aln_t) * n_cand); }
+		if (n_cigar_words) be.d2h(res.cigars.data(), d_cigar.p, 4 * n_cigar_words);
+		be.ev_record(10);
+		be.sync();
+		if ((unsigned long long)res.reg_off[R] != n_cand) { err = "result size mismatch"; return LC_ECUDA; }
+		res.ms[0] = be.ev_ms(0, 1); res.ms[1] = be.ev_ms(2, 3); res.ms[2] = be.ev_ms(3, 4); res.ms[3] = be.ev_ms(4, 5);
+		res.ms[4] = be.ev_ms(5, 6); res.ms[5] = 0; res.ms[6] = be.ev_ms(6, 7); res.ms[7] = be.ev_ms(7, 8);
+		res.ms[8] = be.ev_ms(9, 10); res.ms[9] = be.ev_ms(2, 9);
+		res.launches = launches;
+		memset(&res.counters, 0, sizeof(res.counters));
+		if (counting) be.d2h(&res.counters, (uint8_t *)d_ctl.p + 32 * 8, sizeof(LcCounters)), be.sync();
+		return LC_OK;
+	}
+
+	void release()
+	{
+		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outreg, &d_outaln, &d_nfin };
+		for (auto *x : all) x->release(be);
+	}
+
+	int64_t launches = 0;
+	unsigned long long n_cand = 0, n_cigar_words = 0;
+
+private:
+	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outreg, d_outaln, d_nfin;
+	unsigned long long h_ctl[32];
+	uint32_t h_ctl_ovf = 0;
+	int nomem() { err = "device allocation failed"; return LC_ENOMEM; }
+	void read_ctl()
+	{
+		be.d2h(h_ctl, d_ctl.p, sizeof(h_ctl));
+		be.sync();
+		h_ctl_ovf = (uint32_t)h_ctl[16];
+	}
+};
+

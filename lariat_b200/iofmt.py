@@ -1,4 +1,4 @@
-"""Small binary formats shared by the replay harnesses (oracle/replay.c), tests and bench.
+"""Small binary formats shared with the checker-side replay harnesses, tests and bench.
 
 pairs file ("LRP1"): int32 n_pairs, int32 len[2n] (r1,r2 interleaved), ASCII bases back to back.
 result file ("LRO1"): int32 n_pairs, then per read end: int32 n; n x 88-byte alnreg; n x

@@ -1,0 +1,104 @@
+// hostsim.cpp — TEST-ONLY serial execution of the product's per-read stage bodies on the CPU.
+//
+// The CUDA kernels of libcuda_lariat.so are thin grids around the __host__ __device__ stage bodies in
+// lariat_b200/csrc/lc_mem.cuh.  This harness compiles the same bodies with the host compiler and runs them
+// one "thread" after another through the same pipeline orchestration (lc_pipeline.hpp), so the logic, the
+// pool arithmetic and the result packing can be checked against the oracle on a machine without a GPU.
+// It is NOT part of the product: it is built only by tests (tests/test_hostsim.py) into tests/_build/,
+// never linked into or loaded by libcuda_lariat.so, and the product has no CPU execution path.
+//
+// usage: hostsim <index-prefix> <pairs.bin> <out.bin> [-d score_delta] [-w workers] [-n max_pairs]
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../lariat_b200/csrc/lc_pipeline.hpp"
+
+struct HostBackend {
+	int workers = 3;
+	int n_workers() const { return workers; }
+	void *dmalloc(size_t n) { return malloc(n ? n : 1); }
+	void dfree(void *p) { free(p); }
+	void dzero(void *p, size_t n) { memset(p, 0, n); }
+	void dzero_words(unsigned long long *p, size_t n) { memset(p, 0, 8 * n); }
+	void h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+	void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+	void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+	void sync() {}
+	void ev_record(int) {}
+	float ev_ms(int, int) { return 0.f; }
+	void k_convert(uint8_t *p, unsigned long long n, bool ascii) { for (unsigned long long i = 0; i < n; ++i) p[i] = lc_nt4(p[i], ascii); }
+	// each stage: items are dealt to `workers` scratch slots round-robin, like the grid-stride loops of the kernels
+	void k_seed(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_seed(b, r, r % workers); }
+	void k_sa(const LcBatch &b, unsigned long long n) { for (unsigned long long g = 0; g < n; ++g) lc_stage_sa(b, g); }
+	void k_chain(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_chain(b, r); }
+	void k_extend(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); }
+	void k_pair(const LcBatch &b, int n_pairs) { for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair(b, p, p % workers); }   // reversed: order must not matter
+	void k_cigar(const LcBatch &b, unsigned long long n) { for (unsigned long long c = 0; c < n; ++c) lc_stage_cigar(b, c, (int)(c % workers)); }
+	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r < b.n_reads; ++r) lc_stage_pack(b, pa, r); }
+	void scan_exclusive(const int32_t *in, int64_t *out, int n) { int64_t s = 0; for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; } }
+};
+
+int main(int argc, char **argv)
+{
+	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
+	int delta = 25, maxp = -1, count = 0;
+	HostBackend be;
+	for (int i = 4; i < argc; ++i) {
+		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "-w") && i + 1 < argc) be.workers = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "-n") && i + 1 < argc) maxp = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "-c")) count = 1;
+	}
+	LcHostIndex hix; std::string err;
+	if (!lc_load_index(argv[1], hix, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+	FILE *f = fopen(argv[2], "rb");
+	if (!f) { perror(argv[2]); return 1; }
+	char magic[4]; int32_t n;
+	if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "LRP1", 4) || fread(&n, 4, 1, f) != 1) return 1;
+	std::vector<int32_t> len(2 * (size_t)n);
+	if (fread(len.data(), 4, len.size(), f) != len.size()) return 1;
+	if (maxp >= 0 && maxp < n) n = maxp;
+	std::vector<int64_t> off(2 * (size_t)n + 1, 0);
+	for (int i = 0; i < 2 * n; ++i) off[i + 1] = off[i] + len[i];
+	std::vector<uint8_t> bases((size_t)off[2 * n] + 1);
+	if (fread(bases.data(), 1, (size_t)off[2 * n], f) != (size_t)off[2 * n]) return 1;
+	fclose(f);
+
+	LcIndex ix;
+	ix.primary = hix.primary; memcpy(ix.L2, hix.L2, sizeof(ix.L2)); ix.seq_len = hix.seq_len;
+	ix.bwt = (const uint4 *)hix.bwt.data(); ix.sa = hix.sa.data(); ix.sa_mask = hix.sa_intv - 1;
+	ix.sa_shift = __builtin_ctz(hix.sa_intv);
+	ix.pac = hix.pac.data(); ix.l_pac = hix.l_pac; ix.anns = hix.anns.data(); ix.n_seqs = (int)hix.anns.size();
+	lc_opt_t opt; lc_default_opt(&opt);
+	LcPipeline<HostBackend> pl(be);
+	pl.counting = count;
+	pl.set_index(ix, opt);
+	LcHostResult res;
+	int rc = pl.upload(n, bases.data(), off.data(), true);
+	if (!rc) rc = pl.run(delta);
+	if (!rc) rc = pl.fetch(res);
+	if (rc) { fprintf(stderr, "pipeline error %d: %s\n", rc, pl.err.c_str()); return 1; }
+	FILE *o = fopen(argv[3], "wb");
+	fwrite("LRO1", 1, 4, o); fwrite(&n, 4, 1, o);
+	for (int r = 0; r < 2 * n; ++r) {
+		int32_t k = (int32_t)(res.reg_off[r + 1] - res.reg_off[r]);
+		fwrite(&k, 4, 1, o);
+		if (k) fwrite(&res.regs[res.reg_off[r]], sizeof(lc_alnreg_t), k, o);
+		for (int i = 0; i < k; ++i) {
+			const lc_aln_t &a = res.aln[res.reg_off[r] + i];
+			int64_t pos = a.pos; int32_t h[4] = { a.rid, a.is_rev, a.NM, a.n_cigar };
+			fwrite(&pos, 8, 1, o); fwrite(h, 4, 4, o);
+			if (a.n_cigar) fwrite(&res.cigars[a.cigar_off], 4, a.n_cigar, o);
+		}
+	}
+	fclose(o);
+	if (count) {
+		const LcCounters &c = res.counters;
+		fprintf(stderr, "{\"occ_blocks\": %llu, \"extend_calls\": %llu, \"sa_calls\": %llu, \"lf_steps\": %llu, \"ext_calls\": %llu, \"ext_cells\": %llu, "
+				"\"sw_calls\": %llu, \"sw_cells\": %llu, \"glb_calls\": %llu, \"glb_cells\": %llu}\n", c.occ_blocks, c.extend_calls, c.sa_calls, c.lf_steps,
+				c.ext_calls, c.ext_cells, c.sw_calls, c.sw_cells, c.glb_calls, c.glb_cells);
+	}
+	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches\n", n, (unsigned long long)res.regs.size(), (long long)res.launches);
+	return 0;
+}

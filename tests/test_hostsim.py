@@ -1,0 +1,22 @@
+"""CPU check of the product's per-read stage bodies and host orchestration (tests/hostsim: the same
+__host__ __device__ code the CUDA kernels run, executed serially) against the reference golden.
+This is test scaffolding only; the product library has no CPU execution path."""
+import os
+import subprocess
+
+from conftest import GOLDEN
+
+
+def test_stage_bodies_match_reference_golden(hostsim_bin, tmp_path):
+    out = tmp_path / "sim.out"
+    subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out)],
+                          stderr=subprocess.DEVNULL)
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+
+
+def test_result_independent_of_worker_count_and_delta(hostsim_bin, tmp_path):
+    a, b = tmp_path / "a.out", tmp_path / "b.out"
+    args = [os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs")]
+    subprocess.check_call([hostsim_bin] + args + [str(a), "-w", "1", "-n", "200"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([hostsim_bin] + args + [str(b), "-w", "17", "-n", "200"], stderr=subprocess.DEVNULL)
+    assert a.read_bytes() == b.read_bytes()
