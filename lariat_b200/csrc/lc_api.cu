@@ -323,8 +323,9 @@ int lc_ksw_extend_batch(lc_ctx *c, int n, const uint8_t *q, const int64_t *qoff,
 	j.n = n; j.q = d.up(q, (size_t)qoff[n] + 1); j.qoff = d.up(qoff, (size_t)n + 1); j.t = d.up(t, (size_t)toff[n] + 1); j.toff = d.up(toff, (size_t)n + 1);
 	j.h0 = d.up(h0, n); j.w = w; j.end_bonus = end_bonus; j.zdrop = zdrop; j.sc = score_of(c->opt);
 	j.out = d.alloc<int32_t>(6 * (size_t)n);
-	j.w_int_n = 2 * (qmax + 2);
-	j.w_int = d.alloc<int>((size_t)c->be.n_workers() * j.w_int_n);
+	j.qmax = qmax;
+	j.ctr = d.alloc<unsigned int>(1);
+	cudaMemset(j.ctr, 0, 4);
 	LcCounters *cnt = d.alloc<LcCounters>(1);
 	cudaMemset(cnt, 0, sizeof(LcCounters));
 	j.cnt = cells ? cnt : nullptr;

@@ -8,7 +8,7 @@
 
 struct LcExtJobs {      // batch of independent ksw_extend2 jobs (microbenchmark / parity entry point)
 	int n; const uint8_t *q; const int64_t *qoff; const uint8_t *t; const int64_t *toff; const int32_t *h0;
-	int w, end_bonus, zdrop; LcScore sc; int32_t *out; int *w_int; int w_int_n; LcCounters *cnt;
+	int w, end_bonus, zdrop; LcScore sc; int32_t *out; int qmax; unsigned int *ctr; LcCounters *cnt;
 };
 struct LcSwJobs {       // batch of independent ksw_align2 jobs with mem_matesw's flags
 	int n; const uint8_t *q; const int64_t *qoff; const uint8_t *t; const int64_t *toff;

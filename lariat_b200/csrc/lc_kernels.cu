@@ -15,6 +15,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "lc_backend.cuh"
+#include "lc_sw_warp.cuh"
 
 #define LC_TPB 128
 
@@ -58,10 +59,21 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 	for (int r = worker; r < b.n_reads; r += stride) lc_stage_chain(b, r);
 }
 
+// one warp per read, reads handed out through an atomic counter (reads differ widely in chains and extensions)
 __global__ void __launch_bounds__(LC_TPB) extend_kernel(const LcBatch b)
 {
-	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	for (int r = worker; r < b.n_reads; r += stride) lc_stage_extend(b, r, worker);
+	extern __shared__ int lc_smem[];
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = (b.lmax + 2 + 31) & ~31;
+	LcExecWarp ex;
+	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
+	for (;;) {
+		int r = 0;
+		if (lane == 0) r = (int)atomicAdd(b.work_ctr + 0, 1u);
+		r = __shfl_sync(LC_FULL, r, 0);
+		if (r >= b.n_reads) break;
+		lc_stage_extend_t(b, r, ex);
+		__syncwarp();
+	}
 }
 
 __global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, int n_pairs)
@@ -84,17 +96,27 @@ __global__ void __launch_bounds__(256) pack_kernel(const LcBatch b, const LcPack
 }
 
 // ---- microbenchmark kernels (BASELINE.json configs[4]) -------------------------------------------------------
+// ksw_extend2 on independent jobs: the same warp-cooperative routine extend_kernel uses, one warp per job
 __global__ void __launch_bounds__(LC_TPB) ksw_extend_kernel(const LcExtJobs j)
 {
-	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	int *H = j.w_int + (size_t)worker * j.w_int_n, *E = H + (j.w_int_n >> 1);
-	for (int i = worker; i < j.n; i += stride) {
+	extern __shared__ int lc_smem[];
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(j.qmax), rows = (j.qmax + 2 + 31) & ~31;
+	int *H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per), *E = H + rows;
+	uint8_t *qs = (uint8_t *)(E + rows);
+	for (;;) {
+		int i = 0;
+		if (lane == 0) i = (int)atomicAdd(j.ctr, 1u);
+		i = __shfl_sync(LC_FULL, i, 0);
+		if (i >= j.n) break;
 		LcSeqFwd qf = { j.q + j.qoff[i] };
 		LcSeqFwd tf = { j.t + j.toff[i] };
-		LcExtResult r = lc_extend2((int)(j.qoff[i + 1] - j.qoff[i]), qf, (int)(j.toff[i + 1] - j.toff[i]), tf, j.sc, j.w, j.end_bonus, j.zdrop,
-								   j.h0[i], H, E, j.cnt);
-		int32_t *o = j.out + 6 * (size_t)i;
-		o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
+		LcExtResult r = lc_extend2_warp((int)(j.qoff[i + 1] - j.qoff[i]), qf, (int)(j.toff[i + 1] - j.toff[i]), tf, j.sc, j.w, j.end_bonus, j.zdrop,
+										j.h0[i], H, E, qs, lane, j.cnt);
+		if (lane == 0) {
+			int32_t *o = j.out + 6 * (size_t)i;
+			o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
+		}
+		__syncwarp();
 	}
 }
 
@@ -166,7 +188,12 @@ void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
 void LcCudaBackend::k_seed(const LcBatch &b) { smem_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
 void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
-void LcCudaBackend::k_extend(const LcBatch &b) { extend_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
+void LcCudaBackend::k_extend(const LcBatch &b)
+{
+	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+	cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	extend_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(b);
+}
 void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs) { matesw_kernel<<<grid_for(n_pairs, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_pairs); }
 void LcCudaBackend::k_cigar(const LcBatch &b, unsigned long long n) { global_cigar_kernel<<<grid_for(n, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n); }
 void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for(b.n_reads, 256, 8), 256, 0, stream>>>(b, pa); }
@@ -178,7 +205,12 @@ void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
 	if (need > scan_tmp_bytes) { if (scan_tmp) { cudaStreamSynchronize(stream); cudaFree(scan_tmp); } cudaMalloc(&scan_tmp, need + 256); scan_tmp_bytes = need + 256; }
 	cub::DeviceScan::ExclusiveSum(scan_tmp, need, it, out, n, stream);
 }
-void LcCudaBackend::k_ksw_extend(const LcExtJobs &j) { ksw_extend_kernel<<<grid_for(j.n, LC_TPB, 4), LC_TPB, 0, stream>>>(j); }
+void LcCudaBackend::k_ksw_extend(const LcExtJobs &j)
+{
+	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(j.qmax);
+	cudaFuncSetAttribute(ksw_extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	ksw_extend_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(j);
+}
 void LcCudaBackend::k_ksw_align(const LcSwJobs &j) { ksw_align_kernel<<<grid_for(j.n, LC_TPB, 4), LC_TPB, 0, stream>>>(j); }
 void LcCudaBackend::k_sa_batch(const LcIndex &ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt)
 {

@@ -33,6 +33,7 @@ struct LcBatch {
 	int32_t score_delta, pes_low, pes_high, max_anchors;
 	LcCounters *cnt;               // null = off
 	uint32_t *overflow;            // OR of LC_OVF_* raised by any thread
+	unsigned int *work_ctr;        // [4] dynamic work-distribution counters of the warp-per-item kernels (zeroed per batch)
 	int32_t lmax;                  // longest read of the batch
 	// ---- per-worker scratch (n_workers slots)
 	int32_t n_workers;
@@ -440,20 +441,39 @@ LC_HD int lc_cal_max_gap(const lc_opt_t &opt, int qlen)          // B/bwamem.c:6
 	return lc_min(l, opt.w << 1);
 }
 
-LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
+// Executors: who runs a stage body.  LcExecThread = one thread does everything (scalar SW, per-worker scratch in HBM).
+// LcExecWarp (lc_sw_warp.cuh, device only) = the 32 lanes of a warp run the control flow redundantly, lane 0 owns the
+// side effects, and the SW jobs are computed cooperatively with shared-memory rows and warp shuffles.
+struct LcExecThread {
+	int *H, *E;
+	LC_HD bool leader() const { return true; }
+	LC_HD void sync() const {}
+	LC_HD unsigned long long bcast(unsigned long long v) const { return v; }
+	template <class QF, class TF>
+	LC_HD LcExtResult extend2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int w, int end_bonus, int zdrop, int h0, LcCounters *cnt) const
+	{
+		return lc_extend2(qlen, q, tlen, t, sc, w, end_bonus, zdrop, h0, H, E, cnt);
+	}
+};
+
+template <class Exec>
+LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
 {
 	const lc_opt_t &opt = b.opt;
 	const int l_query = (int)(b.off[r + 1] - b.off[r]);
 	const uint8_t *query = b.seq + b.off[r];
 	const int NC = b.r_n_chain[r], T = b.r_n_cseed[r];
-	b.r_n_reg[r] = 0; b.r_reg_off[r] = 0;
+	if (ex.leader()) { b.r_n_reg[r] = 0; b.r_reg_off[r] = 0; }
 	if (NC == 0) return;
-	unsigned long long ro = lc_carve(b, b.reg_cur, b.reg_cap, T, LC_OVF_REG);
-	unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * T + 8, LC_OVF_SCRATCH);
+	unsigned long long ro = 0, so = 0;
+	if (ex.leader()) {
+		ro = lc_carve(b, b.reg_cur, b.reg_cap, T, LC_OVF_REG);
+		so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * T + 8, LC_OVF_SCRATCH);
+	}
+	ro = ex.bcast(ro); so = ex.bcast(so);
 	if (ro == (unsigned long long)-1 || so == (unsigned long long)-1) return;
 	lc_alnreg_t *av = b.reg + ro;
 	uint64_t *srt = (uint64_t *)lc_align8((size_t)(b.scratch + so));
-	int *H = b.w_int + (size_t)worker * b.w_int_n, *E = H + (b.lmax + 2);
 	const int64_t l_pac = b.ix.l_pac;
 	int n_av = 0;
 	for (int ci = 0; ci < NC; ++ci) {
@@ -471,8 +491,11 @@ LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
 		r0 = lc_max(r0, (int64_t)0); r1 = lc_min(r1, l_pac << 1);
 		if (r0 < l_pac && l_pac < r1) { if (seeds[0].rbeg < l_pac) r1 = l_pac; else r0 = l_pac; }
 		lc_fetch_clamp(b.ix, r0, seeds[0].rbeg, r1);        // bns_fetch_seq clamps to the contig (B/bwamem.c:659)
-		for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;   // score == len (B/bwamem.c:663-665)
-		lc_introsort(srt, (long)c.n, [](uint64_t x, uint64_t y) { return x < y; });
+		if (ex.leader()) {
+			for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;   // score == len (B/bwamem.c:663-665)
+			lc_introsort(srt, (long)c.n, [](uint64_t x, uint64_t y) { return x < y; });
+		}
+		ex.sync();
 		for (int k = c.n - 1; k >= 0; --k) {
 			const LcSeed s = seeds[(uint32_t)srt[k]];
 			int i;
@@ -496,7 +519,7 @@ LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
 					if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
 					if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
 				}
-				if (i == c.n) { srt[k] = 0; continue; }
+				if (i == c.n) { ex.sync(); if (ex.leader()) srt[k] = 0; ex.sync(); continue; }
 			}
 			lc_alnreg_t a;
 			memset(&a, 0, sizeof(a));
@@ -509,7 +532,7 @@ LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
 				for (i = 0; i < 2; ++i) {
 					int prev = a.score;
 					aw0 = opt.w << i;
-					x = lc_extend2(s.qbeg, qf, (int)(s.rbeg - r0), tf, b.sc, aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, H, E, b.cnt);
+					x = ex.extend2(s.qbeg, qf, (int)(s.rbeg - r0), tf, b.sc, aw0, opt.pen_clip5, opt.zdrop, s.len * opt.a, b.cnt);
 					a.score = x.score;
 					if (a.score == prev || x.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
 				}
@@ -525,7 +548,7 @@ LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
 				for (i = 0; i < 2; ++i) {
 					int prev = a.score;
 					aw1 = opt.w << i;
-					x = lc_extend2(l_query - qe, qf, (int)(r1 - re), tf, b.sc, aw1, opt.pen_clip3, opt.zdrop, sc0, H, E, b.cnt);
+					x = ex.extend2(l_query - qe, qf, (int)(r1 - re), tf, b.sc, aw1, opt.pen_clip3, opt.zdrop, sc0, b.cnt);
 					a.score = x.score;
 					if (a.score == prev || x.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
 				}
@@ -540,11 +563,22 @@ LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
 			a.w = lc_max(aw0, aw1);
 			a.seedlen0 = s.len;
 			a.frac_rep = b.r_frac_rep[r];
-			av[n_av++] = a;
+			if (ex.leader()) av[n_av] = a;
+			++n_av;
+			ex.sync();
 		}
 	}
-	b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av;
-	if (n_av) lc_atomic_add(b.reg_total, (unsigned long long)n_av);
+	if (ex.leader()) {
+		b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av;
+		if (n_av) lc_atomic_add(b.reg_total, (unsigned long long)n_av);
+	}
+}
+
+LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
+{
+	LcExecThread ex;
+	ex.H = b.w_int + (size_t)worker * b.w_int_n; ex.E = ex.H + (b.lmax + 2);
+	lc_stage_extend_t(b, r, ex);
 }
 
 // ============================================================================================================

@@ -224,6 +224,7 @@ public:
 			b.reg_cur = c + 5; b.fin_cur = c + 6; b.cand_cur = c + 7; b.cigar_cur = c + 8; b.z_cur = c + 9;
 			b.reg_total = c + 10;
 			b.overflow = (uint32_t *)(c + 16);
+			b.work_ctr = (unsigned int *)(c + 20);
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);

@@ -1,0 +1,146 @@
+// lc_sw_warp.cuh — warp-cooperative Smith-Waterman (device only).
+//
+// One warp per job.  Rows (reference bases) are processed in order, exactly like the reference, because the
+// band pruning, the z-drop test and every tie-break are defined row by row.  Inside a row the 32 lanes take 32
+// consecutive query columns per step.  The only loop-carried dependency along a row is F (a gap in the query
+// direction); it is a max-plus linear recurrence
+//        F(j+1) = max(F(j) - e_ins, T(j)),   T(j) = max(M(j) - o_ins - e_ins, 0)
+// so it is evaluated for the 32 columns at once with a 5-step warp prefix-max of T(j) + j*e_ins.  H/E rows and the
+// query live in shared memory, the row maximum / argmax and the band-shrink scans are warp reductions and ballots.
+// Results are bit-identical to lc_extend2 / lc_sw_pass / lc_global2 (scalar forms, lc_sw.cuh), which follow the
+// reference line by line; tests compare all three against the oracle.
+#pragma once
+#include "lc_sw.cuh"
+
+#ifdef __CUDACC__
+#define LC_FULL 0xffffffffu
+
+__device__ __forceinline__ int lc_warp_prefix_max_incl(int v, int lane)
+{
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		int o = __shfl_up_sync(LC_FULL, v, d);
+		if (lane >= d) v = max(v, o);
+	}
+	return v;
+}
+__device__ __forceinline__ int lc_warp_max(int v)
+{
+#pragma unroll
+	for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(LC_FULL, v, d));
+	return v;
+}
+
+// ksw_extend2 (B/ksw.c:380-479), one warp.  H, E: shared memory, qlen + 2 ints each.  qs: shared memory, qlen bytes.
+template <class QF, class TF>
+__device__ __noinline__ LcExtResult lc_extend2_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int w, int end_bonus, int zdrop,
+													int h0, int *H, int *E, uint8_t *qs, int lane, LcCounters *cnt)
+{
+	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
+	int best = h0, best_i = -1, best_j = -1, g_i = -1, gscore = -1, max_off = 0, beg = 0, end = qlen;
+	unsigned long long cells = 0;
+	// row -1 (B/ksw.c:395-397): H[0] = h0, H[j] = max(h0 - oe_ins - (j-1) e_ins, 0), E = 0
+	for (int j = lane; j <= qlen + 1; j += 32) {
+		int v = 0;
+		if (j == 0) v = h0;
+		else if (j <= qlen) { v = h0 - oe_ins - (j - 1) * e_ins; if (v < 0) v = 0; }
+		H[j] = v; E[j] = 0;
+		if (j < qlen) qs[j] = (uint8_t)query(j);
+	}
+	{
+		int smax = sc.a > 0 ? sc.a : 0;
+		int mi = (int)((double)(qlen * smax + end_bonus - sc.o_ins) / sc.e_ins + 1.);
+		int md = (int)((double)(qlen * smax + end_bonus - sc.o_del) / sc.e_del + 1.);
+		w = min(w, max(mi, 1));
+		w = min(w, max(md, 1));
+	}
+	__syncwarp();
+	for (int i = 0; i < tlen; ++i) {
+		const int tb = target(i);
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		int h_first = 0;
+		if (beg == 0) { h_first = h0 - (sc.o_del + sc.e_del * (i + 1)); if (h_first < 0) h_first = 0; }
+		int f_carry = 0, hl_carry = h_first, key = -1;
+		for (int cs = beg; cs < end; cs += 32) {
+			const int j = cs + lane;
+			const bool act = j < end;
+			const int diag = act ? H[j] : 0, e = act ? E[j] : 0;
+			int M = 0;
+			if (act && diag) M = diag + sc.sub(tb, qs[j]);
+			const int t = max(M - oe_ins, 0);
+			const int pin = lc_warp_prefix_max_incl(t + j * e_ins, lane);
+			const int pex = __shfl_up_sync(LC_FULL, pin, 1);
+			int F = f_carry - lane * e_ins;
+			if (lane > 0) F = max(F, pex - (j - 1) * e_ins);
+			int h = max(M, e);
+			h = max(h, F);
+			const int e2 = max(e - e_del, max(M - oe_del, 0));
+			int hl = __shfl_up_sync(LC_FULL, h, 1);
+			if (lane == 0) hl = hl_carry;
+			if (act) { H[j] = hl; E[j] = e2; key = max(key, (h << 10) | j); }
+			const int last = min(31, end - 1 - cs);
+			hl_carry = __shfl_sync(LC_FULL, h, last);
+			f_carry = max(__shfl_sync(LC_FULL, F, 31) - e_ins, __shfl_sync(LC_FULL, t, 31));
+		}
+		cells += (unsigned long long)(end > beg ? end - beg : 0);
+		const int jfin = beg < end ? end : beg;
+		__syncwarp();
+		if (lane == 0) { H[end] = hl_carry; E[end] = 0; }
+		__syncwarp();
+		if (jfin == qlen) {
+			if (!(gscore > hl_carry)) g_i = i;
+			gscore = max(gscore, hl_carry);
+		}
+		key = lc_warp_max(key);
+		const int rowmax = key < 0 ? 0 : key >> 10, rowarg = key < 0 ? -1 : key & 1023;
+		if (rowmax == 0) break;
+		if (rowmax > best) {
+			best = rowmax; best_i = i; best_j = rowarg;
+			max_off = max(max_off, abs(rowarg - i));
+		} else if (zdrop > 0) {
+			const int di = i - best_i, dj = rowarg - best_j;
+			if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
+			else { if (best - rowmax - (dj - di) * e_ins > zdrop) break; }
+		}
+		// shrink the band where H and E are both zero (B/ksw.c:466-469)
+		int nb = end;
+		for (int cs = beg; cs < end; cs += 32) {
+			const int j = cs + lane;
+			const unsigned m = __ballot_sync(LC_FULL, j < end && (H[j] != 0 || E[j] != 0));
+			if (m) { nb = cs + __ffs(m) - 1; break; }
+		}
+		beg = nb;
+		int jj = beg - 1;
+		for (int top = end; top >= beg; top -= 32) {
+			const int j = top - lane;
+			const unsigned m = __ballot_sync(LC_FULL, j >= beg && (H[j] != 0 || E[j] != 0));
+			if (m) { jj = top - (__ffs(m) - 1); break; }
+		}
+		end = min(jj + 2, qlen);
+	}
+	__syncwarp();
+	if (cnt && lane == 0) { atomicAdd(&cnt->ext_calls, 1ull); atomicAdd(&cnt->ext_cells, cells); }
+	LcExtResult r = { best, best_j + 1, best_i + 1, g_i + 1, gscore, max_off };
+	return r;
+}
+
+struct LcExecWarp {
+	int *H, *E;          // shared memory rows of this warp
+	uint8_t *qs;         // shared memory copy of the query side of the current job
+	int lane;
+	__device__ __forceinline__ bool leader() const { return lane == 0; }
+	__device__ __forceinline__ void sync() const { __syncwarp(); }
+	__device__ __forceinline__ unsigned long long bcast(unsigned long long v) const { return __shfl_sync(LC_FULL, v, 0); }
+	template <class QF, class TF>
+	__device__ __forceinline__ LcExtResult extend2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int w, int end_bonus, int zdrop, int h0,
+												   LcCounters *cnt) const
+	{
+		return lc_extend2_warp(qlen, q, tlen, t, sc, w, end_bonus, zdrop, h0, H, E, qs, lane, cnt);
+	}
+};
+
+// bytes of dynamic shared memory one warp needs for reads up to lmax
+__host__ __device__ inline int lc_warp_smem_bytes(int lmax) { return 2 * 4 * ((lmax + 2 + 31) & ~31) + ((lmax + 31) & ~31); }
+#endif
