@@ -354,8 +354,9 @@ int lc_ksw_align_batch(lc_ctx *c, int n, const uint8_t *q, const int64_t *qoff, 
 	j.n = n; j.q = d.up(q, (size_t)qoff[n] + 1); j.qoff = d.up(qoff, (size_t)n + 1); j.t = d.up(t, (size_t)toff[n] + 1); j.toff = d.up(toff, (size_t)n + 1);
 	j.sc = score_of(c->opt); j.min_seed_len = c->opt.min_seed_len;
 	j.out = d.alloc<int32_t>(7 * (size_t)n);
-	j.w_int_n = 3 * (qmax + 18);
-	j.w_int = d.alloc<int>((size_t)c->be.n_workers() * j.w_int_n);
+	j.qmax = qmax;
+	j.ctr = d.alloc<unsigned int>(1);
+	cudaMemset(j.ctr, 0, 4);
 	j.w_u64_n = tmax / 2 + 8;
 	j.w_u64 = d.alloc<unsigned long long>((size_t)c->be.n_workers() * j.w_u64_n);
 	LcCounters *cnt = d.alloc<LcCounters>(1);

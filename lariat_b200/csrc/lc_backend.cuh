@@ -12,7 +12,7 @@ struct LcExtJobs {      // batch of independent ksw_extend2 jobs (microbenchmark
 };
 struct LcSwJobs {       // batch of independent ksw_align2 jobs with mem_matesw's flags
 	int n; const uint8_t *q; const int64_t *qoff; const uint8_t *t; const int64_t *toff;
-	LcScore sc; int min_seed_len; int32_t *out; int *w_int; int w_int_n; unsigned long long *w_u64; int w_u64_n; LcCounters *cnt;
+	LcScore sc; int min_seed_len; int32_t *out; int qmax; unsigned int *ctr; unsigned long long *w_u64; int w_u64_n; LcCounters *cnt;
 };
 
 struct LcCudaBackend {

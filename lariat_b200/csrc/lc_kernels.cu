@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 __global__ void __launch_bounds__(LC_TPB) extend_kernel(const LcBatch b)
 {
 	extern __shared__ int lc_smem[];
-	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = (b.lmax + 2 + 31) & ~31;
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = lc_warp_row_ints(b.lmax);
 	LcExecWarp ex;
 	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
+	ex.Hmax = nullptr; ex.bl = nullptr;
 	for (;;) {
 		int r = 0;
 		if (lane == 0) r = (int)atomicAdd(b.work_ctr + 0, 1u);
@@ -76,10 +77,23 @@ __global__ void __launch_bounds__(LC_TPB) extend_kernel(const LcBatch b)
 	}
 }
 
+// one warp per read pair: dedup of both ends by lane 0, then the two rescue phases with the warp-cooperative local SW
 __global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, int n_pairs)
 {
-	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	for (int p = worker; p < n_pairs; p += stride) lc_stage_pair(b, p, worker);
+	extern __shared__ int lc_smem[];
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax, 3), rows = lc_warp_row_ints(b.lmax);
+	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	LcExecWarp ex;
+	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.Hmax = ex.E + rows; ex.qs = (uint8_t *)(ex.Hmax + rows);
+	ex.lane = lane; ex.bl = b.w_u64 + (size_t)gwarp * b.w_u64_n;
+	for (;;) {
+		int p = 0;
+		if (lane == 0) p = (int)atomicAdd(b.work_ctr + 1, 1u);
+		p = __shfl_sync(LC_FULL, p, 0);
+		if (p >= n_pairs) break;
+		lc_stage_pair_t(b, p, ex);
+		__syncwarp();
+	}
 }
 
 __global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, unsigned long long n)
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const LcBatch b, const LcPack
 __global__ void __launch_bounds__(LC_TPB) ksw_extend_kernel(const LcExtJobs j)
 {
 	extern __shared__ int lc_smem[];
-	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(j.qmax), rows = (j.qmax + 2 + 31) & ~31;
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(j.qmax), rows = lc_warp_row_ints(j.qmax);
 	int *H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per), *E = H + rows;
 	uint8_t *qs = (uint8_t *)(E + rows);
 	for (;;) {
@@ -120,19 +134,30 @@ __global__ void __launch_bounds__(LC_TPB) ksw_extend_kernel(const LcExtJobs j)
 	}
 }
 
+// ksw_align2 on independent jobs: the warp-cooperative routine matesw_kernel uses, one warp per job
 __global__ void __launch_bounds__(LC_TPB) ksw_align_kernel(const LcSwJobs j)
 {
-	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	int *H = j.w_int + (size_t)worker * j.w_int_n, *E = H + j.w_int_n / 3, *Hmax = H + 2 * (j.w_int_n / 3);
-	unsigned long long *bl = j.w_u64 + (size_t)worker * j.w_u64_n;
-	for (int i = worker; i < j.n; i += stride) {
+	extern __shared__ int lc_smem[];
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(j.qmax, 3), rows = lc_warp_row_ints(j.qmax);
+	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int *H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per), *E = H + rows, *Hmax = E + rows;
+	uint8_t *qs = (uint8_t *)(Hmax + rows);
+	unsigned long long *bl = j.w_u64 + (size_t)gwarp * j.w_u64_n;
+	for (;;) {
+		int i = 0;
+		if (lane == 0) i = (int)atomicAdd(j.ctr, 1u);
+		i = __shfl_sync(LC_FULL, i, 0);
+		if (i >= j.n) break;
 		const int ql = (int)(j.qoff[i + 1] - j.qoff[i]), tl = (int)(j.toff[i + 1] - j.toff[i]);
 		LcSeqFwd qf = { j.q + j.qoff[i] };
 		LcSeqFwd tf = { j.t + j.toff[i] };
 		const int xtra = LC_XSUBO | LC_XSTART | (ql * j.sc.a < 250 ? LC_XBYTE : 0) | (j.min_seed_len * j.sc.a);
-		LcSwResult r = lc_sw_align2(ql, qf, tl, tf, j.sc, xtra, H, E, Hmax, bl, j.cnt);
-		int32_t *o = j.out + 7 * (size_t)i;
-		o[0] = r.score; o[1] = r.te; o[2] = r.qe; o[3] = r.score2; o[4] = r.te2; o[5] = r.tb; o[6] = r.qb;
+		LcSwResult r = lc_sw_align2_warp(ql, qf, tl, tf, j.sc, xtra, H, E, Hmax, qs, bl, lane, j.cnt);
+		if (lane == 0) {
+			int32_t *o = j.out + 7 * (size_t)i;
+			o[0] = r.score; o[1] = r.te; o[2] = r.qe; o[3] = r.score2; o[4] = r.te2; o[5] = r.tb; o[6] = r.qb;
+		}
+		__syncwarp();
 	}
 }
 
@@ -194,7 +219,13 @@ void LcCudaBackend::k_extend(const LcBatch &b)
 	cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	extend_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(b);
 }
-void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs) { matesw_kernel<<<grid_for(n_pairs, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_pairs); }
+void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
+{
+	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
+	cudaFuncSetAttribute(matesw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id
+	matesw_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, n_pairs);
+}
 void LcCudaBackend::k_cigar(const LcBatch &b, unsigned long long n) { global_cigar_kernel<<<grid_for(n, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n); }
 void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for(b.n_reads, 256, 8), 256, 0, stream>>>(b, pa); }
 void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
@@ -211,7 +242,12 @@ void LcCudaBackend::k_ksw_extend(const LcExtJobs &j)
 	cudaFuncSetAttribute(ksw_extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	ksw_extend_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(j);
 }
-void LcCudaBackend::k_ksw_align(const LcSwJobs &j) { ksw_align_kernel<<<grid_for(j.n, LC_TPB, 4), LC_TPB, 0, stream>>>(j); }
+void LcCudaBackend::k_ksw_align(const LcSwJobs &j)
+{
+	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(j.qmax, 3);
+	cudaFuncSetAttribute(ksw_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	ksw_align_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(j);
+}
 void LcCudaBackend::k_sa_batch(const LcIndex &ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt)
 {
 	sa_batch_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, rows, out, n, cnt);

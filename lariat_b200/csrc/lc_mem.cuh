@@ -696,7 +696,8 @@ LC_HD int lc_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t &dist)   /
 
 // mem_matesw (B/bwamem_pair.c:111-180) with Lariat's insert model: only orientation FR (index 1) is enabled
 // (G/gobwa.go:229-237), so at most one SW is run and at most one region is added per call.
-LC_HDN int lc_matesw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const LcSwScratch &ws)
+template <class Exec>
+LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const Exec &ex)
 {
 	const lc_opt_t &opt = b.opt;
 	const int64_t l_pac = b.ix.l_pac;
@@ -717,37 +718,40 @@ LC_HDN int lc_matesw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uin
 	const int xtra = LC_XSUBO | LC_XSTART | (l_ms * opt.a < 250 ? LC_XBYTE : 0) | (opt.min_seed_len * opt.a);
 	LcSeqRevComp qf = { ms, l_ms };
 	LcRefFwd tf = { &b.ix, rb };
-	LcSwResult aln = lc_sw_align2(l_ms, qf, (int)(re - rb), tf, b.sc, xtra, ws.H, ws.E, ws.Hmax, ws.b, b.cnt);
-	if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
-		lc_alnreg_t nb;
-		memset(&nb, 0, sizeof(nb));
-		nb.rid = a.rid;
-		nb.is_alt = a.is_alt;
-		nb.qb = l_ms - (aln.qe + 1);
-		nb.qe = l_ms - aln.qb;
-		nb.rb = (l_pac << 1) - (rb + aln.te + 1);
-		nb.re = (l_pac << 1) - (rb + aln.tb);
-		nb.score = aln.score;
-		nb.csub = aln.score2;
-		nb.secondary = -1;
-		nb.seedcov = (int)((nb.re - nb.rb < nb.qe - nb.qb ? nb.re - nb.rb : nb.qe - nb.qb) >> 1);
-		int at;
-		++n_ma;
-		for (at = 0; at < n_ma - 1; ++at) if (ma[at].score < nb.score) break;     // keep sorted by score (:165-171)
-		for (int i = n_ma - 1; i > at; --i) ma[i] = ma[i - 1];
-		ma[at] = nb;
+	const lc_alnreg_t anchor = a;      // `a` may alias the list that is about to be reshuffled
+	LcSwResult aln = ex.sw_align2(l_ms, qf, (int)(re - rb), tf, b.sc, xtra, b.cnt);
+	ex.sync();
+	int n = n_ma;
+	if (ex.leader()) {
+		if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
+			lc_alnreg_t nb;
+			memset(&nb, 0, sizeof(nb));
+			nb.rid = anchor.rid;
+			nb.is_alt = anchor.is_alt;
+			nb.qb = l_ms - (aln.qe + 1);
+			nb.qe = l_ms - aln.qb;
+			nb.rb = (l_pac << 1) - (rb + aln.te + 1);
+			nb.re = (l_pac << 1) - (rb + aln.tb);
+			nb.score = aln.score;
+			nb.csub = aln.score2;
+			nb.secondary = -1;
+			nb.seedcov = (int)((nb.re - nb.rb < nb.qe - nb.qb ? nb.re - nb.rb : nb.qe - nb.qb) >> 1);
+			int at;
+			++n;
+			for (at = 0; at < n - 1; ++at) if (ma[at].score < nb.score) break;     // keep sorted by score (:165-171)
+			for (int i = n - 1; i > at; --i) ma[i] = ma[i - 1];
+			ma[at] = nb;
+		}
+		n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0);   // :175 (n == 1 here); no patching without a query
 	}
-	n_ma = lc_sort_dedup_patch(b, (const uint8_t *)0, n_ma, ma, ws.H, ws.E);       // :175 (n == 1 here)
+	n_ma = (int)ex.bcast((unsigned long long)n);
+	ex.sync();
 	return 1;
 }
 
-LC_HDN void lc_stage_pair(const LcBatch &b, int p, int worker)
+template <class Exec>
+LC_HD void lc_stage_pair_t(const LcBatch &b, int p, const Exec &ex)
 {
-	const lc_opt_t &opt = b.opt;
-	int *wi = b.w_int + (size_t)worker * b.w_int_n;
-	LcSwScratch ws;
-	ws.H = wi; ws.E = wi + (b.lmax + 18); ws.Hmax = wi + 2 * (b.lmax + 18);
-	ws.b = b.w_u64 + (size_t)worker * b.w_u64_n; ws.z_unused = 0;
 	int n[2], len[2], best[2] = { 0, 0 };
 	const uint8_t *q[2];
 	lc_alnreg_t *src[2];
@@ -755,36 +759,74 @@ LC_HDN void lc_stage_pair(const LcBatch &b, int p, int worker)
 		const int r = 2 * p + e;
 		len[e] = (int)(b.off[r + 1] - b.off[r]); q[e] = b.seq + b.off[r];
 		src[e] = b.reg + b.r_reg_off[r];
-		n[e] = lc_sort_dedup_patch(b, q[e], b.r_n_reg[r], src[e], ws.H, ws.E);      // tail of mem_align1_core (B/bwamem.c:1070)
-		for (int i = 0; i < n[e]; ++i) {
-			if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
-			best[e] = lc_max(best[e], src[e][i].score);                                         // G/gobwa.go:264-283
+		int ne = 0;
+		if (ex.leader()) {
+			ne = lc_sort_dedup_patch(b, q[e], b.r_n_reg[r], src[e], ex.H, ex.E);      // tail of mem_align1_core (B/bwamem.c:1070)
+			for (int i = 0; i < ne; ++i)
+				if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
 		}
+		n[e] = (int)ex.bcast((unsigned long long)ne);
+		ex.sync();
+		for (int i = 0; i < n[e]; ++i) best[e] = lc_max(best[e], src[e][i].score);              // G/gobwa.go:264-283
 	}
 	// capacity of the final lists: every rescue call adds at most one region
 	int a2 = 0;
 	if (len[0] > 0) for (int i = 0; i < n[1] && a2 < b.max_anchors; ++i) if (src[1][i].score >= best[1] - b.score_delta) ++a2;
 	const int cap0 = n[0] + a2;
 	const int cap1 = n[1] + (len[1] > 0 ? lc_min(b.max_anchors, cap0) : 0);
-	unsigned long long fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
-	b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
+	unsigned long long fo = 0;
+	if (ex.leader()) {
+		fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
+		b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
+	}
+	fo = ex.bcast(fo);
 	if (fo == (unsigned long long)-1) return;
 	lc_alnreg_t *f0 = b.fin + fo, *f1 = b.fin + fo + cap0;
-	for (int i = 0; i < n[0]; ++i) f0[i] = src[0][i];
-	for (int i = 0; i < n[1]; ++i) f1[i] = src[1][i];
+	for (int i = ex.lane_id(); i < n[0]; i += ex.n_lanes()) f0[i] = src[0][i];
+	for (int i = ex.lane_id(); i < n[1]; i += ex.n_lanes()) f1[i] = src[1][i];
+	ex.sync();
 	int n0 = n[0], n1 = n[1], num = 0;
 	// phase 1: rescue read 1 from read 2's hits (G/gobwa.go:286-300). read 2's list is not touched in this phase.
 	for (int i = 0; i < n1 && num < b.max_anchors && len[0] > 0; ++i)
-		if (f1[i].score >= best[1] - b.score_delta) { ++num; lc_matesw(b, f1[i], len[0], q[0], f0, n0, ws); }
+		if (f1[i].score >= best[1] - b.score_delta) { ++num; lc_matesw_t(b, f1[i], len[0], q[0], f0, n0, ex); }
 	// phase 2: rescue read 2 from read 1's post-rescue list, gated by the pre-rescue best (G/gobwa.go:302-324)
 	num = 0;
 	for (int i = 0; i < n0 && num < b.max_anchors && len[1] > 0; ++i)
-		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw(b, f0[i], len[1], q[1], f1, n1, ws); }
-	b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n0;
-	b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n1;
-	unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));   // candidate list for stage 6 (sized like fin)
-	for (int i = 0; i < n0; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
-	for (int i = 0; i < n1; ++i) b.cand[co + n0 + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
+		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw_t(b, f0[i], len[1], q[1], f1, n1, ex); }
+	if (ex.leader()) {
+		b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n0;
+		b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n1;
+		unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));   // candidate list for stage 6 (sized like fin)
+		for (int i = 0; i < n0; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
+		for (int i = 0; i < n1; ++i) b.cand[co + n0 + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
+	}
+}
+
+struct LcExecThreadSw : LcExecThread {     // thread executor with the extra rows the local SW needs
+	int *Hmax; unsigned long long *bl;
+	LC_HD int lane_id() const { return 0; }
+	LC_HD int n_lanes() const { return 1; }
+	template <class QF, class TF>
+	LC_HD LcSwResult sw_align2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int xtra, LcCounters *cnt) const
+	{
+		return lc_sw_align2(qlen, q, tlen, t, sc, xtra, H, E, Hmax, bl, cnt);
+	}
+};
+
+LC_HDN int lc_matesw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const LcSwScratch &ws)
+{
+	LcExecThreadSw ex;
+	ex.H = ws.H; ex.E = ws.E; ex.Hmax = ws.Hmax; ex.bl = ws.b;
+	return lc_matesw_t(b, a, l_ms, ms, ma, n_ma, ex);
+}
+
+LC_HDN void lc_stage_pair(const LcBatch &b, int p, int worker)
+{
+	int *wi = b.w_int + (size_t)worker * b.w_int_n;
+	LcExecThreadSw ex;
+	ex.H = wi; ex.E = wi + (b.lmax + 18); ex.Hmax = wi + 2 * (b.lmax + 18);
+	ex.bl = b.w_u64 + (size_t)worker * b.w_u64_n;
+	lc_stage_pair_t(b, p, ex);
 }
 
 // ============================================================================================================

@@ -126,10 +126,111 @@ __device__ __noinline__ LcExtResult lc_extend2_warp(int qlen, QF query, int tlen
 	return r;
 }
 
+// One pass of the local SW with the reference's striped-SSE2 semantics (ksw_u8 / ksw_i16, B/ksw.c:111-334), one warp.
+// Same contract as lc_sw_pass (lc_sw.cuh).  H, E, Hmax: shared memory rows of P ints; qs: P bytes; bl: global scratch list.
+template <class QF, class TF>
+__device__ __noinline__ LcSwResult lc_sw_pass_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int size, int xtra,
+												   int *H, int *E, int *Hmax, uint8_t *qs, unsigned long long *bl, int lane, LcCounters *cnt)
+{
+	const int lanes = size == 1 ? 16 : 8, P = (qlen + lanes - 1) / lanes * lanes;
+	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
+	const int shift = size == 1 ? max(sc.b, 1) : 0;
+	const int minsc = (xtra & LC_XSUBO) ? (xtra & 0xffff) : 0x10000, endsc = (xtra & LC_XSTOP) ? (xtra & 0xffff) : 0x10000;
+	LcSwResult r = { 0, -1, -1, -1, -1, -1, -1 };
+	int gmax = 0, te = -1, n_b = 0, last_i = -2, last_max = 0, rows = 0;
+	for (int j = lane; j < P; j += 32) { H[j] = 0; E[j] = 0; Hmax[j] = 0; qs[j] = j < qlen ? (uint8_t)query(j) : (uint8_t)4; }
+	__syncwarp();
+	for (int i = 0; i < tlen; ++i) {
+		const int tb = target(i);
+		int f_carry = 0, diag_carry = 0, imax = 0;
+		++rows;
+		for (int cs = 0; cs < P; cs += 32) {
+			const int j = cs + lane;
+			const bool act = j < P;
+			const int old = act ? H[j] : 0, e = act ? E[j] : 0;
+			int diag = __shfl_up_sync(LC_FULL, old, 1);
+			if (lane == 0) diag = diag_carry;
+			diag_carry = __shfl_sync(LC_FULL, old, 31);
+			const int s = (act && j < qlen) ? sc.sub(tb, qs[j]) : 0;
+			int hnf = max(diag + s, 0);
+			hnf = max(hnf, e);
+			const int t = max(hnf - oe_ins, 0);
+			const int pin = lc_warp_prefix_max_incl(t + j * e_ins, lane);
+			const int pex = __shfl_up_sync(LC_FULL, pin, 1);
+			int F = max(f_carry - lane * e_ins, 0);
+			if (lane > 0) F = max(F, pex - (j - 1) * e_ins);
+			const int h = max(hnf, F);
+			const int e2 = max(max(e - e_del, h - oe_del), 0);
+			if (act) { H[j] = h; E[j] = e2; imax = max(imax, h); }
+			f_carry = max(__shfl_sync(LC_FULL, F, 31) - e_ins, __shfl_sync(LC_FULL, t, 31));
+		}
+		imax = lc_warp_max(imax);
+		__syncwarp();
+		if (imax >= minsc) {                         // run-length list of rows scoring >= minsc (B/ksw.c:192-200)
+			if (n_b == 0 || last_i + 1 != i) {
+				if (lane == 0) bl[n_b] = (unsigned long long)imax << 32 | (unsigned)i;
+				++n_b; last_i = i; last_max = imax;
+			} else if (last_max < imax) {
+				if (lane == 0) bl[n_b - 1] = (unsigned long long)imax << 32 | (unsigned)i;
+				last_i = i; last_max = imax;
+			}
+		}
+		if (imax > gmax) {
+			gmax = imax; te = i;
+			for (int j = lane; j < P; j += 32) Hmax[j] = H[j];
+			if ((size == 1 && gmax + shift >= 255) || gmax >= endsc) break;
+		}
+	}
+	__syncwarp();
+	if (cnt && lane == 0) { atomicAdd(&cnt->sw_calls, 1ull); atomicAdd(&cnt->sw_cells, (unsigned long long)rows * qlen); }
+	r.score = (size == 1 && gmax + shift >= 255) ? 255 : gmax;
+	r.te = te;
+	if (!(size == 1 && r.score == 255)) {
+		int key = -1;                                 // smallest column holding the row maximum (B/ksw.c:211-216)
+		for (int j = lane; j < P; j += 32) key = max(key, (Hmax[j] << 10) | (1023 - j));
+		key = lc_warp_max(key);
+		if (key >= 0) r.qe = 1023 - (key & 1023);
+		if (n_b) {
+			const int rad = (r.score + sc.a - 1) / sc.a, low = te - rad, high = te + rad;
+			for (int i = 0; i < n_b; ++i) {
+				const unsigned long long v = bl[i];
+				const int e = (int)(unsigned)v;
+				if ((e < low || e > high) && (int)(v >> 32) > r.score2) { r.score2 = (int)(v >> 32); r.te2 = e; }
+			}
+		}
+	}
+	__syncwarp();
+	return r;
+}
+
+// ksw_align2 as mem_matesw calls it (B/ksw.c:343-365), one warp
+template <class QF, class TF>
+__device__ __forceinline__ LcSwResult lc_sw_align2_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int xtra,
+													   int *H, int *E, int *Hmax, uint8_t *qs, unsigned long long *bl, int lane, LcCounters *cnt)
+{
+	const int size = (xtra & LC_XBYTE) ? 1 : 2;
+	LcSwResult r = lc_sw_pass_warp(qlen, query, tlen, target, sc, size, xtra, H, E, Hmax, qs, bl, lane, cnt);
+	if ((xtra & LC_XSTART) == 0 || ((xtra & LC_XSUBO) && r.score < (xtra & 0xffff))) return r;
+	LcPrefixRev<QF> rq = { query, r.qe };
+	LcPrefixRev<TF> rt = { target, r.te };
+	LcSwResult rr = lc_sw_pass_warp(r.qe + 1, rq, tlen, rt, sc, size, LC_XSTOP | r.score, H, E, Hmax, qs, bl, lane, cnt);
+	if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+	return r;
+}
+
 struct LcExecWarp {
 	int *H, *E;          // shared memory rows of this warp
 	uint8_t *qs;         // shared memory copy of the query side of the current job
 	int lane;
+	int *Hmax;           // third shared row (local SW only)
+	unsigned long long *bl;   // global scratch: sub-optimal row list of the local SW
+	__device__ __forceinline__ int lane_id() const { return lane; }
+	__device__ __forceinline__ int n_lanes() const { return 32; }
+	template <class QF, class TF>
+	__device__ __forceinline__ LcSwResult sw_align2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int xtra, LcCounters *cnt) const
+	{
+		return lc_sw_align2_warp(qlen, q, tlen, t, sc, xtra, H, E, Hmax, qs, bl, lane, cnt);
+	}
 	__device__ __forceinline__ bool leader() const { return lane == 0; }
 	__device__ __forceinline__ void sync() const { __syncwarp(); }
 	__device__ __forceinline__ unsigned long long bcast(unsigned long long v) const { return __shfl_sync(LC_FULL, v, 0); }
@@ -141,6 +242,7 @@ struct LcExecWarp {
 	}
 };
 
-// bytes of dynamic shared memory one warp needs for reads up to lmax
-__host__ __device__ inline int lc_warp_smem_bytes(int lmax) { return 2 * 4 * ((lmax + 2 + 31) & ~31) + ((lmax + 31) & ~31); }
+// bytes of dynamic shared memory one warp needs for reads up to lmax: `nrows` int rows of lmax+18 (rounded) + the query bytes
+__host__ __device__ inline int lc_warp_row_ints(int lmax) { return (lmax + 18 + 31) & ~31; }
+__host__ __device__ inline int lc_warp_smem_bytes(int lmax, int nrows = 2) { return nrows * 4 * lc_warp_row_ints(lmax) + lc_warp_row_ints(lmax); }
 #endif
