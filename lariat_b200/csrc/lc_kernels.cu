@@ -96,11 +96,24 @@ __global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, int n_p
 	}
 }
 
+// one warp per candidate: gap-free candidates are a cooperative compare, the rest a cooperative banded NW + lane-0 traceback
 __global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, unsigned long long n)
 {
-	const int worker = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	for (unsigned long long c = worker; c < n; c += stride) lc_stage_cigar(b, c, worker);
+	extern __shared__ int lc_smem[];
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = lc_warp_row_ints(b.lmax);
+	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	LcExecWarp ex;
+	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
+	ex.Hmax = nullptr; ex.bl = nullptr;
+	ex.cig = (uint32_t *)(b.w_int + (size_t)gwarp * b.w_int_n); ex.zloc = b.w_z + (size_t)gwarp * b.w_z_n;
+	for (;;) {
+		unsigned int c = 0;
+		if (lane == 0) c = atomicAdd(b.work_ctr + 2, 1u);
+		c = __shfl_sync(LC_FULL, c, 0);
+		if (c >= n) break;
+		lc_stage_cigar_t(b, (unsigned long long)c, ex);
+		__syncwarp();
+	}
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const LcBatch b, const LcPackArgs pa)
@@ -226,7 +239,13 @@ void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id
 	matesw_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, n_pairs);
 }
-void LcCudaBackend::k_cigar(const LcBatch &b, unsigned long long n) { global_cigar_kernel<<<grid_for(n, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n); }
+void LcCudaBackend::k_cigar(const LcBatch &b, unsigned long long n)
+{
+	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+	cudaFuncSetAttribute(global_cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	cudaMemsetAsync(b.work_ctr + 2, 0, 4, stream);      // the stage may be re-launched after a pool regrow
+	global_cigar_kernel<<<grid_for(n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, n);
+}
 void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for(b.n_reads, 256, 8), 256, 0, stream>>>(b, pa); }
 void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
 {

@@ -840,7 +840,21 @@ LC_HD int lc_infer_bw(int l1, int l2, int score, int a, int q, int r)   // B/bwa
 	return w < d ? d : w;
 }
 
-LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
+struct LcExecThreadCigar : LcExecThread {   // thread executor for the CIGAR stage
+	uint32_t *cig; uint8_t *zloc;
+	LC_HD int lane_id() const { return 0; }
+	LC_HD int n_lanes() const { return 1; }
+	LC_HD int sum(int v) const { return v; }
+	template <class QF, class TF>
+	LC_HD int global2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int w, uint8_t *z, uint32_t *cigar, int cap, int *n_cigar, LcCounters *cnt) const
+	{
+		return lc_global2(qlen, q, tlen, t, sc, w, H, E, z, cigar, cap, n_cigar, cnt);
+	}
+};
+
+// ex.cig: per-worker CIGAR build buffer (2*lmax+8 words); ex.zloc: per-worker traceback scratch of b.w_z_n bytes
+template <class Exec>
+LC_HD void lc_stage_cigar_t(const LcBatch &b, unsigned long long ci, const Exec &ex)
 {
 	const lc_opt_t &opt = b.opt;
 	const uint64_t cd = b.cand[ci];
@@ -851,8 +865,7 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 	const lc_alnreg_t &ar = b.fin[slot];
 	lc_aln_t out;
 	memset(&out, 0, sizeof(out));
-	if (ar.rb < 0 || ar.re < 0) { out.rid = -1; out.pos = -1; b.aln[slot] = out; return; }
-	int *H = b.w_int + (size_t)worker * b.w_int_n, *E = H + (b.lmax + 2);
+	if (ar.rb < 0 || ar.re < 0) { out.rid = -1; out.pos = -1; if (ex.leader()) b.aln[slot] = out; return; }
 	const int64_t l_pac = b.ix.l_pac, rb = ar.rb, re = ar.re;
 	const int qb = ar.qb, qe = ar.qe, lq = qe - qb, rlen = (int)(re - rb);
 	const bool rev = rb >= l_pac;
@@ -863,7 +876,7 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 	// the CIGAR is built in a per-worker buffer (an alignment of lq x rlen has at most 2*min(lq,rlen)+1 merged ops) and
 	// only its final ops are carved from the output pool
 	const int cig_cap = 2 * b.lmax + 8;
-	uint32_t *cig = (uint32_t *)(E + (b.lmax + 2));
+	uint32_t *cig = ex.cig;
 	int n_cigar = 0, score = 0, last_sc = -(1 << 30), i = 0;
 	const bool bad = lq <= 0 || rb >= re || (rb < l_pac && re > l_pac) || re > l_pac << 1;
 	do {
@@ -871,9 +884,12 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 		n_cigar = 0;
 		if (bad) { score = 0; break; }                       // bwa_gen_cigar2 returns no CIGAR (B/bwa.c:132-134)
 		if (lq == rlen && w2 == 0) {                         // gap-free (B/bwa.c:141-149)
-			cig[0] = (uint32_t)lq << 4; n_cigar = 1;
-			score = 0;
-			for (int k = 0; k < lq; ++k) score += b.sc.sub(lc_ref_base(b.ix, rb + k), query[qb + k]);
+			if (ex.leader()) cig[0] = (uint32_t)lq << 4;
+			n_cigar = 1;
+			int part = 0;
+			for (int k = ex.lane_id(); k < lq; k += ex.n_lanes()) part += b.sc.sub(lc_ref_base(b.ix, rb + k), query[qb + k]);
+			score = ex.sum(part);
+			ex.sync();
 		} else {
 			int mi = (int)((double)(((lq + 1) >> 1) * b.sc.a - b.sc.o_ins) / b.sc.e_ins + 1.);
 			int md = (int)((double)(((lq + 1) >> 1) * b.sc.a - b.sc.o_del) / b.sc.e_del + 1.);
@@ -884,18 +900,20 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 			const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
 			const unsigned long long zneed = (unsigned long long)n_col * rlen + 8;
 			uint8_t *z;
-			if (zneed <= (unsigned long long)b.w_z_n) z = b.w_z + (size_t)worker * b.w_z_n;   // common case: per-worker traceback scratch
+			if (zneed <= (unsigned long long)b.w_z_n) z = ex.zloc;   // common case: per-worker traceback scratch
 			else {
-				unsigned long long zo = lc_carve(b, b.z_cur, b.z_cap, zneed, LC_OVF_Z);
+				unsigned long long zo = 0;
+				if (ex.leader()) zo = lc_carve(b, b.z_cur, b.z_cap, zneed, LC_OVF_Z);
+				zo = ex.bcast(zo);
 				if (zo == (unsigned long long)-1) return;
 				z = b.zpool + zo;
 			}
 			if (rev) {
 				LcSeqRev qf = { query + qe - 1 }; LcRefRev tf = { &b.ix, re - 1 };
-				score = lc_global2(lq, qf, rlen, tf, b.sc, w, H, E, z, cig, cig_cap, &n_cigar, b.cnt);
+				score = ex.global2(lq, qf, rlen, tf, b.sc, w, z, cig, cig_cap, &n_cigar, b.cnt);
 			} else {
 				LcSeqFwd qf = { query + qb }; LcRefFwd tf = { &b.ix, rb };
-				score = lc_global2(lq, qf, rlen, tf, b.sc, w, H, E, z, cig, cig_cap, &n_cigar, b.cnt);
+				score = ex.global2(lq, qf, rlen, tf, b.sc, w, z, cig, cig_cap, &n_cigar, b.cnt);
 			}
 		}
 		if (score == last_sc || w2 == opt.w << 2) break;
@@ -904,24 +922,25 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 	} while (++i < 3 && score < ar.truesc - opt.a);
 	// NM = mismatches + gap bases, skipping a leading/trailing deletion (B/bwa.c:169-199)
 	int NM = -1, n_mm = 0;
-	if (!bad) {
-		int x = 0, y = 0, n_gap = 0;
+	if (!bad && n_cigar >= 0) {
+		int x = 0, y = 0, n_gap = 0, part = 0;
 		for (int k = 0; k < n_cigar; ++k) {
 			const int op = cig[k] & 0xf, len = (int)(cig[k] >> 4);
 			if (op == 0) {
-				for (int t = 0; t < len; ++t) {
+				for (int t = ex.lane_id(); t < len; t += ex.n_lanes()) {
 					int qc = rev ? query[qe - 1 - (x + t)] : query[qb + x + t];
 					int rc = rev ? lc_ref_base(b.ix, re - 1 - (y + t)) : lc_ref_base(b.ix, rb + y + t);
-					n_mm += qc != rc;
+					part += qc != rc;
 				}
 				x += len; y += len;
 			} else if (op == 2) { if (k > 0 && k < n_cigar - 1) n_gap += len; y += len; }
 			else if (op == 1) { x += len; n_gap += len; }
 		}
+		n_mm = ex.sum(part);
 		NM = n_mm + n_gap;
 	}
 	int64_t pos = rev ? (l_pac << 1) - 1 - (re - 1) : rb;       // bns_depos (B/bwamem.c:1122)
-	if (n_cigar < 0) { lc_raise(b, LC_OVF_CIGAR); return; }
+	if (n_cigar < 0) { if (ex.leader()) lc_raise(b, LC_OVF_CIGAR); return; }
 	int cs = 0, ce = n_cigar;
 	if (n_cigar > 0) {                                       // squeeze out a leading or trailing deletion (B/bwamem.c:1124-1133)
 		if ((cig[0] & 0xf) == 2) { pos += cig[0] >> 4; cs = 1; }
@@ -930,9 +949,11 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 	const bool clipped = qb != 0 || qe != l_query;          // soft clips (B/bwamem.c:1134-1148)
 	const int clip5 = clipped ? (rev ? l_query - qe : qb) : 0, clip3 = clipped ? (rev ? qb : l_query - qe) : 0;
 	const int o = (clip5 ? 1 : 0) + (ce - cs) + (clip3 ? 1 : 0);
-	unsigned long long co = lc_carve(b, b.cigar_cur, b.cigar_cap, (unsigned long long)o, LC_OVF_CIGAR);
+	unsigned long long co = 0;
+	if (ex.leader()) co = lc_carve(b, b.cigar_cur, b.cigar_cap, (unsigned long long)o, LC_OVF_CIGAR);
+	co = ex.bcast(co);
 	if (co == (unsigned long long)-1) return;
-	{
+	if (ex.leader()) {
 		uint32_t *dst = b.cigar + co;
 		int k = 0;
 		if (clip5) dst[k++] = (uint32_t)clip5 << 4 | 3;
@@ -942,5 +963,13 @@ LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
 	out.pos = pos; out.is_rev = rev ? 1 : 0; out.NM = NM; out.n_cigar = o; out.cigar_off = (uint32_t)co; out.n_mismatch = n_mm;
 	out.rid = lc_pos2rid(b.ix, pos);
 	if (out.rid >= 0) out.pos = pos - b.ix.anns[out.rid].offset;
-	b.aln[slot] = out;
+	if (ex.leader()) b.aln[slot] = out;
+}
+
+LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
+{
+	LcExecThreadCigar ex;
+	ex.H = b.w_int + (size_t)worker * b.w_int_n; ex.E = ex.H + (b.lmax + 2);
+	ex.cig = (uint32_t *)(ex.E + (b.lmax + 2)); ex.zloc = b.w_z + (size_t)worker * b.w_z_n;
+	lc_stage_cigar_t(b, ci, ex);
 }

@@ -218,12 +218,106 @@ __device__ __forceinline__ LcSwResult lc_sw_align2_warp(int qlen, QF query, int 
 	return r;
 }
 
+// Banded global alignment with traceback (ksw_global2, B/ksw.c:504-606), one warp: the fill is cooperative, the
+// pointer-chasing traceback is done by lane 0.  Same contract as lc_global2 (lc_sw.cuh).
+template <class QF, class TF>
+__device__ __noinline__ int lc_global2_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int w, int *H, int *E, uint8_t *qs,
+											uint8_t *z, uint32_t *cigar, int cigar_cap, int *n_cigar, int lane, LcCounters *cnt)
+{
+	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
+	const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+	unsigned long long cells = 0;
+	for (int j = lane; j <= qlen; j += 32) {
+		H[j] = j == 0 ? 0 : (j <= w ? -(sc.o_ins + sc.e_ins * j) : LC_NEG_INF);
+		E[j] = LC_NEG_INF;
+		if (j < qlen) qs[j] = (uint8_t)query(j);
+	}
+	__syncwarp();
+	for (int i = 0; i < tlen; ++i) {
+		const int tb = target(i);
+		const int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+		int f_carry = LC_NEG_INF, hl_carry = beg == 0 ? -(sc.o_del + sc.e_del * (i + 1)) : LC_NEG_INF;
+		uint8_t *zi = z ? z + (size_t)i * n_col : (uint8_t *)0;
+		for (int cs = beg; cs < end; cs += 32) {
+			const int j = cs + lane;
+			const bool act = j < end;
+			const int diag = act ? H[j] : LC_NEG_INF, e = act ? E[j] : LC_NEG_INF;
+			const int M = diag + (act ? sc.sub(tb, qs[j]) : 0);
+			const int t = M - oe_ins;
+			const int pin = lc_warp_prefix_max_incl(t + j * e_ins, lane);
+			const int pex = __shfl_up_sync(LC_FULL, pin, 1);
+			int F = f_carry - lane * e_ins;
+			if (lane > 0) F = max(F, pex - (j - 1) * e_ins);
+			unsigned d = M >= e ? 0u : 1u;
+			int h = M >= e ? M : e;
+			d = h >= F ? d : 2u;
+			h = h >= F ? h : F;
+			const int t2 = M - oe_del, ee = e - e_del;
+			if (ee > t2) d |= 1u << 2;
+			const int e2 = ee > t2 ? ee : t2;
+			if (F - e_ins > t) d |= 2u << 4;
+			int hl = __shfl_up_sync(LC_FULL, h, 1);
+			if (lane == 0) hl = hl_carry;
+			if (act) { H[j] = hl; E[j] = e2; if (zi) zi[j - beg] = (uint8_t)d; }
+			const int last = min(31, end - 1 - cs);
+			hl_carry = __shfl_sync(LC_FULL, h, last);
+			f_carry = max(__shfl_sync(LC_FULL, F, 31) - e_ins, __shfl_sync(LC_FULL, t, 31));
+		}
+		cells += (unsigned long long)(end > beg ? end - beg : 0);
+		__syncwarp();
+		if (lane == 0) { H[end] = hl_carry; E[end] = LC_NEG_INF; }
+		__syncwarp();
+	}
+	const int score = H[qlen];
+	if (cnt && lane == 0) { atomicAdd(&cnt->glb_calls, 1ull); atomicAdd(&cnt->glb_cells, cells); }
+	if (n_cigar) {
+		int n = 0;
+		if (z && cigar && lane == 0) {
+			int state = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+			bool ovf = false;
+			while (i >= 0 && k >= 0) {
+				if (n + 2 > cigar_cap) { ovf = true; break; }
+				int col = k - (i > w ? i - w : 0);
+				col = col < 0 ? 0 : (col >= n_col ? n_col - 1 : col);
+				state = z[(size_t)i * n_col + col] >> (state << 1) & 3;
+				if (state == 0) { n = lc_cigar_push(cigar, n, 0, 1); --i; --k; }
+				else if (state == 1) { n = lc_cigar_push(cigar, n, 2, 1); --i; }
+				else { n = lc_cigar_push(cigar, n, 1, 1); --k; }
+			}
+			if (!ovf && n + 2 > cigar_cap) ovf = true;
+			if (!ovf) {
+				if (i >= 0) n = lc_cigar_push(cigar, n, 2, i + 1);
+				if (k >= 0) n = lc_cigar_push(cigar, n, 1, k + 1);
+				for (int a = 0; a < n >> 1; ++a) { uint32_t tt = cigar[a]; cigar[a] = cigar[n - 1 - a]; cigar[n - 1 - a] = tt; }
+			} else n = -1;
+		}
+		n = __shfl_sync(LC_FULL, n, 0);
+		*n_cigar = n;
+	}
+	__syncwarp();
+	return score;
+}
+
 struct LcExecWarp {
 	int *H, *E;          // shared memory rows of this warp
 	uint8_t *qs;         // shared memory copy of the query side of the current job
 	int lane;
 	int *Hmax;           // third shared row (local SW only)
 	unsigned long long *bl;   // global scratch: sub-optimal row list of the local SW
+	uint32_t *cig;       // global scratch: CIGAR build buffer (CIGAR stage only)
+	uint8_t *zloc;       // global scratch: traceback matrix (CIGAR stage only)
+	__device__ __forceinline__ int sum(int v) const
+	{
+#pragma unroll
+		for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(LC_FULL, v, d);
+		return v;
+	}
+	template <class QF, class TF>
+	__device__ __forceinline__ int global2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int w, uint8_t *z, uint32_t *cigar, int cap,
+										   int *n_cigar, LcCounters *cnt) const
+	{
+		return lc_global2_warp(qlen, q, tlen, t, sc, w, H, E, qs, z, cigar, cap, n_cigar, lane, cnt);
+	}
 	__device__ __forceinline__ int lane_id() const { return lane; }
 	__device__ __forceinline__ int n_lanes() const { return 32; }
 	template <class QF, class TF>
