@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=float(os.environ.get("LARIAT_BENCH_SCALE", "1.0")))
-    ap.add_argument("--cpu-sample", type=int, default=40000)
+    ap.add_argument("--cpu-sample", type=int, default=200000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
