@@ -14,7 +14,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct lc_ctx {
 	int device = 0;
 	LcHostIndex hix;
-	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_anns = nullptr;
+	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_anns = nullptr, *d_sa_dense = nullptr;
 	LcIndex ix;
 	lc_opt_t opt;
 	LcCudaBackend be;
@@ -79,21 +79,50 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	if (!lc_load_index(idx_prefix, c->hix, err)) { fail(LC_EINDEX, err); delete c; return nullptr; }
 	cudaSetDevice(device);
 	LcHostIndex &h = c->hix;
+	LcIndex &ix = c->ix;
+	if (!lc_index_scalars(h, ix, err)) { fail(LC_EINDEX, err); delete c; return nullptr; }
+	// upload the file payloads, then re-lay the BWT on the device as 32-byte blocks (lc_fmindex.cuh) and drop the file layout
+	const uint64_t n_blocks = lc_occ_blocks(h.seq_len);
 	size_t nb = h.bwt.size() * 4, ns = h.sa.size() * 8, np = h.pac.size(), na = h.anns.size() * sizeof(LcAnn);
-	if (cudaMalloc(&c->d_bwt, nb) != cudaSuccess || cudaMalloc(&c->d_sa, ns) != cudaSuccess || cudaMalloc(&c->d_pac, np) != cudaSuccess ||
-		cudaMalloc(&c->d_anns, na ? na : 1) != cudaSuccess) { cudaGetLastError(); fail(LC_ENOMEM, "cannot allocate the index in HBM"); delete c; return nullptr; }
-	cudaMemcpy(c->d_bwt, h.bwt.data(), nb, cudaMemcpyHostToDevice);
+	void *d_file = nullptr;
+	if (cudaMalloc(&d_file, nb) != cudaSuccess || cudaMalloc(&c->d_bwt, 32 * (size_t)n_blocks) != cudaSuccess || cudaMalloc(&c->d_sa, ns) != cudaSuccess ||
+		cudaMalloc(&c->d_pac, np) != cudaSuccess || cudaMalloc(&c->d_anns, na ? na : 1) != cudaSuccess) {
+		cudaGetLastError(); if (d_file) cudaFree(d_file); fail(LC_ENOMEM, "cannot allocate the index in HBM"); lc_destroy(c); return nullptr;
+	}
+	cudaMemcpy(d_file, h.bwt.data(), nb, cudaMemcpyHostToDevice);
 	cudaMemcpy(c->d_sa, h.sa.data(), ns, cudaMemcpyHostToDevice);
 	cudaMemcpy(c->d_pac, h.pac.data(), np, cudaMemcpyHostToDevice);
 	cudaMemcpy(c->d_anns, h.anns.data(), na, cudaMemcpyHostToDevice);
-	if (cudaDeviceSynchronize() != cudaSuccess) { fail(LC_ECUDA, cudaGetErrorString(cudaGetLastError())); delete c; return nullptr; }
-	LcIndex &ix = c->ix;
-	ix.primary = h.primary; memcpy(ix.L2, h.L2, sizeof(ix.L2)); ix.seq_len = h.seq_len;
-	ix.bwt = (const uint4 *)c->d_bwt; ix.sa = (const uint64_t *)c->d_sa; ix.sa_mask = (uint64_t)h.sa_intv - 1;
-	ix.sa_shift = __builtin_ctz((unsigned)h.sa_intv);
-	ix.pac = (const uint8_t *)c->d_pac; ix.l_pac = h.l_pac; ix.anns = (const LcAnn *)c->d_anns; ix.n_seqs = (int)h.anns.size();
+	ix.occ = (const uint4 *)c->d_bwt; ix.sa = (const uint64_t *)c->d_sa;
+	ix.pac = (const uint8_t *)c->d_pac; ix.anns = (const LcAnn *)c->d_anns;
+	c->be.k_occ_convert((const uint32_t *)d_file, (uint4 *)c->d_bwt, n_blocks, ix);
+	{
+		std::string e;
+		if (c->be.check(e)) { cudaFree(d_file); fail(LC_ECUDA, e); lc_destroy(c); return nullptr; }
+	}
+	cudaFree(d_file);
+	// dense suffix array: one entry per BWT row, built from the sampled one with one LF step per row.  Optional: if HBM is
+	// short (or LC_DENSE_SA=0) the kernels fall back to the reference's sampled array + LF walks; results are identical.
+	{
+		const char *env = getenv("LC_DENSE_SA");
+		const bool want = !(env && env[0] == '0');
+		const bool wide = h.seq_len >= 0xffffffffull;
+		const size_t bytes = (size_t)(h.seq_len + 1) * (wide ? 8 : 4);
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		if (want && bytes < free_b / 2 && cudaMalloc(&c->d_sa_dense, bytes) == cudaSuccess) {
+			c->be.k_sa_fill(ix, (unsigned long long)h.sa.size(), c->d_sa_dense, wide);
+			std::string e;
+			if (c->be.check(e)) { fail(LC_ECUDA, e); lc_destroy(c); return nullptr; }
+			if (wide) ix.sa64 = (const uint64_t *)c->d_sa_dense; else ix.sa32 = (const uint32_t *)c->d_sa_dense;
+		} else cudaGetLastError();
+	}
 	c->opt = o;
 	c->pl.set_index(ix, o);
+	// tuning knobs of the seeding state machine (tests use tiny values to force the redo path)
+	if (const char *e = getenv("LC_SEED_LST_CAP")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap = v; }
+	if (const char *e = getenv("LC_SEED_PK_CAP")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap = v; }
+	if (const char *e = getenv("LC_FORCE_WIDE")) c->pl.force_wide = e[0] == '1';
 	// host copies of the big FM-index arrays are not needed any more (pac stays for lc_fetch_seq)
 	std::vector<uint32_t>().swap(h.bwt);
 	std::vector<uint64_t>().swap(h.sa);
@@ -109,7 +138,7 @@ void lc_destroy(lc_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->pl.release();
-	cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_pac); cudaFree(c->d_anns);
+	cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_pac); cudaFree(c->d_anns); cudaFree(c->d_sa_dense);
 	delete c;
 }
 

@@ -24,6 +24,7 @@ struct LcCudaBackend {
 	explicit LcCudaBackend(int device_);
 	~LcCudaBackend();
 	int n_workers() const { return workers; }
+	int n_redo_workers() const { return n_sm * 128; }     // smem_redo_kernel: one CTA of 128 threads per SM
 	void *dmalloc(size_t n);
 	void dfree(void *p);
 	void dzero(void *p, size_t n);
@@ -37,6 +38,12 @@ struct LcCudaBackend {
 	int grid_for(unsigned long long items, int tpb, int ctas_per_sm) const;
 	void k_convert(uint8_t *p, unsigned long long n, bool ascii);
 	void k_seed(const LcBatch &b);
+	int seed_grid(const LcBatch &b);
+	int seed_lanes();
+	void k_seed_finish(const LcBatch &b);
+	void k_seed_redo(const LcBatch &b, int n_redo);
+	void k_occ_convert(const uint32_t *bwa, uint4 *occ, unsigned long long n_blocks, const LcIndex &ix);
+	void k_sa_fill(const LcIndex &ix, unsigned long long n_samples, void *out, bool wide);
 	void k_sa(const LcBatch &b, unsigned long long n);
 	void k_chain(const LcBatch &b);
 	void k_extend(const LcBatch &b);

@@ -58,15 +58,26 @@ struct LcCounters {
 
 struct LcAnn { int64_t offset; int32_t len; int32_t is_alt; };
 
-// The index as it lives in HBM.  bwt = the .bwt payload unchanged: one 64-byte block per 128 BWT symbols,
-// { u64 occ[4]; u32 sym[8] } (2 bits/base, first symbol in the top bits)  (B/bwt.h:72-73, B/bwtindex.c:151-173),
-// viewed as 4 x 16-byte vectors so a block is fetched with 128-bit loads.
+// The FM-index as it lives in HBM — NOT the .bwt file layout.  `bwa index` interleaves {u64 occ[4]; u32 sym[8]} per 128
+// symbols (64 B; B/bwt.h:72-73, B/bwtindex.c:151-173), so one occ lookup touches two 32-byte sectors and needs up to
+// eight masked word popcounts.  At load time the file payload is re-laid on the device (lc_occ_from_bwa) into one
+// 32-byte block per 64 symbols:
+//     { u32 cnt[4]; u64 hi; u64 lo }      cnt[c] = occurrences of c before the block, relative to its 2^32-symbol
+//                                          superblock (absolute bases in LcIndex::sb); hi/lo = the high/low bit planes
+//                                          of the 64 symbols, first symbol in bit 63
+// Same bytes per base (0.5), but a lookup is ONE sector and at most three 64-bit popcounts.  Results are identical:
+// occ(k, c) is a property of the BWT string, not of its packing.
+#define LC_SB_SHIFT 26          // blocks per superblock = 2^26 (2^32 symbols)
+#define LC_MAX_SB 4             // up to 2^34 symbols (the 3.1 Gb reference doubled is 6.2e9)
 struct LcIndex {
 	uint64_t primary, L2[5], seq_len;
-	const uint4 *bwt;
-	const uint64_t *sa;      // sampled suffix array; sa[0] = (u64)-1 (B/bwt.c:83,437)
+	const uint4 *occ;        // 2 x uint4 per block: [0] = cnt[0..3], [1] = {hi.lo32, hi.hi32, lo.lo32, lo.hi32}
+	uint64_t sb[LC_MAX_SB][4];
+	const uint64_t *sa;      // sampled suffix array as in the .sa file; sa[0] = (u64)-1 (B/bwt.c:83,437)
 	uint64_t sa_mask;        // sa_intv - 1
 	int sa_shift;            // log2(sa_intv)
+	const uint32_t *sa32;    // dense suffix array (every row), built on the device at load time when it fits; else null.
+	const uint64_t *sa64;    //   sa32 when seq_len < 2^32 - 1, sa64 otherwise
 	const uint8_t *pac;      // forward strand, 2 bits/base
 	int64_t l_pac;
 	const LcAnn *anns;
@@ -75,51 +86,80 @@ struct LcIndex {
 
 struct LcIntv { uint64_t x0, x1, x2, info; };   // bwtintv_t (B/bwt.h:60-62): x0 fwd, x1 revcomp, x2 size
 
-// per-base counts among the top `n` 2-bit cells of a 32-bit BWT word (n <= 0: none, n >= 16: all)
-LC_HD void lc_count_word(unsigned w, int n, unsigned &c0, unsigned &c1, unsigned &c2, unsigned &c3)
+LC_HD int lc_popcll(uint64_t v)
 {
-	if (n <= 0) return;
-	unsigned valid = n >= 16 ? 0x55555555u : (0x55555555u & ~((1u << ((16 - n) << 1)) - 1u));
-	unsigned hi = (w >> 1) & valid, lo = w & valid;
-	unsigned both = hi & lo;
-	unsigned n3 = lc_popc(both), n2 = lc_popc(hi) - n3, n1 = lc_popc(lo) - n3;
-	c3 += n3; c2 += n2; c1 += n1;
-	c0 += (unsigned)(n >= 16 ? 16 : n) - n3 - n2 - n1;
+#ifdef __CUDA_ARCH__
+	return __popcll(v);
+#else
+	return __builtin_popcountll(v);
+#endif
 }
+// even bits of a 32-bit word gathered into 16 bits (bit 2i -> bit i)
+LC_HD uint32_t lc_even_bits(uint32_t x)
+{
+	x &= 0x55555555u;
+	x = (x | x >> 1) & 0x33333333u;
+	x = (x | x >> 2) & 0x0f0f0f0fu;
+	x = (x | x >> 4) & 0x00ff00ffu;
+	x = (x | x >> 8) & 0x0000ffffu;
+	return x;
+}
+// absolute counts before device block j (64 symbols), straight from the .bwt payload.  `bwa` = the u32 words after the
+// 40-byte file header, zero-padded to whole 64-byte blocks.
+LC_HD void lc_bwa_counts_at(const uint32_t *bwa, uint64_t j, uint64_t cnt[4])
+{
+	const uint32_t *o = bwa + 16 * (j >> 1);
+	for (int c = 0; c < 4; ++c) cnt[c] = (uint64_t)o[2 * c] | (uint64_t)o[2 * c + 1] << 32;
+	if (j & 1)      // add the first 64 symbols of the 128-symbol file block
+		for (int t = 0; t < 4; ++t) {
+			const uint32_t w = o[8 + t], hi = (w >> 1) & 0x55555555u, lo = w & 0x55555555u;
+			const int n3 = lc_popc(hi & lo), n2 = lc_popc(hi) - n3, n1 = lc_popc(lo) - n3;
+			cnt[3] += n3; cnt[2] += n2; cnt[1] += n1; cnt[0] += 16 - n3 - n2 - n1;
+		}
+}
+// device block j from the .bwt payload; sb_base = absolute counts at the start of j's superblock
+LC_HD void lc_occ_from_bwa(const uint32_t *bwa, uint64_t j, const uint64_t sb_base[4], uint4 out[2])
+{
+	const uint32_t *o = bwa + 16 * (j >> 1) + 8 + 4 * (j & 1);
+	uint64_t cnt[4], hi = 0, lo = 0;
+	lc_bwa_counts_at(bwa, j, cnt);
+	for (int t = 0; t < 4; ++t) {
+		hi = hi << 16 | lc_even_bits(o[t] >> 1);
+		lo = lo << 16 | lc_even_bits(o[t]);
+	}
+	out[0].x = (uint32_t)(cnt[0] - sb_base[0]); out[0].y = (uint32_t)(cnt[1] - sb_base[1]);
+	out[0].z = (uint32_t)(cnt[2] - sb_base[2]); out[0].w = (uint32_t)(cnt[3] - sb_base[3]);
+	out[1].x = (uint32_t)hi; out[1].y = (uint32_t)(hi >> 32); out[1].z = (uint32_t)lo; out[1].w = (uint32_t)(lo >> 32);
+}
+LC_HD uint64_t lc_keep_first(int r) { return r >= 64 ? ~0ull : ~(~0ull >> r); }     // mask of the first r symbols (r = 0: none)
 
 // occ(k, .) for the four bases = number of each base in BWT[0..k]   (bwt_occ4, B/bwt.c:169-186)
 LC_HD void lc_occ4(const LcIndex &ix, uint64_t k, uint64_t c[4])
 {
 	if (k == (uint64_t)-1) { c[0] = c[1] = c[2] = c[3] = 0; return; }
 	k -= (k >= ix.primary);
-	const uint4 *b = ix.bwt + ((k >> 7) << 2);
-	uint4 q0 = lc_ld16(b), q1 = lc_ld16(b + 1), q2 = lc_ld16(b + 2);
-	int r = (int)(k & 127) + 1;
-	unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-	lc_count_word(q2.x, r, c0, c1, c2, c3);
-	lc_count_word(q2.y, r - 16, c0, c1, c2, c3);
-	lc_count_word(q2.z, r - 32, c0, c1, c2, c3);
-	lc_count_word(q2.w, r - 48, c0, c1, c2, c3);
-	if (r > 64) {
-		uint4 q3 = lc_ld16(b + 3);
-		lc_count_word(q3.x, r - 64, c0, c1, c2, c3);
-		lc_count_word(q3.y, r - 80, c0, c1, c2, c3);
-		lc_count_word(q3.z, r - 96, c0, c1, c2, c3);
-		lc_count_word(q3.w, r - 112, c0, c1, c2, c3);
-	}
-	c[0] = ((uint64_t)q0.y << 32 | q0.x) + c0;
-	c[1] = ((uint64_t)q0.w << 32 | q0.z) + c1;
-	c[2] = ((uint64_t)q1.y << 32 | q1.x) + c2;
-	c[3] = ((uint64_t)q1.w << 32 | q1.z) + c3;
+	const uint64_t blk = k >> 6;
+	const uint4 q0 = lc_ld16(ix.occ + 2 * blk), q1 = lc_ld16(ix.occ + 2 * blk + 1);
+	const int r = (int)(k & 63) + 1;
+	const uint64_t m = lc_keep_first(r);
+	const uint64_t hi = ((uint64_t)q1.y << 32 | q1.x) & m, lo = ((uint64_t)q1.w << 32 | q1.z) & m;
+	const int n3 = lc_popcll(hi & lo), n2 = lc_popcll(hi) - n3, n1 = lc_popcll(lo) - n3;
+	const uint64_t *sb = ix.sb[blk >> LC_SB_SHIFT];
+	c[0] = sb[0] + q0.x + (uint64_t)(r - n3 - n2 - n1);
+	c[1] = sb[1] + q0.y + (uint64_t)n1;
+	c[2] = sb[2] + q0.z + (uint64_t)n2;
+	c[3] = sb[3] + q0.w + (uint64_t)n3;
 }
 
-// the symbol at BWT row x ('$' removed)   (bwt_B0, B/bwt.h:78)
+// the symbol at BWT position x ('$' removed)   (bwt_B0, B/bwt.h:78)
 LC_HD int lc_bwt_sym(const LcIndex &ix, uint64_t x)
 {
-	const unsigned *w = (const unsigned *)(ix.bwt + ((x >> 7) << 2) + 2);
-	unsigned v = lc_ldg(w + ((x & 127) >> 4));
-	return (v >> ((~x & 15) << 1)) & 3;
+	const uint4 q1 = lc_ld16(ix.occ + 2 * (x >> 6) + 1);
+	const int bit = 63 - (int)(x & 63);
+	const uint64_t hi = (uint64_t)q1.y << 32 | q1.x, lo = (uint64_t)q1.w << 32 | q1.z;
+	return (int)((hi >> bit) & 1) << 1 | (int)((lo >> bit) & 1);
 }
+
 
 LC_HD void lc_set_intv(const LcIndex &ix, int c, LcIntv &ik)   // bwt_set_intv (B/bwt.h:80)
 {
@@ -218,43 +258,57 @@ LC_HDN int lc_seed_strategy1(const LcIndex &ix, int len, const uint8_t *q, int x
 	return len;
 }
 
-// Suffix-array value of BWT row k: LF-walk to a sampled row (bwt_sa / bwt_invPsi / bwt_occ, B/bwt.c:53-59,86-129)
+// One LF step: the BWT row of the suffix that starts one text position earlier   (bwt_invPsi + bwt_occ, B/bwt.c:53-59,107-129).
+// The symbol and its rank come from the same 32-byte block.
+LC_HD uint64_t lc_lf(const LcIndex &ix, uint64_t k)
+{
+	if (k == ix.primary) return 0;
+	const uint64_t x = k - (k > ix.primary);
+	const uint64_t blk = x >> 6;
+	const uint4 q0 = lc_ld16(ix.occ + 2 * blk), q1 = lc_ld16(ix.occ + 2 * blk + 1);
+	const int off = (int)(x & 63), bit = 63 - off;
+	const uint64_t hi = (uint64_t)q1.y << 32 | q1.x, lo = (uint64_t)q1.w << 32 | q1.z;
+	const int c = (int)((hi >> bit) & 1) << 1 | (int)((lo >> bit) & 1);
+	const uint64_t eq = ~(hi ^ ((c & 2) ? ~0ull : 0ull)) & ~(lo ^ ((c & 1) ? ~0ull : 0ull)) & lc_keep_first(off + 1);
+	const uint32_t base = c == 0 ? q0.x : c == 1 ? q0.y : c == 2 ? q0.z : q0.w;
+	return ix.L2[c] + ix.sb[blk >> LC_SB_SHIFT][c] + base + (uint64_t)lc_popcll(eq);
+}
+
+// Suffix-array value of BWT row k (bwt_sa, B/bwt.c:86-96).  With the dense array it is one load; otherwise the reference's
+// LF-walk to a sampled row.  The counters always report the walk the REFERENCE would do.
+LC_HD uint64_t lc_sa_walk(const LcIndex &ix, uint64_t k, uint64_t &steps)
+{
+	steps = 0;
+	while (k & ix.sa_mask) { ++steps; k = lc_lf(ix, k); }
+	return steps + lc_ldg(ix.sa + (k >> ix.sa_shift));
+}
 LC_HD uint64_t lc_sa(const LcIndex &ix, uint64_t k, LcCounters *cnt)
 {
-	uint64_t steps = 0;
-	while (k & ix.sa_mask) {
-		++steps;
-		if (k == ix.primary) { k = 0; continue; }
-		uint64_t x = k - (k > ix.primary);
-		// symbol and its rank come from the same 64-byte block
-		const uint4 *b = ix.bwt + ((x >> 7) << 2);
-		uint4 q2 = lc_ld16(b + 2), q3 = lc_ld16(b + 3), q0 = lc_ld16(b), q1 = lc_ld16(b + 1);
-		unsigned ws[8] = { q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
-		int r = (int)(x & 127) + 1, c = 0;
-		{
-			int wi = (int)((x & 127) >> 4);
-			unsigned v = 0;
-#pragma unroll
-			for (int t = 0; t < 8; ++t) if (t == wi) v = ws[t];
-			c = (v >> ((~x & 15) << 1)) & 3;
-		}
-		unsigned n = 0;
-#pragma unroll
-		for (int t = 0; t < 8; ++t) {
-			int m = r - 16 * t;
-			if (m > 0) {
-				unsigned valid = m >= 16 ? 0x55555555u : (0x55555555u & ~((1u << ((16 - m) << 1)) - 1u));
-				unsigned w = ws[t];
-				unsigned hi = (c & 2) ? (w >> 1) : ~(w >> 1), lo = (c & 1) ? w : ~w;
-				n += lc_popc(hi & lo & valid);
-			}
-		}
-		uint64_t base = c == 0 ? ((uint64_t)q0.y << 32 | q0.x) : c == 1 ? ((uint64_t)q0.w << 32 | q0.z)
-					  : c == 2 ? ((uint64_t)q1.y << 32 | q1.x) : ((uint64_t)q1.w << 32 | q1.z);
-		k = ix.L2[c] + base + n;
+	uint64_t steps = 0, v;
+	if ((ix.sa32 || ix.sa64) && !cnt) {
+		if (ix.sa32) { const uint32_t t = lc_ldg(ix.sa32 + k); return t == 0xffffffffu ? (uint64_t)-1 : t; }
+		return lc_ldg(ix.sa64 + k);
 	}
+	v = lc_sa_walk(ix, k, steps);
 	if (cnt) { lc_atomic_add(&cnt->sa_calls, 1ull); lc_atomic_add(&cnt->lf_steps, (unsigned long long)steps); }
-	return steps + lc_ldg(ix.sa + (k >> ix.sa_shift));
+	return v;
+}
+
+
+// Dense suffix array, one sampled row at a time: SA[LF(k)] = SA[k] - 1, so the walk from sampled row j*intv labels every row it
+// passes until it meets the next sampled row.  Over all samples every BWT row is labelled exactly once (LF is a permutation).
+// T = uint32_t when seq_len < 2^32 - 1, else uint64_t; row 0 keeps the reference's sentinel (u64)-1 (B/bwt.c:83).
+template <typename T> LC_HD void lc_sa_fill_sample(const LcIndex &ix, uint64_t j, T *out)
+{
+	const uint64_t k0 = j << ix.sa_shift;
+	uint64_t v = j == 0 ? ix.seq_len : lc_ldg(ix.sa + j), k = k0;
+	out[k0] = j == 0 ? (T)~(T)0 : (T)v;
+	for (;;) {
+		k = lc_lf(ix, k);
+		if ((k & ix.sa_mask) == 0) break;
+		--v;
+		out[k] = (T)v;
+	}
 }
 
 // ---- packed reference ------------------------------------------------------------------------------

@@ -16,8 +16,10 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "lc_backend.cuh"
 #include "lc_sw_warp.cuh"
+#include "lc_seed.cuh"
 
 #define LC_TPB 128
+#define LC_SEED_TPB 64
 
 __global__ void __launch_bounds__(256) convert_kernel(uint8_t *p, unsigned long long n, int is_ascii)
 {
@@ -41,10 +43,109 @@ __global__ void __launch_bounds__(256) convert_kernel(uint8_t *p, unsigned long 
 	}
 }
 
-__global__ void __launch_bounds__(LC_TPB) smem_kernel(const LcBatch b)
+// ---- index preparation (lc_init): the .bwt payload re-laid as 32-byte blocks, and the dense suffix array ------------
+struct LcSbTable { uint64_t sb[LC_MAX_SB][4]; };
+__global__ void __launch_bounds__(256) occ_convert_kernel(const uint32_t *bwa, uint4 *occ, unsigned long long n_blocks, const LcSbTable t)
+{
+	unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (; j < n_blocks; j += stride) {
+		uint4 o[2];
+		lc_occ_from_bwa(bwa, j, t.sb[j >> LC_SB_SHIFT], o);
+		occ[2 * j] = o[0]; occ[2 * j + 1] = o[1];
+	}
+}
+// every sampled row walks the text backwards and labels the rows it passes until it meets the next sampled row:
+// one LF step per BWT row in total (the reference's bwt_sa pays ~31 steps per LOOKUP, B/bwt.c:86-96)
+template <typename T>
+__global__ void __launch_bounds__(256) sa_fill_kernel(const LcIndex ix, unsigned long long n_samples, T *out)
+{
+	unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (; j < n_samples; j += stride) lc_sa_fill_sample(ix, j, out);
+}
+
+// ---- seeding ---------------------------------------------------------------------------------------------------
+// One lane per read, one bwt_extend per tick (lc_seed.cuh).  Reads are dealt through an atomic counter; a lane that needs a
+// new read gets it copied into its slot by the whole warp (word-wise, coalesced).
+template <typename U>
+__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b)
+{
+	extern __shared__ uint4 lc_seed_smem[];
+	const int lane = threadIdx.x & 31, stride = lc_seed_lane_bytes(b.lmax, b.lst_cap);
+	uint8_t *slot0 = (uint8_t *)lc_seed_smem + (size_t)(threadIdx.x & ~31) * stride;      // slot of lane 0 of this warp
+	uint8_t *mine = slot0 + (size_t)lane * stride;
+	uint8_t *qbuf = mine + b.lst_cap * sizeof(LcPk);
+	LcPk *memv = b.w_pk + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * b.pk_cap;
+	LcSeedLane<U> sd(b, (LcPk *)mine, b.lst_cap, memv, b.pk_cap);
+	for (;;) {
+		unsigned need = __ballot_sync(LC_FULL, sd.phase == LC_SP_FETCH);
+		while (need) {                                       // warp-uniform
+			int base = 0;
+			if (lane == 0) base = (int)atomicAdd(b.work_ctr + 3, (unsigned)__popc(need));
+			base = __shfl_sync(LC_FULL, base, 0);
+			int myr = -1;
+			if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
+			for (unsigned m = need; m; m &= m - 1) {
+				const int L = __ffs(m) - 1;
+				const int rr = __shfl_sync(LC_FULL, myr, L);
+				if (rr < 0) continue;
+				const int64_t o = b.off[rr];
+				const int len = (int)(b.off[rr + 1] - o);
+				if (len < b.opt.min_seed_len) continue;
+				// 8 bases -> one word of 4-bit codes: three aligned words, funnel-shifted by the source misalignment, nibbles compacted
+				const uint8_t *src = b.seq + o;
+				const int mis = (int)((size_t)src & 3), nw = (len + 7) >> 3;
+				const uint32_t *w = (const uint32_t *)(src - mis);
+				uint32_t *dst = (uint32_t *)(slot0 + (size_t)L * stride + b.lst_cap * sizeof(LcPk));
+				for (int t = lane; t < nw; t += 32) {
+					const uint32_t w0 = __ldg(w + 2 * t), w1 = __ldg(w + 2 * t + 1), w2 = __ldg(w + 2 * t + 2);
+					uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
+					lo &= 0x0f0f0f0fu; lo = (lo | lo >> 4) & 0x00ff00ffu; lo = (lo | lo >> 8) & 0xffffu;
+					hi &= 0x0f0f0f0fu; hi = (hi | hi >> 4) & 0x00ff00ffu; hi = (hi | hi >> 8) & 0xffffu;
+					dst[t] = lo | hi << 16;
+				}
+			}
+			__syncwarp();
+			if (need >> lane & 1) {
+				if (myr < 0) sd.phase = LC_SP_DONE;
+				else {
+					const int64_t o = b.off[myr];
+					const int len = (int)(b.off[myr + 1] - o);
+					if (len < b.opt.min_seed_len) { b.r_n_pk[myr] = 0; b.r_pk_off[myr] = 0; }      // B/bwamem.c:260; stays in FETCH
+					else { sd.begin_read(myr, len, qbuf); sd.resolve(); }
+				}
+			}
+			need = __ballot_sync(LC_FULL, sd.phase == LC_SP_FETCH);
+		}
+		if (!__ballot_sync(LC_FULL, sd.phase != LC_SP_DONE)) break;
+		sd.tick();
+		if (__any_sync(LC_FULL, sd.phase < LC_SP_FWD && sd.phase != LC_SP_FETCH)) sd.resolve();
+	}
+}
+
+// 4 lanes per read: sort the seeds, lay out the occurrence schedule, fetch positions (lc_seed_finish)
+struct LcCoopQuad {
+	int lane, gbase;
+	unsigned gmask;
+	__device__ __forceinline__ bool leader() const { return (lane & 3) == 0; }
+	__device__ __forceinline__ int sub() const { return lane & 3; }
+	__device__ __forceinline__ int width() const { return 4; }
+	__device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+	__device__ __forceinline__ unsigned long long bcast(unsigned long long v) const { return __shfl_sync(gmask, v, gbase); }
+};
+template <typename U>
+__global__ void __launch_bounds__(256) seed_finish_kernel(const LcBatch b)
+{
+	LcCoopQuad co;
+	co.lane = threadIdx.x & 31; co.gbase = co.lane & ~3; co.gmask = 0xfu << co.gbase;
+	const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, ng = (gridDim.x * blockDim.x) >> 2;
+	for (int r = g; r < b.n_reads; r += ng) lc_seed_finish<U>(b, co, r);
+}
+
+// reads the state machine could not hold in its fixed-size slots: one thread per read, lists in global memory
+__global__ void __launch_bounds__(LC_TPB) smem_redo_kernel(const LcBatch b, int n_redo)
 {
 	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	for (int r = worker; r < b.n_reads; r += stride) lc_stage_seed(b, r, worker);
+	for (int t = worker; t < n_redo; t += stride) lc_stage_seed(b, b.redo[t], worker);
 }
 
 __global__ void __launch_bounds__(256) sa_lookup_kernel(const LcBatch b, unsigned long long n)
@@ -223,7 +324,48 @@ void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
 	if (!n) return;
 	convert_kernel<<<grid_for((n + 15) / 16, 256, 8), 256, 0, stream>>>(p, n, ascii ? 1 : 0);
 }
-void LcCudaBackend::k_seed(const LcBatch &b) { smem_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
+static bool lc_wide(const LcBatch &b) { return b.ix.seq_len >= 0xffffffffull || b.force_wide; }
+int LcCudaBackend::seed_grid(const LcBatch &b)
+{
+	const int smem = LC_SEED_TPB * lc_seed_lane_bytes(b.lmax, b.lst_cap);
+	int per_sm = 1;
+	if (lc_wide(b)) {
+		cudaFuncSetAttribute(smem_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<uint64_t>, LC_SEED_TPB, smem);
+	} else {
+		cudaFuncSetAttribute(smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<uint32_t>, LC_SEED_TPB, smem);
+	}
+	if (per_sm < 1) per_sm = 1;
+	const long long need = ((long long)b.n_reads + LC_SEED_TPB - 1) / LC_SEED_TPB;
+	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
+	return (int)(need < cap ? (need ? need : 1) : cap);
+}
+void LcCudaBackend::k_seed(const LcBatch &b)
+{
+	const int smem = LC_SEED_TPB * lc_seed_lane_bytes(b.lmax, b.lst_cap), grid = seed_grid(b);
+	if (lc_wide(b)) smem_kernel<uint64_t><<<grid, LC_SEED_TPB, smem, stream>>>(b);
+	else smem_kernel<uint32_t><<<grid, LC_SEED_TPB, smem, stream>>>(b);
+}
+void LcCudaBackend::k_seed_finish(const LcBatch &b)
+{
+	const int grid = grid_for((unsigned long long)b.n_reads * 4, 256, 8);
+	if (lc_wide(b)) seed_finish_kernel<uint64_t><<<grid, 256, 0, stream>>>(b);
+	else seed_finish_kernel<uint32_t><<<grid, 256, 0, stream>>>(b);
+}
+int LcCudaBackend::seed_lanes() { return n_sm * 2048; }      // upper bound on resident lanes of smem_kernel
+void LcCudaBackend::k_seed_redo(const LcBatch &b, int n_redo) { smem_redo_kernel<<<grid_for(n_redo, LC_TPB, 1), LC_TPB, 0, stream>>>(b, n_redo); }
+void LcCudaBackend::k_occ_convert(const uint32_t *bwa, uint4 *occ, unsigned long long n_blocks, const LcIndex &ix)
+{
+	LcSbTable t;
+	memcpy(t.sb, ix.sb, sizeof(t.sb));
+	occ_convert_kernel<<<grid_for(n_blocks, 256, 8), 256, 0, stream>>>(bwa, occ, n_blocks, t);
+}
+void LcCudaBackend::k_sa_fill(const LcIndex &ix, unsigned long long n_samples, void *out, bool wide)
+{
+	if (wide) sa_fill_kernel<uint64_t><<<grid_for(n_samples, 256, 8), 256, 0, stream>>>(ix, n_samples, (uint64_t *)out);
+	else sa_fill_kernel<uint32_t><<<grid_for(n_samples, 256, 8), 256, 0, stream>>>(ix, n_samples, (uint32_t *)out);
+}
 void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
 void LcCudaBackend::k_extend(const LcBatch &b)

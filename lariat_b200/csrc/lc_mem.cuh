@@ -12,6 +12,7 @@
 #include "lc_sw.cuh"
 
 struct LcIntvOut { uint64_t x0, x2; uint32_t qbeg, qend; uint32_t soff, step; };   // 32 B: one seeding interval of a read
+struct LcPk { uint32_t a, b, c, m; };     // 16 B packed bi-interval of the seeding state machine (lc_seed.cuh): x0, x1, x2 < 2^34 + two read positions
 struct LcSeed { int64_t rbeg; int32_t qbeg, len; };                                 // mem_seed_t (B/bwamem.c:168-172); score == len here
 struct LcChainOut { int32_t rid, n; int64_t seed_off; uint32_t w; int32_t is_alt; }; // a kept chain; seeds in cseed[seed_off..+n)
 struct LcChainRec { int64_t pos; int32_t rid, n, head, tail; uint32_t w; int32_t kept, first, is_alt; };
@@ -20,7 +21,7 @@ struct LcChainRec { int64_t pos; int32_t rid, n, head, tail; uint32_t w; int32_t
 struct LcBtNode { int32_t n, internal; int32_t key[LC_BT_MAXK]; int32_t child[LC_BT_MAXK + 1]; };
 
 enum { LC_OVF_INTV = 1, LC_OVF_SEED = 2, LC_OVF_SCRATCH = 4, LC_OVF_CSEED = 8, LC_OVF_REG = 16, LC_OVF_FINAL = 32,
-	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512 };
+	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512, LC_OVF_PK = 1024 };
 
 struct LcBatch {
 	// ---- inputs
@@ -44,6 +45,12 @@ struct LcBatch {
 	unsigned long long *w_u64;     // per worker: w_u64_n (sub-optimal row list of the local SW)
 	int32_t w_u64_n;
 	// ---- stage 1: seeding
+	LcPk *w_pk; int32_t pk_cap;    // per lane of the seeding kernel: the read's seeds so far (pk_cap packed entries)
+	int32_t lst_cap;               // per lane: entries of the shared-memory interval list
+	int32_t force_wide;            // run the 64-bit interval arithmetic even if the index has < 2^32 symbols (tests)
+	int32_t *redo; unsigned int *redo_cur;   // reads the state-machine kernel hands to the one-thread-per-read kernel
+	LcPk *pk_pool; unsigned long long pk_pool_cap, *pk_cur;   // unsorted seeds of every read, handed to lc_seed_finish
+	int64_t *r_pk_off; int32_t *r_n_pk;      // per read: its slice of pk_pool (r_n_pk < 0: redone by lc_stage_seed)
 	LcIntvOut *intv; unsigned long long intv_cap, *intv_cur;
 	uint64_t *seed_row;            // BWT rows, overwritten by their SA values in stage 2
 	unsigned long long seed_cap, *seed_cur;
@@ -155,7 +162,8 @@ LC_HDN void lc_stage_seed(const LcBatch &b, int r, int worker)
 		o.x0 = mem[i].x0; o.x2 = mem[i].x2; o.qbeg = (uint32_t)(mem[i].info >> 32); o.qend = (uint32_t)mem[i].info;
 		o.soff = (uint32_t)s; o.step = (uint32_t)step;
 		b.intv[io + i] = o;
-		for (uint64_t t = 0; t < mem[i].x1; ++t) b.seed_row[so + s + t] = mem[i].x0 + t * step;
+		const bool dense = b.ix.sa32 || b.ix.sa64;     // with the dense suffix array resident the rows become positions right here
+		for (uint64_t t = 0; t < mem[i].x1; ++t) { const uint64_t row = mem[i].x0 + t * step; b.seed_row[so + s + t] = dense ? lc_sa(b.ix, row, b.cnt) : row; }
 		s += mem[i].x1;
 	}
 	b.r_intv_off[r] = (int64_t)io; b.r_n_intv[r] = n; b.r_seed_off[r] = (int64_t)so; b.r_n_seed[r] = (int32_t)S;

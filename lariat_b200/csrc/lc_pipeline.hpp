@@ -12,6 +12,7 @@
 #include <vector>
 #include <algorithm>
 #include "lc_mem.cuh"
+#include "lc_seed.cuh"
 
 struct LcHostIndex {
 	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0;
@@ -49,7 +50,7 @@ static inline bool lc_load_index(const char *prefix, LcHostIndex &ix, std::strin
 	ix.L2[0] = 0;
 	ix.seq_len = ix.L2[4];
 	size_t nw = (raw.size() - 40) / 4;
-	ix.bwt.assign(((nw + 15) / 16) * 16 + 16, 0);   // padded to whole 64-byte blocks
+	ix.bwt.assign(((nw + 15) / 16) * 16 + 32, 0);   // padded to whole 64-byte blocks (+ slack for the one-past-the-end device block)
 	memcpy(ix.bwt.data(), raw.data() + 40, nw * 4);
 	if (!lc_slurp(p + ".sa", raw) || raw.size() < 56) { err = "cannot read " + p + ".sa"; return false; }
 	uint64_t h[7];
@@ -92,6 +93,37 @@ static inline bool lc_load_index(const char *prefix, LcHostIndex &ix, std::strin
 	ix.pac.assign((size_t)(ix.l_pac / 4 + 2) + 16, 0);
 	memcpy(ix.pac.data(), raw.data(), std::min(raw.size(), (size_t)(ix.l_pac / 4 + 1)));
 	if (ix.seq_len != (uint64_t)ix.l_pac * 2) { err = "index does not hold forward+reverse text (seq_len != 2*l_pac)"; return false; }
+	return true;
+}
+
+// number of 32-byte device blocks for an index of seq_len symbols (one spare so that row seq_len itself always has a block)
+static inline uint64_t lc_occ_blocks(uint64_t seq_len) { return (seq_len + 63) / 64 + 1; }
+// everything of LcIndex that does not point into device memory, incl. the superblock bases of the device occ layout
+static inline bool lc_index_scalars(const LcHostIndex &h, LcIndex &ix, std::string &err)
+{
+	memset(&ix, 0, sizeof(ix));
+	ix.primary = h.primary; memcpy(ix.L2, h.L2, sizeof(ix.L2)); ix.seq_len = h.seq_len;
+	ix.sa_mask = (uint64_t)h.sa_intv - 1; ix.sa_shift = __builtin_ctz((unsigned)h.sa_intv);
+	ix.l_pac = h.l_pac; ix.n_seqs = (int)h.anns.size();
+	const uint64_t nb = lc_occ_blocks(h.seq_len);
+	if (((nb - 1) >> LC_SB_SHIFT) >= LC_MAX_SB) { err = "reference too large: more than 2^34 BWT symbols"; return false; }
+	for (uint64_t s = 0; (s << LC_SB_SHIFT) < nb; ++s) lc_bwa_counts_at(h.bwt.data(), s << LC_SB_SHIFT, ix.sb[s]);
+	return true;
+}
+// tests/hostsim only: the device layout built with host loops (the product builds it with kernels, lc_kernels.cu)
+struct LcHostDevIndex { std::vector<uint4> occ; std::vector<uint32_t> sa32; std::vector<uint64_t> sa64; };
+static inline bool lc_host_dev_index(const LcHostIndex &h, LcHostDevIndex &d, LcIndex &ix, bool dense, std::string &err)
+{
+	if (!lc_index_scalars(h, ix, err)) return false;
+	const uint64_t nb = lc_occ_blocks(h.seq_len);
+	d.occ.resize(2 * nb);
+	for (uint64_t j = 0; j < nb; ++j) lc_occ_from_bwa(h.bwt.data(), j, ix.sb[j >> LC_SB_SHIFT], &d.occ[2 * j]);
+	ix.occ = d.occ.data(); ix.sa = h.sa.data(); ix.pac = h.pac.data(); ix.anns = h.anns.data();
+	if (dense) {
+		const uint64_t n_samples = h.sa.size();
+		if (h.seq_len < 0xffffffffull) { d.sa32.assign(h.seq_len + 1, 0); for (uint64_t j = 0; j < n_samples; ++j) lc_sa_fill_sample(ix, j, d.sa32.data()); ix.sa32 = d.sa32.data(); }
+		else { d.sa64.assign(h.seq_len + 1, 0); for (uint64_t j = 0; j < n_samples; ++j) lc_sa_fill_sample(ix, j, d.sa64.data()); ix.sa64 = d.sa64.data(); }
+	}
 	return true;
 }
 
@@ -165,6 +197,9 @@ public:
 	double intv_per_read = 24, seed_per_read = 48, cigar_per_cand = 6;
 	size_t z_pool_bytes = 64u << 20;
 	int memcap = 256;
+	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> redo kernel
+	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
+	bool force_wide = false;
 
 	explicit LcPipeline(BE &be_) : be(be_) { memset(&b, 0, sizeof(b)); }
 	~LcPipeline() { release(); }
@@ -200,7 +235,7 @@ public:
 	{
 		const int R = b.n_reads;
 		launches = 0;
-		if (!d_perread.ensure(be, (size_t)R * (8 * 5 + 4 * 7) + 256) || !d_nfin.ensure(be, 4 * ((size_t)R + 1))) return nomem();
+		if (!d_perread.ensure(be, (size_t)R * (8 * 6 + 4 * 8) + 256) || !d_nfin.ensure(be, 4 * ((size_t)R + 1))) return nomem();
 		b.r_n_fin = (int32_t *)d_nfin.p;
 		be.dzero(d_nfin.p, 4 * ((size_t)R + 1));
 		{
@@ -210,11 +245,13 @@ public:
 			b.r_chain_off = (int64_t *)p; p += 8 * (size_t)R;
 			b.r_reg_off = (int64_t *)p; p += 8 * (size_t)R;
 			b.r_fin_off = (int64_t *)p; p += 8 * (size_t)R;
+			b.r_pk_off = (int64_t *)p; p += 8 * (size_t)R;
 			b.r_n_intv = (int32_t *)p; p += 4 * (size_t)R;
 			b.r_n_seed = (int32_t *)p; p += 4 * (size_t)R;
 			b.r_n_chain = (int32_t *)p; p += 4 * (size_t)R;
 			b.r_n_cseed = (int32_t *)p; p += 4 * (size_t)R;
 			b.r_n_reg = (int32_t *)p; p += 4 * (size_t)R;
+			b.r_n_pk = (int32_t *)p; p += 4 * (size_t)R;
 			b.r_frac_rep = (float *)p;
 		}
 		if (!d_ctl.ensure(be, 4096)) return nomem();
@@ -222,18 +259,27 @@ public:
 			unsigned long long *c = (unsigned long long *)d_ctl.p;
 			b.intv_cur = c + 0; b.seed_cur = c + 1; b.scratch_cur = c + 2; b.chain_cur = c + 3; b.cseed_cur = c + 4;
 			b.reg_cur = c + 5; b.fin_cur = c + 6; b.cand_cur = c + 7; b.cigar_cur = c + 8; b.z_cur = c + 9;
-			b.reg_total = c + 10;
+			b.reg_total = c + 10; b.pk_cur = c + 11;
 			b.overflow = (uint32_t *)(c + 16);
 			b.work_ctr = (unsigned int *)(c + 20);
+			b.redo_cur = (unsigned int *)(c + 22);
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);
 		b.n_workers = be.n_workers();
 		b.memcap = memcap;
+		{
+			// a forward extension pushes one interval per change of size: ~log4(symbols) entries on unique sequence, more in repeats
+			int want = lst_cap;
+			if (want <= 0) { want = 6; for (uint64_t n = b.ix.seq_len; n > 1; n >>= 2) ++want; }
+			b.lst_cap = lc_seed_lst_cap(b.lmax, std::min(want, b.lmax + 1)); b.pk_cap = pk_cap;
+		} b.force_wide = force_wide ? 1 : 0;
+		if (!d_wpk.ensure(be, sizeof(LcPk) * (size_t)be.seed_lanes() * b.pk_cap) || !d_redo.ensure(be, 4 * ((size_t)R + 1))) return nomem();
+		b.w_pk = (LcPk *)d_wpk.p; b.redo = (int32_t *)d_redo.p;
 		b.w_int_n = std::max(3 * (b.lmax + 18), 2 * (b.lmax + 2) + 2 * b.lmax + 8) + 8;
 		b.w_u64_n = (b.pes_high - b.pes_low + b.lmax) / 2 + 8;
 		b.w_z_n = 8192;
-		if (!d_wintv.ensure(be, sizeof(LcIntv) * (size_t)b.n_workers * (3 * (size_t)(b.lmax + 1) + b.memcap)) ||
+		if (!d_wintv.ensure(be, sizeof(LcIntv) * (size_t)be.n_redo_workers() * (3 * (size_t)(b.lmax + 1) + b.memcap)) ||
 			!d_wint.ensure(be, 4 * (size_t)b.n_workers * b.w_int_n) || !d_wu64.ensure(be, 8 * (size_t)b.n_workers * b.w_u64_n) ||
 			!d_wz.ensure(be, (size_t)b.n_workers * b.w_z_n)) return nomem();
 		b.w_intv = (LcIntv *)d_wintv.p; b.w_int = (int32_t *)d_wint.p; b.w_u64 = (unsigned long long *)d_wu64.p; b.w_z = (uint8_t *)d_wz.p;
@@ -249,17 +295,25 @@ public:
 		for (int attempt = 0;; ++attempt) {
 			b.intv_cap = (unsigned long long)(intv_per_read * R) + 1024;
 			b.seed_cap = (unsigned long long)(seed_per_read * R) + 4096;
-			if (!d_intv.ensure(be, sizeof(LcIntvOut) * b.intv_cap) || !d_seed.ensure(be, 8 * b.seed_cap)) return nomem();
-			b.intv = (LcIntvOut *)d_intv.p; b.seed_row = (uint64_t *)d_seed.p;
-			be.k_seed(b); ++launches;
+			b.pk_pool_cap = (unsigned long long)(pk_per_read * R) + 1024;
+			if (!d_intv.ensure(be, sizeof(LcIntvOut) * b.intv_cap) || !d_seed.ensure(be, 8 * b.seed_cap) || !d_pkpool.ensure(be, sizeof(LcPk) * b.pk_pool_cap)) return nomem();
+			b.intv = (LcIntvOut *)d_intv.p; b.seed_row = (uint64_t *)d_seed.p; b.pk_pool = (LcPk *)d_pkpool.p;
+			be.k_seed(b); ++launches;               // the state machine: unsorted seeds per read + the redo list
 			read_ctl();
-			if (!(h_ctl_ovf & (LC_OVF_INTV | LC_OVF_SEED | LC_OVF_MEMLIST))) break;
+			n_redo = (int)(uint32_t)h_ctl[22];
+			if (!(h_ctl_ovf & LC_OVF_PK)) {
+				be.k_seed_finish(b); ++launches;    // sort + occurrence schedule + positions
+				if (n_redo) { be.k_seed_redo(b, n_redo); ++launches; }
+				read_ctl();
+			}
+			if (!(h_ctl_ovf & (LC_OVF_INTV | LC_OVF_SEED | LC_OVF_MEMLIST | LC_OVF_PK))) break;
 			if (attempt > 12) { err = "seeding pools keep overflowing"; return LC_ENOMEM; }
 			if (h_ctl_ovf & LC_OVF_INTV) intv_per_read = std::max(intv_per_read * 2, (double)h_ctl[0] / R * 1.25);
 			if (h_ctl_ovf & LC_OVF_SEED) seed_per_read = std::max(seed_per_read * 2, (double)h_ctl[1] / R * 1.25);
+			if (h_ctl_ovf & LC_OVF_PK) pk_per_read = std::max(pk_per_read * 2, (double)h_ctl[11] / R * 1.25);
 			if (h_ctl_ovf & LC_OVF_MEMLIST) {
 				memcap *= 4; b.memcap = memcap;
-				if (!d_wintv.ensure(be, sizeof(LcIntv) * (size_t)b.n_workers * (3 * (size_t)(b.lmax + 1) + b.memcap))) return nomem();
+				if (!d_wintv.ensure(be, sizeof(LcIntv) * (size_t)be.n_redo_workers() * (3 * (size_t)(b.lmax + 1) + b.memcap))) return nomem();
 				b.w_intv = (LcIntv *)d_wintv.p;
 			}
 			be.dzero(d_ctl.p, 4096);
@@ -310,7 +364,7 @@ public:
 		if (!d_scratch.ensure(be, b.scratch_cap) || !d_chain.ensure(be, sizeof(LcChainOut) * b.chain_cap) ||
 			!d_cseed.ensure(be, sizeof(LcSeed) * b.cseed_cap) || !d_reg.ensure(be, sizeof(lc_alnreg_t) * b.reg_cap)) return nomem();
 		b.scratch = (uint8_t *)d_scratch.p; b.chain = (LcChainOut *)d_chain.p; b.cseed = (LcSeed *)d_cseed.p; b.reg = (lc_alnreg_t *)d_reg.p;
-		if (S) { be.k_sa(b, S); ++launches; }
+		if (S && !(b.ix.sa32 || b.ix.sa64)) { be.k_sa(b, S); ++launches; }     // with the dense suffix array the seeding kernels wrote positions already
 		be.ev_record(4);
 		be.k_chain(b); ++launches;
 		be.ev_record(5);
@@ -378,16 +432,17 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outreg, &d_outaln, &d_nfin };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool };
 		for (auto *x : all) x->release(be);
 	}
 
 	int64_t launches = 0;
+	int n_redo = 0;
 	unsigned long long n_cand = 0, n_cigar_words = 0;
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outreg, d_outaln, d_nfin;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	int nomem() { err = "device allocation failed"; return LC_ENOMEM; }

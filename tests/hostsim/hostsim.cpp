@@ -17,6 +17,8 @@
 struct HostBackend {
 	int workers = 3;
 	int n_workers() const { return workers; }
+	int n_redo_workers() const { return workers; }
+	int seed_lanes() const { return 1; }
 	void *dmalloc(size_t n) { return malloc(n ? n : 1); }
 	void dfree(void *p) { free(p); }
 	void dzero(void *p, size_t n) { memset(p, 0, n); }
@@ -29,7 +31,22 @@ struct HostBackend {
 	float ev_ms(int, int) { return 0.f; }
 	void k_convert(uint8_t *p, unsigned long long n, bool ascii) { for (unsigned long long i = 0; i < n; ++i) p[i] = lc_nt4(p[i], ascii); }
 	// each stage: items are dealt to `workers` scratch slots round-robin, like the grid-stride loops of the kernels
-	void k_seed(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_seed(b, r, r % workers); }
+	// the seeding state machine with a one-lane group (lc_seed.cuh), then the redo list through the one-thread-per-read body
+	void k_seed(const LcBatch &b)
+	{
+		std::vector<LcPk> lst((size_t)b.lst_cap + 1);
+		std::vector<uint8_t> q((size_t)b.lmax + 16);
+		if (b.force_wide || b.ix.seq_len >= 0xffffffffull) lc_seed_run_scalar<uint64_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap);
+		else lc_seed_run_scalar<uint32_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap);
+	}
+	void k_seed_finish(const LcBatch &b)
+	{
+		LcCoopScalar co;
+		for (int r = 0; r < b.n_reads; ++r) {
+			if (b.force_wide || b.ix.seq_len >= 0xffffffffull) lc_seed_finish<uint64_t>(b, co, r); else lc_seed_finish<uint32_t>(b, co, r);
+		}
+	}
+	void k_seed_redo(const LcBatch &b, int n_redo) { for (int t = 0; t < n_redo; ++t) lc_stage_seed(b, b.redo[t], t % workers); }
 	void k_sa(const LcBatch &b, unsigned long long n) { for (unsigned long long g = 0; g < n; ++g) lc_stage_sa(b, g); }
 	void k_chain(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_chain(b, r); }
 	void k_extend(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); }
@@ -42,13 +59,17 @@ struct HostBackend {
 int main(int argc, char **argv)
 {
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
-	int delta = 25, maxp = -1, count = 0;
+	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, dense = 1, wide = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
 		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "-w") && i + 1 < argc) be.workers = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "-n") && i + 1 < argc) maxp = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "-c")) count = 1;
+		else if (!strcmp(argv[i], "-C") && i + 1 < argc) lst_cap = atoi(argv[++i]);     // shared-memory list capacity of the seeding state machine
+		else if (!strcmp(argv[i], "-M") && i + 1 < argc) pk_cap = atoi(argv[++i]);      // per-group seed list capacity
+		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
+		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
 	}
 	LcHostIndex hix; std::string err;
 	if (!lc_load_index(argv[1], hix, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
@@ -66,13 +87,14 @@ int main(int argc, char **argv)
 	fclose(f);
 
 	LcIndex ix;
-	ix.primary = hix.primary; memcpy(ix.L2, hix.L2, sizeof(ix.L2)); ix.seq_len = hix.seq_len;
-	ix.bwt = (const uint4 *)hix.bwt.data(); ix.sa = hix.sa.data(); ix.sa_mask = hix.sa_intv - 1;
-	ix.sa_shift = __builtin_ctz(hix.sa_intv);
-	ix.pac = hix.pac.data(); ix.l_pac = hix.l_pac; ix.anns = hix.anns.data(); ix.n_seqs = (int)hix.anns.size();
+	LcHostDevIndex dix;
+	if (!lc_host_dev_index(hix, dix, ix, dense != 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
 	lc_opt_t opt; lc_default_opt(&opt);
 	LcPipeline<HostBackend> pl(be);
 	pl.counting = count;
+	if (lst_cap > 0) pl.lst_cap = lst_cap;
+	if (pk_cap > 0) pl.pk_cap = pk_cap;
+	pl.force_wide = wide != 0;
 	pl.set_index(ix, opt);
 	LcHostResult res;
 	int rc = pl.upload(n, bases.data(), off.data(), true);
@@ -99,6 +121,6 @@ int main(int argc, char **argv)
 				"\"sw_calls\": %llu, \"sw_cells\": %llu, \"glb_calls\": %llu, \"glb_cells\": %llu}\n", c.occ_blocks, c.extend_calls, c.sa_calls, c.lf_steps,
 				c.ext_calls, c.ext_cells, c.sw_calls, c.sw_cells, c.glb_calls, c.glb_cells);
 	}
-	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches\n", n, (unsigned long long)res.regs.size(), (long long)res.launches);
+	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone\n", n, (unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo);
 	return 0;
 }

@@ -20,3 +20,16 @@ def test_result_independent_of_worker_count_and_delta(hostsim_bin, tmp_path):
     subprocess.check_call([hostsim_bin] + args + [str(a), "-w", "1", "-n", "200"], stderr=subprocess.DEVNULL)
     subprocess.check_call([hostsim_bin] + args + [str(b), "-w", "17", "-n", "200"], stderr=subprocess.DEVNULL)
     assert a.read_bytes() == b.read_bytes()
+
+
+import pytest
+
+
+@pytest.mark.parametrize("extra", [["-S"], ["-W"], ["-C", "6"], ["-C", "3", "-M", "4"], ["-S", "-C", "12", "-w", "5", "-W"]])
+def test_seeding_state_machine_fallbacks(hostsim_bin, tmp_path, extra):
+    """The seeding state machine (lc_seed.cuh) with tiny list capacities (most reads go to the redo body) and with the
+    sampled suffix array instead of the dense one: results must not change."""
+    out = tmp_path / "sim.out"
+    subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out)] + extra,
+                          stderr=subprocess.DEVNULL)
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
