@@ -23,6 +23,12 @@
 #pragma once
 #include "lc_mem.cuh"
 
+#ifdef __CUDA_ARCH__
+#define LC_CONVERGE() __syncwarp()
+#else
+#define LC_CONVERGE() ((void)0)
+#endif
+
 enum { LC_SP_FETCH = 0, LC_SP_OVERFLOW, LC_SP_FINISH, LC_SP_END_SMEM, LC_SP_P1_NEXT, LC_SP_NEXT_RESEED, LC_SP_START_SMEM, LC_SP_FWD_PREP,
 	   LC_SP_START_BWD, LC_SP_BWD_PREP, LC_SP_P3_NEXT, LC_SP_P3_PREP,
 	   LC_SP_FWD, LC_SP_BWD, LC_SP_P3, LC_SP_DONE };      // states >= LC_SP_FWD wait for an extension (or are final)
@@ -151,30 +157,34 @@ template <typename U> struct LcSeedLane {
 		lc_blk_counts<U>(ix, vk, bk, (int)(k & 63) + 1, c, ch, cl, ak, sk);
 		lc_blk_counts<U>(ix, vl, bl, (int)(l & 63) + 1, c, ch, cl, al, sl);
 		const U o2 = al - ak, sn = (U)(ix.L2[c] + 1) + ak, on = oth + (U)adj + (sl - sk);
-		// Strictly structured control flow from here on (no early exits): every branch re-converges before the next statement,
-		// so the warp executes each section once for the lanes that need it.
+		// The bookkeeping is a flat sequence of short guarded sections with a warp-wide convergence point between them
+		// (LC_CONVERGE = __syncwarp on the device).  Without the barriers the compiler threads the jumps of the nested form and
+		// every sub-path of a diverged warp runs its own copy of the common tail (ncu: profiles/r01d, ~4 live lanes there).
 		const int ph = phase;
-		if (ph == LC_SP_BWD) {                                        // backward extension of prev[j] done (B/bwt.c:330-343)
+		const bool isb = ph == LC_SP_BWD, isf = ph == LC_SP_FWD || ph == LC_SP_P3, p3 = ph == LC_SP_P3;
+		LC_CONVERGE();
+		if (isb) {                                                    // backward extension of prev[j] done (B/bwt.c:330-343)
 			if (o2 < (U)min_intv) {
 				if (n_curr == 0 && i + 1 < last_start) emit(i + 1);
 			} else if (n_curr == 0 || o2 != last_x2) {
 				lst[n_fwd - 1 - n_curr] = PK::pack(sn, on, o2, pend, 0);
 				last_x2 = o2; ++n_curr;
 			}
-			if (phase == LC_SP_BWD) {
-				if (++j == n_prev) {
-					if (n_curr == 0) phase = LC_SP_END_SMEM;
-					else {
-						n_prev = n_curr; n_curr = 0; j = 0; --i;
-						const int qc = i >= 0 ? qat(i) : 4;
-						if (qc > 3) phase = LC_SP_BWD_PREP; else c = qc;
-					}
-				}
-				if (phase == LC_SP_BWD) load_entry(j);
+		}
+		LC_CONVERGE();
+		if (isb && phase == LC_SP_BWD && ++j == n_prev) {             // end of a backward round
+			if (n_curr == 0) phase = LC_SP_END_SMEM;
+			else {
+				n_prev = n_curr; n_curr = 0; j = 0; --i;
+				const int qc = i >= 0 ? qat(i) : 4;
+				if (qc > 3) phase = LC_SP_BWD_PREP; else c = qc;
 			}
-		} else if (ph < LC_SP_DONE) {                                 // forward: bwt_smem1a (B/bwt.c:307-316) or bwt_seed_strategy1 (B/bwt.c:368-376)
-			const bool p3 = ph == LC_SP_P3;
-			bool adv = true;
+		}
+		LC_CONVERGE();
+		if (isb && phase == LC_SP_BWD) load_entry(j);
+		LC_CONVERGE();
+		bool adv = isf;
+		if (isf) {                                                    // forward: bwt_smem1a (B/bwt.c:307-316) or bwt_seed_strategy1 (B/bwt.c:368-376)
 			if (p3) {
 				if (o2 < (U)b.opt.max_mem_intv && i - x >= b.opt.min_seed_len) {
 					adv = false;
@@ -189,14 +199,16 @@ template <typename U> struct LcSeedLane {
 				if (phase == LC_SP_OVERFLOW) adv = false;
 				else if (o2 < (U)min_intv) { phase = LC_SP_START_BWD; adv = false; }
 			}
-			if (adv) {
-				src = sn; oth = on; x2 = o2; pend = i + 1; ++i;
-				// next forward step inline; anything unusual (end of read, ambiguous base, dead interval) goes through resolve()
-				const int qc = i < len ? qat(i) : 4;
-				if (qc > 3 || (p3 && o2 == 0)) phase = p3 ? LC_SP_P3_PREP : LC_SP_FWD_PREP;
-				else c = 3 - qc;
-			}
 		}
+		LC_CONVERGE();
+		if (adv) {
+			src = sn; oth = on; x2 = o2; pend = i + 1; ++i;
+			// next forward step inline; anything unusual (end of read, ambiguous base, dead interval) goes through resolve()
+			const int qc = i < len ? qat(i) : 4;
+			if (qc > 3 || (p3 && o2 == 0)) phase = p3 ? LC_SP_P3_PREP : LC_SP_FWD_PREP;
+			else c = 3 - qc;
+		}
+		LC_CONVERGE();
 	}
 
 	// ---- begin read r_ (its codes are at q_[0..len_), len_ >= min_seed_len)
