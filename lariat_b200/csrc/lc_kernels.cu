@@ -17,9 +17,11 @@
 #include "lc_backend.cuh"
 #include "lc_sw_warp.cuh"
 #include "lc_seed.cuh"
+#include "lc_extsm.cuh"
 
 #define LC_TPB 128
 #define LC_SEED_TPB 64
+#define LC_EXT_TPB 64
 
 __global__ void __launch_bounds__(256) convert_kernel(uint8_t *p, unsigned long long n, int is_ascii)
 {
@@ -63,6 +65,24 @@ __global__ void __launch_bounds__(256) sa_fill_kernel(const LcIndex ix, unsigned
 	for (; j < n_samples; j += stride) lc_sa_fill_sample(ix, j, out);
 }
 
+// 8 bases of read `rr` per lane -> one word of 4-bit codes at dst[t * dst_stride] (three aligned words, funnel-shifted by the
+// source misalignment, nibbles compacted).  Whole warp; the caller synchronises.
+__device__ __forceinline__ void lc_warp_pack_read(const LcBatch &b, int rr, int lane, uint32_t *dst, int dst_stride)
+{
+	const int64_t o = b.off[rr];
+	const int len = (int)(b.off[rr + 1] - o);
+	const uint8_t *src = b.seq + o;
+	const int mis = (int)((size_t)src & 3), nw = (len + 7) >> 3;
+	const uint32_t *w = (const uint32_t *)(src - mis);
+	for (int t = lane; t < nw; t += 32) {
+		const uint32_t w0 = __ldg(w + 2 * t), w1 = __ldg(w + 2 * t + 1), w2 = __ldg(w + 2 * t + 2);
+		uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
+		lo &= 0x0f0f0f0fu; lo = (lo | lo >> 4) & 0x00ff00ffu; lo = (lo | lo >> 8) & 0xffffu;
+		hi &= 0x0f0f0f0fu; hi = (hi | hi >> 4) & 0x00ff00ffu; hi = (hi | hi >> 8) & 0xffffu;
+		dst[(size_t)t * dst_stride] = lo | hi << 16;
+	}
+}
+
 // ---- seeding ---------------------------------------------------------------------------------------------------
 // One lane per read, one bwt_extend per tick (lc_seed.cuh).  Reads are dealt through an atomic counter; a lane that needs a
 // new read gets it copied into its slot by the whole warp (word-wise, coalesced).
@@ -91,18 +111,7 @@ __global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b)
 				const int64_t o = b.off[rr];
 				const int len = (int)(b.off[rr + 1] - o);
 				if (len < b.opt.min_seed_len) continue;
-				// 8 bases -> one word of 4-bit codes: three aligned words, funnel-shifted by the source misalignment, nibbles compacted
-				const uint8_t *src = b.seq + o;
-				const int mis = (int)((size_t)src & 3), nw = (len + 7) >> 3;
-				const uint32_t *w = (const uint32_t *)(src - mis);
-				uint32_t *dst = (uint32_t *)(slot0 + (size_t)L * stride + b.lst_cap * sizeof(LcPk));
-				for (int t = lane; t < nw; t += 32) {
-					const uint32_t w0 = __ldg(w + 2 * t), w1 = __ldg(w + 2 * t + 1), w2 = __ldg(w + 2 * t + 2);
-					uint32_t lo = __funnelshift_r(w0, w1, mis * 8), hi = __funnelshift_r(w1, w2, mis * 8);
-					lo &= 0x0f0f0f0fu; lo = (lo | lo >> 4) & 0x00ff00ffu; lo = (lo | lo >> 8) & 0xffffu;
-					hi &= 0x0f0f0f0fu; hi = (hi | hi >> 4) & 0x00ff00ffu; hi = (hi | hi >> 8) & 0xffffu;
-					dst[t] = lo | hi << 16;
-				}
+				lc_warp_pack_read(b, rr, lane, (uint32_t *)(slot0 + (size_t)L * stride + b.lst_cap * sizeof(LcPk)), 1);
 			}
 			__syncwarp();
 			if (need >> lane & 1) {
@@ -160,21 +169,49 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 	for (int r = worker; r < b.n_reads; r += stride) lc_stage_chain(b, r);
 }
 
-// one warp per read, reads handed out through an atomic counter (reads differ widely in chains and extensions)
-__global__ void __launch_bounds__(LC_TPB) extend_kernel(const LcBatch b)
+// Stage 4: one lane per read, mem_chain2aln + ksw_extend2 as a state machine (lc_extsm.cuh).  Per warp the shared memory holds
+// the 32 H/E rows ([column][lane], one packed word per cell) and the 32 reads, forward and reversed (4 bits per base, [word][lane]).
+__host__ __device__ inline int lc_ext_warp_words(int lmax) { return (lc_ext_he_cols(lmax) + 2 * lc_ext_q_words(lmax)) * 32; }
+__global__ void __launch_bounds__(LC_EXT_TPB) extend_kernel(const LcBatch b)
 {
-	extern __shared__ int lc_smem[];
-	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = lc_warp_row_ints(b.lmax);
-	LcExecWarp ex;
-	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
-	ex.Hmax = nullptr; ex.bl = nullptr;
+	extern __shared__ uint32_t lc_ext_smem[];
+	const int lane = threadIdx.x & 31, nqw = lc_ext_q_words(b.lmax);
+	uint32_t *wbase = lc_ext_smem + (size_t)(threadIdx.x >> 5) * lc_ext_warp_words(b.lmax);
+	uint32_t *qf = wbase + lc_ext_he_cols(b.lmax) * 32, *qr = qf + nqw * 32;
+	LcExtLane<32> ex(b, wbase + lane, qf + lane, qr + lane);
 	for (;;) {
-		int r = 0;
-		if (lane == 0) r = (int)atomicAdd(b.work_ctr + 0, 1u);
-		r = __shfl_sync(LC_FULL, r, 0);
-		if (r >= b.n_reads) break;
-		lc_stage_extend_t(b, r, ex);
-		__syncwarp();
+		const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
+		if (need) {                                          // warp-uniform
+			int base = 0;
+			if (lane == 0) base = (int)atomicAdd(b.work_ctr + 0, (unsigned)__popc(need));
+			base = __shfl_sync(LC_FULL, base, 0);
+			int myr = -1;
+			if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
+			for (unsigned m = need; m; m &= m - 1) {
+				const int L = __ffs(m) - 1;
+				const int rr = __shfl_sync(LC_FULL, myr, L);
+				if (rr >= 0 && b.r_n_chain[rr] > 0) lc_warp_pack_read(b, rr, lane, qf + L, 32);
+			}
+			__syncwarp();
+			for (unsigned m = need; m; m &= m - 1) {           // the reversed copies, from the forward ones
+				const int L = __ffs(m) - 1;
+				const int rr = __shfl_sync(LC_FULL, myr, L);
+				if (rr < 0 || b.r_n_chain[rr] <= 0) continue;
+				const int len = (int)(b.off[rr + 1] - b.off[rr]);
+				for (int t = lane; 8 * t < len; t += 32) {
+					const int s0 = len - 8 * t - 8, wi = s0 >> 3;          // bases s0..s0+7 of the read, reversed, are word t
+					const uint32_t lo = wi >= 0 ? qf[wi * 32 + L] : 0u, hi = qf[(wi + 1) * 32 + L];
+					uint32_t v = __funnelshift_r(lo, hi, (s0 & 7) << 2);
+					v = __byte_perm(v, 0, 0x0123);
+					qr[t * 32 + L] = (v & 0x0f0f0f0fu) << 4 | ((v >> 4) & 0x0f0f0f0fu);
+				}
+			}
+			__syncwarp();
+			if (need >> lane & 1) { if (myr < 0) ex.phase = LC_XP_DONE; else ex.begin_read(myr); }
+		}
+		if (!__ballot_sync(LC_FULL, ex.phase != LC_XP_DONE)) break;
+		if (__any_sync(LC_FULL, ex.phase < LC_XP_DP && ex.phase != LC_XP_FETCH)) ex.resolve();
+		ex.tick();
 	}
 }
 
@@ -370,9 +407,13 @@ void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_ker
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
 void LcCudaBackend::k_extend(const LcBatch &b)
 {
-	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+	const int smem = (LC_EXT_TPB / 32) * lc_ext_warp_words(b.lmax) * 4;
+	int per_sm = 1;
 	cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	extend_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(b);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel, LC_EXT_TPB, smem);
+	if (per_sm < 1) per_sm = 1;
+	const long long need = ((long long)b.n_reads + LC_EXT_TPB - 1) / LC_EXT_TPB, cap = (long long)n_sm * per_sm;
+	extend_kernel<<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b);
 }
 void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {

@@ -442,8 +442,9 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 // ============================================================================================================
 LC_HD int lc_cal_max_gap(const lc_opt_t &opt, int qlen)          // B/bwamem.c:621-628
 {
-	int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
-	int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+	// (int)((double)x / e + 1.) — for e == 1 (the default) the division is exact, so plain integer arithmetic gives the same value
+	int l_del = opt.e_del == 1 ? qlen * opt.a - opt.o_del + 1 : (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
+	int l_ins = opt.e_ins == 1 ? qlen * opt.a - opt.o_ins + 1 : (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
 	int l = lc_max(l_del, l_ins);
 	l = lc_max(l, 1);
 	return lc_min(l, opt.w << 1);

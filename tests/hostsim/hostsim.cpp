@@ -13,6 +13,7 @@
 #include <string.h>
 #include <vector>
 #include "../../lariat_b200/csrc/lc_pipeline.hpp"
+#include "../../lariat_b200/csrc/lc_extsm.cuh"
 
 struct HostBackend {
 	int workers = 3;
@@ -49,7 +50,14 @@ struct HostBackend {
 	void k_seed_redo(const LcBatch &b, int n_redo) { for (int t = 0; t < n_redo; ++t) lc_stage_seed(b, b.redo[t], t % workers); }
 	void k_sa(const LcBatch &b, unsigned long long n) { for (unsigned long long g = 0; g < n; ++g) lc_stage_sa(b, g); }
 	void k_chain(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_chain(b, r); }
-	void k_extend(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); }
+	// the extension state machine with stride-1 rows (lc_extsm.cuh); -X runs the older one-call-per-read body instead
+	bool old_extend = false;
+	void k_extend(const LcBatch &b)
+	{
+		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); return; }
+		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax)), qr((size_t)lc_ext_q_words(b.lmax));
+		lc_ext_run_scalar(b, he.data(), qw.data(), qr.data());
+	}
 	void k_pair(const LcBatch &b, int n_pairs) { for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair(b, p, p % workers); }   // reversed: order must not matter
 	void k_cigar(const LcBatch &b, unsigned long long n) { for (unsigned long long c = 0; c < n; ++c) lc_stage_cigar(b, c, (int)(c % workers)); }
 	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r < b.n_reads; ++r) lc_stage_pack(b, pa, r); }
@@ -69,6 +77,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-C") && i + 1 < argc) lst_cap = atoi(argv[++i]);     // shared-memory list capacity of the seeding state machine
 		else if (!strcmp(argv[i], "-M") && i + 1 < argc) pk_cap = atoi(argv[++i]);      // per-group seed list capacity
 		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
+		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
 	}
 	LcHostIndex hix; std::string err;
