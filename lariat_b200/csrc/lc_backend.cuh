@@ -48,7 +48,10 @@ struct LcCudaBackend {
 	void k_chain(const LcBatch &b);
 	void k_extend(const LcBatch &b);
 	void k_pair(const LcBatch &b, int n_pairs);
-	void k_cigar(const LcBatch &b, unsigned long long n);
+	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev);
+	void k_cigar_plan(const LcBatch &b, unsigned long long n);
+	int k_cigar_band(const LcBatch &b, unsigned long long n_max);
+	void k_cigar_fallback(const LcBatch &b, unsigned long long n_max);
 	void k_pack(const LcBatch &b, const LcPackArgs &pa);
 	void scan_exclusive(const int32_t *in, int64_t *out, int n);
 	void k_ksw_extend(const LcExtJobs &j);

@@ -18,6 +18,7 @@
 #include "lc_sw_warp.cuh"
 #include "lc_seed.cuh"
 #include "lc_extsm.cuh"
+#include "lc_cigar.cuh"
 
 #define LC_TPB 128
 #define LC_SEED_TPB 64
@@ -234,12 +235,29 @@ __global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, int n_p
 	}
 }
 
-// one warp per candidate: gap-free candidates are a cooperative compare, the rest a cooperative banded NW + lane-0 traceback
-__global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, unsigned long long n)
+// Stage 6 (lc_cigar.cuh): one thread per candidate finishes the gap-free ones and bins the rest by band width ...
+__global__ void __launch_bounds__(256) cigar_plan_kernel(const LcBatch b, unsigned long long n)
+{
+	unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (; c < n; c += stride) lc_cig_plan(b, b.cand[c]);
+}
+// ... one thread per binned job runs the banded global alignment with the band in registers, traces back and writes the CIGAR ...
+template <int NB>
+__global__ void __launch_bounds__(128) cigar_band_kernel(const LcBatch b, int cls)
+{
+	const unsigned int n = b.cig_n[cls];
+	const uint64_t *jobs = b.cig_jobs + (size_t)cls * b.cig_jobs_cap;
+	for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) lc_cig_band<NB>(b, jobs[t]);
+}
+// ... and whatever those two hand back (wide bands, band-doubling retries, degenerate regions) gets a warp per candidate:
+// gap-free candidates are a cooperative compare, the rest a cooperative banded NW + lane-0 traceback.
+// n_dev != null: the list length is read from device memory (no host round trip between the kernels of the stage).
+__global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, const uint64_t *list, unsigned long long n_host, const unsigned int *n_dev)
 {
 	extern __shared__ int lc_smem[];
 	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = lc_warp_row_ints(b.lmax);
 	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const unsigned long long n = n_dev ? (unsigned long long)*n_dev : n_host;
 	LcExecWarp ex;
 	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
 	ex.Hmax = nullptr; ex.bl = nullptr;
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, u
 		if (lane == 0) c = atomicAdd(b.work_ctr + 2, 1u);
 		c = __shfl_sync(LC_FULL, c, 0);
 		if (c >= n) break;
-		lc_stage_cigar_t(b, (unsigned long long)c, ex);
+		lc_stage_cigar_t(b, list[c], ex);
 		__syncwarp();
 	}
 }
@@ -422,12 +440,28 @@ void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id
 	matesw_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, n_pairs);
 }
-void LcCudaBackend::k_cigar(const LcBatch &b, unsigned long long n)
+void LcCudaBackend::k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 {
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
 	cudaFuncSetAttribute(global_cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaMemsetAsync(b.work_ctr + 2, 0, 4, stream);      // the stage may be re-launched after a pool regrow
-	global_cigar_kernel<<<grid_for(n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, n);
+	global_cigar_kernel<<<grid_for(n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n, n_dev);
+}
+void LcCudaBackend::k_cigar_plan(const LcBatch &b, unsigned long long n) { cigar_plan_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
+int LcCudaBackend::k_cigar_band(const LcBatch &b, unsigned long long n_max)
+{
+	// list lengths are only known on the device: grids are sized for the worst case (every candidate in one list) and stride over the real length
+	const int grid = grid_for(n_max, 128, 8);
+	cigar_band_kernel<24><<<grid, 128, 0, stream>>>(b, 0);
+	cigar_band_kernel<32><<<grid, 128, 0, stream>>>(b, 1);
+	cigar_band_kernel<48><<<grid, 128, 0, stream>>>(b, 2);
+	cigar_band_kernel<64><<<grid, 128, 0, stream>>>(b, 3);
+	return 4;
+}
+void LcCudaBackend::k_cigar_fallback(const LcBatch &b, unsigned long long n_max)
+{
+	// sized for a small list (the usual case); the warps pull candidates from a counter, so a long list only takes longer
+	k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, n_max < 65536 ? n_max : 65536, b.cig_n + LC_CIG_FALLBACK);
 }
 void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for(b.n_reads, 256, 8), 256, 0, stream>>>(b, pa); }
 void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)

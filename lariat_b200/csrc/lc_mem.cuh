@@ -72,6 +72,8 @@ struct LcBatch {
 	uint32_t *cigar; unsigned long long cigar_cap, *cigar_cur;
 	uint8_t *zpool; unsigned long long z_cap, *z_cur;   // traceback matrices too large for the per-worker scratch
 	uint8_t *w_z; int32_t w_z_n;                         // per worker: w_z_n bytes of traceback scratch
+	uint64_t *cig_jobs; unsigned long long cig_jobs_cap; // LC_CIG_NLIST job lists of cig_jobs_cap entries each (lc_cigar.cuh)
+	unsigned int *cig_n;                                 // their lengths
 };
 
 LC_HD void lc_raise(const LcBatch &b, uint32_t flag)
@@ -863,10 +865,9 @@ struct LcExecThreadCigar : LcExecThread {   // thread executor for the CIGAR sta
 
 // ex.cig: per-worker CIGAR build buffer (2*lmax+8 words); ex.zloc: per-worker traceback scratch of b.w_z_n bytes
 template <class Exec>
-LC_HD void lc_stage_cigar_t(const LcBatch &b, unsigned long long ci, const Exec &ex)
+LC_HD void lc_stage_cigar_t(const LcBatch &b, uint64_t cd, const Exec &ex)
 {
 	const lc_opt_t &opt = b.opt;
-	const uint64_t cd = b.cand[ci];
 	const int r = (int)(cd >> 32), idx = (int)(uint32_t)cd;
 	const int l_query = (int)(b.off[r + 1] - b.off[r]);
 	const uint8_t *query = b.seq + b.off[r];
@@ -975,10 +976,10 @@ LC_HD void lc_stage_cigar_t(const LcBatch &b, unsigned long long ci, const Exec 
 	if (ex.leader()) b.aln[slot] = out;
 }
 
-LC_HDN void lc_stage_cigar(const LcBatch &b, unsigned long long ci, int worker)
+LC_HDN void lc_stage_cigar(const LcBatch &b, uint64_t cd, int worker)
 {
 	LcExecThreadCigar ex;
 	ex.H = b.w_int + (size_t)worker * b.w_int_n; ex.E = ex.H + (b.lmax + 2);
 	ex.cig = (uint32_t *)(ex.E + (b.lmax + 2)); ex.zloc = b.w_z + (size_t)worker * b.w_z_n;
-	lc_stage_cigar_t(b, ci, ex);
+	lc_stage_cigar_t(b, cd, ex);
 }

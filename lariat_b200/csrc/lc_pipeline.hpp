@@ -13,6 +13,7 @@
 #include <algorithm>
 #include "lc_mem.cuh"
 #include "lc_seed.cuh"
+#include "lc_cigar.cuh"
 
 struct LcHostIndex {
 	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0;
@@ -196,6 +197,7 @@ public:
 	// tunables (bytes / elements per read); grown on overflow
 	double intv_per_read = 24, seed_per_read = 48, cigar_per_cand = 6;
 	size_t z_pool_bytes = 64u << 20;
+	double z_per_cand = 1024;           // traceback pool of the register-band CIGAR kernels (4 bits per band cell)
 	int memcap = 256;
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> redo kernel
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
@@ -263,6 +265,7 @@ public:
 			b.overflow = (uint32_t *)(c + 16);
 			b.work_ctr = (unsigned int *)(c + 20);
 			b.redo_cur = (unsigned int *)(c + 22);
+			b.cig_n = (unsigned int *)(c + 24);
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);
@@ -339,7 +342,7 @@ public:
 		b.cigar_cap = 4 * (unsigned long long)b.lmax + 64; b.z_cap = need;
 		if (!d_cigar.ensure(be, 4 * b.cigar_cap) || !d_z.ensure(be, b.z_cap)) return nomem();
 		b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p;
-		be.k_cigar(b, 1); ++launches;
+		be.k_cigar(b, b.cand, 1, nullptr); ++launches;
 		read_ctl();
 		if (h_ctl_ovf) { err = "overflow in single cigar"; return LC_ENOMEM; }
 		res.aln.resize(1); res.cigars.resize((size_t)h_ctl[8]);
@@ -383,19 +386,28 @@ public:
 		read_ctl();
 		if (h_ctl_ovf) { err = "internal pool overflow in pair stage"; return LC_ENOMEM; }
 		const unsigned long long NC = h_ctl[7];
-		// ---- stage 6: CIGARs (regrow + rerun on overflow)
+		// ---- stage 6: CIGARs (lc_cigar.cuh: plan -> register-band kernels -> warp fallback; regrow + rerun on overflow)
+		b.cig_jobs_cap = NC + 1;
+		if (!d_cigjobs.ensure(be, 8 * (size_t)LC_CIG_NLIST * b.cig_jobs_cap)) return nomem();
+		b.cig_jobs = (uint64_t *)d_cigjobs.p;
 		for (int attempt = 0;; ++attempt) {
 			b.cigar_cap = (unsigned long long)(cigar_per_cand * NC) + 1024;
-			b.z_cap = z_pool_bytes;
+			b.z_cap = std::max<unsigned long long>(z_pool_bytes, (unsigned long long)(z_per_cand * NC));
 			if (!d_cigar.ensure(be, 4 * b.cigar_cap) || !d_z.ensure(be, b.z_cap)) return nomem();
 			b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p;
-			if (NC) { be.k_cigar(b, NC); ++launches; }
+			if (NC) {
+				be.k_cigar_plan(b, NC); ++launches;
+				launches += be.k_cigar_band(b, NC);
+				be.k_cigar_fallback(b, NC); ++launches;
+			}
 			read_ctl();
+			n_cig_fallback = (unsigned long long)(uint32_t)(h_ctl[24 + LC_CIG_FALLBACK / 2] >> (32 * (LC_CIG_FALLBACK & 1)));
 			if (!h_ctl_ovf) break;
 			if (attempt > 12) { err = "cigar pools keep overflowing"; return LC_ENOMEM; }
 			if (h_ctl_ovf & LC_OVF_CIGAR) cigar_per_cand = std::max(cigar_per_cand * 2, (double)h_ctl[8] / std::max<double>(NC, 1) * 1.25);
-			if (h_ctl_ovf & LC_OVF_Z) z_pool_bytes = std::max<size_t>(z_pool_bytes * 2, (size_t)(h_ctl[9] * 1.25));
+			if (h_ctl_ovf & LC_OVF_Z) { z_pool_bytes = std::max<size_t>(z_pool_bytes * 2, (size_t)(h_ctl[9] * 1.25)); z_per_cand = std::max(z_per_cand, (double)h_ctl[9] / std::max<double>(NC, 1) * 1.25); }
 			be.dzero_words(b.cigar_cur, 1); be.dzero_words(b.z_cur, 1); be.dzero_words((unsigned long long *)b.overflow, 1);
+			be.dzero(b.cig_n, 4 * LC_CIG_NLIST);
 		}
 		be.ev_record(8);
 		n_cand = NC; n_cigar_words = h_ctl[8];
@@ -432,17 +444,18 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs };
 		for (auto *x : all) x->release(be);
 	}
 
 	int64_t launches = 0;
 	int n_redo = 0;
+	unsigned long long n_cig_fallback = 0;
 	unsigned long long n_cand = 0, n_cigar_words = 0;
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	int nomem() { err = "device allocation failed"; return LC_ENOMEM; }

@@ -59,7 +59,31 @@ struct HostBackend {
 		lc_ext_run_scalar(b, he.data(), qw.data(), qr.data());
 	}
 	void k_pair(const LcBatch &b, int n_pairs) { for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair(b, p, p % workers); }   // reversed: order must not matter
-	void k_cigar(const LcBatch &b, unsigned long long n) { for (unsigned long long c = 0; c < n; ++c) lc_stage_cigar(b, c, (int)(c % workers)); }
+	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
+	{
+		if (n_dev) n = *n_dev;
+		for (unsigned long long c = 0; c < n; ++c) lc_stage_cigar(b, list[c], (int)(c % workers));
+	}
+	// the register-band CIGAR path (lc_cigar.cuh); -G sends every candidate through the warp-kernel body instead
+	bool old_cigar = false;
+	void k_cigar_plan(const LcBatch &b, unsigned long long n)
+	{
+		for (unsigned long long c = 0; c < n; ++c) { if (old_cigar) lc_cig_push_job(b, LC_CIG_FALLBACK, b.cand[c]); else lc_cig_plan(b, b.cand[c]); }
+	}
+	int k_cigar_band(const LcBatch &b, unsigned long long)
+	{
+		for (int cls = 0; cls < LC_CIG_NCLASS; ++cls) {
+			const uint64_t *jobs = b.cig_jobs + (size_t)cls * b.cig_jobs_cap;
+			for (unsigned int t = 0; t < b.cig_n[cls]; ++t) {
+				if (cls == 0) lc_cig_band<24>(b, jobs[t]); else if (cls == 1) lc_cig_band<32>(b, jobs[t]);
+				else if (cls == 2) lc_cig_band<48>(b, jobs[t]); else lc_cig_band<64>(b, jobs[t]);
+			}
+			n_band[cls] += b.cig_n[cls];
+		}
+		return 4;
+	}
+	unsigned long long n_band[LC_CIG_NCLASS] = {0, 0, 0, 0};
+	void k_cigar_fallback(const LcBatch &b, unsigned long long) { k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, 0, b.cig_n + LC_CIG_FALLBACK); }
 	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r < b.n_reads; ++r) lc_stage_pack(b, pa, r); }
 	void scan_exclusive(const int32_t *in, int64_t *out, int n) { int64_t s = 0; for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; } }
 };
@@ -78,6 +102,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-M") && i + 1 < argc) pk_cap = atoi(argv[++i]);      // per-group seed list capacity
 		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
+		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
 	}
 	LcHostIndex hix; std::string err;
@@ -130,6 +155,7 @@ int main(int argc, char **argv)
 				"\"sw_calls\": %llu, \"sw_cells\": %llu, \"glb_calls\": %llu, \"glb_cells\": %llu}\n", c.occ_blocks, c.extend_calls, c.sa_calls, c.lf_steps,
 				c.ext_calls, c.ext_cells, c.sw_calls, c.sw_cells, c.glb_calls, c.glb_cells);
 	}
-	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone\n", n, (unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo);
+	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu, fallback %llu\n", n,
+			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], pl.n_cig_fallback);
 	return 0;
 }
