@@ -25,15 +25,58 @@
 
 #define LC_XT_CELLS 8
 
+// ---- the H/E row in (shared) memory.  Two packings, chosen by the longest read of the batch:
+//   LcCells16: one column per 32-bit word, h | e << 16                        (any read length up to LC_MAX_READ_LEN)
+//   LcCells8 : two columns per word, (h | e << 8) << 16 * (column & 1)        (lmax * a <= 255: no cell of ksw_extend2 can exceed
+//              the score of the whole read matching, so h and e fit a byte) — half the shared memory, twice the resident warps
+template <int STRIDE> struct LcCells16 {
+	static LC_HD int words(int cols) { return cols; }
+	static LC_HD void load8(const uint32_t *he, int col0, int *h, int *e)
+	{
+#pragma unroll
+		for (int c = 0; c < 8; ++c) { const uint32_t v = he[(col0 + c) * STRIDE]; h[c] = (int)(v & 0xffffu); e[c] = (int)(v >> 16); }
+	}
+	static LC_HD void store8(uint32_t *he, int col0, const int *h, const int *e)
+	{
+#pragma unroll
+		for (int c = 0; c < 8; ++c) he[(col0 + c) * STRIDE] = (uint32_t)h[c] | (uint32_t)e[c] << 16;
+	}
+	static LC_HD void put(uint32_t *he, int col, int h, int e) { he[col * STRIDE] = (uint32_t)h | (uint32_t)e << 16; }
+};
+template <int STRIDE> struct LcCells8 {
+	static LC_HD int words(int cols) { return cols >> 1; }
+	static LC_HD void load8(const uint32_t *he, int col0, int *h, int *e)      // col0 is a multiple of 8
+	{
+#pragma unroll
+		for (int c = 0; c < 8; c += 2) {
+			const uint32_t v = he[((col0 + c) >> 1) * STRIDE];
+			h[c] = (int)(v & 0xffu); e[c] = (int)(v >> 8 & 0xffu); h[c + 1] = (int)(v >> 16 & 0xffu); e[c + 1] = (int)(v >> 24);
+		}
+	}
+	static LC_HD void store8(uint32_t *he, int col0, const int *h, const int *e)
+	{
+#pragma unroll
+		for (int c = 0; c < 8; c += 2)
+			he[((col0 + c) >> 1) * STRIDE] = (uint32_t)h[c] | (uint32_t)e[c] << 8 | (uint32_t)h[c + 1] << 16 | (uint32_t)e[c + 1] << 24;
+	}
+	static LC_HD void put(uint32_t *he, int col, int h, int e)
+	{
+		uint32_t *p = he + (col >> 1) * STRIDE;
+		const int sh = (col & 1) << 4;
+		*p = (*p & ~(0xffffu << sh)) | ((uint32_t)h | (uint32_t)e << 8) << sh;
+	}
+};
+
 enum { LC_XP_FETCH = 0, LC_XP_AFTER_LEFT, LC_XP_AFTER_RIGHT, LC_XP_RIGHT_CHECK, LC_XP_FINALIZE, LC_XP_READ_START, LC_XP_CHAIN_START, LC_XP_SEED_NEXT,
 	   LC_XP_LEFT_SETUP, LC_XP_RIGHT_SETUP, LC_XP_READ_DONE,
 	   LC_XP_DP, LC_XP_DONE };          // states >= LC_XP_DP: a DP row is in progress (or the lane is finished)
 
-template <int STRIDE> struct LcExtLane {
+template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	const LcBatch &b;
-	uint32_t *he;            // H/E row: he[j * STRIDE] = h | e << 16 for column j (lmax + 2 columns)
-	uint32_t *qw;            // the read: qw[w * STRIDE] holds bases 8w..8w+7, 4 bits each, first base in the low nibble;
-	uint32_t *qr;            //   qr = the same for the reversed read (left extensions run on reversed sequences, B/bwamem.c:715-721)
+	uint32_t *he;            // H/E row of lmax + 2 columns, packed by CELLS
+	uint32_t *qw;            // the read: qw[w * STRIDE] holds bases 8w..8w+7, 4 bits each, first base in the low nibble; qw[-STRIDE] is
+	                         //   addressable.  Left extensions run on reversed sequences (B/bwamem.c:715-721): their columns are read from the
+	                         //   same copy back to front
 	int phase;
 	// ---- read-level state (mem_chain2aln's locals)
 	int r, l_query, NC, ci, n_av, k, cn, tryi, prev;
@@ -51,7 +94,7 @@ template <int STRIDE> struct LcExtLane {
 	int q0, qdir;            // the extension's query column c is base q0 + c of the forward (qdir > 0) or reversed (qdir < 0) read copy
 	unsigned long long cells;
 
-	LC_HD LcExtLane(const LcBatch &b_, uint32_t *he_, uint32_t *qw_, uint32_t *qr_) : b(b_), he(he_), qw(qw_), qr(qr_), phase(LC_XP_FETCH), j(0), end(0), q0(0), qdir(1), tb(0) {}
+	LC_HD LcExtLane(const LcBatch &b_, uint32_t *he_, uint32_t *qw_) : b(b_), he(he_), qw(qw_), phase(LC_XP_FETCH), l_query(0), j(0), end(0), q0(0), qdir(1), tb(0) {}
 
 	LC_HD uint32_t pac_word(int64_t wi) const { return lc_ldg((const uint32_t *)b.ix.pac + (wi < 0 ? 0 : wi)); }
 	LC_HD int target_base()              // base of the current row: bns_get_seq's decoding (B/bntseq.c:398-419) out of the cached word
@@ -72,8 +115,16 @@ template <int STRIDE> struct LcExtLane {
 		best = h0; best_i = best_j = -1; g_i = -1; gscore = -1; max_off = 0; beg = 0; end = qlen; cells = 0;
 		{
 			int v = h0 > oe_ins ? h0 - oe_ins : 0;           // row -1: H[0] = h0, H[1] = h0 - oe_ins, then -e_ins per column while positive; E = 0
-			he[0] = (uint32_t)h0;
-			for (int t = 1; t <= qlen + 1; ++t) { he[t * STRIDE] = (uint32_t)v; v = v > sc.e_ins ? v - sc.e_ins : 0; }
+			int hh[LC_XT_CELLS], ee[LC_XT_CELLS];
+			for (int t0 = 0; t0 <= qlen + 1; t0 += LC_XT_CELLS) {
+#pragma unroll
+				for (int c = 0; c < LC_XT_CELLS; ++c) {
+					ee[c] = 0;
+					if (t0 + c == 0) hh[c] = h0;
+					else { hh[c] = v; v = v > sc.e_ins ? v - sc.e_ins : 0; }
+				}
+				CELLS::store8(he, t0, hh, ee);
+			}
 		}
 		{
 			const int smax = sc.a > 0 ? sc.a : 0;
@@ -117,21 +168,32 @@ template <int STRIDE> struct LcExtLane {
 		const bool run = phase == LC_XP_DP;
 		const int col0 = j;
 		{
-			// query codes of the eight columns: one funnel shift over two words of the oriented read copy
-			const uint32_t *qa = qdir > 0 ? qw : qr;
-			const int qi = q0 + col0;
-			const uint32_t w0 = qa[(qi >> 3) * STRIDE], w1 = qa[((qi >> 3) + 1) * STRIDE];
-			const uint32_t qword = (uint32_t)(((uint64_t)w1 << 32 | w0) >> ((qi & 7) << 2));
+			// query codes of the eight columns: one funnel shift over two words of the read copy; a left extension reads the read
+			// back to front (column c of the reversed read = base l_query - 1 - q0 - c), so its window is nibble-reversed
+			uint32_t qword;
+			{
+				const int qi = qdir > 0 ? q0 + col0 : l_query - LC_XT_CELLS - q0 - col0;      // first base of the window, >= -8
+				const uint32_t w0 = qw[(qi >> 3) * STRIDE], w1 = qw[((qi >> 3) + 1) * STRIDE];
+				uint32_t v = (uint32_t)(((uint64_t)w1 << 32 | w0) >> ((qi & 7) << 2));
+				if (qdir < 0) {
+#ifdef __CUDA_ARCH__
+					v = __byte_perm(v, 0, 0x0123);
+#else
+					v = v >> 24 | (v >> 8 & 0xff00u) | (v << 8 & 0xff0000u) | v << 24;
+#endif
+					v = (v & 0x0f0f0f0fu) << 4 | (v >> 4 & 0x0f0f0f0fu);
+				}
+				qword = v;
+			}
 			// substitution score without compares per base: x has a zero nibble where the base equals the target base
 			const uint32_t x = qword ^ (tb < 4 ? (uint32_t)tb * 0x11111111u : 0x88888888u);
 			const int pen = tb < 4 ? -sc.b : -1;
-			uint32_t hv[LC_XT_CELLS];
+			int hd[LC_XT_CELLS], ev[LC_XT_CELLS];
 			int M[LC_XT_CELLS], e2[LC_XT_CELLS], ti[LC_XT_CELLS];
-#pragma unroll
-			for (int c = 0; c < LC_XT_CELLS; ++c) hv[c] = he[(col0 + c) * STRIDE];
+			CELLS::load8(he, col0, hd, ev);
 #pragma unroll
 			for (int c = 0; c < LC_XT_CELLS; ++c) {
-				const int diag = (int)(hv[c] & 0xffffu), e = (int)(hv[c] >> 16);
+				const int diag = hd[c], e = ev[c];
 				const int s = (x & (0xfu << (4 * c))) == 0 ? sc.a : ((qword & (0x4u << (4 * c))) ? -1 : pen);
 				M[c] = diag ? diag + s : 0;
 				e2[c] = lc_max(e - e_del, lc_max(M[c] - oe_del, 0));
@@ -141,18 +203,17 @@ template <int STRIDE> struct LcExtLane {
 			for (int c = 0; c < LC_XT_CELLS; ++c) {
 				const int col = col0 + c;
 				const bool act = run && col >= beg && col < end;
-				const int e = (int)(hv[c] >> 16);
-				const int h = lc_max(lc_max(M[c], e), f);
+				const int h = lc_max(lc_max(M[c], ev[c]), f);
 				if (act) {
-					const uint32_t word = (uint32_t)hleft | (uint32_t)e2[c] << 16;
-					he[col * STRIDE] = word;
-					if (word) { nz_first = lc_min(nz_first, col); nz_last = col; }
+					hd[c] = hleft; ev[c] = e2[c];                      // H[j] = h of the column to the left, E[j] for the next row
+					if (hleft | e2[c]) { nz_first = lc_min(nz_first, col); nz_last = col; }
 					if (!(rowmax > h)) rowarg = col;
 					rowmax = lc_max(rowmax, h);
 					f = lc_max(f - e_ins, ti[c]);
 					hleft = h;
 				}
 			}
+			if (run) CELLS::store8(he, col0, hd, ev);
 			if (run) j = col0 + LC_XT_CELLS;
 		}
 		LC_CONVERGE();
@@ -160,7 +221,7 @@ template <int STRIDE> struct LcExtLane {
 			bool stop = false;
 			const int jfin = beg < end ? end : beg;            // the reference's loop variable after the column loop
 			if (b.cnt) cells += (unsigned long long)(end > beg ? end - beg : 0);
-			he[end * STRIDE] = (uint32_t)hleft;
+			CELLS::put(he, end, hleft, 0);
 			if (jfin == qlen) {
 				if (!(gscore > hleft)) g_i = i;
 				gscore = lc_max(gscore, hleft);
@@ -326,35 +387,36 @@ template <int STRIDE> struct LcExtLane {
 	}
 };
 
-// words per oriented read copy / columns of the H/E row for reads up to lmax (the tick reads whole groups, hence the slack)
-LC_HD int lc_ext_q_words(int lmax) { return (lmax + 7) / 8 + 2; }
+// words of the read copy (one spare word in front: a reversed window may start up to 8 bases before the read) / columns of the
+// H/E row for reads up to lmax (the tick reads whole groups, hence the slack)
+LC_HD int lc_ext_q_words(int lmax) { return (lmax + 7) / 8 + 3; }
 LC_HD int lc_ext_he_cols(int lmax) { return ((lmax + 2 + LC_XT_CELLS - 1) & ~(LC_XT_CELLS - 1)) + LC_XT_CELLS; }
 
-// nibble-pack read r into qw[w * STRIDE] and its reverse into qr[w * STRIDE] (scalar form; the device kernel uses the whole warp)
-template <int STRIDE> LC_HD void lc_ext_load_read(const LcBatch &b, int r, uint32_t *qw, uint32_t *qr, int n_words)
+// nibble-pack read r into qw[w * STRIDE] (scalar form; the device kernel uses the whole warp)
+template <int STRIDE> LC_HD void lc_ext_load_read(const LcBatch &b, int r, uint32_t *qw, int n_words)
 {
 	const int len = (int)(b.off[r + 1] - b.off[r]);
 	const uint8_t *src = b.seq + b.off[r];
 	for (int w = 0; w < n_words; ++w) {
-		uint32_t v = 0, u = 0;
+		uint32_t v = 0;
 		for (int t = 0; t < 8; ++t) {
 			const int p = 8 * w + t;
-			if (p < len) { v |= (uint32_t)(src[p] & 15) << (4 * t); u |= (uint32_t)(src[len - 1 - p] & 15) << (4 * t); }
+			if (p < len) v |= (uint32_t)(src[p] & 15) << (4 * t);
 		}
-		qw[w * STRIDE] = v; qr[w * STRIDE] = u;
+		qw[w * STRIDE] = v;
 	}
 }
 
-// scalar driver (tests/hostsim): all reads, one after another, through the same state machine
-static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *qw, uint32_t *qr)
+// scalar driver (tests/hostsim): all reads, one after another, through the same state machine; cells8 selects the byte packing
+template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, uint32_t *he, uint32_t *qw)
 {
-	LcExtLane<1> ex(b, he, qw, qr);
+	LcExtLane<1, CELLS> ex(b, he, qw + 1);
 	int next = 0;
 	for (;;) {
 		while (ex.phase == LC_XP_FETCH) {
 			if (next >= b.n_reads) { ex.phase = LC_XP_DONE; break; }
 			const int r = next++;
-			lc_ext_load_read<1>(b, r, qw, qr, lc_ext_q_words(b.lmax));
+			lc_ext_load_read<1>(b, r, qw + 1, lc_ext_q_words(b.lmax) - 1);
 			ex.begin_read(r);
 			ex.resolve();
 		}
@@ -362,4 +424,9 @@ static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *q
 		ex.tick();
 		ex.resolve();
 	}
+}
+LC_HD bool lc_ext_cells8_ok(const LcBatch &b) { return b.lmax * b.opt.a <= 255 && b.opt.a > 0; }
+static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *qw, bool cells8)
+{
+	if (cells8) lc_ext_run_scalar_t<LcCells8<1> >(b, he, qw); else lc_ext_run_scalar_t<LcCells16<1> >(b, he, qw);
 }

@@ -171,15 +171,16 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 }
 
 // Stage 4: one lane per read, mem_chain2aln + ksw_extend2 as a state machine (lc_extsm.cuh).  Per warp the shared memory holds
-// the 32 H/E rows ([column][lane], one packed word per cell) and the 32 reads, forward and reversed (4 bits per base, [word][lane]).
-__host__ __device__ inline int lc_ext_warp_words(int lmax) { return (lc_ext_he_cols(lmax) + 2 * lc_ext_q_words(lmax)) * 32; }
+// the 32 H/E rows ([column][lane], packed by CELLS) and the 32 reads (4 bits per base, [word][lane], one spare word in front).
+template <class CELLS> __host__ __device__ inline int lc_ext_warp_words(int lmax) { return (CELLS::words(lc_ext_he_cols(lmax)) + lc_ext_q_words(lmax)) * 32; }
+template <class CELLS>
 __global__ void __launch_bounds__(LC_EXT_TPB) extend_kernel(const LcBatch b)
 {
 	extern __shared__ uint32_t lc_ext_smem[];
-	const int lane = threadIdx.x & 31, nqw = lc_ext_q_words(b.lmax);
-	uint32_t *wbase = lc_ext_smem + (size_t)(threadIdx.x >> 5) * lc_ext_warp_words(b.lmax);
-	uint32_t *qf = wbase + lc_ext_he_cols(b.lmax) * 32, *qr = qf + nqw * 32;
-	LcExtLane<32> ex(b, wbase + lane, qf + lane, qr + lane);
+	const int lane = threadIdx.x & 31;
+	uint32_t *wbase = lc_ext_smem + (size_t)(threadIdx.x >> 5) * lc_ext_warp_words<CELLS>(b.lmax);
+	uint32_t *qf = wbase + (CELLS::words(lc_ext_he_cols(b.lmax)) + 1) * 32;         // word 0 of the read copies; word -1 is the spare
+	LcExtLane<32, CELLS> ex(b, wbase + lane, qf + lane);
 	for (;;) {
 		const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
 		if (need) {                                          // warp-uniform
@@ -194,20 +195,6 @@ __global__ void __launch_bounds__(LC_EXT_TPB) extend_kernel(const LcBatch b)
 				if (rr >= 0 && b.r_n_chain[rr] > 0) lc_warp_pack_read(b, rr, lane, qf + L, 32);
 			}
 			__syncwarp();
-			for (unsigned m = need; m; m &= m - 1) {           // the reversed copies, from the forward ones
-				const int L = __ffs(m) - 1;
-				const int rr = __shfl_sync(LC_FULL, myr, L);
-				if (rr < 0 || b.r_n_chain[rr] <= 0) continue;
-				const int len = (int)(b.off[rr + 1] - b.off[rr]);
-				for (int t = lane; 8 * t < len; t += 32) {
-					const int s0 = len - 8 * t - 8, wi = s0 >> 3;          // bases s0..s0+7 of the read, reversed, are word t
-					const uint32_t lo = wi >= 0 ? qf[wi * 32 + L] : 0u, hi = qf[(wi + 1) * 32 + L];
-					uint32_t v = __funnelshift_r(lo, hi, (s0 & 7) << 2);
-					v = __byte_perm(v, 0, 0x0123);
-					qr[t * 32 + L] = (v & 0x0f0f0f0fu) << 4 | ((v >> 4) & 0x0f0f0f0fu);
-				}
-			}
-			__syncwarp();
 			if (need >> lane & 1) { if (myr < 0) ex.phase = LC_XP_DONE; else ex.begin_read(myr); }
 		}
 		if (!__ballot_sync(LC_FULL, ex.phase != LC_XP_DONE)) break;
@@ -216,21 +203,29 @@ __global__ void __launch_bounds__(LC_EXT_TPB) extend_kernel(const LcBatch b)
 	}
 }
 
-// one warp per read pair: dedup of both ends by lane 0, then the two rescue phases with the warp-cooperative local SW
-__global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, int n_pairs)
+// Stage 5a: one thread per pair — dedup of both ends, final lists, and the rescue phases for as long as they are no-ops
+__global__ void __launch_bounds__(LC_TPB) pair_prepare_kernel(const LcBatch b, int n_pairs)
+{
+	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	int *wi = b.w_int + (size_t)worker * b.w_int_n;
+	for (int p = worker; p < n_pairs; p += stride) lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
+}
+// Stage 5b: one warp per pair that needs a Smith-Waterman — the two rescue phases with the warp-cooperative local SW
+__global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b)
 {
 	extern __shared__ int lc_smem[];
 	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax, 3), rows = lc_warp_row_ints(b.lmax);
 	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const unsigned int n = *b.resc_n;
 	LcExecWarp ex;
 	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.Hmax = ex.E + rows; ex.qs = (uint8_t *)(ex.Hmax + rows);
 	ex.lane = lane; ex.bl = b.w_u64 + (size_t)gwarp * b.w_u64_n;
 	for (;;) {
-		int p = 0;
-		if (lane == 0) p = (int)atomicAdd(b.work_ctr + 1, 1u);
-		p = __shfl_sync(LC_FULL, p, 0);
-		if (p >= n_pairs) break;
-		lc_stage_pair_t(b, p, ex);
+		unsigned int t = 0;
+		if (lane == 0) t = atomicAdd(b.work_ctr + 1, 1u);
+		t = __shfl_sync(LC_FULL, t, 0);
+		if (t >= n) break;
+		lc_pair_rescue_t(b, b.redo[t], ex);
 		__syncwarp();
 	}
 }
@@ -423,22 +418,31 @@ void LcCudaBackend::k_sa_fill(const LcIndex &ix, unsigned long long n_samples, v
 }
 void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
-void LcCudaBackend::k_extend(const LcBatch &b)
+template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream)
 {
-	const int smem = (LC_EXT_TPB / 32) * lc_ext_warp_words(b.lmax) * 4;
+	const int smem = (LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) * 4;
 	int per_sm = 1;
-	cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel, LC_EXT_TPB, smem);
+	cudaFuncSetAttribute(extend_kernel<CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<CELLS>, LC_EXT_TPB, smem);
 	if (per_sm < 1) per_sm = 1;
 	const long long need = ((long long)b.n_reads + LC_EXT_TPB - 1) / LC_EXT_TPB, cap = (long long)n_sm * per_sm;
-	extend_kernel<<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b);
+	extend_kernel<CELLS><<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b);
+}
+void LcCudaBackend::k_extend(const LcBatch &b)
+{
+	// byte-packed H/E cells whenever no score of the batch can exceed 255 (half the shared memory per warp, twice the resident warps)
+	if (lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS")) lc_launch_extend<LcCells8<32> >(b, n_sm, stream);
+	else lc_launch_extend<LcCells16<32> >(b, n_sm, stream);
 }
 void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {
+	// at most n_workers threads: the patch scratch (w_int) is indexed by global thread id
+	pair_prepare_kernel<<<grid_for((unsigned long long)n_pairs, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_pairs);
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
 	cudaFuncSetAttribute(matesw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id
-	matesw_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, n_pairs);
+	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id.
+	// The list length is only known on the device; the grid is sized for the worst case (every pair listed).
+	matesw_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b);
 }
 void LcCudaBackend::k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 {

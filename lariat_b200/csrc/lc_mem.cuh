@@ -74,6 +74,7 @@ struct LcBatch {
 	uint8_t *w_z; int32_t w_z_n;                         // per worker: w_z_n bytes of traceback scratch
 	uint64_t *cig_jobs; unsigned long long cig_jobs_cap; // LC_CIG_NLIST job lists of cig_jobs_cap entries each (lc_cigar.cuh)
 	unsigned int *cig_n;                                 // their lengths
+	unsigned int *resc_n;                                // stage 5: number of pairs listed (in `redo`) for the rescue kernel
 };
 
 LC_HD void lc_raise(const LcBatch &b, uint32_t flag)
@@ -705,27 +706,36 @@ LC_HD int lc_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t &dist)   /
 	return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
 }
 
-// mem_matesw (B/bwamem_pair.c:111-180) with Lariat's insert model: only orientation FR (index 1) is enabled
-// (G/gobwa.go:229-237), so at most one SW is run and at most one region is added per call.
-template <class Exec>
-LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const Exec &ex)
+// The part of mem_matesw (B/bwamem_pair.c:118-147) that decides whether a Smith-Waterman is run for anchor `a`, with Lariat's
+// insert model: only orientation FR (index 1) is enabled (G/gobwa.go:229-237), so at most one SW is run per call.
+// Returns false when the call changes nothing; else [rb, re) is the reference window.
+LC_HD bool lc_matesw_wants_sw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const lc_alnreg_t *ma, int n_ma, int64_t &rb, int64_t &re)
 {
-	const lc_opt_t &opt = b.opt;
 	const int64_t l_pac = b.ix.l_pac;
 	const int low = b.pes_low, high = b.pes_high;
 	for (int i = 0; i < n_ma; ++i) {                       // an existing mate hit in range satisfies the orientation (:118-124)
 		int64_t dist;
 		int r = lc_infer_dir(l_pac, a.rb, ma[i].rb, dist);
-		if (r == 1 && dist >= low && dist <= high) return 0;
+		if (r == 1 && dist >= low && dist <= high) return false;
 	}
 	// r = 1: is_rev = 1 (mate is reverse-complemented), is_larger = 1 (:130-143)
-	int64_t rb = a.rb + low - l_ms, re = a.rb + high;
+	rb = a.rb + low - l_ms; re = a.rb + high;
 	if (rb < 0) rb = 0;
 	if (re > l_pac << 1) re = l_pac << 1;
 	int rid = -1;
 	if (rb < re) rid = lc_fetch_clamp(b.ix, rb, (rb + re) >> 1, re);
 	// (when rb >= re the reference compares against an uninitialised rid, :147; treated as "no window")
-	if (a.rid != rid || re - rb < opt.min_seed_len) return 0;
+	return a.rid == rid && re - rb >= b.opt.min_seed_len;
+}
+
+// mem_matesw (B/bwamem_pair.c:111-180)
+template <class Exec>
+LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const Exec &ex)
+{
+	const lc_opt_t &opt = b.opt;
+	const int64_t l_pac = b.ix.l_pac;
+	int64_t rb, re;
+	if (!lc_matesw_wants_sw(b, a, l_ms, ma, n_ma, rb, re)) return 0;
 	const int xtra = LC_XSUBO | LC_XSTART | (l_ms * opt.a < 250 ? LC_XBYTE : 0) | (opt.min_seed_len * opt.a);
 	LcSeqRevComp qf = { ms, l_ms };
 	LcRefFwd tf = { &b.ix, rb };
@@ -760,43 +770,63 @@ LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const ui
 	return 1;
 }
 
-template <class Exec>
-LC_HD void lc_stage_pair_t(const LcBatch &b, int p, const Exec &ex)
+// Stage 5a, one THREAD per pair: the tail of mem_align1_core for both ends (mem_sort_dedup_patch, is_alt: B/bwamem.c:1070-1082),
+// the final lists carved and filled, and the two rescue phases of GoBwaMemMateSW (G/gobwa.go:264-324) replayed for as long as
+// every mem_matesw call is a no-op (the usual case: a properly paired hit satisfies every anchor).  The first anchor that needs
+// a Smith-Waterman sends the pair to the rescue list; stage 5b (one warp per listed pair) then runs the phases for real.
+LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 {
 	int n[2], len[2], best[2] = { 0, 0 };
-	const uint8_t *q[2];
 	lc_alnreg_t *src[2];
 	for (int e = 0; e < 2; ++e) {
 		const int r = 2 * p + e;
-		len[e] = (int)(b.off[r + 1] - b.off[r]); q[e] = b.seq + b.off[r];
+		len[e] = (int)(b.off[r + 1] - b.off[r]);
 		src[e] = b.reg + b.r_reg_off[r];
-		int ne = 0;
-		if (ex.leader()) {
-			ne = lc_sort_dedup_patch(b, q[e], b.r_n_reg[r], src[e], ex.H, ex.E);      // tail of mem_align1_core (B/bwamem.c:1070)
-			for (int i = 0; i < ne; ++i)
-				if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
+		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], b.r_n_reg[r], src[e], H, E);      // tail of mem_align1_core (B/bwamem.c:1070)
+		for (int i = 0; i < n[e]; ++i) {
+			if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
+			best[e] = lc_max(best[e], src[e][i].score);                                         // G/gobwa.go:264-283
 		}
-		n[e] = (int)ex.bcast((unsigned long long)ne);
-		ex.sync();
-		for (int i = 0; i < n[e]; ++i) best[e] = lc_max(best[e], src[e][i].score);              // G/gobwa.go:264-283
 	}
 	// capacity of the final lists: every rescue call adds at most one region
 	int a2 = 0;
 	if (len[0] > 0) for (int i = 0; i < n[1] && a2 < b.max_anchors; ++i) if (src[1][i].score >= best[1] - b.score_delta) ++a2;
 	const int cap0 = n[0] + a2;
 	const int cap1 = n[1] + (len[1] > 0 ? lc_min(b.max_anchors, cap0) : 0);
-	unsigned long long fo = 0;
-	if (ex.leader()) {
-		fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
-		b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
-	}
-	fo = ex.bcast(fo);
+	b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
+	const unsigned long long fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
 	if (fo == (unsigned long long)-1) return;
 	lc_alnreg_t *f0 = b.fin + fo, *f1 = b.fin + fo + cap0;
-	for (int i = ex.lane_id(); i < n[0]; i += ex.n_lanes()) f0[i] = src[0][i];
-	for (int i = ex.lane_id(); i < n[1]; i += ex.n_lanes()) f1[i] = src[1][i];
+	for (int i = 0; i < n[0]; ++i) f0[i] = src[0][i];
+	for (int i = 0; i < n[1]; ++i) f1[i] = src[1][i];
+	b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n[0];
+	b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n[1];
+	bool need = false;
+	int64_t rb, re;
+	int num = 0;
+	for (int i = 0; i < n[1] && num < b.max_anchors && len[0] > 0 && !need; ++i)
+		if (f1[i].score >= best[1] - b.score_delta) { ++num; need = lc_matesw_wants_sw(b, f1[i], len[0], f0, n[0], rb, re); }
+	num = 0;
+	for (int i = 0; i < n[0] && num < b.max_anchors && len[1] > 0 && !need; ++i)
+		if (f0[i].score >= best[0] - b.score_delta) { ++num; need = lc_matesw_wants_sw(b, f0[i], len[1], f1, n[1], rb, re); }
+	if (need) { b.redo[lc_atomic_add(b.resc_n, 1u)] = p; return; }
+	const unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
+	for (int i = 0; i < n[0]; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
+	for (int i = 0; i < n[1]; ++i) b.cand[co + n[0] + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
+}
+
+// Stage 5b, one warp (or thread) per listed pair: the two rescue phases on the lists lc_pair_prepare filled
+template <class Exec>
+LC_HD void lc_pair_rescue_t(const LcBatch &b, int p, const Exec &ex)
+{
+	int len[2], best[2] = { 0, 0 };
+	const uint8_t *q[2];
+	for (int e = 0; e < 2; ++e) { const int r = 2 * p + e; len[e] = (int)(b.off[r + 1] - b.off[r]); q[e] = b.seq + b.off[r]; }
+	lc_alnreg_t *f0 = b.fin + b.r_fin_off[2 * p], *f1 = b.fin + b.r_fin_off[2 * p + 1];
+	int n0 = b.r_n_fin[2 * p], n1 = b.r_n_fin[2 * p + 1], num = 0;
+	for (int i = 0; i < n0; ++i) best[0] = lc_max(best[0], f0[i].score);      // the pre-rescue best scores (G/gobwa.go:264-283)
+	for (int i = 0; i < n1; ++i) best[1] = lc_max(best[1], f1[i].score);
 	ex.sync();
-	int n0 = n[0], n1 = n[1], num = 0;
 	// phase 1: rescue read 1 from read 2's hits (G/gobwa.go:286-300). read 2's list is not touched in this phase.
 	for (int i = 0; i < n1 && num < b.max_anchors && len[0] > 0; ++i)
 		if (f1[i].score >= best[1] - b.score_delta) { ++num; lc_matesw_t(b, f1[i], len[0], q[0], f0, n0, ex); }
@@ -805,9 +835,8 @@ LC_HD void lc_stage_pair_t(const LcBatch &b, int p, const Exec &ex)
 	for (int i = 0; i < n0 && num < b.max_anchors && len[1] > 0; ++i)
 		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw_t(b, f0[i], len[1], q[1], f1, n1, ex); }
 	if (ex.leader()) {
-		b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n0;
-		b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n1;
-		unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));   // candidate list for stage 6 (sized like fin)
+		b.r_n_fin[2 * p] = n0; b.r_n_fin[2 * p + 1] = n1;
+		unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));
 		for (int i = 0; i < n0; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
 		for (int i = 0; i < n1; ++i) b.cand[co + n0 + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
 	}
@@ -831,13 +860,19 @@ LC_HDN int lc_matesw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uin
 	return lc_matesw_t(b, a, l_ms, ms, ma, n_ma, ex);
 }
 
-LC_HDN void lc_stage_pair(const LcBatch &b, int p, int worker)
+// thread forms of the two halves of stage 5 (tests/hostsim; the device runs lc_pair_rescue_t with a warp)
+LC_HDN void lc_stage_pair_prepare(const LcBatch &b, int p, int worker)
+{
+	int *wi = b.w_int + (size_t)worker * b.w_int_n;
+	lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
+}
+LC_HDN void lc_stage_pair_rescue(const LcBatch &b, int p, int worker)
 {
 	int *wi = b.w_int + (size_t)worker * b.w_int_n;
 	LcExecThreadSw ex;
 	ex.H = wi; ex.E = wi + (b.lmax + 18); ex.Hmax = wi + 2 * (b.lmax + 18);
 	ex.bl = b.w_u64 + (size_t)worker * b.w_u64_n;
-	lc_stage_pair_t(b, p, ex);
+	lc_pair_rescue_t(b, p, ex);
 }
 
 // ============================================================================================================

@@ -266,6 +266,7 @@ public:
 			b.work_ctr = (unsigned int *)(c + 20);
 			b.redo_cur = (unsigned int *)(c + 22);
 			b.cig_n = (unsigned int *)(c + 24);
+			b.resc_n = (unsigned int *)(c + 27);
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);
@@ -381,11 +382,12 @@ public:
 		if (!d_fin.ensure(be, sizeof(lc_alnreg_t) * b.fin_cap) || !d_aln.ensure(be, sizeof(lc_aln_t) * b.fin_cap) ||
 			!d_cand.ensure(be, 8 * b.fin_cap)) return nomem();
 		b.fin = (lc_alnreg_t *)d_fin.p; b.aln = (lc_aln_t *)d_aln.p; b.cand = (uint64_t *)d_cand.p;
-		be.k_pair(b, n_pairs); ++launches;
+		be.k_pair(b, n_pairs); launches += 2;
 		be.ev_record(7);
 		read_ctl();
 		if (h_ctl_ovf) { err = "internal pool overflow in pair stage"; return LC_ENOMEM; }
 		const unsigned long long NC = h_ctl[7];
+		n_rescue_pairs = (unsigned long long)(uint32_t)h_ctl[27];
 		// ---- stage 6: CIGARs (lc_cigar.cuh: plan -> register-band kernels -> warp fallback; regrow + rerun on overflow)
 		b.cig_jobs_cap = NC + 1;
 		if (!d_cigjobs.ensure(be, 8 * (size_t)LC_CIG_NLIST * b.cig_jobs_cap)) return nomem();
@@ -450,7 +452,7 @@ public:
 
 	int64_t launches = 0;
 	int n_redo = 0;
-	unsigned long long n_cig_fallback = 0;
+	unsigned long long n_cig_fallback = 0, n_rescue_pairs = 0;
 	unsigned long long n_cand = 0, n_cigar_words = 0;
 
 private:

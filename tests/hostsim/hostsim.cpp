@@ -55,10 +55,15 @@ struct HostBackend {
 	void k_extend(const LcBatch &b)
 	{
 		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); return; }
-		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax)), qr((size_t)lc_ext_q_words(b.lmax));
-		lc_ext_run_scalar(b, he.data(), qw.data(), qr.data());
+		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax));
+		lc_ext_run_scalar(b, he.data(), qw.data(), lc_ext_cells8_ok(b) && !wide_cells);
 	}
-	void k_pair(const LcBatch &b, int n_pairs) { for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair(b, p, p % workers); }   // reversed: order must not matter
+	bool wide_cells = false;     // -H: 16-bit H/E cells even when the batch would fit the byte packing
+	void k_pair(const LcBatch &b, int n_pairs)
+	{
+		for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair_prepare(b, p, p % workers);   // reversed: order must not matter
+		for (unsigned int t = 0; t < *b.resc_n; ++t) lc_stage_pair_rescue(b, b.redo[t], (int)(t % workers));
+	}
 	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 	{
 		if (n_dev) n = *n_dev;
@@ -103,6 +108,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
+		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
 		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
 	}
 	LcHostIndex hix; std::string err;
@@ -155,7 +161,7 @@ int main(int argc, char **argv)
 				"\"sw_calls\": %llu, \"sw_cells\": %llu, \"glb_calls\": %llu, \"glb_cells\": %llu}\n", c.occ_blocks, c.extend_calls, c.sa_calls, c.lf_steps,
 				c.ext_calls, c.ext_cells, c.sw_calls, c.sw_cells, c.glb_calls, c.glb_cells);
 	}
-	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu, fallback %llu\n", n,
-			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], pl.n_cig_fallback);
+	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu, fallback %llu; %llu pairs to the rescue kernel\n", n,
+			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], pl.n_cig_fallback, pl.n_rescue_pairs);
 	return 0;
 }
