@@ -188,6 +188,10 @@ int64_t lc_collect_intv_batch(lc_ctx *ctx, int n, const uint8_t *codes, const in
 int lc_sa_batch(lc_ctx *ctx, int64_t n, const uint64_t *rows, uint64_t *out, float *ms);
 
 void lc_set_counting(lc_ctx *ctx, int on);
+/* Device-side stopwatch for bench.py: CUDA events recorded on the library's own stream (torch.cuda.Event only sees
+ * torch's current stream).  lc_timer_stop synchronises the stream and returns the milliseconds since lc_timer_start. */
+int lc_timer_start(lc_ctx *ctx);
+int lc_timer_stop(lc_ctx *ctx, float *ms);
 /* library build info: "sm_100a", version */
 const char *lc_build_info(void);
 

@@ -144,6 +144,25 @@ void lc_destroy(lc_ctx *c)
 
 const lc_contigs_t *lc_contigs(const lc_ctx *c) { return c ? &c->contigs : nullptr; }
 void lc_set_counting(lc_ctx *c, int on) { if (c) c->pl.counting = on != 0; }
+int lc_timer_start(lc_ctx *c)
+{
+	if (!c) return fail(LC_EARG, "null ctx");
+	std::lock_guard<std::mutex> g(c->mu);
+	cudaSetDevice(c->device);
+	c->be.ev_record(14);
+	return LC_OK;
+}
+int lc_timer_stop(lc_ctx *c, float *ms)
+{
+	if (!c || !ms) return fail(LC_EARG, "bad arguments");
+	std::lock_guard<std::mutex> g(c->mu);
+	cudaSetDevice(c->device);
+	c->be.ev_record(15);
+	std::string e;
+	if (c->be.check(e)) return fail(LC_ECUDA, e);
+	*ms = c->be.ev_ms(14, 15);
+	return LC_OK;
+}
 
 static void fill_result(lc_ctx *c)
 {

@@ -25,39 +25,85 @@
 
 #define LC_XT_CELLS 8
 
+// ---- two 16-bit lanes per register: the DP arithmetic of a tick runs on column pairs (low half = even column).  On sm_100a each of
+// these is one instruction (VIADD.16x2, VIMNMX.S16x2, VIADDMNMX.S16x2[.RELU], VIMNMX3.S16x2, VIMNMX.U16x2, PRMT); tests/hostsim
+// runs the portable forms.
+#ifdef __CUDA_ARCH__
+LC_HD uint32_t lc_p2_add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+LC_HD uint32_t lc_p2_max(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+LC_HD uint32_t lc_p2_min(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+LC_HD uint32_t lc_p2_minu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+LC_HD uint32_t lc_p2_max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+LC_HD uint32_t lc_p2_addmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }            // max(a + b, c)
+LC_HD uint32_t lc_p2_addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }  // max(a + b, c, 0)
+LC_HD uint32_t lc_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#else
+LC_HD int lc_p2_lo(uint32_t a) { return (int)(int16_t)(a & 0xffffu); }
+LC_HD int lc_p2_hi(uint32_t a) { return (int)(int16_t)(a >> 16); }
+LC_HD uint32_t lc_p2_mk(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi & 0xffffu) << 16; }
+LC_HD uint32_t lc_p2_add(uint32_t a, uint32_t b) { return lc_p2_mk(lc_p2_lo(a) + lc_p2_lo(b), lc_p2_hi(a) + lc_p2_hi(b)); }
+LC_HD uint32_t lc_p2_max(uint32_t a, uint32_t b) { return lc_p2_mk(lc_max(lc_p2_lo(a), lc_p2_lo(b)), lc_max(lc_p2_hi(a), lc_p2_hi(b))); }
+LC_HD uint32_t lc_p2_min(uint32_t a, uint32_t b) { return lc_p2_mk(lc_min(lc_p2_lo(a), lc_p2_lo(b)), lc_min(lc_p2_hi(a), lc_p2_hi(b))); }
+LC_HD uint32_t lc_p2_minu(uint32_t a, uint32_t b) { return lc_min(a & 0xffffu, b & 0xffffu) | lc_min(a >> 16, b >> 16) << 16; }
+LC_HD uint32_t lc_p2_max3(uint32_t a, uint32_t b, uint32_t c) { return lc_p2_max(lc_p2_max(a, b), c); }
+LC_HD uint32_t lc_p2_addmax(uint32_t a, uint32_t b, uint32_t c) { return lc_p2_max(lc_p2_add(a, b), c); }
+LC_HD uint32_t lc_p2_addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return lc_p2_max(lc_p2_max(lc_p2_add(a, b), c), 0u); }
+LC_HD uint32_t lc_prmt(uint32_t a, uint32_t b, uint32_t sel)      // PTX prmt.b32, default mode (selector bit 3 = replicate the byte's sign)
+{
+	const uint64_t pool = (uint64_t)b << 32 | a;
+	uint32_t r = 0;
+	for (int i = 0; i < 4; ++i) {
+		const uint32_t n = (sel >> (4 * i)) & 15u;
+		uint32_t byte = (uint32_t)(pool >> (8 * (n & 7u))) & 0xffu;
+		if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+		r |= byte << (8 * i);
+	}
+	return r;
+}
+#endif
+LC_HD uint32_t lc_p2_dup(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }      // the same 16-bit value in both halves
+
 // ---- the H/E row in (shared) memory.  Two packings, chosen by the longest read of the batch:
 //   LcCells16: one column per 32-bit word, h | e << 16                        (any read length up to LC_MAX_READ_LEN)
 //   LcCells8 : two columns per word, (h | e << 8) << 16 * (column & 1)        (lmax * a <= 255: no cell of ksw_extend2 can exceed
 //              the score of the whole read matching, so h and e fit a byte) — half the shared memory, twice the resident warps
+// load8/store8 move the eight columns of a tick as four column pairs: h[k] = {h(col0 + 2k), h(col0 + 2k + 1)} in 16-bit halves.
 template <int STRIDE> struct LcCells16 {
 	static LC_HD int words(int cols) { return cols; }
-	static LC_HD void load8(const uint32_t *he, int col0, int *h, int *e)
+	static LC_HD void load8(const uint32_t *he, int col0, uint32_t *h, uint32_t *e)
 	{
 #pragma unroll
-		for (int c = 0; c < 8; ++c) { const uint32_t v = he[(col0 + c) * STRIDE]; h[c] = (int)(v & 0xffffu); e[c] = (int)(v >> 16); }
+		for (int k = 0; k < 4; ++k) {
+			const uint32_t w0 = he[(col0 + 2 * k) * STRIDE], w1 = he[(col0 + 2 * k + 1) * STRIDE];
+			h[k] = lc_prmt(w0, w1, 0x5410u); e[k] = lc_prmt(w0, w1, 0x7632u);
+		}
 	}
-	static LC_HD void store8(uint32_t *he, int col0, const int *h, const int *e)
+	static LC_HD void store8(uint32_t *he, int col0, const uint32_t *h, const uint32_t *e)
 	{
 #pragma unroll
-		for (int c = 0; c < 8; ++c) he[(col0 + c) * STRIDE] = (uint32_t)h[c] | (uint32_t)e[c] << 16;
+		for (int k = 0; k < 4; ++k) {
+			he[(col0 + 2 * k) * STRIDE] = lc_prmt(h[k], e[k], 0x5410u);
+			he[(col0 + 2 * k + 1) * STRIDE] = lc_prmt(h[k], e[k], 0x7632u);
+		}
 	}
 	static LC_HD void put(uint32_t *he, int col, int h, int e) { he[col * STRIDE] = (uint32_t)h | (uint32_t)e << 16; }
 };
 template <int STRIDE> struct LcCells8 {
 	static LC_HD int words(int cols) { return cols >> 1; }
-	static LC_HD void load8(const uint32_t *he, int col0, int *h, int *e)      // col0 is a multiple of 8
+	static LC_HD void load8(const uint32_t *he, int col0, uint32_t *h, uint32_t *e)      // col0 is a multiple of 8
 	{
 #pragma unroll
-		for (int c = 0; c < 8; c += 2) {
-			const uint32_t v = he[((col0 + c) >> 1) * STRIDE];
-			h[c] = (int)(v & 0xffu); e[c] = (int)(v >> 8 & 0xffu); h[c + 1] = (int)(v >> 16 & 0xffu); e[c + 1] = (int)(v >> 24);
+		for (int k = 0; k < 4; ++k) {
+			const uint32_t v = he[((col0 >> 1) + k) * STRIDE];
+			h[k] = lc_prmt(v, 0u, 0x4240u); e[k] = lc_prmt(v, 0u, 0x4341u);
 		}
 	}
-	static LC_HD void store8(uint32_t *he, int col0, const int *h, const int *e)
+	// live columns hold values < 256; a column at or right of the row's end may hold 256 and spill into its own e byte or into the
+	// column to its right, which is dead as well (see tick())
+	static LC_HD void store8(uint32_t *he, int col0, const uint32_t *h, const uint32_t *e)
 	{
 #pragma unroll
-		for (int c = 0; c < 8; c += 2)
-			he[((col0 + c) >> 1) * STRIDE] = (uint32_t)h[c] | (uint32_t)e[c] << 8 | (uint32_t)h[c + 1] << 16 | (uint32_t)e[c + 1] << 24;
+		for (int k = 0; k < 4; ++k) he[((col0 >> 1) + k) * STRIDE] = h[k] + (e[k] << 8);
 	}
 	static LC_HD void put(uint32_t *he, int col, int h, int e)
 	{
@@ -66,6 +112,13 @@ template <int STRIDE> struct LcCells8 {
 		*p = (*p & ~(0xffffu << sh)) | ((uint32_t)h | (uint32_t)e << 8) << sh;
 	}
 };
+
+// masks of the columns c < hi of a tick (hi = 0..8) as four column pairs; the device kernel keeps the table in shared memory
+LC_HD void lc_ext_fill_masks(uint32_t *tab)      // 9 x 4 words
+{
+	for (int hi = 0; hi <= 8; ++hi)
+		for (int k = 0; k < 4; ++k) tab[4 * hi + k] = (2 * k < hi ? 0xffffu : 0u) | (2 * k + 1 < hi ? 0xffff0000u : 0u);
+}
 
 enum { LC_XP_FETCH = 0, LC_XP_AFTER_LEFT, LC_XP_AFTER_RIGHT, LC_XP_RIGHT_CHECK, LC_XP_FINALIZE, LC_XP_READ_START, LC_XP_CHAIN_START, LC_XP_SEED_NEXT,
 	   LC_XP_LEFT_SETUP, LC_XP_RIGHT_SETUP, LC_XP_READ_DONE,
@@ -87,14 +140,16 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	int64_t r0, r1, s_rbeg, a_rb, a_re, re0;
 	int s_qbeg, s_len, c_rid, a_qb, a_qe, a_score, a_truesc, aw0, aw1, qe0, sc0;
 	// ---- the extension in progress (ksw_extend2's locals)
-	int qlen, tlen, w, h0, zdrop, i, j, beg, end, f, hleft, rowmax, rowarg, best, best_i, best_j, g_i, gscore, max_off, tb;
+	int qlen, tlen, w, h0, zdrop, i, j, beg, end, f, hleft, hleft0, rowkey, best, best_i, best_j, g_i, gscore, max_off, tb;
 	int nz_first, nz_last;   // first / last column of the row whose updated {h, e} word is non-zero (the band shrink of B/ksw.c:466-469)
+	const uint32_t *mtab;    // lc_ext_fill_masks table (shared memory on the device)
 	int64_t fpos; int fdir, comp;          // forward-strand coordinate of the current row's target base, its step per row, 3 on the reverse strand
 	uint32_t pw, pwn; int64_t pwi;         // the 16 packed reference bases around fpos, the next such word in walking direction (prefetched), word index
 	int q0, qdir;            // the extension's query column c is base q0 + c of the forward (qdir > 0) or reversed (qdir < 0) read copy
 	unsigned long long cells;
 
-	LC_HD LcExtLane(const LcBatch &b_, uint32_t *he_, uint32_t *qw_) : b(b_), he(he_), qw(qw_), phase(LC_XP_FETCH), l_query(0), j(0), end(0), q0(0), qdir(1), tb(0) {}
+	LC_HD LcExtLane(const LcBatch &b_, uint32_t *he_, uint32_t *qw_, const uint32_t *mtab_)
+		: b(b_), he(he_), qw(qw_), phase(LC_XP_FETCH), l_query(0), j(0), beg(0), end(0), f(0), hleft(0), tb(0), mtab(mtab_), q0(0), qdir(1) {}
 
 	LC_HD uint32_t pac_word(int64_t wi) const { return lc_ldg((const uint32_t *)b.ix.pac + (wi < 0 ? 0 : wi)); }
 	LC_HD int target_base()              // base of the current row: bns_get_seq's decoding (B/bntseq.c:398-419) out of the cached word
@@ -115,13 +170,19 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 		best = h0; best_i = best_j = -1; g_i = -1; gscore = -1; max_off = 0; beg = 0; end = qlen; cells = 0;
 		{
 			int v = h0 > oe_ins ? h0 - oe_ins : 0;           // row -1: H[0] = h0, H[1] = h0 - oe_ins, then -e_ins per column while positive; E = 0
-			int hh[LC_XT_CELLS], ee[LC_XT_CELLS];
+			uint32_t hh[4], ee[4] = { 0u, 0u, 0u, 0u };
 			for (int t0 = 0; t0 <= qlen + 1; t0 += LC_XT_CELLS) {
 #pragma unroll
-				for (int c = 0; c < LC_XT_CELLS; ++c) {
-					ee[c] = 0;
-					if (t0 + c == 0) hh[c] = h0;
-					else { hh[c] = v; v = v > sc.e_ins ? v - sc.e_ins : 0; }
+				for (int k = 0; k < 4; ++k) {
+					uint32_t pr = 0;
+#pragma unroll
+					for (int hf = 0; hf < 2; ++hf) {
+						int x;
+						if (t0 + 2 * k + hf == 0) x = h0;
+						else { x = v; v = v > sc.e_ins ? v - sc.e_ins : 0; }
+						pr |= (uint32_t)x << (16 * hf);
+					}
+					hh[k] = pr;
 				}
 				CELLS::store8(he, t0, hh, ee);
 			}
@@ -142,12 +203,18 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	LC_HD void row_start()                                    // B/ksw.c:421-430
 	{
 		const LcScore &sc = b.sc;
-		if (beg < i - w) beg = i - w;
+		if (beg < i - w) {
+			// the band cuts live columns off on the left (B/ksw.c:421).  tick() relies on every column left of beg holding {0, 0}
+			// (true for columns dropped by the zero scan of B/ksw.c:466); clear the ones that share the first tick with beg
+			beg = i - w;
+			for (int c = beg & ~(LC_XT_CELLS - 1); c < beg; ++c) CELLS::put(he, c, 0, 0);
+		}
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
 		hleft = 0;
 		if (beg == 0) { hleft = h0 - (sc.o_del + sc.e_del * (i + 1)); if (hleft < 0) hleft = 0; }
-		f = 0; rowmax = 0; rowarg = -1; j = beg & ~(LC_XT_CELLS - 1);      // ticks are aligned to groups of LC_XT_CELLS columns
+		hleft0 = hleft;
+		f = 0; rowkey = -1; j = beg & ~(LC_XT_CELLS - 1);      // ticks are aligned to groups of LC_XT_CELLS columns
 		nz_first = 1 << 30; nz_last = -1;
 		tb = target_base();
 	}
@@ -158,15 +225,23 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	}
 
 	// ---- one tick: the LC_XT_CELLS columns j..j+7 of the current row (B/ksw.c:431-456), then, if the row is complete, the
-	// end-of-row work (B/ksw.c:457-478).  The cell loop is branch-free: everything that does not depend on the running F/H
-	// chain is computed for the eight columns first, the chain itself is a few instructions per cell, and cells outside
-	// [beg, end) are computed but not committed.
+	// end-of-row work (B/ksw.c:457-478).  The eight cells are computed branch-free on column pairs (two 16-bit lanes per register):
+	//   M = H(i-1,j-1) ? H(i-1,j-1) + s : 0      as   min(max(diag + s, 0), diag * (a + 1))     [a negative M acts like 0 everywhere it is used]
+	//   E' = max(E - e_del, M - oe_del, 0)        one VIADD + one VIADDMNMX.RELU per pair
+	//   F(j+1) = max(F(j) - e_ins, M - oe_ins, 0) does not depend on H, so the eight F values are a decayed prefix maximum: a three-step
+	//                                             scan over the four pairs, then the carried-in f joins with its own decay
+	//   H = max(M, E, F)
+	// Substitution scores come from an 8-entry byte table indexed by (query code ^ target code) through PRMT.
+	// Columns left of beg hold {0, 0} (row_start) and stay {0, 0} under these recurrences, so they need no mask; columns at or right of
+	// end are never read by a later row before `put` rewrites them (each row reads at most one column past the previous end), so
+	// they are computed and stored as garbage, and only kept out of the row maximum and the non-zero scan (mask table mtab).
 	LC_HD void tick()
 	{
 		const LcScore &sc = b.sc;
-		const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_del = sc.e_del, e_ins = sc.e_ins;
+		const int e_del = sc.e_del, e_ins = sc.e_ins;
 		const bool run = phase == LC_XP_DP;
-		const int col0 = j;
+		const int col0 = run ? j : 0;
+		uint32_t h[4], e2[4], hs[4];
 		{
 			// query codes of the eight columns: one funnel shift over two words of the read copy; a left extension reads the read
 			// back to front (column c of the reversed read = base l_query - 1 - q0 - c), so its window is nibble-reversed
@@ -176,51 +251,98 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				const uint32_t w0 = qw[(qi >> 3) * STRIDE], w1 = qw[((qi >> 3) + 1) * STRIDE];
 				uint32_t v = (uint32_t)(((uint64_t)w1 << 32 | w0) >> ((qi & 7) << 2));
 				if (qdir < 0) {
-#ifdef __CUDA_ARCH__
-					v = __byte_perm(v, 0, 0x0123);
-#else
-					v = v >> 24 | (v >> 8 & 0xff00u) | (v << 8 & 0xff0000u) | v << 24;
-#endif
+					v = lc_prmt(v, 0u, 0x0123u);
 					v = (v & 0x0f0f0f0fu) << 4 | (v >> 4 & 0x0f0f0f0fu);
 				}
 				qword = v;
 			}
-			// substitution score without compares per base: x has a zero nibble where the base equals the target base
-			const uint32_t x = qword ^ (tb < 4 ? (uint32_t)tb * 0x11111111u : 0x88888888u);
-			const int pen = tb < 4 ? -sc.b : -1;
-			int hd[LC_XT_CELLS], ev[LC_XT_CELLS];
-			int M[LC_XT_CELLS], e2[LC_XT_CELLS], ti[LC_XT_CELLS];
+			// 255 - penalty per column: 0 for a match, a + b for a mismatch, a + 1 when either base is ambiguous (score -1, B/bwa.c:109-118)
+			const uint32_t x = tb < 4 ? qword ^ ((uint32_t)tb * 0x11111111u) : 0x44444444u;
+			const uint32_t qmm = 255u - (uint32_t)(sc.a + sc.b), qn = 255u - (uint32_t)(sc.a + 1);
+			const uint32_t lut_lo = 255u | qmm << 8 | qmm << 16 | qmm << 24, lut_hi = qn * 0x01010101u;
+			const uint32_t pa = lc_prmt(lut_lo, lut_hi, x), pb = lc_prmt(lut_lo, lut_hi, x >> 16);
+			uint32_t Q[4];
+			Q[0] = lc_prmt(pa, 0u, 0x4140u); Q[1] = lc_prmt(pa, 0u, 0x4342u); Q[2] = lc_prmt(pb, 0u, 0x4140u); Q[3] = lc_prmt(pb, 0u, 0x4342u);
+			const uint32_t c_a = lc_p2_dup(sc.a - 255), n_oe_del = lc_p2_dup(-(sc.o_del + e_del)), n_e_del = lc_p2_dup(-e_del),
+				n_oe_ins = lc_p2_dup(-(sc.o_ins + e_ins)), n_e1 = lc_p2_dup(-e_ins), n_e2 = lc_p2_dup(-2 * e_ins), n_e4 = lc_p2_dup(-4 * e_ins);
+			const uint32_t kmul = (uint32_t)(sc.a + 1);
+			uint32_t hd[4], ev[4], me[4], A[4];
 			CELLS::load8(he, col0, hd, ev);
 #pragma unroll
-			for (int c = 0; c < LC_XT_CELLS; ++c) {
-				const int diag = hd[c], e = ev[c];
-				const int s = (x & (0xfu << (4 * c))) == 0 ? sc.a : ((qword & (0x4u << (4 * c))) ? -1 : pen);
-				M[c] = diag ? diag + s : 0;
-				e2[c] = lc_max(e - e_del, lc_max(M[c] - oe_del, 0));
-				ti[c] = lc_max(M[c] - oe_ins, 0);
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t mr = lc_p2_addmax_relu(lc_p2_add(hd[k], c_a), Q[k], 0u);
+				const uint32_t M = lc_p2_min(mr, hd[k] * kmul);
+				e2[k] = lc_p2_addmax_relu(ev[k], n_e_del, lc_p2_add(M, n_oe_del));
+				A[k] = lc_p2_addmax_relu(M, n_oe_ins, 0u);
+				me[k] = lc_p2_max(M, ev[k]);
 			}
+			// decayed inclusive prefix maximum of A over the eight columns (A >= 0, so a mildly negative filler never wins)
+			const uint32_t neg = 0xc000c000u;
+			{
+				const uint32_t s0 = lc_prmt(neg, A[0], 0x5432u), s1 = lc_prmt(A[0], A[1], 0x5432u), s2 = lc_prmt(A[1], A[2], 0x5432u), s3 = lc_prmt(A[2], A[3], 0x5432u);
+				A[0] = lc_p2_addmax(s0, n_e1, A[0]); A[1] = lc_p2_addmax(s1, n_e1, A[1]); A[2] = lc_p2_addmax(s2, n_e1, A[2]); A[3] = lc_p2_addmax(s3, n_e1, A[3]);
+			}
+			A[3] = lc_p2_addmax(A[2], n_e2, A[3]); A[2] = lc_p2_addmax(A[1], n_e2, A[2]); A[1] = lc_p2_addmax(A[0], n_e2, A[1]);
+			A[3] = lc_p2_addmax(A[1], n_e4, A[3]); A[2] = lc_p2_addmax(A[0], n_e4, A[2]);
+			// G(c) = F entering column c + 1: the scan joined with the carried-in f, which has decayed c + 1 times by then
+			const uint32_t fb = lc_p2_dup(f);
+			uint32_t G[4];
 #pragma unroll
-			for (int c = 0; c < LC_XT_CELLS; ++c) {
-				const int col = col0 + c;
-				const bool act = run && col >= beg && col < end;
-				const int h = lc_max(lc_max(M[c], ev[c]), f);
-				if (act) {
-					hd[c] = hleft; ev[c] = e2[c];                      // H[j] = h of the column to the left, E[j] for the next row
-					if (hleft | e2[c]) { nz_first = lc_min(nz_first, col); nz_last = col; }
-					if (!(rowmax > h)) rowarg = col;
-					rowmax = lc_max(rowmax, h);
-					f = lc_max(f - e_ins, ti[c]);
-					hleft = h;
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t dec = ((uint32_t)(-(2 * k + 1) * e_ins) & 0xffffu) | ((uint32_t)(-(2 * k + 2) * e_ins) & 0xffffu) << 16;
+				G[k] = lc_p2_addmax(fb, dec, A[k]);
+			}
+			// F entering each column = G shifted right by one column with f in front; H = max(M, E, F)
+			h[0] = lc_p2_max(me[0], lc_prmt(fb, G[0], 0x5432u));
+			h[1] = lc_p2_max(me[1], lc_prmt(G[0], G[1], 0x5432u));
+			h[2] = lc_p2_max(me[2], lc_prmt(G[1], G[2], 0x5432u));
+			h[3] = lc_p2_max(me[3], lc_prmt(G[2], G[3], 0x5432u));
+			// what the next row reads at column c is H(i, c - 1): the row shifted right by one column with hleft in front
+			hs[0] = lc_prmt((uint32_t)hleft << 16, h[0], 0x5432u); hs[1] = lc_prmt(h[0], h[1], 0x5432u);
+			hs[2] = lc_prmt(h[1], h[2], 0x5432u); hs[3] = lc_prmt(h[2], h[3], 0x5432u);
+			if (run) CELLS::store8(he, col0, hs, e2);
+			// row maximum with the reference's tie rule (the last column wins, B/ksw.c:443-444): keys h * 8 + column, dead columns -1
+			int hi = end - col0;
+			hi = hi < 0 ? 0 : (hi > LC_XT_CELLS ? LC_XT_CELLS : hi);
+			const uint32_t *mrow = mtab + 4 * hi;
+			const uint32_t m0 = mrow[0], m1 = mrow[1], m2 = mrow[2], m3 = mrow[3];
+			{
+				const uint32_t k0 = (h[0] * 8u + 0x00010000u) | ~m0, k1 = (h[1] * 8u + 0x00030002u) | ~m1,
+					k2 = (h[2] * 8u + 0x00050004u) | ~m2, k3 = (h[3] * 8u + 0x00070006u) | ~m3;
+				const uint32_t kk = lc_p2_max(lc_p2_max3(k0, k1, k2), k3);
+				const int klo = (int)lc_prmt(kk, 0u, 0x9910u), khi = (int)kk >> 16;
+				const int tk = klo > khi ? klo : khi;                      // -1 when no column of the tick is live
+				const int tk32 = (tk & ~7) * 128 + (tk & 7) + col0;        // h << 10 | column; negative for tk == -1 (columns stay below 1017)
+				rowkey = rowkey > tk32 ? rowkey : tk32;
+			}
+			// first / last live column of the row whose stored {h, e} is non-zero
+			{
+				const uint32_t one = 0x00010001u;
+				const uint32_t b0 = lc_p2_minu((hs[0] | e2[0]) & m0, one), b1 = lc_p2_minu((hs[1] | e2[1]) & m1, one),
+					b2 = lc_p2_minu((hs[2] | e2[2]) & m2, one), b3 = lc_p2_minu((hs[3] | e2[3]) & m3, one);
+				const uint32_t acc = b0 + b1 * 4u + b2 * 16u + b3 * 64u;
+				const uint32_t b8 = (acc | acc >> 15) & 0xffu;               // bit c = column col0 + c
+				if (b8) {
+					const int first = col0 + lc_ctz(b8), last = col0 + 31 - lc_clz(b8);
+					nz_first = nz_first < first ? nz_first : first;
+					nz_last = last;
 				}
 			}
-			if (run) CELLS::store8(he, col0, hd, ev);
-			if (run) j = col0 + LC_XT_CELLS;
+			f = (int)G[3] >> 16;
+			hleft = (int)(h[3] >> 16);
+			j = col0 + LC_XT_CELLS;
 		}
 		LC_CONVERGE();
 		if (run && j >= end) {                                 // the row is complete
 			bool stop = false;
 			const int jfin = beg < end ? end : beg;            // the reference's loop variable after the column loop
 			if (b.cnt) cells += (unsigned long long)(end > beg ? end - beg : 0);
+			if (end > beg) {                                   // h of the row's last live column (this tick's column end - 1 - col0)
+				const int idx = end - 1 - (j - LC_XT_CELLS);
+				const uint32_t pr = idx < 4 ? (idx < 2 ? h[0] : h[1]) : (idx < 6 ? h[2] : h[3]);
+				hleft = (int)((idx & 1) ? pr >> 16 : pr & 0xffffu);
+			} else hleft = hleft0;
+			const int rowmax = rowkey < 0 ? 0 : rowkey >> 10, rowarg = rowkey < 0 ? -1 : (rowkey & 1023);
 			CELLS::put(he, end, hleft, 0);
 			if (jfin == qlen) {
 				if (!(gscore > hleft)) g_i = i;
@@ -410,7 +532,9 @@ template <int STRIDE> LC_HD void lc_ext_load_read(const LcBatch &b, int r, uint3
 // scalar driver (tests/hostsim): all reads, one after another, through the same state machine; cells8 selects the byte packing
 template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, uint32_t *he, uint32_t *qw)
 {
-	LcExtLane<1, CELLS> ex(b, he, qw + 1);
+	uint32_t mtab[36];
+	lc_ext_fill_masks(mtab);
+	LcExtLane<1, CELLS> ex(b, he, qw + 1, mtab);
 	int next = 0;
 	for (;;) {
 		while (ex.phase == LC_XP_FETCH) {

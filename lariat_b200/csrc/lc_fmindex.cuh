@@ -94,6 +94,22 @@ LC_HD int lc_popcll(uint64_t v)
 	return __builtin_popcountll(v);
 #endif
 }
+LC_HD int lc_ctz(uint32_t v)      // v != 0
+{
+#ifdef __CUDA_ARCH__
+	return __ffs((int)v) - 1;
+#else
+	return __builtin_ctz(v);
+#endif
+}
+LC_HD int lc_clz(uint32_t v)      // v != 0
+{
+#ifdef __CUDA_ARCH__
+	return __clz((int)v);
+#else
+	return __builtin_clz(v);
+#endif
+}
 // even bits of a 32-bit word gathered into 16 bits (bit 2i -> bit i)
 LC_HD uint32_t lc_even_bits(uint32_t x)
 {

@@ -173,14 +173,17 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 // Stage 4: one lane per read, mem_chain2aln + ksw_extend2 as a state machine (lc_extsm.cuh).  Per warp the shared memory holds
 // the 32 H/E rows ([column][lane], packed by CELLS) and the 32 reads (4 bits per base, [word][lane], one spare word in front).
 template <class CELLS> __host__ __device__ inline int lc_ext_warp_words(int lmax) { return (CELLS::words(lc_ext_he_cols(lmax)) + lc_ext_q_words(lmax)) * 32; }
+#define LC_EXT_MTAB_WORDS 64      // lc_ext_fill_masks table (36 words) in front of the per-warp areas
 template <class CELLS>
-__global__ void __launch_bounds__(LC_EXT_TPB) extend_kernel(const LcBatch b)
+__global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b)
 {
 	extern __shared__ uint32_t lc_ext_smem[];
 	const int lane = threadIdx.x & 31;
-	uint32_t *wbase = lc_ext_smem + (size_t)(threadIdx.x >> 5) * lc_ext_warp_words<CELLS>(b.lmax);
+	uint32_t *wbase = lc_ext_smem + LC_EXT_MTAB_WORDS + (size_t)(threadIdx.x >> 5) * lc_ext_warp_words<CELLS>(b.lmax);
 	uint32_t *qf = wbase + (CELLS::words(lc_ext_he_cols(b.lmax)) + 1) * 32;         // word 0 of the read copies; word -1 is the spare
-	LcExtLane<32, CELLS> ex(b, wbase + lane, qf + lane);
+	if (threadIdx.x == 0) lc_ext_fill_masks(lc_ext_smem);
+	__syncthreads();
+	LcExtLane<32, CELLS> ex(b, wbase + lane, qf + lane, lc_ext_smem);
 	for (;;) {
 		const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
 		if (need) {                                          // warp-uniform
@@ -420,7 +423,7 @@ void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_ker
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
 template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream)
 {
-	const int smem = (LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) * 4;
+	const int smem = ((LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) + LC_EXT_MTAB_WORDS) * 4;
 	int per_sm = 1;
 	cudaFuncSetAttribute(extend_kernel<CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<CELLS>, LC_EXT_TPB, smem);
