@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("LARIAT_BENCH_SCALE", "1.0")))
     ap.add_argument("--cpu-sample", type=int, default=200000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunk-pairs", type=int, default=-1, help="lc_set_chunk_pairs for the e2e arm (-1: library default)")
+    ap.add_argument("--e2e-sweep", default="", help="comma list of chunk sizes: time the e2e arm for each (stderr), then go on with --chunk-pairs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,6 +235,19 @@ def main():
     value = total_pairs * args.steps / dt_max
 
     # ---- end-to-end arm: host buffers in, host results out, every step
+    all_keys = ("ms_h2d", "ms_seed", "ms_sa", "ms_chain", "ms_extend", "ms_pair", "ms_cigar", "ms_d2h", "ms_total")
+    for cp in [int(x) for x in args.e2e_sweep.split(",") if x]:
+        check(lib.lc_set_chunk_pairs(ctx, cp))
+        for _ in range(2):
+            check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+        tw = time.perf_counter()
+        for _ in range(args.steps):
+            check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+        tw = (time.perf_counter() - tw) / args.steps
+        log(f"[bench] e2e sweep chunk_pairs={cp}: {1e3 * tw:.2f} ms/step wall, {n_pairs / tw:.0f} pairs/s; last call " +
+            json.dumps({k: round(float(getattr(res.contents, k)), 2) for k in all_keys}))
+    if args.chunk_pairs >= 0:
+        check(lib.lc_set_chunk_pairs(ctx, args.chunk_pairs))
     for _ in range(max(1, args.warmup - 1)):
         check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
     sync_all()
@@ -249,7 +264,7 @@ def main():
     rr = res.contents
     h2d = int(bases.nbytes + off.nbytes)
     d2h = int(rr.n_regs * (88 + 32) + rr.n_cigar_words * 4 + (rr.n_reads + 1) * 8)
-    e2e_ms = {k: float(getattr(rr, k)) for k in ("ms_h2d", "ms_d2h", "ms_total")}
+    e2e_ms = {k: float(getattr(rr, k)) for k in all_keys}     # stage times are sums over the chunks of the call (chunks of the two lanes overlap)
 
     if rank != 0:
         if world > 1:

@@ -188,6 +188,11 @@ int64_t lc_collect_intv_batch(lc_ctx *ctx, int n, const uint8_t *codes, const in
 int lc_sa_batch(lc_ctx *ctx, int64_t n, const uint64_t *rows, uint64_t *out, float *ms);
 
 void lc_set_counting(lc_ctx *ctx, int on);
+/* Calls of more than 1.5 x n_pairs pairs are cut into chunks of about n_pairs pairs that alternate between two CUDA streams, so that the
+ * H2D / D2H copies of one chunk run under the kernels of the other (the reference's analogue: barcode groups flowing through the
+ * goroutine pool of I/lariat.go:348-350 while the BAM thread drains results).  0 = never chunk.  Default 500000 (env LC_CHUNK_PAIRS).
+ * Results do not depend on it. */
+int lc_set_chunk_pairs(lc_ctx *ctx, int n_pairs);
 /* Device-side stopwatch for bench.py: CUDA events recorded on the library's own stream (torch.cuda.Event only sees
  * torch's current stream).  lc_timer_stop synchronises the stream and returns the milliseconds since lc_timer_start. */
 int lc_timer_start(lc_ctx *ctx);

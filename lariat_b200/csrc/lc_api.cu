@@ -2,14 +2,43 @@
 // Index load + upload to HBM, the batched alignment call, the split upload/run/fetch form used for timing,
 // single-read source-compatible forms, and the kernel-level entry points of the microbenchmark config.
 #include <cuda_runtime.h>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include <stdlib.h>
 #include "lc_backend.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+// A growable pinned host buffer (cudaHostAlloc): D2H into it runs at PCIe speed and overlaps with kernels of the other lane.
+struct LcPinned {
+	void *p = nullptr; size_t cap = 0;
+	bool ensure(size_t bytes, size_t keep)
+	{
+		if (bytes <= cap) return true;
+		size_t want = bytes + bytes / 4 + 4096;
+		void *np = nullptr;
+		if (cudaHostAlloc(&np, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+		if (p && keep) memcpy(np, p, keep < cap ? keep : cap);
+		if (p) cudaFreeHost(p);
+		p = np; cap = want;
+		return true;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// A second stream + pool set: large calls are cut into chunks of barcode groups that alternate between two lanes, so that one
+// chunk's H2D / D2H and kernel tails overlap the other's kernels.
+struct LcLane {
+	LcCudaBackend be;
+	LcPipeline<LcCudaBackend> pl;
+	explicit LcLane(int dev) : be(dev), pl(be) {}
+};
 
 struct lc_ctx {
 	int device = 0;
@@ -30,6 +59,10 @@ struct lc_ctx {
 	std::vector<int64_t> stage_off;
 	bool have_batch = false;
 	int last_delta = 25;
+	// results of the batched calls: pinned host arrays, valid until the next call on this ctx
+	LcPinned h_off, h_regs, h_aln, h_cig;
+	std::unique_ptr<LcLane> lane2;
+	int chunk_pairs = 500000;       // LC_CHUNK_PAIRS; calls of more than 1.5 chunks run chunked over two lanes, 0 = never
 	explicit lc_ctx(int dev) : device(dev), be(dev), pl(be) {}
 };
 
@@ -123,6 +156,7 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	if (const char *e = getenv("LC_SEED_LST_CAP")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap = v; }
 	if (const char *e = getenv("LC_SEED_PK_CAP")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap = v; }
 	if (const char *e = getenv("LC_FORCE_WIDE")) c->pl.force_wide = e[0] == '1';
+	if (const char *e = getenv("LC_CHUNK_PAIRS")) { int v = atoi(e); if (v >= 0) c->chunk_pairs = v; }
 	// host copies of the big FM-index arrays are not needed any more (pac stays for lc_fetch_seq)
 	std::vector<uint32_t>().swap(h.bwt);
 	std::vector<uint64_t>().swap(h.sa);
@@ -138,12 +172,21 @@ void lc_destroy(lc_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->pl.release();
+	c->lane2.reset();
+	c->h_off.release(); c->h_regs.release(); c->h_aln.release(); c->h_cig.release();
 	cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_pac); cudaFree(c->d_anns); cudaFree(c->d_sa_dense);
 	delete c;
 }
 
 const lc_contigs_t *lc_contigs(const lc_ctx *c) { return c ? &c->contigs : nullptr; }
 void lc_set_counting(lc_ctx *c, int on) { if (c) c->pl.counting = on != 0; }
+int lc_set_chunk_pairs(lc_ctx *c, int n_pairs)
+{
+	if (!c || n_pairs < 0) return fail(LC_EARG, "bad arguments");
+	std::lock_guard<std::mutex> g(c->mu);
+	c->chunk_pairs = n_pairs;
+	return LC_OK;
+}
 int lc_timer_start(lc_ctx *c)
 {
 	if (!c) return fail(LC_EARG, "null ctx");
@@ -213,6 +256,127 @@ static int do_fetch(lc_ctx *c, lc_result_t **out)
 	return LC_OK;
 }
 
+// ---- the batched call: upload -> stages -> pack -> D2H into the pinned result arrays; large calls chunked over two lanes -----
+struct LcChunkShared {
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<int64_t> cum_reg;       // [n_chunks + 1] candidates before chunk k, valid once ready[k]
+	std::vector<int64_t> cum_cig;
+	std::vector<char> ready;
+	std::shared_mutex res_mu;           // shared: a D2H into the pinned arrays is in flight; exclusive: the arrays are being regrown
+	int rc = LC_OK;
+	std::string err;
+	float ms[10] = {0};
+	int64_t launches = 0;
+	LcCounters cnt;
+	void fail_with(int code, const std::string &e) { std::lock_guard<std::mutex> g(mu); if (rc == LC_OK) { rc = code; err = e; } }
+};
+
+static void add_counters(LcCounters &a, const LcCounters &b)
+{
+	a.occ_blocks += b.occ_blocks; a.extend_calls += b.extend_calls; a.sa_calls += b.sa_calls; a.lf_steps += b.lf_steps;
+	a.ext_calls += b.ext_calls; a.ext_cells += b.ext_cells; a.sw_calls += b.sw_calls; a.sw_cells += b.sw_cells;
+	a.glb_calls += b.glb_calls; a.glb_cells += b.glb_cells;
+}
+
+// chunks first, first + stride, ... of the call on one lane (its own stream, pools and host thread)
+static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> *pl, LcChunkShared *sh, int first, int stride, int n_chunks, int n_pairs,
+						const uint8_t *bases, const int64_t *off, int score_delta)
+{
+	cudaSetDevice(c->device);
+	for (int k = first; k < n_chunks; k += stride) {
+		const int p0 = (int)((int64_t)n_pairs * k / n_chunks), p1 = (int)((int64_t)n_pairs * (k + 1) / n_chunks);
+		int rc = LC_OK;
+		{ std::lock_guard<std::mutex> g(sh->mu); rc = sh->rc; }
+		if (!rc) rc = pl->upload(p1 - p0, bases, off + 2 * (size_t)p0, true);
+		if (!rc) rc = pl->run_stages(score_delta);
+		if (rc) sh->fail_with(rc, pl->err);
+		int64_t reg_base, cig_base;
+		{   // chunk k's place in the call's arrays = totals of the chunks before it (known when their CIGAR stage is done)
+			std::unique_lock<std::mutex> g(sh->mu);
+			sh->cv.wait(g, [&] { return sh->ready[k] != 0; });
+			reg_base = sh->cum_reg[k]; cig_base = sh->cum_cig[k];
+			sh->cum_reg[k + 1] = reg_base + (rc ? 0 : (int64_t)pl->n_cand);
+			sh->cum_cig[k + 1] = cig_base + (rc ? 0 : (int64_t)pl->n_cigar_words);
+			sh->ready[k + 1] = 1;
+			if (!rc && sh->cum_cig[k + 1] > 0xffffffffll) { rc = LC_ENOMEM; if (sh->rc == LC_OK) { sh->rc = rc; sh->err = "more than 2^32 CIGAR words in one call"; } }
+		}
+		sh->cv.notify_all();
+		if (rc) continue;
+		rc = pl->run_pack(reg_base, (uint32_t)cig_base);
+		if (rc) { sh->fail_with(rc, pl->err); continue; }
+		const size_t need_reg = (size_t)(reg_base + (int64_t)pl->n_cand), need_cig = (size_t)(cig_base + (int64_t)pl->n_cigar_words);
+		if (need_reg * sizeof(lc_alnreg_t) > c->h_regs.cap || need_reg * sizeof(lc_aln_t) > c->h_aln.cap || need_cig * 4 > c->h_cig.cap) {
+			// regrow (rare: capacities persist across calls): extrapolate from the chunks seen so far, wait out in-flight copies, keep what is there
+			std::unique_lock<std::shared_mutex> g(sh->res_mu);
+			const double f = 1.2 * n_chunks / (double)(k + 1);
+			const size_t want_reg = (size_t)(need_reg * f) + 1024, want_cig = (size_t)(need_cig * f) + 1024;
+			if (!c->h_regs.ensure(want_reg * sizeof(lc_alnreg_t), c->h_regs.cap) || !c->h_aln.ensure(want_reg * sizeof(lc_aln_t), c->h_aln.cap) ||
+				!c->h_cig.ensure(want_cig * 4, c->h_cig.cap)) { sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue; }
+		}
+		float ms[10]; LcCounters cn;
+		{
+			std::shared_lock<std::shared_mutex> g(sh->res_mu);
+			const size_t n_off = 2 * (size_t)(p1 - p0) + (k == n_chunks - 1 ? 1 : 0);
+			pl->fetch_into((int64_t *)c->h_off.p + 2 * (size_t)p0, n_off, (lc_alnreg_t *)c->h_regs.p + reg_base, (lc_aln_t *)c->h_aln.p + reg_base,
+						   (uint32_t *)c->h_cig.p + cig_base);
+			be->sync();
+		}
+		std::string e;
+		if (be->check(e)) { sh->fail_with(LC_ECUDA, e); continue; }
+		pl->fetch_done(ms, cn);
+		std::lock_guard<std::mutex> g(sh->mu);
+		for (int i = 0; i < 10; ++i) sh->ms[i] += ms[i];
+		sh->launches += pl->launches;
+		add_counters(sh->cnt, cn);
+	}
+}
+
+static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out)
+{
+	if (!c || n_pairs < 0 || !off || (n_pairs && !bases && off[2 * (size_t)n_pairs] > off[0])) return fail(LC_EARG, "bad arguments");
+	cudaSetDevice(c->device);
+	int n_chunks = 1;
+	if (c->chunk_pairs > 0 && (double)n_pairs > 1.5 * c->chunk_pairs) n_chunks = (n_pairs + c->chunk_pairs - 1) / c->chunk_pairs;
+	const int n_lanes = n_chunks > 1 ? 2 : 1;
+	if (n_lanes == 2 && !c->lane2) {
+		c->lane2.reset(new LcLane(c->device));
+		c->lane2->pl.set_index(c->ix, c->opt);
+		c->lane2->pl.lst_cap = c->pl.lst_cap; c->lane2->pl.pk_cap = c->pl.pk_cap; c->lane2->pl.force_wide = c->pl.force_wide;
+	}
+	if (c->lane2) c->lane2->pl.counting = c->pl.counting;
+	if (!c->h_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results");
+	LcChunkShared sh;
+	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.ready.assign(n_chunks + 1, 0); sh.ready[0] = 1;
+	memset(&sh.cnt, 0, sizeof(sh.cnt));
+	c->be.ev_record(12);
+	if (n_lanes == 1) lane_worker(c, &c->be, &c->pl, &sh, 0, 1, 1, n_pairs, bases, off, score_delta);
+	else {
+		std::thread t2(lane_worker, c, &c->lane2->be, &c->lane2->pl, &sh, 1, 2, n_chunks, n_pairs, bases, off, score_delta);
+		lane_worker(c, &c->be, &c->pl, &sh, 0, 2, n_chunks, n_pairs, bases, off, score_delta);
+		t2.join();
+	}
+	c->be.ev_record(13);
+	c->be.sync();
+	c->have_batch = n_lanes == 1;      // lc_batch_run / lc_batch_fetch continue from a single-lane call only
+	if (sh.rc) return fail(sh.rc, sh.err);
+	lc_result_t &r = c->res;
+	memset(&r, 0, sizeof(r));
+	r.n_reads = 2 * n_pairs; r.n_regs = sh.cum_reg[n_chunks]; r.n_cigar_words = sh.cum_cig[n_chunks];
+	r.reg_off = (const int64_t *)c->h_off.p; r.regs = (const lc_alnreg_t *)c->h_regs.p; r.aln = (const lc_aln_t *)c->h_aln.p; r.cigars = (const uint32_t *)c->h_cig.p;
+	if (r.reg_off[r.n_reads] != r.n_regs) return fail(LC_ECUDA, "result size mismatch");
+	// stage times: summed over the chunks (chunks of the two lanes overlap); ms_total: the whole call on the device clock, copies included when chunked
+	r.ms_h2d = sh.ms[0]; r.ms_seed = sh.ms[1]; r.ms_sa = sh.ms[2]; r.ms_chain = sh.ms[3]; r.ms_extend = sh.ms[4]; r.ms_dedup = sh.ms[5];
+	r.ms_pair = sh.ms[6]; r.ms_cigar = sh.ms[7]; r.ms_d2h = sh.ms[8]; r.ms_total = n_chunks > 1 ? c->be.ev_ms(12, 13) : sh.ms[9];
+	r.gpu_launches = sh.launches;
+	const LcCounters &k = sh.cnt;
+	r.cnt_occ_blocks = k.occ_blocks; r.cnt_extend_calls = k.extend_calls; r.cnt_sa_calls = k.sa_calls; r.cnt_lf_steps = k.lf_steps;
+	r.cnt_ext_calls = k.ext_calls; r.cnt_ext_cells = k.ext_cells; r.cnt_sw_calls = k.sw_calls; r.cnt_sw_cells = k.sw_cells;
+	r.cnt_glb_calls = k.glb_calls; r.cnt_glb_cells = k.glb_cells;
+	if (out) *out = &c->res;
+	return LC_OK;
+}
+
 int lc_batch_upload(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off)
 {
 	if (!c) return fail(LC_EARG, "null ctx");
@@ -237,10 +401,7 @@ int lc_align_packed(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 {
 	if (!c) return fail(LC_EARG, "null ctx");
 	std::lock_guard<std::mutex> g(c->mu);
-	int rc = do_upload(c, n_pairs, bases, off, true);
-	if (!rc) rc = do_run(c, score_delta);
-	if (!rc) rc = do_fetch(c, out);
-	return rc;
+	return do_align(c, n_pairs, bases, off, score_delta, out);
 }
 
 int lc_align_pairs(lc_ctx *c, int n_pairs, const uint8_t *const *seq1, const int32_t *len1, const uint8_t *const *seq2, const int32_t *len2,
@@ -259,10 +420,7 @@ int lc_align_pairs(lc_ctx *c, int n_pairs, const uint8_t *const *seq1, const int
 		if (len1[p]) memcpy(&c->stage[c->stage_off[2 * p]], seq1[p], len1[p]);
 		if (len2[p]) memcpy(&c->stage[c->stage_off[2 * p + 1]], seq2[p], len2[p]);
 	}
-	int rc = do_upload(c, n_pairs, c->stage.data(), c->stage_off.data(), true);
-	if (!rc) rc = do_run(c, score_delta);
-	if (!rc) rc = do_fetch(c, out);
-	return rc;
+	return do_align(c, n_pairs, c->stage.data(), c->stage_off.data(), score_delta, out);
 }
 
 int64_t lc_fetch_seq(const lc_ctx *c, int rid, int64_t start, int64_t end, uint8_t *out)

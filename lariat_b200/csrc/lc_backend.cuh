@@ -53,6 +53,7 @@ struct LcCudaBackend {
 	int k_cigar_band(const LcBatch &b, unsigned long long n_max);
 	void k_cigar_fallback(const LcBatch &b, unsigned long long n_max);
 	void k_pack(const LcBatch &b, const LcPackArgs &pa);
+	void k_rebase(int64_t *off, int n, int64_t off0);
 	void scan_exclusive(const int32_t *in, int64_t *out, int n);
 	void k_ksw_extend(const LcExtJobs &j);
 	void k_ksw_align(const LcSwJobs &j);

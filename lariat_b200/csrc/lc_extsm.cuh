@@ -36,7 +36,8 @@ LC_HD uint32_t lc_p2_minu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 LC_HD uint32_t lc_p2_max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 LC_HD uint32_t lc_p2_addmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }            // max(a + b, c)
 LC_HD uint32_t lc_p2_addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }  // max(a + b, c, 0)
-LC_HD uint32_t lc_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// PRMT through inline PTX: __byte_perm() masks selector bit 3 (the sign-replicate mode used for 16 -> 32 bit sign extension)
+__device__ __forceinline__ uint32_t lc_prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
 #else
 LC_HD int lc_p2_lo(uint32_t a) { return (int)(int16_t)(a & 0xffffu); }
 LC_HD int lc_p2_hi(uint32_t a) { return (int)(int16_t)(a >> 16); }

@@ -273,7 +273,12 @@ __global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, c
 __global__ void __launch_bounds__(256) pack_kernel(const LcBatch b, const LcPackArgs pa)
 {
 	const int stride = gridDim.x * blockDim.x;
-	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += stride) lc_stage_pack(b, pa, r);
+	for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= b.n_reads; r += stride) lc_stage_pack(b, pa, r);
+}
+__global__ void __launch_bounds__(256) rebase_kernel(int64_t *off, int n, int64_t off0)
+{
+	const int stride = gridDim.x * blockDim.x;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) off[i] -= off0;
 }
 
 // ---- microbenchmark kernels (BASELINE.json configs[4]) -------------------------------------------------------
@@ -470,7 +475,8 @@ void LcCudaBackend::k_cigar_fallback(const LcBatch &b, unsigned long long n_max)
 	// sized for a small list (the usual case); the warps pull candidates from a counter, so a long list only takes longer
 	k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, n_max < 65536 ? n_max : 65536, b.cig_n + LC_CIG_FALLBACK);
 }
-void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for(b.n_reads, 256, 8), 256, 0, stream>>>(b, pa); }
+void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for((unsigned long long)b.n_reads + 1, 256, 8), 256, 0, stream>>>(b, pa); }
+void LcCudaBackend::k_rebase(int64_t *off, int n, int64_t off0) { rebase_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(off, n, off0); }
 void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
 {
 	cub::TransformInputIterator<int64_t, LcCastI64, const int32_t *> it(in, LcCastI64());

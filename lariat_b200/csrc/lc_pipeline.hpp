@@ -151,13 +151,25 @@ LC_HD uint8_t lc_nt4(uint8_t c, bool is_ascii)
 struct LcPackArgs {            // stage 7: dense result arrays
 	const int64_t *out_off;    // [n_reads+1] exclusive scan of r_n_fin
 	lc_alnreg_t *out_reg; lc_aln_t *out_aln;
+	// a batch that is one chunk of a larger call (lc_api.cu): its candidates / CIGAR words start at these positions of the call's arrays
+	int64_t *off_final;        // [n_reads+1] out_off + reg_base
+	int64_t reg_base; uint32_t cig_base;
 };
 
+// r in [0, n_reads]: entry n_reads only carries the total
 LC_HD void lc_stage_pack(const LcBatch &b, const LcPackArgs &pa, int r)
 {
+	const int64_t dst = pa.out_off[r];
+	pa.off_final[r] = dst + pa.reg_base;
+	if (r >= b.n_reads) return;
 	const int n = b.r_n_fin[r];
-	const int64_t src = b.r_fin_off[r], dst = pa.out_off[r];
-	for (int i = 0; i < n; ++i) { pa.out_reg[dst + i] = b.fin[src + i]; pa.out_aln[dst + i] = b.aln[src + i]; }
+	const int64_t src = b.r_fin_off[r];
+	for (int i = 0; i < n; ++i) {
+		pa.out_reg[dst + i] = b.fin[src + i];
+		lc_aln_t a = b.aln[src + i];
+		a.cigar_off += pa.cig_base;
+		pa.out_aln[dst + i] = a;
+	}
 }
 
 struct LcHostResult {
@@ -218,14 +230,15 @@ public:
 	{
 		n_pairs = n_pairs_;
 		const int R = 2 * n_pairs;
-		const int64_t total = off[R];
+		const int64_t off0 = off[0], total = off[R] - off0;     // off0 != 0: the batch is a slice of a larger packed array
 		int lmax = 1;
 		for (int r = 0; r < R; ++r) lmax = std::max<int>(lmax, (int)(off[r + 1] - off[r]));
 		if (lmax > LC_MAX_READ_LEN) { err = "read longer than LC_MAX_READ_LEN"; return LC_EARG; }
 		be.ev_record(0);
 		if (!d_seq.ensure(be, (size_t)total + 16) || !d_off.ensure(be, sizeof(int64_t) * (R + 1))) return nomem();
-		if (total) be.h2d(d_seq.p, bases, (size_t)total);
+		if (total) be.h2d(d_seq.p, bases + off0, (size_t)total);
 		be.h2d(d_off.p, off, sizeof(int64_t) * (R + 1));
+		if (off0) be.k_rebase((int64_t *)d_off.p, R + 1, off0);
 		be.k_convert((uint8_t *)d_seq.p, (unsigned long long)total, is_ascii);   // ASCII -> 2-bit codes on the device (G/gobwa.go:159-167)
 		be.ev_record(1);
 		b.n_reads = R; b.seq = (const uint8_t *)d_seq.p; b.off = (const int64_t *)d_off.p; b.lmax = lmax;
@@ -355,6 +368,14 @@ public:
 
 	int run(int score_delta)
 	{
+		int rc = run_stages(score_delta);
+		if (!rc) rc = run_pack(0, 0);
+		return rc;
+	}
+
+	// stages 1-6; afterwards n_cand / n_cigar_words are known on the host
+	int run_stages(int score_delta)
+	{
 		const int R = b.n_reads;
 		b.score_delta = score_delta;
 		int rc0 = setup();
@@ -413,14 +434,40 @@ public:
 		}
 		be.ev_record(8);
 		n_cand = NC; n_cigar_words = h_ctl[8];
-		// ---- stage 7: pack into dense arrays
-		if (!d_outoff.ensure(be, 8 * ((size_t)R + 1)) || !d_outreg.ensure(be, sizeof(lc_alnreg_t) * (NC + 1)) ||
+		return LC_OK;
+	}
+
+	// ---- stage 7: pack into dense arrays (candidate indices offset by reg_base, CIGAR indices by cig_base)
+	int run_pack(int64_t reg_base, uint32_t cig_base)
+	{
+		const int R = b.n_reads;
+		const unsigned long long NC = n_cand;
+		if (!d_outoff.ensure(be, 8 * ((size_t)R + 1)) || !d_outoff2.ensure(be, 8 * ((size_t)R + 1)) || !d_outreg.ensure(be, sizeof(lc_alnreg_t) * (NC + 1)) ||
 			!d_outaln.ensure(be, sizeof(lc_aln_t) * (NC + 1))) return nomem();
 		be.scan_exclusive(b.r_n_fin, (int64_t *)d_outoff.p, R + 1); ++launches;   // r_n_fin[R] == 0, so out[R] = total
 		LcPackArgs pa; pa.out_off = (const int64_t *)d_outoff.p; pa.out_reg = (lc_alnreg_t *)d_outreg.p; pa.out_aln = (lc_aln_t *)d_outaln.p;
+		pa.off_final = (int64_t *)d_outoff2.p; pa.reg_base = reg_base; pa.cig_base = cig_base;
 		be.k_pack(b, pa); ++launches;
 		be.ev_record(9);
 		return LC_OK;
+	}
+
+	// D2H of the packed arrays into caller-provided host memory (pinned in lc_api.cu); n_off = how many offsets to copy
+	// (n_reads for an inner chunk, n_reads + 1 for the last).  Asynchronous: call fetch_done() after be.sync().
+	void fetch_into(int64_t *h_off, size_t n_off, lc_alnreg_t *h_regs, lc_aln_t *h_aln, uint32_t *h_cig)
+	{
+		be.d2h(h_off, d_outoff2.p, 8 * n_off);
+		if (n_cand) { be.d2h(h_regs, d_outreg.p, sizeof(lc_alnreg_t) * n_cand); be.d2h(h_aln, d_outaln.p, sizeof(lc_aln_t) * n_cand); }
+		if (n_cigar_words) be.d2h(h_cig, d_cigar.p, 4 * n_cigar_words);
+		if (counting) be.d2h(&h_counters, (uint8_t *)d_ctl.p + 32 * 8, sizeof(LcCounters));
+		be.ev_record(10);
+	}
+	void fetch_done(float ms[10], LcCounters &cnt)
+	{
+		ms[0] = be.ev_ms(0, 1); ms[1] = be.ev_ms(2, 3); ms[2] = be.ev_ms(3, 4); ms[3] = be.ev_ms(4, 5);
+		ms[4] = be.ev_ms(5, 6); ms[5] = 0; ms[6] = be.ev_ms(6, 7); ms[7] = be.ev_ms(7, 8);
+		ms[8] = be.ev_ms(9, 10); ms[9] = be.ev_ms(2, 9);
+		if (counting) cnt = h_counters; else memset(&cnt, 0, sizeof(cnt));
 	}
 
 	int fetch(LcHostResult &res)
@@ -428,7 +475,7 @@ public:
 		const int R = b.n_reads;
 		res.reg_off.resize(R + 1);
 		res.regs.resize(n_cand); res.aln.resize(n_cand); res.cigars.resize(n_cigar_words);
-		be.d2h(res.reg_off.data(), d_outoff.p, 8 * ((size_t)R + 1));
+		be.d2h(res.reg_off.data(), d_outoff2.p, 8 * ((size_t)R + 1));
 		if (n_cand) { be.d2h(res.regs.data(), d_outreg.p, sizeof(lc_alnreg_t) * n_cand); be.d2h(res.aln.data(), d_outaln.p, sizeof(lc_aln_t) * n_cand); }
 		if (n_cigar_words) be.d2h(res.cigars.data(), d_cigar.p, 4 * n_cigar_words);
 		be.ev_record(10);
@@ -446,7 +493,7 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs };
 		for (auto *x : all) x->release(be);
 	}
 
@@ -457,9 +504,10 @@ public:
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
+	LcCounters h_counters;
 	int nomem() { err = "device allocation failed"; return LC_ENOMEM; }
 	void read_ctl()
 	{

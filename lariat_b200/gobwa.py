@@ -78,7 +78,7 @@ class lc_alnreg_v(C.Structure):
 EXPORTS = ["lc_opt_init", "lc_init", "lc_destroy", "lc_last_error", "lc_contigs", "lc_align_pairs", "lc_align_packed",
            "lc_batch_upload", "lc_batch_run", "lc_batch_fetch", "lc_free_result", "lc_fetch_seq", "lc_mem_align1_core",
            "lc_mem_matesw", "lc_mem_reg2aln", "lc_ksw_extend_batch", "lc_ksw_align_batch", "lc_collect_intv_batch",
-           "lc_sa_batch", "lc_set_counting", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
+           "lc_sa_batch", "lc_set_counting", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
 
 _lib = None
 
@@ -115,6 +115,7 @@ def load_library(path: str = LIB_PATH):
     lib.lc_collect_intv_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int64, f32p]; lib.lc_collect_intv_batch.restype = C.c_int64
     lib.lc_sa_batch.argtypes = [vp, C.c_int64, vp, vp, f32p]
     lib.lc_set_counting.argtypes = [vp, C.c_int]; lib.lc_set_counting.restype = None
+    lib.lc_set_chunk_pairs.argtypes = [vp, C.c_int]; lib.lc_set_chunk_pairs.restype = C.c_int
     lib.lc_timer_start.argtypes = [vp]
     lib.lc_timer_stop.argtypes = [vp, f32p]
     _lib = lib

@@ -10,6 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 nproc >> gpurun_out/${TAG}_smi.txt
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest.log 2>&1
 tail -5 gpurun_out/${TAG}_pytest.log
+if ! grep -q " passed" gpurun_out/${TAG}_pytest.log || grep -q " failed" gpurun_out/${TAG}_pytest.log; then echo "parity tests not green: stopping"; exit 1; fi
 ( time timeout 900 python bench.py --scale $SCALE ) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -3 gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERN" -c 400 --csv \

@@ -89,14 +89,15 @@ struct HostBackend {
 	}
 	unsigned long long n_band[LC_CIG_NCLASS] = {0, 0, 0, 0};
 	void k_cigar_fallback(const LcBatch &b, unsigned long long) { k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, 0, b.cig_n + LC_CIG_FALLBACK); }
-	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r < b.n_reads; ++r) lc_stage_pack(b, pa, r); }
+	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r <= b.n_reads; ++r) lc_stage_pack(b, pa, r); }
+	void k_rebase(int64_t *off, int n, int64_t off0) { for (int i = 0; i < n; ++i) off[i] -= off0; }
 	void scan_exclusive(const int32_t *in, int64_t *out, int n) { int64_t s = 0; for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; } }
 };
 
 int main(int argc, char **argv)
 {
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
-	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, dense = 1, wide = 0;
+	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, dense = 1, wide = 0, chunk = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
 		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
@@ -109,6 +110,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
+		else if (!strcmp(argv[i], "-K") && i + 1 < argc) chunk = atoi(argv[++i]);       // run the batch as chunks of this many pairs (the way lc_align_packed splits large calls)
 		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
 	}
 	LcHostIndex hix; std::string err;
@@ -137,9 +139,29 @@ int main(int argc, char **argv)
 	pl.force_wide = wide != 0;
 	pl.set_index(ix, opt);
 	LcHostResult res;
-	int rc = pl.upload(n, bases.data(), off.data(), true);
-	if (!rc) rc = pl.run(delta);
-	if (!rc) rc = pl.fetch(res);
+	int rc = 0;
+	if (chunk > 0 && chunk < n) {
+		// chunked form: slices of the packed arrays, results appended at the running candidate / CIGAR-word totals
+		res.reg_off.assign(2 * (size_t)n + 1, 0);
+		int64_t reg_base = 0; uint32_t cig_base = 0;
+		std::vector<uint8_t> raw(bases);          // every chunk converts its own slice in place on its own copy
+		for (int p0 = 0; p0 < n && !rc; p0 += chunk) {
+			const int np = std::min(chunk, n - p0);
+			rc = pl.upload(np, raw.data(), off.data() + 2 * (size_t)p0, true);
+			if (!rc) rc = pl.run_stages(delta);
+			if (!rc) rc = pl.run_pack(reg_base, cig_base);
+			if (rc) break;
+			res.regs.resize((size_t)reg_base + pl.n_cand); res.aln.resize((size_t)reg_base + pl.n_cand); res.cigars.resize((size_t)cig_base + pl.n_cigar_words);
+			pl.fetch_into(res.reg_off.data() + 2 * (size_t)p0, 2 * (size_t)np + 1, res.regs.data() + reg_base, res.aln.data() + reg_base, res.cigars.data() + cig_base);
+			float ms[10]; LcCounters cn; pl.fetch_done(ms, cn);
+			res.launches += pl.launches;
+			reg_base += (int64_t)pl.n_cand; cig_base += (uint32_t)pl.n_cigar_words;
+		}
+	} else {
+		rc = pl.upload(n, bases.data(), off.data(), true);
+		if (!rc) rc = pl.run(delta);
+		if (!rc) rc = pl.fetch(res);
+	}
 	if (rc) { fprintf(stderr, "pipeline error %d: %s\n", rc, pl.err.c_str()); return 1; }
 	FILE *o = fopen(argv[3], "wb");
 	fwrite("LRO1", 1, 4, o); fwrite(&n, 4, 1, o);

@@ -56,6 +56,22 @@ def test_golden_tiny_fallback_paths(env, lib_path, monkeypatch):
     ref.close()
 
 
+@pytest.mark.parametrize("chunk", ["40", "97", "0"])
+def test_golden_tiny_chunked_two_lanes(chunk, lib_path, monkeypatch):
+    """Large calls are cut into chunks of pairs that alternate between two streams (H2D / D2H of one chunk under the kernels of
+    the other); the call's flat result arrays must be the same bytes.  LC_CHUNK_PAIRS=0 turns chunking off."""
+    monkeypatch.setenv("LC_CHUNK_PAIRS", chunk)
+    ref = gobwa.GoBwaLoadReference(os.path.join(GOLDEN, "tiny", "tiny.fa"))
+    assert ref is not None, gobwa.last_error()
+    bases, off = _load_pairs(os.path.join(GOLDEN, "tiny", "tiny.pairs"))
+    want = open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+    for _ in range(3):          # repeated calls reuse the pools and the pinned result arrays
+        br = ref.align_packed(bases, off, 25)
+        assert br.dump() == want
+    assert int(br.reg_off[-1]) == len(br.regs)
+    ref.close()
+
+
 def test_batch_split_invariance(tiny_ref):
     """Barcode groups are independent: aligning a sub-batch gives the same per-pair results as the big batch."""
     bases, off = _load_pairs(os.path.join(GOLDEN, "tiny", "tiny.pairs"))

@@ -33,3 +33,13 @@ def test_seeding_state_machine_fallbacks(hostsim_bin, tmp_path, extra):
     subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out)] + extra,
                           stderr=subprocess.DEVNULL)
     assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+
+
+@pytest.mark.parametrize("chunk", ["64", "101", "600"])
+def test_chunked_call_equals_one_batch(hostsim_bin, tmp_path, chunk):
+    """lc_align_packed cuts large calls into chunks of pairs (slices of the packed arrays; candidate and CIGAR indices offset by the
+    totals of the chunks before): the pipeline pieces it uses for that (rebased upload, run_stages, run_pack, fetch_into)."""
+    out = tmp_path / "sim.out"
+    subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out), "-K", chunk],
+                          stderr=subprocess.DEVNULL)
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
