@@ -20,6 +20,8 @@ struct LcCudaBackend {
 	cudaStream_t stream = 0;
 	cudaEvent_t ev[LC_N_EVENTS];
 	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
+	int seed_gate_mask = 0, seed_gate_n = 1, ext_gate_mask = 0, ext_gate_n = 1;
 
 	explicit LcCudaBackend(int device_);
 	~LcCudaBackend();

@@ -87,48 +87,56 @@ __device__ __forceinline__ void lc_warp_pack_read(const LcBatch &b, int rr, int 
 // ---- seeding ---------------------------------------------------------------------------------------------------
 // One lane per read, one bwt_extend per tick (lc_seed.cuh).  Reads are dealt through an atomic counter; a lane that needs a
 // new read gets it copied into its slot by the whole warp (word-wise, coalesced).
-template <typename U>
-__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b)
+// Housekeeping (resolve() and the read fetch) is divergent code that runs with a handful of live lanes; running it after every
+// tick — some lane of 32 nearly always wants it — made it a third of the kernel's instructions (profiles/r01m).  Lanes that
+// need it now wait (their tick() is a no-op on a stale interval) until `gate_n` lanes are waiting or the tick number is a
+// multiple of gate_mask + 1, and are then served together.
+template <typename U, bool COUNT>
+__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b, const unsigned gate_mask, const int gate_n)
 {
-	extern __shared__ uint4 lc_seed_smem[];
-	const int lane = threadIdx.x & 31, stride = lc_seed_lane_bytes(b.lmax, b.lst_cap);
-	uint8_t *slot0 = (uint8_t *)lc_seed_smem + (size_t)(threadIdx.x & ~31) * stride;      // slot of lane 0 of this warp
-	uint8_t *mine = slot0 + (size_t)lane * stride;
-	uint8_t *qbuf = mine + b.lst_cap * sizeof(LcPk);
+	extern __shared__ uint32_t lc_seed_smem[];
+	const int lane = threadIdx.x & 31;
+	uint32_t *wbase = lc_seed_smem + (size_t)(threadIdx.x >> 5) * lc_seed_warp_words(b.lmax, b.lst_cap);      // this warp's lists, then its reads
+	uint32_t *qbase = wbase + LC_SEED_ENT_WORDS * b.lst_cap * 32;
 	LcPk *memv = b.w_pk + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * b.pk_cap;
-	LcSeedLane<U> sd(b, (LcPk *)mine, b.lst_cap, memv, b.pk_cap);
-	for (;;) {
-		unsigned need = __ballot_sync(LC_FULL, sd.phase == LC_SP_FETCH);
-		while (need) {                                       // warp-uniform
-			int base = 0;
-			if (lane == 0) base = (int)atomicAdd(b.work_ctr + 3, (unsigned)__popc(need));
-			base = __shfl_sync(LC_FULL, base, 0);
-			int myr = -1;
-			if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
-			for (unsigned m = need; m; m &= m - 1) {
-				const int L = __ffs(m) - 1;
-				const int rr = __shfl_sync(LC_FULL, myr, L);
-				if (rr < 0) continue;
-				const int64_t o = b.off[rr];
-				const int len = (int)(b.off[rr + 1] - o);
-				if (len < b.opt.min_seed_len) continue;
-				lc_warp_pack_read(b, rr, lane, (uint32_t *)(slot0 + (size_t)L * stride + b.lst_cap * sizeof(LcPk)), 1);
-			}
-			__syncwarp();
-			if (need >> lane & 1) {
-				if (myr < 0) sd.phase = LC_SP_DONE;
-				else {
-					const int64_t o = b.off[myr];
-					const int len = (int)(b.off[myr + 1] - o);
-					if (len < b.opt.min_seed_len) { b.r_n_pk[myr] = 0; b.r_pk_off[myr] = 0; }      // B/bwamem.c:260; stays in FETCH
-					else { sd.begin_read(myr, len, qbuf); sd.resolve(); }
+	LcSeedLane<U, COUNT, 32> sd(b, wbase + lane, b.lst_cap, qbase + lane, memv, b.pk_cap);
+	for (unsigned it = 0;; ++it) {
+		const unsigned pend = __ballot_sync(LC_FULL, sd.phase < LC_SP_FWD);               // waiting for resolve() or for a read
+		if (pend && ((it & gate_mask) == 0 || __popc(pend) >= gate_n)) {                  // warp-uniform
+			if (__any_sync(LC_FULL, sd.phase < LC_SP_FWD && sd.phase != LC_SP_FETCH)) sd.resolve();
+			unsigned need = __ballot_sync(LC_FULL, sd.phase == LC_SP_FETCH);
+			while (need) {
+				int base = 0;
+				if (lane == 0) base = (int)atomicAdd(b.work_ctr + 3, (unsigned)__popc(need));
+				base = __shfl_sync(LC_FULL, base, 0);
+				int myr = -1;
+				if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
+				for (unsigned m = need; m; m &= m - 1) {
+					const int L = __ffs(m) - 1;
+					const int rr = __shfl_sync(LC_FULL, myr, L);
+					if (rr < 0) continue;
+					const int64_t o = b.off[rr];
+					const int len = (int)(b.off[rr + 1] - o);
+					if (len < b.opt.min_seed_len) continue;
+					lc_warp_pack_read(b, rr, lane, qbase + L, 32);
 				}
+				__syncwarp();
+				if (need >> lane & 1) {
+					if (myr < 0) sd.phase = LC_SP_DONE;
+					else {
+						const int64_t o = b.off[myr];
+						const int len = (int)(b.off[myr + 1] - o);
+						if (len < b.opt.min_seed_len) { b.r_n_pk[myr] = 0; b.r_pk_off[myr] = 0; }      // B/bwamem.c:260; stays in FETCH
+						else sd.begin_read(myr, len);
+					}
+				}
+				__syncwarp();
+				if (__any_sync(LC_FULL, sd.phase < LC_SP_FWD && sd.phase != LC_SP_FETCH)) sd.resolve();     // the new reads' first steps
+				need = __ballot_sync(LC_FULL, sd.phase == LC_SP_FETCH);
 			}
-			need = __ballot_sync(LC_FULL, sd.phase == LC_SP_FETCH);
 		}
 		if (!__ballot_sync(LC_FULL, sd.phase != LC_SP_DONE)) break;
 		sd.tick();
-		if (__any_sync(LC_FULL, sd.phase < LC_SP_FWD && sd.phase != LC_SP_FETCH)) sd.resolve();
 	}
 }
 
@@ -351,6 +359,9 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventCreate(&ev[i]);
 	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
+	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
+	env_int("LC_SEED_GATE_MASK", seed_gate_mask, 0, 255); env_int("LC_SEED_GATE_N", seed_gate_n, 1, 33);     // tuning knobs; mask must be 2^k - 1
+	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_GATE_N", ext_gate_n, 1, 33);
 }
 LcCudaBackend::~LcCudaBackend()
 {
@@ -385,15 +396,14 @@ void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
 static bool lc_wide(const LcBatch &b) { return b.ix.seq_len >= 0xffffffffull || b.force_wide; }
 int LcCudaBackend::seed_grid(const LcBatch &b)
 {
-	const int smem = LC_SEED_TPB * lc_seed_lane_bytes(b.lmax, b.lst_cap);
+	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
 	int per_sm = 1;
-	if (lc_wide(b)) {
-		cudaFuncSetAttribute(smem_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<uint64_t>, LC_SEED_TPB, smem);
-	} else {
-		cudaFuncSetAttribute(smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel<uint32_t>, LC_SEED_TPB, smem);
-	}
+	auto prep = [&](auto kern) {
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC_SEED_TPB, smem);
+	};
+	if (lc_wide(b)) { if (b.cnt) prep(smem_kernel<uint64_t, true>); else prep(smem_kernel<uint64_t, false>); }
+	else { if (b.cnt) prep(smem_kernel<uint32_t, true>); else prep(smem_kernel<uint32_t, false>); }
 	if (per_sm < 1) per_sm = 1;
 	const long long need = ((long long)b.n_reads + LC_SEED_TPB - 1) / LC_SEED_TPB;
 	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
@@ -401,9 +411,16 @@ int LcCudaBackend::seed_grid(const LcBatch &b)
 }
 void LcCudaBackend::k_seed(const LcBatch &b)
 {
-	const int smem = LC_SEED_TPB * lc_seed_lane_bytes(b.lmax, b.lst_cap), grid = seed_grid(b);
-	if (lc_wide(b)) smem_kernel<uint64_t><<<grid, LC_SEED_TPB, smem, stream>>>(b);
-	else smem_kernel<uint32_t><<<grid, LC_SEED_TPB, smem, stream>>>(b);
+	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4, grid = seed_grid(b);
+	const unsigned gm = (unsigned)seed_gate_mask;
+	const int gn = seed_gate_n;
+	if (lc_wide(b)) {
+		if (b.cnt) smem_kernel<uint64_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
+		else smem_kernel<uint64_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
+	} else {
+		if (b.cnt) smem_kernel<uint32_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
+		else smem_kernel<uint32_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
+	}
 }
 void LcCudaBackend::k_seed_finish(const LcBatch &b)
 {

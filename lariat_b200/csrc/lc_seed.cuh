@@ -58,14 +58,17 @@ template <> struct LcPkOps<uint64_t> {      // x < 2^34, positions < 4096
 	static LC_HD int e2(const LcPk &p) { return (int)(p.m >> 20); }
 };
 
-// ---- one 32-byte block of the device FM-index, fetched with a single 256-bit load on the device
+// ---- one 32-byte block of the device FM-index, fetched with a single 256-bit load on the device.
+// L1::no_allocate matters: the kernel's shared memory leaves almost no L1, and every in-flight miss of an allocating load holds an
+// L1 line — measured with scripts/microbench/randsector.cu (profiles/r01_randsector.txt): random 32-byte reads from a 100 MB table
+// run at 44 G sectors/s with plain ld.global.nc and at 137 G sectors/s with the no-allocate form (carve-out at 100 %).
 struct LcBlk { uint32_t cnt[4]; uint64_t hi, lo; };
 LC_HD LcBlk lc_ld_blk(const uint4 *p)
 {
 	LcBlk v;
 #ifdef __CUDA_ARCH__
 	uint64_t a, b;
-	asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(v.hi), "=l"(v.lo) : "l"(p));
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(v.hi), "=l"(v.lo) : "l"(p));
 	v.cnt[0] = (uint32_t)a; v.cnt[1] = (uint32_t)(a >> 32); v.cnt[2] = (uint32_t)b; v.cnt[3] = (uint32_t)(b >> 32);
 #else
 	v.cnt[0] = p[0].x; v.cnt[1] = p[0].y; v.cnt[2] = p[0].z; v.cnt[3] = p[0].w;
@@ -74,6 +77,7 @@ LC_HD LcBlk lc_ld_blk(const uint4 *p)
 	return v;
 }
 // a = occ(row, c), s = sum over bases above c of occ(row, b); `r` = symbols of the block that count, ch/cl = c's bit planes
+// (general form: 64-bit intervals with superblock bases)
 template <typename U> LC_HD void lc_blk_counts(const LcIndex &ix, const LcBlk &v, uint64_t blk, int r, int c, uint64_t ch, uint64_t cl, U &a, U &s)
 {
 	const uint64_t m = lc_keep_first(r);
@@ -87,23 +91,73 @@ template <typename U> LC_HD void lc_blk_counts(const LcIndex &ix, const LcBlk &v
 		s += (U)((c < 3 ? sb[3] : 0ull) + (c < 2 ? sb[2] : 0ull) + (c < 1 ? sb[1] : 0ull));
 	}
 }
-
-// per-lane shared-memory slot of the device kernel: interval list + the read (4 bits per base); the stride is 16 mod 128 bytes so that the
-// eight 16-byte accesses of a quarter warp to one list index fall into distinct banks
-LC_HD int lc_seed_qbytes(int lmax) { return ((lmax + 1) / 2 + 15) & ~15; }
-LC_HD int lc_seed_lane_bytes(int lmax, int lst_cap)
+// x >> s with PTX semantics: a shift of 32 or more gives 0
+LC_HD uint32_t lc_shr_clamp(uint32_t x, uint32_t s)
 {
-	int n = lst_cap * (int)sizeof(LcPk) + lc_seed_qbytes(lmax);
-	while ((n & 127) != 16) n += 16;
-	return n;
+#ifdef __CUDA_ARCH__
+	uint32_t r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s)); return r;
+#else
+	return s >= 32 ? 0u : x >> s;
+#endif
 }
-LC_HD int lc_seed_lst_cap(int lmax, int want) { return (lc_seed_lane_bytes(lmax, want) - lc_seed_qbytes(lmax)) / (int)sizeof(LcPk); }   // the padding holds entries too
+// among the first r symbols (1..64) of a block: e = how many equal c, g = how many are greater; chw/clw = c's two bits as word masks.
+// Written on 32-bit halves (the planes keep their first symbol in bit 63) with excluded-symbol masks: ten LOP3, four POPC.
+LC_HD void lc_blk_popc(const LcBlk &v, int r, uint32_t chw, uint32_t clw, uint32_t &e, uint32_t &g)
+{
+	const uint32_t xt = lc_shr_clamp(0xffffffffu, (uint32_t)r), xb = lc_shr_clamp(0xffffffffu, (uint32_t)(r > 32 ? r - 32 : 0));   // 1 = symbol does not count
+	const uint32_t Ht = (uint32_t)(v.hi >> 32), Hb = (uint32_t)v.hi, Lt = (uint32_t)(v.lo >> 32), Lb = (uint32_t)v.lo;
+	const uint32_t t1 = ~(Ht ^ chw) & ~xt, b1 = ~(Hb ^ chw) & ~xb;                  // high bit equal
+	const uint32_t eqt = t1 & ~(Lt ^ clw), eqb = b1 & ~(Lb ^ clw);
+	const uint32_t gtt = (Ht & ~chw & ~xt) | (t1 & Lt & ~clw), gtb = (Hb & ~chw & ~xb) | (b1 & Lb & ~clw);
+	e = (uint32_t)(lc_popc(eqt) + lc_popc(eqb));
+	g = (uint32_t)(lc_popc(gtt) + lc_popc(gtb));
+}
+// 32-bit intervals (one superblock): ak = occ(k, c), o2 = occ(l, c) - occ(k, c), sd = sum over bases above c of occ(l, b) - occ(k, b).
+// The block counts enter only as differences (except ak), so the base selection is done once on the difference vector.
+LC_HD void lc_blk_pair32(const LcBlk &vk, const LcBlk &vl, int rk, int rl, int c, uint32_t &ak, uint32_t &o2, uint32_t &sd)
+{
+	const bool c1 = (c & 1) != 0, c2 = (c & 2) != 0;
+	const uint32_t chw = c2 ? ~0u : 0u, clw = c1 ? ~0u : 0u;
+	uint32_t ek, gk, el, gl;
+	lc_blk_popc(vk, rk, chw, clw, ek, gk);
+	lc_blk_popc(vl, rl, chw, clw, el, gl);
+	const uint32_t d0 = vl.cnt[0] - vk.cnt[0], d1 = vl.cnt[1] - vk.cnt[1], d2 = vl.cnt[2] - vk.cnt[2], d3 = vl.cnt[3] - vk.cnt[3];
+	const uint32_t k01 = c1 ? vk.cnt[1] : vk.cnt[0], k23 = c1 ? vk.cnt[3] : vk.cnt[2];
+	const uint32_t d01 = c1 ? d1 : d0, d23 = c1 ? d3 : d2;
+	const uint32_t t23 = d2 + d3, s0 = c1 ? t23 : t23 + d1, s1 = c1 ? 0u : d3;
+	ak = (c2 ? k23 : k01) + ek;
+	o2 = (c2 ? d23 : d01) + (el - ek);
+	sd = (c2 ? s1 : s0) + (gl - gk);
+}
 
-template <typename U> struct LcSeedLane {
+// Shared memory of the device kernel, per warp: the 32 interval lists (three words per entry) and the 32 reads (4 bits per base), both
+// laid out [word][lane] — a lane only ever touches bank `lane`, whatever list index or read position it is at, so no access conflicts.
+// A list entry is {x0, x2, end-on-read}: the reverse-complement interval x1 is needed only while the match grows forward (it stays in
+// registers); the backward phase of bwt_smem1a and the emitted seeds use x0 and x2 alone (B/bwt.c:326-345, B/bwamem.c:277-283).
+#define LC_SEED_ENT_WORDS 3
+LC_HD int lc_seed_q_words(int lmax) { return (lmax + 7) / 8; }
+LC_HD int lc_seed_warp_words(int lmax, int lst_cap) { return (LC_SEED_ENT_WORDS * lst_cap + lc_seed_q_words(lmax)) * 32; }
+
+// list entry <-> three words
+template <typename U> struct LcEntOps;
+template <> struct LcEntOps<uint32_t> {
+	static LC_HD void pack(uint32_t x0, uint32_t x2, int e, uint32_t &w0, uint32_t &w1, uint32_t &w2) { w0 = x0; w1 = x2; w2 = (uint32_t)e; }
+	static LC_HD void unpack(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &x0, uint32_t &x2, int &e) { x0 = w0; x2 = w1; e = (int)w2; }
+};
+template <> struct LcEntOps<uint64_t> {      // x < 2^34
+	static LC_HD void pack(uint64_t x0, uint64_t x2, int e, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+	{ w0 = (uint32_t)x0; w1 = (uint32_t)x2; w2 = (uint32_t)(x0 >> 32) | (uint32_t)(x2 >> 32) << 2 | (uint32_t)e << 4; }
+	static LC_HD void unpack(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t &x0, uint64_t &x2, int &e)
+	{ x0 = (uint64_t)(w2 & 3) << 32 | w0; x2 = (uint64_t)((w2 >> 2) & 3) << 32 | w1; e = (int)(w2 >> 4); }
+};
+
+template <typename U, bool COUNT = true, int STRIDE = 1> struct LcSeedLane {      // COUNT = false: the work counters are compiled out; STRIDE: words between
+	                                                                                   // consecutive list/read words of this lane (32 on the device)
 	typedef LcPkOps<U> PK;
 	const LcBatch &b;
-	LcPk *lst; int C;        // interval list of the current bwt_smem1a call (shared memory on the device)
-	const uint8_t *q;        // the current read, two codes per byte, first code in the low nibble (shared memory on the device)
+	typedef LcEntOps<U> EN;
+	uint32_t *lst; int C;    // interval list of the current bwt_smem1a call: entry t = words lst[(3t + 0..2) * STRIDE] (shared memory on the device)
+	const uint32_t *qw;      // the current read: qw[w * STRIDE] holds bases 8w..8w+7, 4 bits each, first base in the low nibble
 	LcPk *memv; int M;       // seeds of the read so far, unsorted (global scratch of this lane)
 	// ---- state
 	int phase, r, len;
@@ -116,20 +170,31 @@ template <typename U> struct LcSeedLane {
 	int n_mem, old_n, k2, pass;
 	unsigned int cnt_ext, cnt_blk;   // algorithmic work of this read, flushed when the read completes
 
-	LC_HD LcSeedLane(const LcBatch &b_, LcPk *lst_, int C_, LcPk *memv_, int M_)
-		: b(b_), lst(lst_), C(C_), q(nullptr), memv(memv_), M(M_), phase(LC_SP_FETCH), r(0), len(0), src(1), oth(1), x2(0), c(0) {}
+	LC_HD LcSeedLane(const LcBatch &b_, uint32_t *lst_, int C_, const uint32_t *qw_, LcPk *memv_, int M_)
+		: b(b_), lst(lst_), C(C_), qw(qw_), memv(memv_), M(M_), phase(LC_SP_FETCH), r(0), len(0), src(1), oth(1), x2(0), c(0) {}
 
-	LC_HD int qat(int t) const { return (q[t >> 1] >> ((t & 1) << 2)) & 15; }
+	LC_HD int qat(int t) const { return (int)(qw[(t >> 3) * STRIDE] >> ((t & 7) << 2)) & 15; }
+	LC_HD void lst_put(int t, U x0_, U x2_, int e)
+	{
+		uint32_t w0, w1, w2;
+		EN::pack(x0_, x2_, e, w0, w1, w2);
+		uint32_t *p = lst + (size_t)(LC_SEED_ENT_WORDS * t) * STRIDE;
+		p[0] = w0; p[STRIDE] = w1; p[2 * STRIDE] = w2;
+	}
 	LC_HD void set_intv(int base) { src = (U)(b.ix.L2[3 - base] + 1); oth = (U)(b.ix.L2[base] + 1); x2 = (U)(b.ix.L2[base + 1] - b.ix.L2[base]); }   // bwt_set_intv, forward roles
 	LC_HD void push_fwd()            // forward phase: (x0, x1) = (oth, src)
 	{
 		if (n_fwd == C) { phase = LC_SP_OVERFLOW; return; }
-		lst[n_fwd++] = PK::pack(oth, src, x2, pend, 0);
+		lst_put(n_fwd++, oth, x2, pend);
 		ret = pend;
 	}
-	// backward phase: prev[j] and curr[j] of B/bwt.c:326-345 are both lst[n_fwd - 1 - j] (longest match first; curr is written
-	// behind the read position, so one array serves both); (x0, x1) = (src, oth)
-	LC_HD void load_entry(int jj) { const LcPk e = lst[n_fwd - 1 - jj]; src = PK::x0(e); oth = PK::x1(e); x2 = PK::x2(e); pend = PK::e1(e); }
+	// backward phase: prev[j] and curr[j] of B/bwt.c:326-345 are both entry n_fwd - 1 - j (longest match first; curr is written
+	// behind the read position, so one array serves both); src = x0, and x1 (`oth`) is dead from here on
+	LC_HD void load_entry(int jj)
+	{
+		const uint32_t *p = lst + (size_t)(LC_SEED_ENT_WORDS * (n_fwd - 1 - jj)) * STRIDE;
+		EN::unpack(p[0], p[STRIDE], p[2 * STRIDE], src, x2, pend);
+	}
 	LC_HD void emit(int start)       // a maximal match [start, pend) of the current call (B/bwt.c:334-338); backward roles
 	{
 		last_start = start;
@@ -145,18 +210,25 @@ template <typename U> struct LcSeedLane {
 		const LcIndex &ix = b.ix;
 		const U prim = (U)ix.primary;
 		U k = src - 1, l = k + x2;      // src >= 1 for every valid interval, so the row -1 of bwt_occ4 never occurs
-		const uint64_t ch = (c & 2) ? ~0ull : 0ull, cl = (c & 1) ? ~0ull : 0ull;
-		const bool adj = src <= prim && src + x2 - 1 >= prim;
-		k -= (k >= prim); l -= (l >= prim);
-		if (b.cnt && phase < LC_SP_DONE) { ++cnt_ext; cnt_blk += (k >> 7) != (l >> 7) ? 2u : 1u; }   // 64-byte blocks of the REFERENCE layout (bwt_2occ4, B/bwt.c:194)
+		const bool kp = k >= prim, lp = l >= prim, adj = lp && !kp;      // adj: the interval contains the row of '$' (B/bwt.c:270)
+		k -= (U)kp; l -= (U)lp;
+		if (COUNT && b.cnt && phase >= LC_SP_FWD && phase < LC_SP_DONE) { ++cnt_ext; cnt_blk += (k >> 7) != (l >> 7) ? 2u : 1u; }   // 64-byte blocks of the REFERENCE layout (bwt_2occ4, B/bwt.c:194)
 		const uint64_t bk = (uint64_t)(k >> 6), bl = (uint64_t)(l >> 6);
+		// both blocks are requested before either is used, so their latencies overlap (same block: the second request hits L1)
 		const LcBlk vk = lc_ld_blk(ix.occ + 2 * bk);
-		LcBlk vl = vk;
-		if (bl != bk) vl = lc_ld_blk(ix.occ + 2 * bl);
-		U ak, sk, al, sl;
-		lc_blk_counts<U>(ix, vk, bk, (int)(k & 63) + 1, c, ch, cl, ak, sk);
-		lc_blk_counts<U>(ix, vl, bl, (int)(l & 63) + 1, c, ch, cl, al, sl);
-		const U o2 = al - ak, sn = (U)(ix.L2[c] + 1) + ak, on = oth + (U)adj + (sl - sk);
+		const LcBlk vl = lc_ld_blk(ix.occ + 2 * bl);
+		U o2, sn, on;
+		if (sizeof(U) == 4) {
+			uint32_t ak, d, sd;
+			lc_blk_pair32(vk, vl, (int)(k & 63) + 1, (int)(l & 63) + 1, c, ak, d, sd);
+			o2 = (U)d; sn = (U)((uint32_t)ix.L2[c] + 1u + ak); on = oth + (U)adj + (U)sd;
+		} else {
+			const uint64_t ch = (c & 2) ? ~0ull : 0ull, cl = (c & 1) ? ~0ull : 0ull;
+			U ak, sk, al, sl;
+			lc_blk_counts<U>(ix, vk, bk, (int)(k & 63) + 1, c, ch, cl, ak, sk);
+			lc_blk_counts<U>(ix, vl, bl, (int)(l & 63) + 1, c, ch, cl, al, sl);
+			o2 = al - ak; sn = (U)(ix.L2[c] + 1) + ak; on = oth + (U)adj + (sl - sk);
+		}
 		// The bookkeeping is a flat sequence of short guarded sections with a warp-wide convergence point between them
 		// (LC_CONVERGE = __syncwarp on the device).  Without the barriers the compiler threads the jumps of the nested form and
 		// every sub-path of a diverged warp runs its own copy of the common tail (ncu: profiles/r01d, ~4 live lanes there).
@@ -167,7 +239,7 @@ template <typename U> struct LcSeedLane {
 			if (o2 < (U)min_intv) {
 				if (n_curr == 0 && i + 1 < last_start) emit(i + 1);
 			} else if (n_curr == 0 || o2 != last_x2) {
-				lst[n_fwd - 1 - n_curr] = PK::pack(sn, on, o2, pend, 0);
+				lst_put(n_fwd - 1 - n_curr, sn, o2, pend);
 				last_x2 = o2; ++n_curr;
 			}
 		}
@@ -212,9 +284,9 @@ template <typename U> struct LcSeedLane {
 	}
 
 	// ---- begin read r_ (its codes are at q_[0..len_), len_ >= min_seed_len)
-	LC_HD void begin_read(int r_, int len_, const uint8_t *q_)
+	LC_HD void begin_read(int r_, int len_)
 	{
-		r = r_; len = len_; q = q_;
+		r = r_; len = len_;
 		n_mem = 0; pass = 1; ret = 0; cnt_ext = cnt_blk = 0;
 		phase = LC_SP_P1_NEXT;
 	}
@@ -231,7 +303,7 @@ template <typename U> struct LcSeedLane {
 				break;
 			}
 			if (phase == LC_SP_FINISH) {                          // hand the unsorted seeds to lc_seed_finish
-				if (b.cnt) { lc_atomic_add(&b.cnt->extend_calls, (unsigned long long)cnt_ext); lc_atomic_add(&b.cnt->occ_blocks, (unsigned long long)cnt_blk); }
+				if (COUNT && b.cnt) { lc_atomic_add(&b.cnt->extend_calls, (unsigned long long)cnt_ext); lc_atomic_add(&b.cnt->occ_blocks, (unsigned long long)cnt_blk); }
 				unsigned long long po = n_mem ? lc_carve(b, b.pk_cur, b.pk_pool_cap, (unsigned long long)n_mem, LC_OVF_PK) : 0ull;
 				if (po == (unsigned long long)-1) { po = 0; n_mem = 0; }
 				for (int t = 0; t < n_mem; ++t) b.pk_pool[po + t] = memv[t];
@@ -314,23 +386,27 @@ template <typename U> struct LcSeedLane {
 	}
 };
 
-// scalar driver (tests/hostsim): all reads, one after another, through the same state machine
-template <typename U> static inline void lc_seed_run_scalar(const LcBatch &b, LcPk *lst, int C, uint8_t *qbuf, LcPk *memv, int M)
+// scalar driver (tests/hostsim): all reads, one after another, through the same state machine.  The device kernel does not run
+// resolve() after every tick (lc_kernels.cu: lanes wait, ticking on their stale interval, until the warp's next housekeeping
+// round); `idle_ticks` such ticks are inserted here before every resolve() so that the tests cover their harmlessness.
+template <typename U> static inline void lc_seed_run_scalar(const LcBatch &b, uint32_t *lst, int C, uint32_t *qbuf, LcPk *memv, int M, int idle_ticks = 0)
 {
-	LcSeedLane<U> sd(b, lst, C, memv, M);
+	LcSeedLane<U> sd(b, lst, C, qbuf, memv, M);
 	int next = 0;
 	for (;;) {
 		while (sd.phase == LC_SP_FETCH) {
 			if (next >= b.n_reads) { sd.phase = LC_SP_DONE; break; }
 			const int r = next++, len = (int)(b.off[r + 1] - b.off[r]);
 			if (len < b.opt.min_seed_len) { b.r_n_pk[r] = 0; b.r_pk_off[r] = 0; continue; }      // B/bwamem.c:260
-			for (int t = 0; t < (len + 1) / 2; ++t) qbuf[t] = 0;
-			for (int t = 0; t < len; ++t) qbuf[t >> 1] |= (uint8_t)((b.seq[b.off[r] + t] & 15) << ((t & 1) << 2));
-			sd.begin_read(r, len, qbuf);
+			for (int t = 0; t < (len + 7) / 8; ++t) qbuf[t] = 0;
+			for (int t = 0; t < len; ++t) qbuf[t >> 3] |= (uint32_t)(b.seq[b.off[r] + t] & 15) << ((t & 7) << 2);
+			sd.begin_read(r, len);
+			for (int t = 0; t < idle_ticks; ++t) sd.tick();
 			sd.resolve();
 		}
 		if (sd.phase == LC_SP_DONE) break;
 		sd.tick();
+		if (sd.phase < LC_SP_FWD) for (int t = 0; t < idle_ticks; ++t) sd.tick();
 		sd.resolve();
 	}
 }

@@ -35,11 +35,11 @@ struct HostBackend {
 	// the seeding state machine with a one-lane group (lc_seed.cuh), then the redo list through the one-thread-per-read body
 	void k_seed(const LcBatch &b)
 	{
-		std::vector<LcPk> lst((size_t)b.lst_cap + 1);
-		std::vector<uint8_t> q((size_t)b.lmax + 16);
-		if (b.force_wide || b.ix.seq_len >= 0xffffffffull) lc_seed_run_scalar<uint64_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap);
-		else lc_seed_run_scalar<uint32_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap);
+		std::vector<uint32_t> lst((size_t)LC_SEED_ENT_WORDS * b.lst_cap + 4), q((size_t)lc_seed_q_words(b.lmax) + 4);
+		if (b.force_wide || b.ix.seq_len >= 0xffffffffull) lc_seed_run_scalar<uint64_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap, idle_ticks);
+		else lc_seed_run_scalar<uint32_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap, idle_ticks);
 	}
+	int idle_ticks = 0;      // ticks a lane spends waiting for the warp's next housekeeping round (device kernels), simulated
 	void k_seed_finish(const LcBatch &b)
 	{
 		LcCoopScalar co;
@@ -107,6 +107,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-C") && i + 1 < argc) lst_cap = atoi(argv[++i]);     // shared-memory list capacity of the seeding state machine
 		else if (!strcmp(argv[i], "-M") && i + 1 < argc) pk_cap = atoi(argv[++i]);      // per-group seed list capacity
 		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
+		else if (!strcmp(argv[i], "-I") && i + 1 < argc) be.idle_ticks = atoi(argv[++i]);  // idle ticks before every housekeeping step of the state machines
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;

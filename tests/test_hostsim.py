@@ -25,7 +25,7 @@ def test_result_independent_of_worker_count_and_delta(hostsim_bin, tmp_path):
 import pytest
 
 
-@pytest.mark.parametrize("extra", [["-S"], ["-W"], ["-C", "6"], ["-C", "3", "-M", "4"], ["-S", "-C", "12", "-w", "5", "-W"]])
+@pytest.mark.parametrize("extra", [["-S"], ["-W"], ["-C", "6"], ["-C", "3", "-M", "4"], ["-S", "-C", "12", "-w", "5", "-W"], ["-I", "3"], ["-I", "2", "-W", "-C", "7"]])
 def test_seeding_state_machine_fallbacks(hostsim_bin, tmp_path, extra):
     """The seeding state machine (lc_seed.cuh) with tiny list capacities (most reads go to the redo body) and with the
     sampled suffix array instead of the dense one: results must not change."""
