@@ -21,7 +21,7 @@ struct LcCudaBackend {
 	cudaEvent_t ev[LC_N_EVENTS];
 	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
 	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
-	int seed_gate_mask = 0, seed_gate_n = 1, ext_gate_mask = 0, ext_gate_n = 1;
+	int seed_gate_mask = 3, seed_gate_n = 12, ext_gate_mask = 7, ext_row_mask = 1;
 
 	explicit LcCudaBackend(int device_);
 	~LcCudaBackend();

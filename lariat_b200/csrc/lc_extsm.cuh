@@ -88,6 +88,10 @@ template <int STRIDE> struct LcCells16 {
 		}
 	}
 	static LC_HD void put(uint32_t *he, int col, int h, int e) { he[col * STRIDE] = (uint32_t)h | (uint32_t)e << 16; }
+	static LC_HD void clear_left(uint32_t *he, int beg, const uint32_t *)      // columns [beg & ~7, beg) := {0, 0}
+	{
+		for (int c = beg & ~(LC_XT_CELLS - 1); c < beg; ++c) he[c * STRIDE] = 0u;
+	}
 };
 template <int STRIDE> struct LcCells8 {
 	static LC_HD int words(int cols) { return cols >> 1; }
@@ -112,6 +116,13 @@ template <int STRIDE> struct LcCells8 {
 		const int sh = (col & 1) << 4;
 		*p = (*p & ~(0xffffu << sh)) | ((uint32_t)h | (uint32_t)e << 8) << sh;
 	}
+	static LC_HD void clear_left(uint32_t *he, int beg, const uint32_t *mtab)      // columns [beg & ~7, beg) := {0, 0}: four masked words, no loop
+	{
+		const uint32_t *m = mtab + 4 * (beg & (LC_XT_CELLS - 1));                   // masks of the columns c < (beg & 7) of the group
+		uint32_t *p = he + ((beg & ~(LC_XT_CELLS - 1)) >> 1) * STRIDE;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) p[k * STRIDE] &= ~m[k];
+	}
 };
 
 // masks of the columns c < hi of a tick (hi = 0..8) as four column pairs; the device kernel keeps the table in shared memory
@@ -123,7 +134,7 @@ LC_HD void lc_ext_fill_masks(uint32_t *tab)      // 9 x 4 words
 
 enum { LC_XP_FETCH = 0, LC_XP_AFTER_LEFT, LC_XP_AFTER_RIGHT, LC_XP_RIGHT_CHECK, LC_XP_FINALIZE, LC_XP_READ_START, LC_XP_CHAIN_START, LC_XP_SEED_NEXT,
 	   LC_XP_LEFT_SETUP, LC_XP_RIGHT_SETUP, LC_XP_READ_DONE,
-	   LC_XP_DP, LC_XP_DONE };          // states >= LC_XP_DP: a DP row is in progress (or the lane is finished)
+	   LC_XP_DP, LC_XP_ROWEND, LC_XP_DONE };   // states >= LC_XP_DP: a DP row is in progress or waits for its end-of-row work (or the lane is finished)
 
 template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	const LcBatch &b;
@@ -208,7 +219,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 			// the band cuts live columns off on the left (B/ksw.c:421).  tick() relies on every column left of beg holding {0, 0}
 			// (true for columns dropped by the zero scan of B/ksw.c:466); clear the ones that share the first tick with beg
 			beg = i - w;
-			for (int c = beg & ~(LC_XT_CELLS - 1); c < beg; ++c) CELLS::put(he, c, 0, 0);
+			CELLS::clear_left(he, beg, mtab);
 		}
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
@@ -236,7 +247,9 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	// Columns left of beg hold {0, 0} (row_start) and stay {0, 0} under these recurrences, so they need no mask; columns at or right of
 	// end are never read by a later row before `put` rewrites them (each row reads at most one column past the previous end), so
 	// they are computed and stored as garbage, and only kept out of the row maximum and the non-zero scan (mask table mtab).
-	LC_HD void tick()
+	// `row_gate`: the end-of-row work runs only on ticks where the whole warp does it (lc_kernels.cu); a lane whose row completed on
+	// another tick waits in LC_XP_ROWEND (its DP part idles) until then.
+	LC_HD void tick(bool row_gate = true)
 	{
 		const LcScore &sc = b.sc;
 		const int e_del = sc.e_del, e_ins = sc.e_ins;
@@ -313,7 +326,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				const uint32_t kk = lc_p2_max(lc_p2_max3(k0, k1, k2), k3);
 				const int klo = (int)lc_prmt(kk, 0u, 0x9910u), khi = (int)kk >> 16;
 				const int tk = klo > khi ? klo : khi;                      // -1 when no column of the tick is live
-				const int tk32 = (tk & ~7) * 128 + (tk & 7) + col0;        // h << 10 | column; negative for tk == -1 (columns stay below 1017)
+				const int tk32 = run ? (tk & ~7) * 128 + (tk & 7) + col0 : -1;   // h << 10 | column; negative for tk == -1 (columns stay below 1017)
 				rowkey = rowkey > tk32 ? rowkey : tk32;
 			}
 			// first / last live column of the row whose stored {h, e} is non-zero
@@ -322,7 +335,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				const uint32_t b0 = lc_p2_minu((hs[0] | e2[0]) & m0, one), b1 = lc_p2_minu((hs[1] | e2[1]) & m1, one),
 					b2 = lc_p2_minu((hs[2] | e2[2]) & m2, one), b3 = lc_p2_minu((hs[3] | e2[3]) & m3, one);
 				const uint32_t acc = b0 + b1 * 4u + b2 * 16u + b3 * 64u;
-				const uint32_t b8 = (acc | acc >> 15) & 0xffu;               // bit c = column col0 + c
+				const uint32_t b8 = run ? (acc | acc >> 15) & 0xffu : 0u;    // bit c = column col0 + c
 				if (b8) {
 					const int first = col0 + lc_ctz(b8), last = col0 + 31 - lc_clz(b8);
 					nz_first = nz_first < first ? nz_first : first;
@@ -330,19 +343,24 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				}
 			}
 			f = (int)G[3] >> 16;
-			hleft = (int)(h[3] >> 16);
-			j = col0 + LC_XT_CELLS;
+			if (run) {
+				j = col0 + LC_XT_CELLS;
+				hleft = (int)(h[3] >> 16);
+				if (j >= end) {                                    // the row is complete: keep h of its last live column (this tick's column end - 1 - col0)
+					if (end > beg) {
+						const int idx = end - 1 - col0;
+						const uint32_t pr = idx < 4 ? (idx < 2 ? h[0] : h[1]) : (idx < 6 ? h[2] : h[3]);
+						hleft = (int)((idx & 1) ? pr >> 16 : pr & 0xffffu);
+					} else hleft = hleft0;
+					phase = LC_XP_ROWEND;
+				}
+			}
 		}
 		LC_CONVERGE();
-		if (run && j >= end) {                                 // the row is complete
+		if (row_gate && phase == LC_XP_ROWEND) {               // end-of-row work (B/ksw.c:457-478)
 			bool stop = false;
 			const int jfin = beg < end ? end : beg;            // the reference's loop variable after the column loop
 			if (b.cnt) cells += (unsigned long long)(end > beg ? end - beg : 0);
-			if (end > beg) {                                   // h of the row's last live column (this tick's column end - 1 - col0)
-				const int idx = end - 1 - (j - LC_XT_CELLS);
-				const uint32_t pr = idx < 4 ? (idx < 2 ? h[0] : h[1]) : (idx < 6 ? h[2] : h[3]);
-				hleft = (int)((idx & 1) ? pr >> 16 : pr & 0xffffu);
-			} else hleft = hleft0;
 			const int rowmax = rowkey < 0 ? 0 : rowkey >> 10, rowarg = rowkey < 0 ? -1 : (rowkey & 1023);
 			CELLS::put(he, end, hleft, 0);
 			if (jfin == qlen) {
@@ -369,7 +387,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				if (++i >= tlen) stop = true;
 			}
 			if (stop) dp_finish();
-			else { fpos += fdir; row_start(); }
+			else { fpos += fdir; row_start(); phase = LC_XP_DP; }
 		}
 		LC_CONVERGE();
 	}
@@ -531,7 +549,7 @@ template <int STRIDE> LC_HD void lc_ext_load_read(const LcBatch &b, int r, uint3
 }
 
 // scalar driver (tests/hostsim): all reads, one after another, through the same state machine; cells8 selects the byte packing
-template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, uint32_t *he, uint32_t *qw)
+template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, uint32_t *he, uint32_t *qw, int idle_ticks = 0)
 {
 	uint32_t mtab[36];
 	lc_ext_fill_masks(mtab);
@@ -546,12 +564,17 @@ template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, 
 			ex.resolve();
 		}
 		if (ex.phase == LC_XP_DONE) break;
-		ex.tick();
+		if (idle_ticks == 0) ex.tick();
+		else {                                  // the device kernel's gates: end-of-row work and resolve() wait for the warp's next round
+			ex.tick(false);
+			if (ex.phase == LC_XP_ROWEND) { for (int t = 0; t < idle_ticks; ++t) ex.tick(false); ex.tick(true); }
+			if (ex.phase < LC_XP_DP) for (int t = 0; t < idle_ticks; ++t) ex.tick(false);
+		}
 		ex.resolve();
 	}
 }
 LC_HD bool lc_ext_cells8_ok(const LcBatch &b) { return b.lmax * b.opt.a <= 255 && b.opt.a > 0; }
-static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *qw, bool cells8)
+static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *qw, bool cells8, int idle_ticks = 0)
 {
-	if (cells8) lc_ext_run_scalar_t<LcCells8<1> >(b, he, qw); else lc_ext_run_scalar_t<LcCells16<1> >(b, he, qw);
+	if (cells8) lc_ext_run_scalar_t<LcCells8<1> >(b, he, qw, idle_ticks); else lc_ext_run_scalar_t<LcCells16<1> >(b, he, qw, idle_ticks);
 }

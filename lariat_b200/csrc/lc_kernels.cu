@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 // the 32 H/E rows ([column][lane], packed by CELLS) and the 32 reads (4 bits per base, [word][lane], one spare word in front).
 template <class CELLS> __host__ __device__ inline int lc_ext_warp_words(int lmax) { return (CELLS::words(lc_ext_he_cols(lmax)) + lc_ext_q_words(lmax)) * 32; }
 #define LC_EXT_MTAB_WORDS 64      // lc_ext_fill_masks table (36 words) in front of the per-warp areas
+// Gates (as in smem_kernel): the read fetch and resolve() run on ticks that are multiples of hk_mask + 1, the end-of-row work on
+// multiples of row_mask + 1; lanes that need either idle until then, so that the divergent code runs with several live lanes.
 template <class CELLS>
-__global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b)
+__global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, const unsigned hk_mask, const unsigned row_mask)
 {
 	extern __shared__ uint32_t lc_ext_smem[];
 	const int lane = threadIdx.x & 31;
@@ -192,25 +194,27 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b)
 	if (threadIdx.x == 0) lc_ext_fill_masks(lc_ext_smem);
 	__syncthreads();
 	LcExtLane<32, CELLS> ex(b, wbase + lane, qf + lane, lc_ext_smem);
-	for (;;) {
-		const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
-		if (need) {                                          // warp-uniform
-			int base = 0;
-			if (lane == 0) base = (int)atomicAdd(b.work_ctr + 0, (unsigned)__popc(need));
-			base = __shfl_sync(LC_FULL, base, 0);
-			int myr = -1;
-			if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
-			for (unsigned m = need; m; m &= m - 1) {
-				const int L = __ffs(m) - 1;
-				const int rr = __shfl_sync(LC_FULL, myr, L);
-				if (rr >= 0 && b.r_n_chain[rr] > 0) lc_warp_pack_read(b, rr, lane, qf + L, 32);
+	for (unsigned it = 0;; ++it) {
+		if ((it & hk_mask) == 0) {                               // warp-uniform
+			const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
+			if (need) {
+				int base = 0;
+				if (lane == 0) base = (int)atomicAdd(b.work_ctr + 0, (unsigned)__popc(need));
+				base = __shfl_sync(LC_FULL, base, 0);
+				int myr = -1;
+				if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
+				for (unsigned m = need; m; m &= m - 1) {
+					const int L = __ffs(m) - 1;
+					const int rr = __shfl_sync(LC_FULL, myr, L);
+					if (rr >= 0 && b.r_n_chain[rr] > 0) lc_warp_pack_read(b, rr, lane, qf + L, 32);
+				}
+				__syncwarp();
+				if (need >> lane & 1) { if (myr < 0) ex.phase = LC_XP_DONE; else ex.begin_read(myr); }
 			}
-			__syncwarp();
-			if (need >> lane & 1) { if (myr < 0) ex.phase = LC_XP_DONE; else ex.begin_read(myr); }
+			if (!__ballot_sync(LC_FULL, ex.phase != LC_XP_DONE)) break;
+			if (__any_sync(LC_FULL, ex.phase < LC_XP_DP && ex.phase != LC_XP_FETCH)) ex.resolve();
 		}
-		if (!__ballot_sync(LC_FULL, ex.phase != LC_XP_DONE)) break;
-		if (__any_sync(LC_FULL, ex.phase < LC_XP_DP && ex.phase != LC_XP_FETCH)) ex.resolve();
-		ex.tick();
+		ex.tick((it & row_mask) == 0);
 	}
 }
 
@@ -361,7 +365,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
 	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
 	env_int("LC_SEED_GATE_MASK", seed_gate_mask, 0, 255); env_int("LC_SEED_GATE_N", seed_gate_n, 1, 33);     // tuning knobs; mask must be 2^k - 1
-	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_GATE_N", ext_gate_n, 1, 33);
+	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_ROW_MASK", ext_row_mask, 0, 255);
 }
 LcCudaBackend::~LcCudaBackend()
 {
@@ -443,7 +447,7 @@ void LcCudaBackend::k_sa_fill(const LcIndex &ix, unsigned long long n_samples, v
 }
 void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
-template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream)
+template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
 {
 	const int smem = ((LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) + LC_EXT_MTAB_WORDS) * 4;
 	int per_sm = 1;
@@ -451,13 +455,13 @@ template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, 
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<CELLS>, LC_EXT_TPB, smem);
 	if (per_sm < 1) per_sm = 1;
 	const long long need = ((long long)b.n_reads + LC_EXT_TPB - 1) / LC_EXT_TPB, cap = (long long)n_sm * per_sm;
-	extend_kernel<CELLS><<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b);
+	extend_kernel<CELLS><<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b, hk_mask, row_mask);
 }
 void LcCudaBackend::k_extend(const LcBatch &b)
 {
 	// byte-packed H/E cells whenever no score of the batch can exceed 255 (half the shared memory per warp, twice the resident warps)
-	if (lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS")) lc_launch_extend<LcCells8<32> >(b, n_sm, stream);
-	else lc_launch_extend<LcCells16<32> >(b, n_sm, stream);
+	if (lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS")) lc_launch_extend<LcCells8<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
+	else lc_launch_extend<LcCells16<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
 }
 void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {

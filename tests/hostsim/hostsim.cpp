@@ -56,7 +56,7 @@ struct HostBackend {
 	{
 		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); return; }
 		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax));
-		lc_ext_run_scalar(b, he.data(), qw.data(), lc_ext_cells8_ok(b) && !wide_cells);
+		lc_ext_run_scalar(b, he.data(), qw.data(), lc_ext_cells8_ok(b) && !wide_cells, idle_ticks);
 	}
 	bool wide_cells = false;     // -H: 16-bit H/E cells even when the batch would fit the byte packing
 	void k_pair(const LcBatch &b, int n_pairs)
