@@ -24,6 +24,7 @@ __device__ __forceinline__ int lc_warp_prefix_max_incl(int v, int lane)
 	}
 	return v;
 }
+__device__ __forceinline__ uint32_t lc_prmt_dev(uint32_t a, uint32_t b, uint32_t sel) { uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
 __device__ __forceinline__ int lc_warp_max(int v)
 {
 #pragma unroll
@@ -129,8 +130,8 @@ __device__ __noinline__ LcExtResult lc_extend2_warp(int qlen, QF query, int tlen
 // One pass of the local SW with the reference's striped-SSE2 semantics (ksw_u8 / ksw_i16, B/ksw.c:111-334), one warp.
 // Same contract as lc_sw_pass (lc_sw.cuh).  H, E, Hmax: shared memory rows of P ints; qs: P bytes; bl: global scratch list.
 template <class QF, class TF>
-__device__ __noinline__ LcSwResult lc_sw_pass_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int size, int xtra,
-												   int *H, int *E, int *Hmax, uint8_t *qs, unsigned long long *bl, int lane, LcCounters *cnt)
+__device__ __noinline__ LcSwResult lc_sw_pass_warp_smem(int qlen, QF query, int tlen, TF target, const LcScore &sc, int size, int xtra,
+														int *H, int *E, int *Hmax, uint8_t *qs, unsigned long long *bl, int lane, LcCounters *cnt)
 {
 	const int lanes = size == 1 ? 16 : 8, P = (qlen + lanes - 1) / lanes * lanes;
 	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
@@ -201,6 +202,122 @@ __device__ __noinline__ LcSwResult lc_sw_pass_warp(int qlen, QF query, int tlen,
 	}
 	__syncwarp();
 	return r;
+}
+
+// The same pass with the H/E row in REGISTERS: lane L owns the K consecutive columns L*K .. L*K+K-1 (K * 32 >= P, so reads up to 255
+// bases), a row is one sweep — no shared-memory traffic, one shuffle for the diagonal, one 5-step warp scan for F across lanes and one
+// warp reduction for the row maximum, instead of all of that per 32-column chunk.  F inside a lane's block is the scalar recurrence
+// F(j+1) = max(F(j) - e_ins, T(j)); the value entering the block comes from the scan over the blocks' outgoing values.  The row that
+// last raised the maximum is not copied (Hmax): its smallest maximal column is tracked with the row maximum as one key.
+// Cell arithmetic uses the DPX three-input forms (VIADDMNMX[.RELU]); substitution scores come from one PRMT on a per-column byte table.
+// Target bases are fetched 32 rows at a time (one per lane) and handed out by shuffle, so no load sits on the row-to-row chain.
+template <int K, class QF, class TF>
+__device__ __noinline__ LcSwResult lc_sw_pass_warp_reg(int qlen, QF query, int tlen, TF target, const LcScore &sc, int size, int xtra,
+													   unsigned long long *bl, int lane, LcCounters *cnt)
+{
+	const int lanes = size == 1 ? 16 : 8, P = (qlen + lanes - 1) / lanes * lanes;
+	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
+	const int shift = size == 1 ? max(sc.b, 1) : 0;
+	const int minsc = (xtra & LC_XSUBO) ? (xtra & 0xffff) : 0x10000, endsc = (xtra & LC_XSTOP) ? (xtra & 0xffff) : 0x10000;
+	LcSwResult r = { 0, -1, -1, -1, -1, -1, -1 };
+	int gmax = 0, te = -1, qe_key = -1, n_b = 0, last_i = -2, last_max = 0, rows = 0;
+	const int j0 = lane * K;
+	int h[K], e[K];
+	uint32_t stab[K];            // byte t = score of target base t against this column's query base (t = 0..3); padding columns score 0
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		h[k] = 0; e[k] = 0;
+		const int j = j0 + k;
+		uint32_t w = 0;
+		if (j < qlen) {
+			const int q = query(j);
+#pragma unroll
+			for (int t = 0; t < 4; ++t) w |= ((uint32_t)sc.sub(t, q) & 0xffu) << (8 * t);
+		}
+		stab[k] = w;
+	}
+	for (int i0 = 0; i0 < tlen; i0 += 32) {
+		const int tmine = i0 + lane < tlen ? target(i0 + lane) : 4;
+		const int nrow = min(32, tlen - i0);
+		bool stop = false;
+		for (int ii = 0; ii < nrow; ++ii) {
+			const int i = i0 + ii;
+			const int tb = __shfl_sync(LC_FULL, tmine, ii);
+			++rows;
+			// PRMT selector: byte tb of the column's table, sign-extended; an ambiguous target base selects byte 4 = the low byte of the
+			// second operand (-1 on real columns, 0 on padding columns)
+			const uint32_t tsel = (uint32_t)(tb > 3 ? 4 : tb), sel = tsel | (tsel | 8u) << 4 | (tsel | 8u) << 8 | (tsel | 8u) << 12;
+			int dprev = __shfl_up_sync(LC_FULL, h[K - 1], 1);          // H(i-1, j0-1)
+			if (lane == 0) dprev = 0;
+			int hnf[K], t[K];
+			int g = 0;
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				const int diag = k == 0 ? dprev : h[k - 1];
+				const int s = (int)lc_prmt_dev(stab[k], (j0 + k < qlen) ? 0xffu : 0u, sel);
+				hnf[k] = __viaddmax_s32_relu(diag, s, e[k]);                 // max(diag + s, e, 0)
+				t[k] = __viaddmax_s32(hnf[k], -oe_ins, 0);
+				g = k == 0 ? t[0] : __viaddmax_s32(g, -e_ins, t[k]);          // F leaving column k if nothing entered the block
+			}
+			// F entering each lane's block: exclusive prefix maximum over the blocks' outgoing values, position-normalised
+			const int pin = lc_warp_prefix_max_incl(g + (j0 + K - 1) * e_ins, lane);
+			const int pex = __shfl_up_sync(LC_FULL, pin, 1);
+			int f = lane > 0 ? max(pex - (j0 - 1) * e_ins, 0) : 0;
+			int key = -1;
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				const int hk = max(hnf[k], f);
+				f = __viaddmax_s32(f, -e_ins, t[k]);
+				h[k] = hk;
+				e[k] = __viaddmax_s32_relu(hk, -oe_del, e[k] - e_del);        // max(h - oe_del, e - e_del, 0)
+				if (j0 + k < P) key = max(key, (hk << 10) | (1023 - (j0 + k)));
+			}
+			key = lc_warp_max(key);
+			const int imax = key < 0 ? 0 : key >> 10;
+			if (imax >= minsc) {                         // run-length list of rows scoring >= minsc (B/ksw.c:192-200)
+				if (n_b == 0 || last_i + 1 != i) {
+					if (lane == 0) bl[n_b] = (unsigned long long)imax << 32 | (unsigned)i;
+					++n_b; last_i = i; last_max = imax;
+				} else if (last_max < imax) {
+					if (lane == 0) bl[n_b - 1] = (unsigned long long)imax << 32 | (unsigned)i;
+					last_i = i; last_max = imax;
+				}
+			}
+			if (imax > gmax) {
+				gmax = imax; te = i; qe_key = key;
+				if ((size == 1 && gmax + shift >= 255) || gmax >= endsc) { stop = true; break; }
+			}
+		}
+		if (stop) break;
+	}
+	__syncwarp();
+	if (cnt && lane == 0) { atomicAdd(&cnt->sw_calls, 1ull); atomicAdd(&cnt->sw_cells, (unsigned long long)rows * qlen); }
+	r.score = (size == 1 && gmax + shift >= 255) ? 255 : gmax;
+	r.te = te;
+	if (!(size == 1 && r.score == 255)) {
+		if (qe_key >= 0) r.qe = 1023 - (qe_key & 1023);      // smallest column holding the maximum of the row that set it (B/ksw.c:211-216)
+		if (n_b) {
+			const int rad = (r.score + sc.a - 1) / sc.a, low = te - rad, high = te + rad;
+			for (int i = 0; i < n_b; ++i) {
+				const unsigned long long v = bl[i];
+				const int ee = (int)(unsigned)v;
+				if ((ee < low || ee > high) && (int)(v >> 32) > r.score2) { r.score2 = (int)(v >> 32); r.te2 = ee; }
+			}
+		}
+	}
+	__syncwarp();
+	return r;
+}
+
+template <class QF, class TF>
+__device__ __forceinline__ LcSwResult lc_sw_pass_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int size, int xtra,
+													  int *H, int *E, int *Hmax, uint8_t *qs, unsigned long long *bl, int lane, LcCounters *cnt)
+{
+	const int lanes = size == 1 ? 16 : 8, P = (qlen + lanes - 1) / lanes * lanes;
+	if (P <= 128) return lc_sw_pass_warp_reg<4>(qlen, query, tlen, target, sc, size, xtra, bl, lane, cnt);
+	if (P <= 160) return lc_sw_pass_warp_reg<5>(qlen, query, tlen, target, sc, size, xtra, bl, lane, cnt);
+	if (P <= 256) return lc_sw_pass_warp_reg<8>(qlen, query, tlen, target, sc, size, xtra, bl, lane, cnt);
+	return lc_sw_pass_warp_smem(qlen, query, tlen, target, sc, size, xtra, H, E, Hmax, qs, bl, lane, cnt);
 }
 
 // ksw_align2 as mem_matesw calls it (B/ksw.c:343-365), one warp
