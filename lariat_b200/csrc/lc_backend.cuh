@@ -19,9 +19,11 @@ struct LcCudaBackend {
 	int device, n_sm = 0, workers = 0;
 	cudaStream_t stream = 0;
 	cudaEvent_t ev[LC_N_EVENTS];
+	cudaStream_t aux[4] = { 0, 0, 0, 0 };      // side streams: the four band classes of the CIGAR stage run concurrently (fork/join on events)
+	cudaEvent_t ev_fork = 0, ev_join[4] = { 0, 0, 0, 0 };
 	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
 	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
-	int seed_gate_mask = 3, seed_gate_n = 12, ext_gate_mask = 7, ext_row_mask = 1;
+	int seed_gate_mask = 3, seed_gate_n = 12, ext_gate_mask = 15, ext_row_mask = 1;
 
 	explicit LcCudaBackend(int device_);
 	~LcCudaBackend();

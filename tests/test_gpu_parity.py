@@ -144,19 +144,40 @@ def _fresh_dataset(tmp_path, name, gspec, rspec):
     return fa, pairs
 
 
-@pytest.mark.parametrize("kind", ["c1like", "repeat"])
-def test_fresh_synthetic_vs_oracle(kind, lib_path, oracle_port, tmp_path):
-    """Seeded synthetic data of the BASELINE configs' shape at oracle-in-seconds size, compared with the oracle replay."""
+def _oracle_replay(oracle_port):
+    """The compiled reference's replay when it travelled to this box, else the plain-C port (both are the checker, never the product)."""
+    ref = os.path.join(oracle_port, "_ref", "replay_ref")
+    return ref if os.path.exists(ref) else os.path.join(oracle_port, "replay_port")
+
+
+@pytest.mark.parametrize("kind", ["c1like", "repeat", "c2like", "c3like", "c4like"])
+def test_fresh_synthetic_vs_oracle(kind, lib_path, oracle_port, tmp_path, monkeypatch):
+    """Seeded synthetic data of every BASELINE config's shape (c1 uniform, c2 segmental duplications, c3 repeat families + tandem arrays
+    on 24 contigs with 64-bit interval arithmetic forced as for the 3.1 Gb index, c4 long molecules / degraded mates / repeat-biased
+    sampling) at sizes the oracle finishes in seconds, compared byte for byte with the oracle replay."""
     if kind == "c1like":
         g = synth.GenomeSpec(2_000_000, 4, 12345, name="c1chr")
         r = synth.ReadSpec(6000, 60, seed=777)
-    else:
+    elif kind == "repeat":
         g = synth.GenomeSpec(1_500_000, 3, 2024, segdup_frac=0.10, segdup_len=(1000, 8000), segdup_div=0.005,
                              families=[(300, 700, 0.03, 0.10), (2500, 40, 0.01, 0.03)], n_tandem=50, name="rchr")
         r = synth.ReadSpec(2500, 25, degraded_frac=0.3, repeat_bias=0.8, indel_rate=0.002, seed=9)
+    elif kind == "c2like":
+        g = synth.GenomeSpec(8_000_000, 8, 2345, segdup_frac=0.05, name="c2chr")
+        r = synth.ReadSpec(20_000, 200, seed=778)
+    else:
+        scale = 12_000_000 / 3_100_000_000
+        g = synth.GenomeSpec(12_000_000, 24, 3345, segdup_frac=0.02,
+                             families=[(300, int(1_000_000 * scale), 0.10, 0.15), (6000, int(100_000 * scale), 0.02, 0.08)],
+                             n_tandem=int(20_000 * scale), name="c3chr")
+        if kind == "c3like":
+            r = synth.ReadSpec(12_000, 120, seed=779)
+            monkeypatch.setenv("LC_FORCE_WIDE", "1")
+        else:
+            r = synth.ReadSpec(8_000, 80, mol_len=200_000, mols_per_barcode=50, degraded_frac=0.30, repeat_bias=0.8, seed=780)
     fa, pairs = _fresh_dataset(tmp_path, kind, g, r)
     want = str(tmp_path / "want.out")
-    subprocess.check_call([os.path.join(oracle_port, "replay_port"), fa, pairs, want, "-t", "8"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([_oracle_replay(oracle_port), fa, pairs, want, "-t", "8"], stderr=subprocess.DEVNULL)
     ref = gobwa.GoBwaLoadReference(fa)
     assert ref is not None, gobwa.last_error()
     bases, off = _load_pairs(pairs)
