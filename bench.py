@@ -166,6 +166,7 @@ def main():
         raise SystemExit("bench.py --impl cuda needs a GPU: libcuda_lariat has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # data: rank 0 builds the shared index, every rank simulates its own shard of barcode groups (weak scaling)
     if rank == 0:
