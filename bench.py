@@ -33,8 +33,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+PAIRS_OVERRIDE = 0
+
+
 def config_sizes(name, scale):
     g, r = synth.config_specs(name)
+    if PAIRS_OVERRIDE:
+        r.n_barcodes = max(20, int(r.n_barcodes * PAIRS_OVERRIDE / r.n_pairs))
+        r.n_pairs = PAIRS_OVERRIDE
     if scale != 1.0:
         g.total_bp = int(g.total_bp * scale)
         r.n_pairs = max(2000, int(r.n_pairs * scale))
@@ -46,11 +52,12 @@ def prepare_data(name, scale, rank_seed=0, need_index=True, device="cuda"):
     """Genome + index (own GPU builder, byte-identical to `bwa index`) + read pairs; cached under data/cache."""
     g, r = config_sizes(name, scale)
     r.seed += 1000 * rank_seed
-    tag = f"{name}_s{scale:g}"
+    gname = "c3" if name == "c4" else name      # c4 runs on the c3 reference
+    tag = f"{gname}_s{scale:g}" + (f"_bp{g.total_bp}" if gname == "c3" else "")
     d = os.path.join(CACHE, tag)
     os.makedirs(d, exist_ok=True)
-    fa = os.path.join(d, f"{name}.fa")
-    pairs = os.path.join(d, f"{name}.r{rank_seed}.pairs")
+    fa = os.path.join(d, f"{gname}.fa")
+    pairs = os.path.join(d, f"{name}.r{rank_seed}.n{r.n_pairs}.pairs")
     contigs = loci = None
     if need_index and not all(os.path.exists(fa + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
         t = time.time()
@@ -124,17 +131,22 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--scale", type=float, default=float(os.environ.get("LARIAT_BENCH_SCALE", "1.0")))
+    ap.add_argument("--pairs", type=int, default=0, help="override the config's number of read pairs (barcodes scale with it); diagnostic runs only")
     ap.add_argument("--cpu-sample", type=int, default=200000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--chunk-pairs", type=int, default=-1, help="lc_set_chunk_pairs for the e2e arm (-1: library default)")
     ap.add_argument("--e2e-sweep", default="", help="comma list of chunk sizes: time the e2e arm for each (stderr), then go on with --chunk-pairs")
     args = ap.parse_args()
+    global PAIRS_OVERRIDE
+    PAIRS_OVERRIDE = args.pairs
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
     workload = {"c1": "synthetic 10 Mb reference, 20k 2x150 pairs / 200 barcodes",
-                "c2": "synthetic 100 Mb reference with 5% segmental duplications, 1M 2x150 read pairs / 10k barcodes, 50 kb molecules"}.get(args.config, args.config)
+                "c2": "synthetic 100 Mb reference with 5% segmental duplications, 1M 2x150 read pairs / 10k barcodes, 50 kb molecules",
+                "c3": "synthetic reference with repeat families + tandem arrays on 24 contigs (LARIAT_C3_BP bases; 3.1 Gb when the index can be built), 50 kb molecules",
+                "c4": "long-molecule repeat stress: 200 kb molecules, 30% degraded mates, reads sampled from repeat copies, the c3 reference"}.get(args.config, args.config)
     cfg = {"workload": workload, "config": args.config, "scale": args.scale, "reads": "2x150", "batch": "one launch sequence per step over all barcode groups of the rank",
            "l2_policy": "inputs (index 175 MB + per-step pools > 1 GB) exceed the 126 MB L2", "sharding": f"barcode groups split over {world} rank(s), index replicated"}
 

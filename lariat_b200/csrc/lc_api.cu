@@ -155,6 +155,10 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	// tuning knobs of the seeding state machine (tests use tiny values to force the redo path)
 	if (const char *e = getenv("LC_SEED_LST_CAP")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap = v; }
 	if (const char *e = getenv("LC_SEED_PK_CAP")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap = v; }
+	if (const char *e = getenv("LC_SEED_LST_CAP2")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap2 = v; }
+	if (const char *e = getenv("LC_SEED_PK_CAP2")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap2 = v; }
+	if (const char *e = getenv("LC_EXT_HEAVY_SEEDS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_seeds = v; }
+	if (const char *e = getenv("LC_EXT_HEAVY_CHAINS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_chains = v; }
 	if (const char *e = getenv("LC_FORCE_WIDE")) c->pl.force_wide = e[0] == '1';
 	if (const char *e = getenv("LC_CHUNK_PAIRS")) { int v = atoi(e); if (v >= 0) c->chunk_pairs = v; }
 	// host copies of the big FM-index arrays are not needed any more (pac stays for lc_fetch_seq)
@@ -343,6 +347,8 @@ static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 		c->lane2.reset(new LcLane(c->device));
 		c->lane2->pl.set_index(c->ix, c->opt);
 		c->lane2->pl.lst_cap = c->pl.lst_cap; c->lane2->pl.pk_cap = c->pl.pk_cap; c->lane2->pl.force_wide = c->pl.force_wide;
+		c->lane2->pl.lst_cap2 = c->pl.lst_cap2; c->lane2->pl.pk_cap2 = c->pl.pk_cap2;
+		c->lane2->pl.ext_heavy_seeds = c->pl.ext_heavy_seeds; c->lane2->pl.ext_heavy_chains = c->pl.ext_heavy_chains;
 	}
 	if (c->lane2) c->lane2->pl.counting = c->pl.counting;
 	if (!c->h_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results");

@@ -41,8 +41,9 @@ struct LcCudaBackend {
 	float ev_ms(int a, int b);
 	int grid_for(unsigned long long items, int tpb, int ctas_per_sm) const;
 	void k_convert(uint8_t *p, unsigned long long n, bool ascii);
-	void k_seed(const LcBatch &b);
-	int seed_grid(const LcBatch &b);
+	void k_seed(const LcBatch &b, const int32_t *list, int n_items);      // list: read ids of a second pass, null = reads 0..n_items-1
+	int seed_grid(const LcBatch &b, int n_items);
+	int seed_pass_lanes(const LcBatch &b, int n_items);                   // threads k_seed would launch for this pass (sizes the per-lane seed lists)
 	int seed_lanes();
 	void k_seed_finish(const LcBatch &b);
 	void k_seed_redo(const LcBatch &b, int n_redo);

@@ -442,7 +442,12 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				n_av = 0; ci = 0; ro = 0;
 				phase = LC_XP_CHAIN_START;
 				if (NC == 0) phase = LC_XP_FETCH;
-				else {
+				else if ((b.ext_heavy_seeds > 0 && T > b.ext_heavy_seeds) || (b.ext_heavy_chains > 0 && NC > b.ext_heavy_chains)) {
+					// a read with very many chains (repeats) would keep this lane — and with it the kernel — busy long after the others are
+					// done: it goes to a list that a warp-per-read kernel works off (lc_stage_extend_t, cooperative rows)
+					b.redo[lc_atomic_add(b.ext_heavy_n, 1u)] = r;
+					phase = LC_XP_FETCH;
+				} else {
 					ro = lc_carve(b, b.reg_cur, b.reg_cap, (unsigned long long)T, LC_OVF_REG);
 					const unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * T + 8, LC_OVF_SCRATCH);
 					if (ro == (unsigned long long)-1 || so == (unsigned long long)-1) phase = LC_XP_FETCH;

@@ -92,8 +92,8 @@ __device__ __forceinline__ void lc_warp_pack_read(const LcBatch &b, int rr, int 
 // need it now wait (their tick() is a no-op on a stale interval) until `gate_n` lanes are waiting or the tick number is a
 // multiple of gate_mask + 1, and are then served together.
 template <typename U, bool COUNT>
-__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b, const unsigned gate_mask, const int gate_n)
-{
+__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b, const unsigned gate_mask, const int gate_n, const int32_t *list, const int n_items)
+{   // list: read ids of a second pass (the reads whose lists outgrew the first pass' slots), null: reads 0 .. n_items-1
 	extern __shared__ uint32_t lc_seed_smem[];
 	const int lane = threadIdx.x & 31;
 	uint32_t *wbase = lc_seed_smem + (size_t)(threadIdx.x >> 5) * lc_seed_warp_words(b.lmax, b.lst_cap);      // this warp's lists, then its reads
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b, cons
 				if (lane == 0) base = (int)atomicAdd(b.work_ctr + 3, (unsigned)__popc(need));
 				base = __shfl_sync(LC_FULL, base, 0);
 				int myr = -1;
-				if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
+				if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); myr = myr >= n_items ? -1 : (list ? list[myr] : myr); }
 				for (unsigned m = need; m; m &= m - 1) {
 					const int L = __ffs(m) - 1;
 					const int rr = __shfl_sync(LC_FULL, myr, L);
@@ -215,6 +215,25 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 			if (__any_sync(LC_FULL, ex.phase < LC_XP_DP && ex.phase != LC_XP_FETCH)) ex.resolve();
 		}
 		ex.tick((it & row_mask) == 0);
+	}
+}
+
+// Stage 4b: the reads extend_kernel set aside (very many chains): one warp per read, cooperative ksw_extend2 rows (lc_sw_warp.cuh)
+__global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b)
+{
+	extern __shared__ int lc_smem[];
+	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = lc_warp_row_ints(b.lmax);
+	const unsigned int n = *b.ext_heavy_n;
+	LcExecWarp ex;
+	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
+	ex.Hmax = nullptr; ex.bl = nullptr; ex.cig = nullptr; ex.zloc = nullptr;
+	for (;;) {
+		unsigned int t = 0;
+		if (lane == 0) t = atomicAdd(b.ext_heavy_n + 1, 1u);
+		t = __shfl_sync(LC_FULL, t, 0);
+		if (t >= n) break;
+		lc_stage_extend_t(b, b.redo[t], ex);
+		__syncwarp();
 	}
 }
 
@@ -402,7 +421,7 @@ void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
 	convert_kernel<<<grid_for((n + 15) / 16, 256, 8), 256, 0, stream>>>(p, n, ascii ? 1 : 0);
 }
 static bool lc_wide(const LcBatch &b) { return b.ix.seq_len >= 0xffffffffull || b.force_wide; }
-int LcCudaBackend::seed_grid(const LcBatch &b)
+int LcCudaBackend::seed_grid(const LcBatch &b, int n_items)
 {
 	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
 	int per_sm = 1;
@@ -413,21 +432,23 @@ int LcCudaBackend::seed_grid(const LcBatch &b)
 	if (lc_wide(b)) { if (b.cnt) prep(smem_kernel<uint64_t, true>); else prep(smem_kernel<uint64_t, false>); }
 	else { if (b.cnt) prep(smem_kernel<uint32_t, true>); else prep(smem_kernel<uint32_t, false>); }
 	if (per_sm < 1) per_sm = 1;
-	const long long need = ((long long)b.n_reads + LC_SEED_TPB - 1) / LC_SEED_TPB;
+	const long long need = ((long long)n_items + LC_SEED_TPB - 1) / LC_SEED_TPB;
 	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
 	return (int)(need < cap ? (need ? need : 1) : cap);
 }
-void LcCudaBackend::k_seed(const LcBatch &b)
+int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { return seed_grid(b, n_items) * LC_SEED_TPB; }
+void LcCudaBackend::k_seed(const LcBatch &b, const int32_t *list, int n_items)
 {
-	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4, grid = seed_grid(b);
+	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4, grid = seed_grid(b, n_items);
+	cudaMemsetAsync(b.work_ctr + 3, 0, 4, stream);
 	const unsigned gm = (unsigned)seed_gate_mask;
 	const int gn = seed_gate_n;
 	if (lc_wide(b)) {
-		if (b.cnt) smem_kernel<uint64_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
-		else smem_kernel<uint64_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
+		if (b.cnt) smem_kernel<uint64_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
+		else smem_kernel<uint64_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
 	} else {
-		if (b.cnt) smem_kernel<uint32_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
-		else smem_kernel<uint32_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn);
+		if (b.cnt) smem_kernel<uint32_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
+		else smem_kernel<uint32_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
 	}
 }
 void LcCudaBackend::k_seed_finish(const LcBatch &b)
@@ -466,6 +487,10 @@ void LcCudaBackend::k_extend(const LcBatch &b)
 	// byte-packed H/E cells whenever no score of the batch can exceed 255 (half the shared memory per warp, twice the resident warps)
 	if (lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS")) lc_launch_extend<LcCells8<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
 	else lc_launch_extend<LcCells16<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
+	// the list length is only known on the device: a persistent grid that pulls reads from a counter
+	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+	cudaFuncSetAttribute(extend_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	extend_heavy_kernel<<<n_sm * 4, LC_TPB, smem, stream>>>(b);
 }
 void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {

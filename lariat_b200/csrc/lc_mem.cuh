@@ -75,6 +75,8 @@ struct LcBatch {
 	uint64_t *cig_jobs; unsigned long long cig_jobs_cap; // LC_CIG_NLIST job lists of cig_jobs_cap entries each (lc_cigar.cuh)
 	unsigned int *cig_n;                                 // their lengths
 	unsigned int *resc_n;                                // stage 5: number of pairs listed (in `redo`) for the rescue kernel
+	unsigned int *ext_heavy_n;                           // stage 4: reads listed (in `redo`) for the warp-per-read extension kernel, then its work counter
+	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read is "heavy" above this many chained seeds / chains (0 = never)
 };
 
 LC_HD void lc_raise(const LcBatch &b, uint32_t flag)

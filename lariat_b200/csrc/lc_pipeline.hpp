@@ -211,7 +211,9 @@ public:
 	size_t z_pool_bytes = 64u << 20;
 	double z_per_cand = 1024;           // traceback pool of the register-band CIGAR kernels (4 bits per band cell)
 	int memcap = 256;
-	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> redo kernel
+	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
+	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
+	int lst_cap2 = 150, pk_cap2 = 2048;   // the second pass' capacities; overflow there -> the one-thread-per-read redo kernel
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
 	bool force_wide = false;
 
@@ -280,6 +282,8 @@ public:
 			b.redo_cur = (unsigned int *)(c + 22);
 			b.cig_n = (unsigned int *)(c + 24);
 			b.resc_n = (unsigned int *)(c + 27);
+			b.ext_heavy_n = (unsigned int *)(c + 28);
+			b.ext_heavy_seeds = ext_heavy_seeds; b.ext_heavy_chains = ext_heavy_chains;
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);
@@ -315,12 +319,27 @@ public:
 			b.pk_pool_cap = (unsigned long long)(pk_per_read * R) + 1024;
 			if (!d_intv.ensure(be, sizeof(LcIntvOut) * b.intv_cap) || !d_seed.ensure(be, 8 * b.seed_cap) || !d_pkpool.ensure(be, sizeof(LcPk) * b.pk_pool_cap)) return nomem();
 			b.intv = (LcIntvOut *)d_intv.p; b.seed_row = (uint64_t *)d_seed.p; b.pk_pool = (LcPk *)d_pkpool.p;
-			be.k_seed(b); ++launches;               // the state machine: unsorted seeds per read + the redo list
+			be.k_seed(b, nullptr, R); ++launches;   // the state machine: unsorted seeds per read + the redo list
 			read_ctl();
 			n_redo = (int)(uint32_t)h_ctl[22];
+			n_redo_pass1 = n_redo;
+			LcBatch bf = b;                         // the batch as the fallback kernel sees it (its redo list)
+			if (n_redo && !(h_ctl_ovf & LC_OVF_PK)) {
+				// second pass: the reads whose lists outgrew the slots (repeats: many interval sizes, many seeds) run through the same
+				// state machine with lists several times as long — fewer resident warps, but only these reads
+				LcBatch b2 = b;
+				b2.lst_cap = std::min(lst_cap2, b.lmax + 1); b2.pk_cap = pk_cap2;
+				if (!d_redo2.ensure(be, 4 * ((size_t)n_redo + 1)) ||
+					!d_wpk2.ensure(be, sizeof(LcPk) * (size_t)be.seed_pass_lanes(b2, n_redo) * b2.pk_cap)) return nomem();
+				b2.w_pk = (LcPk *)d_wpk2.p; b2.redo = (int32_t *)d_redo2.p; b2.redo_cur = b.redo_cur + 2;      // control word 23
+				be.k_seed(b2, b.redo, n_redo); ++launches;
+				read_ctl();
+				n_redo = (int)(uint32_t)h_ctl[23];
+				bf.redo = b2.redo;
+			}
 			if (!(h_ctl_ovf & LC_OVF_PK)) {
 				be.k_seed_finish(b); ++launches;    // sort + occurrence schedule + positions
-				if (n_redo) { be.k_seed_redo(b, n_redo); ++launches; }
+				if (n_redo) { be.k_seed_redo(bf, n_redo); ++launches; }
 				read_ctl();
 			}
 			if (!(h_ctl_ovf & (LC_OVF_INTV | LC_OVF_SEED | LC_OVF_MEMLIST | LC_OVF_PK))) break;
@@ -393,7 +412,7 @@ public:
 		be.ev_record(4);
 		be.k_chain(b); ++launches;
 		be.ev_record(5);
-		be.k_extend(b); ++launches;
+		be.k_extend(b); launches += 2;          // lanes (one read each), then a warp per read for the heavy ones
 		be.ev_record(6);
 		read_ctl();
 		if (h_ctl_ovf) { err = "internal pool overflow in chain/extend (flags " + std::to_string(h_ctl_ovf) + ")"; return LC_ENOMEM; }
@@ -493,18 +512,18 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2 };
 		for (auto *x : all) x->release(be);
 	}
 
 	int64_t launches = 0;
-	int n_redo = 0;
+	int n_redo = 0, n_redo_pass1 = 0;
 	unsigned long long n_cig_fallback = 0, n_rescue_pairs = 0;
 	unsigned long long n_cand = 0, n_cigar_words = 0;
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

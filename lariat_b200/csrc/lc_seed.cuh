@@ -389,14 +389,18 @@ template <typename U, bool COUNT = true, int STRIDE = 1> struct LcSeedLane {    
 // scalar driver (tests/hostsim): all reads, one after another, through the same state machine.  The device kernel does not run
 // resolve() after every tick (lc_kernels.cu: lanes wait, ticking on their stale interval, until the warp's next housekeeping
 // round); `idle_ticks` such ticks are inserted here before every resolve() so that the tests cover their harmlessness.
-template <typename U> static inline void lc_seed_run_scalar(const LcBatch &b, uint32_t *lst, int C, uint32_t *qbuf, LcPk *memv, int M, int idle_ticks = 0)
+// `list` (n_items read ids) = a second pass over the reads an earlier pass handed back (larger lists); null = reads 0..n_items-1.
+template <typename U> static inline void lc_seed_run_scalar(const LcBatch &b, uint32_t *lst, int C, uint32_t *qbuf, LcPk *memv, int M, int idle_ticks = 0,
+															const int32_t *list = nullptr, int n_items = -1)
 {
 	LcSeedLane<U> sd(b, lst, C, qbuf, memv, M);
 	int next = 0;
+	if (n_items < 0) n_items = b.n_reads;
 	for (;;) {
 		while (sd.phase == LC_SP_FETCH) {
-			if (next >= b.n_reads) { sd.phase = LC_SP_DONE; break; }
-			const int r = next++, len = (int)(b.off[r + 1] - b.off[r]);
+			if (next >= n_items) { sd.phase = LC_SP_DONE; break; }
+			const int r = list ? list[next] : next, len = (int)(b.off[r + 1] - b.off[r]);
+			++next;
 			if (len < b.opt.min_seed_len) { b.r_n_pk[r] = 0; b.r_pk_off[r] = 0; continue; }      // B/bwamem.c:260
 			for (int t = 0; t < (len + 7) / 8; ++t) qbuf[t] = 0;
 			for (int t = 0; t < len; ++t) qbuf[t >> 3] |= (uint32_t)(b.seq[b.off[r] + t] & 15) << ((t & 7) << 2);

@@ -260,9 +260,14 @@ __device__ __noinline__ LcSwResult lc_sw_pass_warp_reg(int qlen, QF query, int t
 				g = k == 0 ? t[0] : __viaddmax_s32(g, -e_ins, t[k]);          // F leaving column k if nothing entered the block
 			}
 			// F entering each lane's block: exclusive prefix maximum over the blocks' outgoing values, position-normalised
-			const int pin = lc_warp_prefix_max_incl(g + (j0 + K - 1) * e_ins, lane);
-			const int pex = __shfl_up_sync(LC_FULL, pin, 1);
-			int f = lane > 0 ? max(pex - (j0 - 1) * e_ins, 0) : 0;
+			// (g is what a block hands to the next lane's first column: when it is 0 in every lane — no cell of the row above the gap-open
+			// cost, the usual case away from the alignment — nothing positive enters any block and the five-step scan is skipped)
+			int f = 0;
+			if (__any_sync(LC_FULL, g > 0)) {
+				const int pin = lc_warp_prefix_max_incl(g + (j0 + K - 1) * e_ins, lane);
+				const int pex = __shfl_up_sync(LC_FULL, pin, 1);
+				f = lane > 0 ? max(pex - (j0 - 1) * e_ins, 0) : 0;
+			}
 			int key = -1;
 #pragma unroll
 			for (int k = 0; k < K; ++k) {
@@ -272,7 +277,7 @@ __device__ __noinline__ LcSwResult lc_sw_pass_warp_reg(int qlen, QF query, int t
 				e[k] = __viaddmax_s32_relu(hk, -oe_del, e[k] - e_del);        // max(h - oe_del, e - e_del, 0)
 				if (j0 + k < P) key = max(key, (hk << 10) | (1023 - (j0 + k)));
 			}
-			key = lc_warp_max(key);
+			key = __reduce_max_sync(LC_FULL, key);       // REDUX: one instruction instead of five shuffle rounds
 			const int imax = key < 0 ? 0 : key >> 10;
 			if (imax >= minsc) {                         // run-length list of rows scoring >= minsc (B/ksw.c:192-200)
 				if (n_b == 0 || last_i + 1 != i) {

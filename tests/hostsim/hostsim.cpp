@@ -33,11 +33,12 @@ struct HostBackend {
 	void k_convert(uint8_t *p, unsigned long long n, bool ascii) { for (unsigned long long i = 0; i < n; ++i) p[i] = lc_nt4(p[i], ascii); }
 	// each stage: items are dealt to `workers` scratch slots round-robin, like the grid-stride loops of the kernels
 	// the seeding state machine with a one-lane group (lc_seed.cuh), then the redo list through the one-thread-per-read body
-	void k_seed(const LcBatch &b)
+	int seed_pass_lanes(const LcBatch &, int) const { return 1; }
+	void k_seed(const LcBatch &b, const int32_t *list, int n_items)
 	{
 		std::vector<uint32_t> lst((size_t)LC_SEED_ENT_WORDS * b.lst_cap + 4), q((size_t)lc_seed_q_words(b.lmax) + 4);
-		if (b.force_wide || b.ix.seq_len >= 0xffffffffull) lc_seed_run_scalar<uint64_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap, idle_ticks);
-		else lc_seed_run_scalar<uint32_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap, idle_ticks);
+		if (b.force_wide || b.ix.seq_len >= 0xffffffffull) lc_seed_run_scalar<uint64_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap, idle_ticks, list, n_items);
+		else lc_seed_run_scalar<uint32_t>(b, lst.data(), b.lst_cap, q.data(), b.w_pk, b.pk_cap, idle_ticks, list, n_items);
 	}
 	int idle_ticks = 0;      // ticks a lane spends waiting for the warp's next housekeeping round (device kernels), simulated
 	void k_seed_finish(const LcBatch &b)
@@ -57,6 +58,7 @@ struct HostBackend {
 		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); return; }
 		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax));
 		lc_ext_run_scalar(b, he.data(), qw.data(), lc_ext_cells8_ok(b) && !wide_cells, idle_ticks);
+		for (unsigned int t = 0; t < *b.ext_heavy_n; ++t) lc_stage_extend(b, b.redo[t], (int)(t % workers));     // the heavy reads' kernel
 	}
 	bool wide_cells = false;     // -H: 16-bit H/E cells even when the batch would fit the byte packing
 	void k_pair(const LcBatch &b, int n_pairs)
@@ -97,7 +99,7 @@ struct HostBackend {
 int main(int argc, char **argv)
 {
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
-	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, dense = 1, wide = 0, chunk = 0;
+	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
 		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
@@ -106,8 +108,11 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-c")) count = 1;
 		else if (!strcmp(argv[i], "-C") && i + 1 < argc) lst_cap = atoi(argv[++i]);     // shared-memory list capacity of the seeding state machine
 		else if (!strcmp(argv[i], "-M") && i + 1 < argc) pk_cap = atoi(argv[++i]);      // per-group seed list capacity
+		else if (!strcmp(argv[i], "-D") && i + 1 < argc) lst_cap2 = atoi(argv[++i]);    // the same two capacities for the second pass (overflow there -> lc_stage_seed)
+		else if (!strcmp(argv[i], "-E") && i + 1 < argc) pk_cap2 = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
 		else if (!strcmp(argv[i], "-I") && i + 1 < argc) be.idle_ticks = atoi(argv[++i]);  // idle ticks before every housekeeping step of the state machines
+		else if (!strcmp(argv[i], "-J") && i + 1 < argc) heavy_seeds = atoi(argv[++i]);   // extension: reads above this many chained seeds take the per-read body
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
@@ -137,6 +142,9 @@ int main(int argc, char **argv)
 	pl.counting = count;
 	if (lst_cap > 0) pl.lst_cap = lst_cap;
 	if (pk_cap > 0) pl.pk_cap = pk_cap;
+	if (lst_cap2 > 0) pl.lst_cap2 = lst_cap2;
+	if (heavy_seeds >= 0) pl.ext_heavy_seeds = heavy_seeds;
+	if (pk_cap2 > 0) pl.pk_cap2 = pk_cap2;
 	pl.force_wide = wide != 0;
 	pl.set_index(ix, opt);
 	LcHostResult res;
