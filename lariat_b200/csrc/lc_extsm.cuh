@@ -272,14 +272,13 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 			}
 			// 255 - penalty per column: 0 for a match, a + b for a mismatch, a + 1 when either base is ambiguous (score -1, B/bwa.c:109-118)
 			const uint32_t x = tb < 4 ? qword ^ ((uint32_t)tb * 0x11111111u) : 0x44444444u;
-			const uint32_t qmm = 255u - (uint32_t)(sc.a + sc.b), qn = 255u - (uint32_t)(sc.a + 1);
-			const uint32_t lut_lo = 255u | qmm << 8 | qmm << 16 | qmm << 24, lut_hi = qn * 0x01010101u;
+			const LcExtConst &xc = b.xc;
+			const uint32_t lut_lo = xc.lut_lo, lut_hi = xc.lut_hi;
 			const uint32_t pa = lc_prmt(lut_lo, lut_hi, x), pb = lc_prmt(lut_lo, lut_hi, x >> 16);
 			uint32_t Q[4];
 			Q[0] = lc_prmt(pa, 0u, 0x4140u); Q[1] = lc_prmt(pa, 0u, 0x4342u); Q[2] = lc_prmt(pb, 0u, 0x4140u); Q[3] = lc_prmt(pb, 0u, 0x4342u);
-			const uint32_t c_a = lc_p2_dup(sc.a - 255), n_oe_del = lc_p2_dup(-(sc.o_del + e_del)), n_e_del = lc_p2_dup(-e_del),
-				n_oe_ins = lc_p2_dup(-(sc.o_ins + e_ins)), n_e1 = lc_p2_dup(-e_ins), n_e2 = lc_p2_dup(-2 * e_ins), n_e4 = lc_p2_dup(-4 * e_ins);
-			const uint32_t kmul = (uint32_t)(sc.a + 1);
+			const uint32_t c_a = xc.c_a, n_oe_del = xc.n_oe_del, n_e_del = xc.n_e_del, n_oe_ins = xc.n_oe_ins, n_e1 = xc.n_e1, n_e2 = xc.n_e2, n_e4 = xc.n_e4;
+			const uint32_t kmul = xc.kmul;
 			uint32_t hd[4], ev[4], me[4], A[4];
 			CELLS::load8(he, col0, hd, ev);
 #pragma unroll
@@ -303,8 +302,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 			uint32_t G[4];
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
-				const uint32_t dec = ((uint32_t)(-(2 * k + 1) * e_ins) & 0xffffu) | ((uint32_t)(-(2 * k + 2) * e_ins) & 0xffffu) << 16;
-				G[k] = lc_p2_addmax(fb, dec, A[k]);
+				G[k] = lc_p2_addmax(fb, xc.dec[k], A[k]);
 			}
 			// F entering each column = G shifted right by one column with f in front; H = max(M, E, F)
 			h[0] = lc_p2_max(me[0], lc_prmt(fb, G[0], 0x5432u));

@@ -23,6 +23,21 @@ struct LcBtNode { int32_t n, internal; int32_t key[LC_BT_MAXK]; int32_t child[LC
 enum { LC_OVF_INTV = 1, LC_OVF_SEED = 2, LC_OVF_SCRATCH = 4, LC_OVF_CSEED = 8, LC_OVF_REG = 16, LC_OVF_FINAL = 32,
 	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512, LC_OVF_PK = 1024 };
 
+// packed 16x2 constants of the extension tick (lc_extsm.cuh), derived from the scoring options once on the host: as kernel
+// parameters they are constant-bank operands, not per-tick arithmetic
+struct LcExtConst { uint32_t c_a, n_oe_del, n_e_del, n_oe_ins, n_e1, n_e2, n_e4, lut_lo, lut_hi, kmul, dec[4]; };
+static inline uint32_t lc_dup16(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+static inline LcExtConst lc_ext_const(const LcScore &sc)
+{
+	LcExtConst x;
+	const uint32_t qmm = 255u - (uint32_t)(sc.a + sc.b), qn = 255u - (uint32_t)(sc.a + 1);
+	x.c_a = lc_dup16(sc.a - 255); x.n_oe_del = lc_dup16(-(sc.o_del + sc.e_del)); x.n_e_del = lc_dup16(-sc.e_del);
+	x.n_oe_ins = lc_dup16(-(sc.o_ins + sc.e_ins)); x.n_e1 = lc_dup16(-sc.e_ins); x.n_e2 = lc_dup16(-2 * sc.e_ins); x.n_e4 = lc_dup16(-4 * sc.e_ins);
+	x.lut_lo = 255u | qmm << 8 | qmm << 16 | qmm << 24; x.lut_hi = qn * 0x01010101u; x.kmul = (uint32_t)(sc.a + 1);
+	for (int k = 0; k < 4; ++k) x.dec[k] = ((uint32_t)(-(2 * k + 1) * sc.e_ins) & 0xffffu) | ((uint32_t)(-(2 * k + 2) * sc.e_ins) & 0xffffu) << 16;
+	return x;
+}
+
 struct LcBatch {
 	// ---- inputs
 	int32_t n_reads;
@@ -31,6 +46,7 @@ struct LcBatch {
 	LcIndex ix;
 	lc_opt_t opt;
 	LcScore sc;
+	LcExtConst xc;                 // = lc_ext_const(sc)
 	int32_t score_delta, pes_low, pes_high, max_anchors;
 	LcCounters *cnt;               // null = off
 	uint32_t *overflow;            // OR of LC_OVF_* raised by any thread

@@ -224,6 +224,7 @@ public:
 	{
 		b.ix = ix; b.opt = opt;
 		b.sc.a = opt.a; b.sc.b = opt.b; b.sc.o_del = opt.o_del; b.sc.e_del = opt.e_del; b.sc.o_ins = opt.o_ins; b.sc.e_ins = opt.e_ins;
+		b.xc = lc_ext_const(b.sc);
 		b.pes_low = -35; b.pes_high = 500; b.max_anchors = 50;     // G/gobwa.go:229-237,287,311
 	}
 

@@ -436,7 +436,9 @@ template <typename U, class Coop> LC_HD void lc_seed_finish(const LcBatch &b, co
 	const LcPk *memv = b.pk_pool + b.r_pk_off[r];
 	const uint64_t max_occ = (uint64_t)b.opt.max_occ;
 	auto occ_step = [max_occ](uint64_t w) -> uint64_t { return w > max_occ ? w / max_occ : 1; };
-	auto occ_count = [max_occ, occ_step](uint64_t w) -> uint32_t { const uint64_t st = occ_step(w); uint64_t cnt = (w + st - 1) / st; return (uint32_t)(cnt > max_occ ? max_occ : cnt); };
+	auto occ_count = [max_occ, occ_step](uint64_t w) -> uint32_t {
+		if (w <= max_occ) return (uint32_t)w;                 // step 1: every occurrence (and no 64-bit division in the common case)
+		const uint64_t st = occ_step(w); uint64_t cnt = (w + st - 1) / st; return (uint32_t)(cnt > max_occ ? max_occ : cnt); };
 	unsigned long long S = 0;
 	for (int f = 0; f < n; ++f) S += occ_count(PK::x2(memv[f]));
 	unsigned long long io = 0, so = 0;
