@@ -336,12 +336,30 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 	}
 }
 
+static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out, int n_chunks);
+
+// The batch pools scale with the seeds of the batch (~250 bytes per seed between chaining and extension), and repeat-rich reads have
+// hundreds of seeds each: a call that cannot get its pools is retried in more, smaller chunks (results do not depend on the
+// chunking), and the smaller chunk size is kept for the calls that follow.
 static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out)
 {
 	if (!c || n_pairs < 0 || !off || (n_pairs && !bases && off[2 * (size_t)n_pairs] > off[0])) return fail(LC_EARG, "bad arguments");
 	cudaSetDevice(c->device);
 	int n_chunks = 1;
 	if (c->chunk_pairs > 0 && (double)n_pairs > 1.5 * c->chunk_pairs) n_chunks = (n_pairs + c->chunk_pairs - 1) / c->chunk_pairs;
+	for (int attempt = 0;; ++attempt) {
+		const int rc = do_align_chunks(c, n_pairs, bases, off, score_delta, out, n_chunks);
+		if (rc != LC_ENOMEM || attempt >= 8 || n_pairs / n_chunks < 2000) return rc;
+		c->pl.release();
+		if (c->lane2) c->lane2->pl.release();
+		cudaGetLastError();
+		n_chunks = n_chunks < 2 ? 4 : 2 * n_chunks;
+		c->chunk_pairs = n_pairs / n_chunks + 1;
+	}
+}
+
+static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out, int n_chunks)
+{
 	const int n_lanes = n_chunks > 1 ? 2 : 1;
 	if (n_lanes == 2 && !c->lane2) {
 		c->lane2.reset(new LcLane(c->device));
