@@ -61,7 +61,8 @@ struct lc_ctx {
 	int last_delta = 25;
 	// results of the batched calls: pinned host arrays, valid until the next call on this ctx
 	LcPinned h_off, h_regs, h_aln, h_cig;
-	std::unique_ptr<LcLane> lane2;
+	std::vector<std::unique_ptr<LcLane> > lanes;      // lanes 2..n of chunked calls (lane 1 is be/pl above): own stream, pools and host thread
+	int max_lanes = 2;              // LC_LANES
 	int chunk_pairs = 500000;       // LC_CHUNK_PAIRS; calls of more than 1.5 chunks run chunked over two lanes, 0 = never
 	explicit lc_ctx(int dev) : device(dev), be(dev), pl(be) {}
 };
@@ -161,6 +162,7 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	if (const char *e = getenv("LC_EXT_HEAVY_CHAINS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_chains = v; }
 	if (const char *e = getenv("LC_FORCE_WIDE")) c->pl.force_wide = e[0] == '1';
 	if (const char *e = getenv("LC_CHUNK_PAIRS")) { int v = atoi(e); if (v >= 0) c->chunk_pairs = v; }
+	if (const char *e = getenv("LC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 8) c->max_lanes = v; }
 	// host copies of the big FM-index arrays are not needed any more (pac stays for lc_fetch_seq)
 	std::vector<uint32_t>().swap(h.bwt);
 	std::vector<uint64_t>().swap(h.sa);
@@ -176,7 +178,7 @@ void lc_destroy(lc_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->pl.release();
-	c->lane2.reset();
+	c->lanes.clear();
 	c->h_off.release(); c->h_regs.release(); c->h_aln.release(); c->h_cig.release();
 	cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_pac); cudaFree(c->d_anns); cudaFree(c->d_sa_dense);
 	delete c;
@@ -351,7 +353,7 @@ static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 		const int rc = do_align_chunks(c, n_pairs, bases, off, score_delta, out, n_chunks);
 		if (rc != LC_ENOMEM || attempt >= 8 || n_pairs / n_chunks < 2000) return rc;
 		c->pl.release();
-		if (c->lane2) c->lane2->pl.release();
+		for (auto &l : c->lanes) l->pl.release();
 		cudaGetLastError();
 		n_chunks = n_chunks < 2 ? 4 : 2 * n_chunks;
 		c->chunk_pairs = n_pairs / n_chunks + 1;
@@ -360,25 +362,27 @@ static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 
 static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out, int n_chunks)
 {
-	const int n_lanes = n_chunks > 1 ? 2 : 1;
-	if (n_lanes == 2 && !c->lane2) {
-		c->lane2.reset(new LcLane(c->device));
-		c->lane2->pl.set_index(c->ix, c->opt);
-		c->lane2->pl.lst_cap = c->pl.lst_cap; c->lane2->pl.pk_cap = c->pl.pk_cap; c->lane2->pl.force_wide = c->pl.force_wide;
-		c->lane2->pl.lst_cap2 = c->pl.lst_cap2; c->lane2->pl.pk_cap2 = c->pl.pk_cap2;
-		c->lane2->pl.ext_heavy_seeds = c->pl.ext_heavy_seeds; c->lane2->pl.ext_heavy_chains = c->pl.ext_heavy_chains;
+	const int n_lanes = std::max(1, std::min(n_chunks, c->max_lanes));
+	while ((int)c->lanes.size() < n_lanes - 1) {
+		std::unique_ptr<LcLane> l(new LcLane(c->device));
+		l->pl.set_index(c->ix, c->opt);
+		l->pl.lst_cap = c->pl.lst_cap; l->pl.pk_cap = c->pl.pk_cap; l->pl.force_wide = c->pl.force_wide;
+		l->pl.lst_cap2 = c->pl.lst_cap2; l->pl.pk_cap2 = c->pl.pk_cap2;
+		l->pl.ext_heavy_seeds = c->pl.ext_heavy_seeds; l->pl.ext_heavy_chains = c->pl.ext_heavy_chains;
+		c->lanes.push_back(std::move(l));
 	}
-	if (c->lane2) c->lane2->pl.counting = c->pl.counting;
+	for (auto &l : c->lanes) l->pl.counting = c->pl.counting;
 	if (!c->h_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results");
 	LcChunkShared sh;
 	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.ready.assign(n_chunks + 1, 0); sh.ready[0] = 1;
 	memset(&sh.cnt, 0, sizeof(sh.cnt));
 	c->be.ev_record(12);
-	if (n_lanes == 1) lane_worker(c, &c->be, &c->pl, &sh, 0, 1, 1, n_pairs, bases, off, score_delta);
-	else {
-		std::thread t2(lane_worker, c, &c->lane2->be, &c->lane2->pl, &sh, 1, 2, n_chunks, n_pairs, bases, off, score_delta);
-		lane_worker(c, &c->be, &c->pl, &sh, 0, 2, n_chunks, n_pairs, bases, off, score_delta);
-		t2.join();
+	{
+		std::vector<std::thread> th;
+		for (int l = 1; l < n_lanes; ++l)
+			th.emplace_back(lane_worker, c, &c->lanes[l - 1]->be, &c->lanes[l - 1]->pl, &sh, l, n_lanes, n_chunks, n_pairs, bases, off, score_delta);
+		lane_worker(c, &c->be, &c->pl, &sh, 0, n_lanes, n_chunks, n_pairs, bases, off, score_delta);
+		for (auto &t : th) t.join();
 	}
 	c->be.ev_record(13);
 	c->be.sync();

@@ -56,11 +56,12 @@ def test_golden_tiny_fallback_paths(env, lib_path, monkeypatch):
     ref.close()
 
 
-@pytest.mark.parametrize("chunk", ["40", "97", "0"])
-def test_golden_tiny_chunked_two_lanes(chunk, lib_path, monkeypatch):
-    """Large calls are cut into chunks of pairs that alternate between two streams (H2D / D2H of one chunk under the kernels of
-    the other); the call's flat result arrays must be the same bytes.  LC_CHUNK_PAIRS=0 turns chunking off."""
+@pytest.mark.parametrize("chunk,lanes", [("40", "2"), ("97", "2"), ("0", "2"), ("61", "3"), ("33", "4"), ("50", "1")])
+def test_golden_tiny_chunked_two_lanes(chunk, lanes, lib_path, monkeypatch):
+    """Large calls are cut into chunks of pairs that rotate over LC_LANES streams (H2D / D2H of one chunk under the kernels of
+    the others); the call's flat result arrays must be the same bytes.  LC_CHUNK_PAIRS=0 turns chunking off."""
     monkeypatch.setenv("LC_CHUNK_PAIRS", chunk)
+    monkeypatch.setenv("LC_LANES", lanes)
     ref = gobwa.GoBwaLoadReference(os.path.join(GOLDEN, "tiny", "tiny.fa"))
     assert ref is not None, gobwa.last_error()
     bases, off = _load_pairs(os.path.join(GOLDEN, "tiny", "tiny.pairs"))
