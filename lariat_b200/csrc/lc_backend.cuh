@@ -53,6 +53,7 @@ struct LcCudaBackend {
 	void k_chain(const LcBatch &b);
 	void k_extend(const LcBatch &b);
 	void k_pair(const LcBatch &b, int n_pairs);
+	const uint64_t *sort_worklist(const LcBatch &b, const unsigned int *n_dev, unsigned int &n);
 	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev);
 	void k_cigar_plan(const LcBatch &b, unsigned long long n);
 	int k_cigar_band(const LcBatch &b, unsigned long long n_max);

@@ -443,7 +443,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				else if ((b.ext_heavy_seeds > 0 && T > b.ext_heavy_seeds) || (b.ext_heavy_chains > 0 && NC > b.ext_heavy_chains)) {
 					// a read with very many chains (repeats) would keep this lane — and with it the kernel — busy long after the others are
 					// done: it goes to a list that a warp-per-read kernel works off (lc_stage_extend_t, cooperative rows)
-					b.redo[lc_atomic_add(b.ext_heavy_n, 1u)] = r;
+					b.wl_in[lc_atomic_add(b.ext_heavy_n, 1u)] = (uint64_t)(uint32_t)lc_min(T, 0xffff) << 32 | (uint32_t)r;
 					phase = LC_XP_FETCH;
 				} else {
 					ro = lc_carve(b, b.reg_cur, b.reg_cap, (unsigned long long)T, LC_OVF_REG);

@@ -13,6 +13,7 @@
 // All are integer/byte kernels; grids are sized in multiples of the SM count and stride over the batch.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include "lc_backend.cuh"
 #include "lc_sw_warp.cuh"
@@ -219,11 +220,10 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 }
 
 // Stage 4b: the reads extend_kernel set aside (very many chains): one warp per read, cooperative ksw_extend2 rows (lc_sw_warp.cuh)
-__global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b)
+__global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
 {
 	extern __shared__ int lc_smem[];
 	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax), rows = lc_warp_row_ints(b.lmax);
-	const unsigned int n = *b.ext_heavy_n;
 	LcExecWarp ex;
 	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.qs = (uint8_t *)(ex.E + rows); ex.lane = lane;
 	ex.Hmax = nullptr; ex.bl = nullptr; ex.cig = nullptr; ex.zloc = nullptr;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b)
 		if (lane == 0) t = atomicAdd(b.ext_heavy_n + 1, 1u);
 		t = __shfl_sync(LC_FULL, t, 0);
 		if (t >= n) break;
-		lc_stage_extend_t(b, b.redo[t], ex);
+		lc_stage_extend_t(b, (int)(uint32_t)list[t], ex);
 		__syncwarp();
 	}
 }
@@ -245,12 +245,11 @@ __global__ void __launch_bounds__(LC_TPB) pair_prepare_kernel(const LcBatch b, i
 	for (int p = worker; p < n_pairs; p += stride) lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
 }
 // Stage 5b: one warp per pair that needs a Smith-Waterman — the two rescue phases with the warp-cooperative local SW
-__global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b)
+__global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
 {
 	extern __shared__ int lc_smem[];
 	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax, 3), rows = lc_warp_row_ints(b.lmax);
 	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const unsigned int n = *b.resc_n;
 	LcExecWarp ex;
 	ex.H = (int *)((char *)lc_smem + (threadIdx.x >> 5) * per); ex.E = ex.H + rows; ex.Hmax = ex.E + rows; ex.qs = (uint8_t *)(ex.Hmax + rows);
 	ex.lane = lane; ex.bl = b.w_u64 + (size_t)gwarp * b.w_u64_n;
@@ -259,7 +258,7 @@ __global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b)
 		if (lane == 0) t = atomicAdd(b.work_ctr + 1, 1u);
 		t = __shfl_sync(LC_FULL, t, 0);
 		if (t >= n) break;
-		lc_pair_rescue_t(b, b.redo[t], ex);
+		lc_pair_rescue_t(b, (int)(uint32_t)list[t], ex);
 		__syncwarp();
 	}
 }
@@ -487,10 +486,28 @@ void LcCudaBackend::k_extend(const LcBatch &b)
 	// byte-packed H/E cells whenever no score of the batch can exceed 255 (half the shared memory per warp, twice the resident warps)
 	if (lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS")) lc_launch_extend<LcCells8<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
 	else lc_launch_extend<LcCells16<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
-	// the list length is only known on the device: a persistent grid that pulls reads from a counter
-	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
-	cudaFuncSetAttribute(extend_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	extend_heavy_kernel<<<n_sm * 4, LC_TPB, smem, stream>>>(b);
+	// the heavy reads, heaviest first; the warps pull them from a counter
+	unsigned int n = 0;
+	const uint64_t *list = sort_worklist(b, b.ext_heavy_n, n);
+	if (n) {
+		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+		cudaFuncSetAttribute(extend_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		extend_heavy_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
+	}
+}
+// Length of a device work list (one small D2H + stream sync), and the list sorted by weight, heaviest first (LPT order): the
+// kernels that give a whole warp to an item finish when their slowest item does, so the slow ones must not start last.
+const uint64_t *LcCudaBackend::sort_worklist(const LcBatch &b, const unsigned int *n_dev, unsigned int &n)
+{
+	n = 0;
+	cudaMemcpyAsync(&n, n_dev, 4, cudaMemcpyDeviceToHost, stream);
+	cudaStreamSynchronize(stream);
+	if (n < 2) return b.wl_in;
+	size_t need = 0;
+	cub::DeviceRadixSort::SortKeysDescending(nullptr, need, b.wl_in, b.wl_out, (int)n, 32, 48, stream);
+	if (need > scan_tmp_bytes) { if (scan_tmp) cudaFree(scan_tmp); cudaMalloc(&scan_tmp, need + 256); scan_tmp_bytes = need + 256; }
+	cub::DeviceRadixSort::SortKeysDescending(scan_tmp, need, b.wl_in, b.wl_out, (int)n, 32, 48, stream);
+	return b.wl_out;
 }
 void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {
@@ -499,8 +516,9 @@ void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
 	cudaFuncSetAttribute(matesw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id.
-	// The list length is only known on the device; the grid is sized for the worst case (every pair listed).
-	matesw_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b);
+	unsigned int n = 0;
+	const uint64_t *list = sort_worklist(b, b.resc_n, n);      // pairs that need a Smith-Waterman, heaviest first
+	if (n) matesw_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
 }
 void LcCudaBackend::k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 {

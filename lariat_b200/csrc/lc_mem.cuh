@@ -91,6 +91,9 @@ struct LcBatch {
 	uint64_t *cig_jobs; unsigned long long cig_jobs_cap; // LC_CIG_NLIST job lists of cig_jobs_cap entries each (lc_cigar.cuh)
 	unsigned int *cig_n;                                 // their lengths
 	unsigned int *resc_n;                                // stage 5: number of pairs listed (in `redo`) for the rescue kernel
+	uint64_t *wl_in, *wl_out;                            // work lists of the warp-per-item kernels (heavy reads of stage 4, rescue pairs of stage 5):
+	                                                     //   entries weight << 32 | id, appended to wl_in; the backend sorts them by weight,
+	                                                     //   heaviest first, into wl_out so that the long items do not start last
 	unsigned int *ext_heavy_n;                           // stage 4: reads listed (in `redo`) for the warp-per-read extension kernel, then its work counter
 	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read is "heavy" above this many chained seeds / chains (0 = never)
 };
@@ -827,7 +830,11 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 	num = 0;
 	for (int i = 0; i < n[0] && num < b.max_anchors && len[1] > 0 && !need; ++i)
 		if (f0[i].score >= best[0] - b.score_delta) { ++num; need = lc_matesw_wants_sw(b, f0[i], len[1], f1, n[1], rb, re); }
-	if (need) { b.redo[lc_atomic_add(b.resc_n, 1u)] = p; return; }
+	if (need) {                                          // weight = candidates of the pair (anchors to try, lists to re-sort)
+		const int wgt = lc_min(n[0] + n[1], 0xffff);
+		b.wl_in[lc_atomic_add(b.resc_n, 1u)] = (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
+		return;
+	}
 	const unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
 	for (int i = 0; i < n[0]; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
 	for (int i = 0; i < n[1]; ++i) b.cand[co + n[0] + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;

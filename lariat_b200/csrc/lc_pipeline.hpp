@@ -298,6 +298,8 @@ public:
 		} b.force_wide = force_wide ? 1 : 0;
 		if (!d_wpk.ensure(be, sizeof(LcPk) * (size_t)be.seed_lanes() * b.pk_cap) || !d_redo.ensure(be, 4 * ((size_t)R + 1))) return nomem();
 		b.w_pk = (LcPk *)d_wpk.p; b.redo = (int32_t *)d_redo.p;
+		if (!d_wl.ensure(be, 16 * ((size_t)R + 1))) return nomem();
+		b.wl_in = (uint64_t *)d_wl.p; b.wl_out = b.wl_in + (R + 1);
 		b.w_int_n = std::max(3 * (b.lmax + 18), 2 * (b.lmax + 2) + 2 * b.lmax + 8) + 8;
 		b.w_u64_n = (b.pes_high - b.pes_low + b.lmax) / 2 + 8;
 		b.w_z_n = 8192;
@@ -513,7 +515,7 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2 };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_wl };
 		for (auto *x : all) x->release(be);
 	}
 
@@ -524,7 +526,7 @@ public:
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_wl;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

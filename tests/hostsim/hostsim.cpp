@@ -58,13 +58,13 @@ struct HostBackend {
 		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); return; }
 		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax));
 		lc_ext_run_scalar(b, he.data(), qw.data(), lc_ext_cells8_ok(b) && !wide_cells, idle_ticks);
-		for (unsigned int t = 0; t < *b.ext_heavy_n; ++t) lc_stage_extend(b, b.redo[t], (int)(t % workers));     // the heavy reads' kernel
+		for (unsigned int t = 0; t < *b.ext_heavy_n; ++t) lc_stage_extend(b, (int)(uint32_t)b.wl_in[t], (int)(t % workers));     // the heavy reads' kernel
 	}
 	bool wide_cells = false;     // -H: 16-bit H/E cells even when the batch would fit the byte packing
 	void k_pair(const LcBatch &b, int n_pairs)
 	{
 		for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair_prepare(b, p, p % workers);   // reversed: order must not matter
-		for (unsigned int t = 0; t < *b.resc_n; ++t) lc_stage_pair_rescue(b, b.redo[t], (int)(t % workers));
+		for (unsigned int t = 0; t < *b.resc_n; ++t) lc_stage_pair_rescue(b, (int)(uint32_t)b.wl_in[t], (int)(t % workers));
 	}
 	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 	{
