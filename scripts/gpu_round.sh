@@ -3,7 +3,7 @@
 # of the dominant kernel.  Usage (from the build container):  gpurun --timeout 1500 -- bash scripts/gpu_round.sh [tag] [scale]
 TAG=${1:-r01}
 SCALE=${2:-1.0}
-KERN='regex:smem_kernel|sa_lookup_kernel|chain_kernel|extend_kernel|matesw_kernel|pair_prepare_kernel|global_cigar_kernel|cigar_plan_kernel|cigar_band_kernel|seed_finish_kernel|smem_redo_kernel|pack_kernel|convert_kernel|DeviceScan'
+KERN='regex:smem_kernel|sa_lookup_kernel|chain_kernel|extend_kernel|extend_heavy_kernel|matesw_kernel|pair_prepare_kernel|global_cigar_kernel|cigar_plan_kernel|cigar_band_kernel|seed_finish_kernel|smem_redo_kernel|pack_kernel|convert_kernel|DeviceScan'
 TOP=${3:-smem_kernel}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
