@@ -34,8 +34,8 @@ __device__ __forceinline__ int lc_warp_max(int v)
 
 // ksw_extend2 (B/ksw.c:380-479), one warp.  H, E: shared memory, qlen + 2 ints each.  qs: shared memory, qlen bytes.
 template <class QF, class TF>
-__device__ __noinline__ LcExtResult lc_extend2_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int w, int end_bonus, int zdrop,
-													int h0, int *H, int *E, uint8_t *qs, int lane, LcCounters *cnt)
+__device__ __noinline__ LcExtResult lc_extend2_warp_smem(int qlen, QF query, int tlen, TF target, const LcScore &sc, int w, int end_bonus, int zdrop,
+														 int h0, int *H, int *E, uint8_t *qs, int lane, LcCounters *cnt)
 {
 	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
 	int best = h0, best_i = -1, best_j = -1, g_i = -1, gscore = -1, max_off = 0, beg = 0, end = qlen;
@@ -125,6 +125,151 @@ __device__ __noinline__ LcExtResult lc_extend2_warp(int qlen, QF query, int tlen
 	if (cnt && lane == 0) { atomicAdd(&cnt->ext_calls, 1ull); atomicAdd(&cnt->ext_cells, cells); }
 	LcExtResult r = { best, best_j + 1, best_i + 1, g_i + 1, gscore, max_off };
 	return r;
+}
+
+// ksw_extend2 with the H/E row in REGISTERS (same layout idea as lc_sw_pass_warp_reg below): lane L owns the K consecutive columns
+// L*K .. L*K+K-1 of the row arrays (K * 32 >= qlen + 2).  The row arrays hold, as in the reference, H(i-1, j-1) at index j, so the
+// diagonal needs no shuffle; what moves between lanes per row is the previous column's new h (one shuffle), the F scan across lanes
+// (skipped when no lane hands a positive F on), the row maximum (REDUX) and the two band-shrink scans (two ballots).  Columns outside
+// [beg, end) keep their values, contribute T = 0 to the F chain (so F enters `beg` as 0, B/ksw.c:424) and stay out of the maxima.
+template <int K, class QF, class TF>
+__device__ __noinline__ LcExtResult lc_extend2_warp_reg(int qlen, QF query, int tlen, TF target, const LcScore &sc, int w, int end_bonus, int zdrop,
+														int h0, int lane, LcCounters *cnt)
+{
+	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_ins = sc.e_ins, e_del = sc.e_del;
+	int best = h0, best_i = -1, best_j = -1, g_i = -1, gscore = -1, max_off = 0, beg = 0, end = qlen;
+	unsigned long long cells = 0;
+	const int j0 = lane * K;
+	int Hs[K], Es[K];
+	uint32_t stab[K];            // byte t = score of target base t (0..3) against this column's query base
+#pragma unroll
+	for (int k = 0; k < K; ++k) {                       // row -1 (B/ksw.c:395-397)
+		const int j = j0 + k;
+		int v = 0;
+		if (j == 0) v = h0;
+		else if (j <= qlen) { v = h0 - oe_ins - (j - 1) * e_ins; if (v < 0) v = 0; }
+		Hs[k] = v; Es[k] = 0;
+		uint32_t tw = 0;
+		if (j < qlen) {
+			const int q = query(j);
+#pragma unroll
+			for (int t = 0; t < 4; ++t) tw |= ((uint32_t)sc.sub(t, q) & 0xffu) << (8 * t);
+		}
+		stab[k] = tw;
+	}
+	{
+		int smax = sc.a > 0 ? sc.a : 0;
+		int mi = (int)((double)(qlen * smax + end_bonus - sc.o_ins) / sc.e_ins + 1.);
+		int md = (int)((double)(qlen * smax + end_bonus - sc.o_del) / sc.e_del + 1.);
+		w = min(w, max(mi, 1));
+		w = min(w, max(md, 1));
+	}
+	bool stop = false;
+	for (int i0 = 0; i0 < tlen && !stop; i0 += 32) {
+		const int tmine = i0 + lane < tlen ? target(i0 + lane) : 4;
+		const int nrow = min(32, tlen - i0);
+		for (int ii = 0; ii < nrow; ++ii) {
+			const int i = i0 + ii;
+			const int tb = __shfl_sync(LC_FULL, tmine, ii);
+			if (beg < i - w) beg = i - w;
+			if (end > i + w + 1) end = i + w + 1;
+			if (end > qlen) end = qlen;
+			int h_first = 0;
+			if (beg == 0) { h_first = h0 - (sc.o_del + sc.e_del * (i + 1)); if (h_first < 0) h_first = 0; }
+			const uint32_t tsel = (uint32_t)(tb > 3 ? 4 : tb), sel = tsel | (tsel | 8u) << 4 | (tsel | 8u) << 8 | (tsel | 8u) << 12;
+			int M[K], t[K], g = 0;
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				const int j = j0 + k;
+				const bool act = j >= beg && j < end;
+				const int s = (int)lc_prmt_dev(stab[k], 0xffu, sel);      // ambiguous target base: -1 (B/bwa.c:109-118)
+				const int m = (act && Hs[k]) ? Hs[k] + s : 0;
+				M[k] = m;
+				t[k] = __viaddmax_s32(m, -oe_ins, 0);
+				g = k == 0 ? t[0] : __viaddmax_s32(g, -e_ins, t[k]);
+			}
+			int f = 0;
+			if (__any_sync(LC_FULL, g > 0)) {
+				const int pin = lc_warp_prefix_max_incl(g + (j0 + K - 1) * e_ins, lane);
+				const int pex = __shfl_up_sync(LC_FULL, pin, 1);
+				f = lane > 0 ? max(pex - (j0 - 1) * e_ins, 0) : 0;
+			}
+			int h[K], e2[K], key = -1, cand = 0;
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				const int j = j0 + k;
+				const bool act = j >= beg && j < end;
+				const int hk = max(max(M[k], Es[k]), f);
+				f = __viaddmax_s32(f, -e_ins, t[k]);
+				e2[k] = __viaddmax_s32_relu(M[k], -oe_del, Es[k] - e_del);
+				h[k] = hk;
+				if (act) key = max(key, (hk << 10) | j);
+				if (j == end - 1) cand = hk;
+			}
+			const bool nonempty = beg < end;
+			int hl_carry = __shfl_sync(LC_FULL, cand, nonempty ? (end - 1) / K : 0);        // h of the row's last column
+			if (!nonempty) hl_carry = h_first;
+			const int hprev0 = __shfl_up_sync(LC_FULL, h[K - 1], 1);
+			unsigned nz = 0;                                                                  // bit k: column j0 + k of the new row arrays is non-zero
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				const int j = j0 + k;
+				const int hp = k == 0 ? hprev0 : h[k - 1];
+				if (j >= beg && j < end) { Hs[k] = j == beg ? h_first : hp; Es[k] = e2[k]; }
+				else if (j == end) { Hs[k] = hl_carry; Es[k] = 0; }
+				if ((Hs[k] | Es[k]) != 0) nz |= 1u << k;
+			}
+			cells += (unsigned long long)(nonempty ? end - beg : 0);
+			const int jfin = nonempty ? end : beg;
+			if (jfin == qlen) {
+				if (!(gscore > hl_carry)) g_i = i;
+				gscore = max(gscore, hl_carry);
+			}
+			key = __reduce_max_sync(LC_FULL, key);
+			const int rowmax = key < 0 ? 0 : key >> 10, rowarg = key < 0 ? -1 : key & 1023;
+			if (rowmax == 0) { stop = true; break; }
+			if (rowmax > best) {
+				best = rowmax; best_i = i; best_j = rowarg;
+				max_off = max(max_off, abs(rowarg - i));
+			} else if (zdrop > 0) {
+				const int di = i - best_i, dj = rowarg - best_j;
+				if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) { stop = true; break; } }
+				else { if (best - rowmax - (dj - di) * e_ins > zdrop) { stop = true; break; } }
+			}
+			// shrink the band where H and E are both zero (B/ksw.c:466-469)
+			{
+				unsigned m1 = 0, m2 = 0;                    // my columns in [beg, end) / in [beg, end] that are non-zero
+#pragma unroll
+				for (int k = 0; k < K; ++k) {
+					const int j = j0 + k;
+					if ((nz >> k & 1u) && j >= beg && j < end) m1 |= 1u << k;
+					if ((nz >> k & 1u) && j >= beg && j <= end) m2 |= 1u << k;
+				}
+				const unsigned b1 = __ballot_sync(LC_FULL, m1 != 0);
+				int nb = end;
+				if (b1) { const int L = __ffs(b1) - 1; nb = L * K + (__ffs(__shfl_sync(LC_FULL, m1, L)) - 1); }
+				// the last non-zero column in [nb, end]: columns of m2 left of nb are zero by construction of nb (they are in [beg, nb))
+				const unsigned b2 = __ballot_sync(LC_FULL, m2 != 0);
+				int jj = nb - 1;
+				if (b2) { const int L = 31 - __clz(b2); jj = L * K + (31 - __clz(__shfl_sync(LC_FULL, m2, L))); }
+				beg = nb;
+				end = min(jj + 2, qlen);
+			}
+		}
+	}
+	if (cnt && lane == 0) { atomicAdd(&cnt->ext_calls, 1ull); atomicAdd(&cnt->ext_cells, cells); }
+	LcExtResult r = { best, best_j + 1, best_i + 1, g_i + 1, gscore, max_off };
+	return r;
+}
+
+template <class QF, class TF>
+__device__ __forceinline__ LcExtResult lc_extend2_warp(int qlen, QF query, int tlen, TF target, const LcScore &sc, int w, int end_bonus, int zdrop,
+													   int h0, int *H, int *E, uint8_t *qs, int lane, LcCounters *cnt)
+{
+	if (qlen + 2 <= 128) return lc_extend2_warp_reg<4>(qlen, query, tlen, target, sc, w, end_bonus, zdrop, h0, lane, cnt);
+	if (qlen + 2 <= 160) return lc_extend2_warp_reg<5>(qlen, query, tlen, target, sc, w, end_bonus, zdrop, h0, lane, cnt);
+	if (qlen + 2 <= 256) return lc_extend2_warp_reg<8>(qlen, query, tlen, target, sc, w, end_bonus, zdrop, h0, lane, cnt);
+	return lc_extend2_warp_smem(qlen, query, tlen, target, sc, w, end_bonus, zdrop, h0, H, E, qs, lane, cnt);
 }
 
 // One pass of the local SW with the reference's striped-SSE2 semantics (ksw_u8 / ksw_i16, B/ksw.c:111-334), one warp.
