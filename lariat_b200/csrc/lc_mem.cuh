@@ -328,8 +328,12 @@ LC_HD size_t lc_chain_scratch_bytes(int S)
 		   lc_align8(4 * (size_t)S) * 6 /* s_q, s_len, s_next, order, srt, kept_idx */ + 64;
 }
 
+#define LC_CHAIN_SMALL 12
+#define LC_CHAIN_SMALL_BYTES 1408       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in lc_stage_chain)
 LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 {
+	static_assert(sizeof(LcChainRec) * LC_CHAIN_SMALL + 8 + sizeof(LcBtNode) * (LC_CHAIN_SMALL / (LC_BT_T - 1) + 2) + 8 + (4 * LC_CHAIN_SMALL + 8) * 6 + 64 + 8
+				  <= LC_CHAIN_SMALL_BYTES, "LC_CHAIN_SMALL_BYTES too small");
 	const lc_opt_t &opt = b.opt;
 	const int S = b.r_n_seed[r], NI = b.r_n_intv[r];
 	const int len = (int)(b.off[r + 1] - b.off[r]);
@@ -347,9 +351,16 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 	const float frac_rep = (float)l_rep / len;
 	b.r_frac_rep[r] = frac_rep;
 	if (S == 0) return;
-	unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, lc_chain_scratch_bytes(S), LC_OVF_SCRATCH);
-	if (so == (unsigned long long)-1) return;
-	uint8_t *p = b.scratch + so;
+	// A read with a handful of seeds (the usual case outside repeats) keeps the chainer's arrays in thread-local memory: the pool is
+	// cold global memory, and chaining is a string of dependent accesses to it (ncu: the kernel is latency, not work).
+	uint64_t small[LC_CHAIN_SMALL_BYTES / 8];
+	uint8_t *p;
+	if (S <= LC_CHAIN_SMALL) p = (uint8_t *)small;
+	else {
+		unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, lc_chain_scratch_bytes(S), LC_OVF_SCRATCH);
+		if (so == (unsigned long long)-1) return;
+		p = b.scratch + so;
+	}
 	p = (uint8_t *)lc_align8((size_t)p);
 	LcChainer c;
 	c.ch = (LcChainRec *)p; p += lc_align8(sizeof(LcChainRec) * (size_t)S);
