@@ -158,6 +158,8 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	if (const char *e = getenv("LC_SEED_PK_CAP")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap = v; }
 	if (const char *e = getenv("LC_SEED_LST_CAP2")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap2 = v; }
 	if (const char *e = getenv("LC_SEED_PK_CAP2")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap2 = v; }
+	if (const char *e = getenv("LC_SEED_LST_CAP3")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap3 = v; }
+	if (const char *e = getenv("LC_SEED_PK_CAP3")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap3 = v; }
 	if (const char *e = getenv("LC_EXT_HEAVY_SEEDS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_seeds = v; }
 	if (const char *e = getenv("LC_EXT_HEAVY_CHAINS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_chains = v; }
 	if (const char *e = getenv("LC_FORCE_WIDE")) c->pl.force_wide = e[0] == '1';
@@ -367,7 +369,7 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 		std::unique_ptr<LcLane> l(new LcLane(c->device));
 		l->pl.set_index(c->ix, c->opt);
 		l->pl.lst_cap = c->pl.lst_cap; l->pl.pk_cap = c->pl.pk_cap; l->pl.force_wide = c->pl.force_wide;
-		l->pl.lst_cap2 = c->pl.lst_cap2; l->pl.pk_cap2 = c->pl.pk_cap2;
+		l->pl.lst_cap2 = c->pl.lst_cap2; l->pl.pk_cap2 = c->pl.pk_cap2; l->pl.lst_cap3 = c->pl.lst_cap3; l->pl.pk_cap3 = c->pl.pk_cap3;
 		l->pl.ext_heavy_seeds = c->pl.ext_heavy_seeds; l->pl.ext_heavy_chains = c->pl.ext_heavy_chains;
 		c->lanes.push_back(std::move(l));
 	}

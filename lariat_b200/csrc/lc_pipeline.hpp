@@ -213,7 +213,8 @@ public:
 	int memcap = 256;
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
 	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
-	int lst_cap2 = 150, pk_cap2 = 2048;   // the second pass' capacities; overflow there -> the one-thread-per-read redo kernel
+	int lst_cap2 = 40, pk_cap2 = 256;     // the second and third pass' capacities; overflow of the third -> the one-thread-per-read redo kernel
+	int lst_cap3 = 150, pk_cap3 = 2048;
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
 	bool force_wide = false;
 
@@ -327,18 +328,22 @@ public:
 			n_redo = (int)(uint32_t)h_ctl[22];
 			n_redo_pass1 = n_redo;
 			LcBatch bf = b;                         // the batch as the fallback kernel sees it (its redo list)
-			if (n_redo && !(h_ctl_ovf & LC_OVF_PK)) {
-				// second pass: the reads whose lists outgrew the slots (repeats: many interval sizes, many seeds) run through the same
-				// state machine with lists several times as long — fewer resident warps, but only these reads
+			// further passes: the reads whose lists outgrew the slots (repeats: many interval sizes, many seeds) run through the same
+			// state machine with longer and longer lists — fewer resident warps each time, but only for the reads that need them.
+			// The overflow lists alternate between two buffers; pass p counts its overflows in control word 23 (low / high half).
+			const int caps[2][2] = { { lst_cap2, pk_cap2 }, { lst_cap3, pk_cap3 } };
+			const int32_t *in_list = b.redo;
+			for (int pass = 0; pass < 2 && n_redo && !(h_ctl_ovf & LC_OVF_PK); ++pass) {
 				LcBatch b2 = b;
-				b2.lst_cap = std::min(lst_cap2, b.lmax + 1); b2.pk_cap = pk_cap2;
-				if (!d_redo2.ensure(be, 4 * ((size_t)n_redo + 1)) ||
+				b2.lst_cap = std::min(caps[pass][0], b.lmax + 1); b2.pk_cap = caps[pass][1];
+				LcBuf<BE> &out = pass == 0 ? d_redo2 : d_redo3;
+				if (!out.ensure(be, 4 * ((size_t)n_redo + 1)) ||
 					!d_wpk2.ensure(be, sizeof(LcPk) * (size_t)be.seed_pass_lanes(b2, n_redo) * b2.pk_cap)) return nomem();
-				b2.w_pk = (LcPk *)d_wpk2.p; b2.redo = (int32_t *)d_redo2.p; b2.redo_cur = b.redo_cur + 2;      // control word 23
-				be.k_seed(b2, b.redo, n_redo); ++launches;
+				b2.w_pk = (LcPk *)d_wpk2.p; b2.redo = (int32_t *)out.p; b2.redo_cur = b.redo_cur + 2 + pass;
+				be.k_seed(b2, in_list, n_redo); ++launches;
 				read_ctl();
-				n_redo = (int)(uint32_t)h_ctl[23];
-				bf.redo = b2.redo;
+				n_redo = (int)(uint32_t)(h_ctl[23] >> (32 * pass));
+				bf.redo = b2.redo; in_list = b2.redo;
 			}
 			if (!(h_ctl_ovf & LC_OVF_PK)) {
 				be.k_seed_finish(b); ++launches;    // sort + occurrence schedule + positions
@@ -515,7 +520,7 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_wl };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_redo3, &d_wl };
 		for (auto *x : all) x->release(be);
 	}
 
@@ -526,7 +531,7 @@ public:
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_wl;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_redo3, d_wl;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

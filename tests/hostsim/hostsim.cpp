@@ -142,9 +142,9 @@ int main(int argc, char **argv)
 	pl.counting = count;
 	if (lst_cap > 0) pl.lst_cap = lst_cap;
 	if (pk_cap > 0) pl.pk_cap = pk_cap;
-	if (lst_cap2 > 0) pl.lst_cap2 = lst_cap2;
+	if (lst_cap2 > 0) { pl.lst_cap2 = lst_cap2; pl.lst_cap3 = lst_cap2 + 2; }      // (third pass: barely larger, so that the last fallback still gets reads)
 	if (heavy_seeds >= 0) pl.ext_heavy_seeds = heavy_seeds;
-	if (pk_cap2 > 0) pl.pk_cap2 = pk_cap2;
+	if (pk_cap2 > 0) { pl.pk_cap2 = pk_cap2; pl.pk_cap3 = pk_cap2 + 2; }
 	pl.force_wide = wide != 0;
 	pl.set_index(ix, opt);
 	LcHostResult res;
