@@ -294,7 +294,7 @@ public:
 		{
 			// a forward extension pushes one interval per change of size: ~log4(symbols) entries on unique sequence, more in repeats
 			int want = lst_cap;
-			if (want <= 0) { want = 6; for (uint64_t n = b.ix.seq_len; n > 1; n >>= 2) ++want; }
+			if (want <= 0) { want = 2; for (uint64_t n = b.ix.seq_len; n > 1; n >>= 2) ++want; }
 			b.lst_cap = std::min(want, b.lmax + 1); b.pk_cap = pk_cap;
 		} b.force_wide = force_wide ? 1 : 0;
 		if (!d_wpk.ensure(be, sizeof(LcPk) * (size_t)be.seed_lanes() * b.pk_cap) || !d_redo.ensure(be, 4 * ((size_t)R + 1))) return nomem();
