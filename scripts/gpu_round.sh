@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERN"
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --scale $SCALE --steps 2 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log
 for K in $TOP; do
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f -o gpurun_out/${TAG}_${K} \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$K -s 2 -c 1 -f -o gpurun_out/${TAG}_${K} \
     python bench.py --scale $SCALE --steps 1 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_full_${K}.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full_${K}.log
 done
