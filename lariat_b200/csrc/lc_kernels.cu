@@ -5,10 +5,12 @@
 //   smem_kernel         mem_collect_intv: SMEM / re-seed / LAST-like seeding   (B/bwamem.c:114-162, B/bwt.c:262-379)
 //   sa_lookup_kernel    bwt_sa for every scheduled occurrence                  (B/bwt.c:53-59,86-129; B/bwamem.c:283)
 //   chain_kernel        mem_chain tree insert/merge + mem_chain_flt            (B/bwamem.c:190-385)
-//   extend_kernel       mem_chain2aln -> ksw_extend2                           (B/bwamem.c:632-786, B/ksw.c:380-479)
+//   extend_kernel       mem_chain2aln -> ksw_extend2, one lane per read        (B/bwamem.c:632-786, B/ksw.c:380-479)
+//   extend_heavy_kernel the same for reads with very many chains, one warp per read
 //   matesw_kernel       mem_sort_dedup_patch + the two rescue phases + mem_matesw/ksw_align2
 //                                                                              (B/bwamem.c:437-489, G/gobwa.go:264-324, B/bwamem_pair.c:111-180)
-//   global_cigar_kernel mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2           (B/bwamem.c:1086-1156, B/bwa.c:121-207, B/ksw.c:504-606)
+//   cigar_plan_kernel / cigar_band_kernel<NB> / global_cigar_kernel
+//                       mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2           (B/bwamem.c:1086-1156, B/bwa.c:121-207, B/ksw.c:504-606)
 //   pack_kernel         dense result arrays in barcode/read order
 // All are integer/byte kernels; grids are sized in multiples of the SM count and stride over the batch.
 #include <cuda_runtime.h>

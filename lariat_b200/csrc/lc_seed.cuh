@@ -7,8 +7,10 @@
 // short tick — "do the pending extension (two 256-bit block loads + popcounts), then advance this read's state" — so the
 // expensive part is always converged.  The three passes of mem_collect_intv, the forward/backward phases of bwt_smem1a
 // (B/bwt.c:289-351) and bwt_seed_strategy1 (B/bwt.c:358-379) are states; the interval lists of bwt_smem1a live in shared
-// memory as one packed 16-byte entry per interval, compacted in place.  Frequent transitions are handled inline in the
-// two `after_*` paths; everything rare goes through resolve(), a single ordered sweep over the bookkeeping states.
+// memory as three words per interval ({x0, x2, end}: x1 is only needed while the match grows forward and stays in registers),
+// laid out [word][lane] and compacted in place.  Frequent transitions are handled inline in the two `after_*` paths;
+// everything rare goes through resolve(), a single ordered sweep over the bookkeeping states, which the kernel runs only
+// every few ticks for all lanes that wait for it (lc_kernels.cu).
 // A first design with 4 lanes per read (two per lookup) was measured at 469 warp-instructions per 8 extensions
 // (profiles/r01b_*): replicated bookkeeping, not the lookups, was the cost — hence one lane per read.
 //
@@ -19,7 +21,9 @@
 // U = uint32_t when the index has < 2^32 BWT symbols (intervals fit 32 bits), uint64_t otherwise (< 2^34).
 //
 // Capacity: reads whose interval list outgrows the shared-memory slot (`lst_cap`) or whose seed list outgrows `pk_cap`
-// are appended to a redo list and re-done by the one-thread-per-read kernel (lc_stage_seed), which has no such limits.
+// are appended to a redo list; the host runs the state machine again over that list with larger capacities (up to three
+// passes, lc_pipeline.hpp), and what still does not fit goes to the one-thread-per-read kernel (lc_stage_seed), which
+// has no such limits.
 #pragma once
 #include "lc_mem.cuh"
 
