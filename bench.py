@@ -171,6 +171,12 @@ def main():
                           "e2e": {"value": v, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # stdout carries exactly one JSON line: whatever native libraries write to fd 1 (NCCL prints its version banner there when the box sets
+    # NCCL_DEBUG) goes to stderr instead; the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from lariat_b200 import gobwa
@@ -332,7 +338,7 @@ def main():
            "e2e": {"value": e2e, "unit": "read-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "stage_ms": e2e_ms},
            "gpu_launches": launches * args.steps, "stage_ms_last_step": stage_ms, "counters_per_step": counters,
            "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary()}
-    print(json.dumps(out))
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
