@@ -65,4 +65,9 @@ struct LcCudaBackend {
 	void k_ksw_align(const LcSwJobs &j);
 	void k_sa_batch(const LcIndex &ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt);
 	int check(std::string &err);
+	// first launch error seen since the last check(): a failed launch leaves a stage's outputs uninitialised, so the pipeline
+	// asks after every host round trip instead of carrying on with garbage counts
+	cudaError_t launch_err = cudaSuccess;
+	void note_launch() { const cudaError_t e = cudaGetLastError(); if (e != cudaSuccess && launch_err == cudaSuccess) launch_err = e; }
+	bool launch_failed() { note_launch(); return launch_err != cudaSuccess; }
 };

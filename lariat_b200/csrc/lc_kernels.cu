@@ -14,6 +14,7 @@
 //   pack_kernel         dense result arrays in barcode/read order
 // All are integer/byte kernels; grids are sized in multiples of the SM count and stride over the batch.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -422,6 +423,12 @@ void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
 	convert_kernel<<<grid_for((n + 15) / 16, 256, 8), 256, 0, stream>>>(p, n, ascii ? 1 : 0);
 }
 static bool lc_wide(const LcBatch &b) { return b.ix.seq_len >= 0xffffffffull || b.force_wide; }
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is state of the FUNCTION, not of a stream or a launch, and the lanes of a
+// chunked call launch the same kernels from several host threads with different sizes (seeding passes, chunks with different
+// read lengths): without this lock one thread can lower the limit between another thread's set and its launch, the launch then
+// fails and the stage's outputs stay uninitialised.  Every "set the limit, then launch" pair runs under it.
+static std::recursive_mutex lc_launch_mu;
+#define LC_LAUNCH_GUARD std::lock_guard<std::recursive_mutex> lc_launch_guard_(lc_launch_mu)
 int LcCudaBackend::seed_grid(const LcBatch &b, int n_items)
 {
 	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
@@ -437,9 +444,10 @@ int LcCudaBackend::seed_grid(const LcBatch &b, int n_items)
 	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
 	return (int)(need < cap ? (need ? need : 1) : cap);
 }
-int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { return seed_grid(b, n_items) * LC_SEED_TPB; }
+int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { LC_LAUNCH_GUARD; return seed_grid(b, n_items) * LC_SEED_TPB; }
 void LcCudaBackend::k_seed(const LcBatch &b, const int32_t *list, int n_items)
 {
+	LC_LAUNCH_GUARD;
 	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4, grid = seed_grid(b, n_items);
 	cudaMemsetAsync(b.work_ctr + 3, 0, 4, stream);
 	const unsigned gm = (unsigned)seed_gate_mask;
@@ -475,6 +483,7 @@ void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_ker
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
 template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
 {
+	LC_LAUNCH_GUARD;
 	const int smem = ((LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) + LC_EXT_MTAB_WORDS) * 4;
 	int per_sm = 1;
 	cudaFuncSetAttribute(extend_kernel<CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -492,6 +501,7 @@ void LcCudaBackend::k_extend(const LcBatch &b)
 	unsigned int n = 0;
 	const uint64_t *list = sort_worklist(b, b.ext_heavy_n, n);
 	if (n) {
+		LC_LAUNCH_GUARD;
 		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
 		cudaFuncSetAttribute(extend_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		extend_heavy_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
@@ -515,15 +525,19 @@ void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {
 	// at most n_workers threads: the patch scratch (w_int) is indexed by global thread id
 	pair_prepare_kernel<<<grid_for((unsigned long long)n_pairs, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_pairs);
-	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
-	cudaFuncSetAttribute(matesw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id.
 	unsigned int n = 0;
 	const uint64_t *list = sort_worklist(b, b.resc_n, n);      // pairs that need a Smith-Waterman, heaviest first
-	if (n) matesw_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
+	if (n) {
+		LC_LAUNCH_GUARD;
+		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
+		cudaFuncSetAttribute(matesw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		matesw_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
+	}
 }
 void LcCudaBackend::k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 {
+	LC_LAUNCH_GUARD;
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
 	cudaFuncSetAttribute(global_cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaMemsetAsync(b.work_ctr + 2, 0, 4, stream);      // the stage may be re-launched after a pool regrow
@@ -562,12 +576,14 @@ void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
 }
 void LcCudaBackend::k_ksw_extend(const LcExtJobs &j)
 {
+	LC_LAUNCH_GUARD;
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(j.qmax);
 	cudaFuncSetAttribute(ksw_extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	ksw_extend_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(j);
 }
 void LcCudaBackend::k_ksw_align(const LcSwJobs &j)
 {
+	LC_LAUNCH_GUARD;
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(j.qmax, 3);
 	cudaFuncSetAttribute(ksw_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	ksw_align_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(j);
@@ -580,6 +596,7 @@ int LcCudaBackend::check(std::string &err)
 {
 	cudaError_t e = cudaStreamSynchronize(stream);
 	if (e == cudaSuccess) e = cudaGetLastError();
+	if (e == cudaSuccess && launch_err != cudaSuccess) { e = launch_err; launch_err = cudaSuccess; }
 	if (e != cudaSuccess) { err = std::string("CUDA error: ") + cudaGetErrorString(e); return -1; }
 	return 0;
 }

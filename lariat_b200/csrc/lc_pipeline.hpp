@@ -253,7 +253,7 @@ public:
 	int setup()
 	{
 		const int R = b.n_reads;
-		launches = 0;
+		launches = 0; launch_broken = false;
 		if (!d_perread.ensure(be, (size_t)R * (8 * 6 + 4 * 8) + 256) || !d_nfin.ensure(be, 4 * ((size_t)R + 1))) return nomem();
 		b.r_n_fin = (int32_t *)d_nfin.p;
 		be.dzero(d_nfin.p, 4 * ((size_t)R + 1));
@@ -350,6 +350,7 @@ public:
 				if (n_redo) { be.k_seed_redo(bf, n_redo); ++launches; }
 				read_ctl();
 			}
+			if (launch_broken) { err = "a CUDA kernel launch failed in the seeding stage"; return LC_ECUDA; }
 			if (!(h_ctl_ovf & (LC_OVF_INTV | LC_OVF_SEED | LC_OVF_MEMLIST | LC_OVF_PK))) break;
 			if (attempt > 12) { err = "seeding pools keep overflowing"; return LC_ENOMEM; }
 			if (h_ctl_ovf & LC_OVF_INTV) intv_per_read = std::max(intv_per_read * 2, (double)h_ctl[0] / R * 1.25);
@@ -423,6 +424,7 @@ public:
 		be.k_extend(b); launches += 2;          // lanes (one read each), then a warp per read for the heavy ones
 		be.ev_record(6);
 		read_ctl();
+		if (launch_broken) { err = "a CUDA kernel launch failed in the chain/extend stages"; return LC_ECUDA; }
 		if (h_ctl_ovf) { err = "internal pool overflow in chain/extend (flags " + std::to_string(h_ctl_ovf) + ")"; return LC_ENOMEM; }
 		const unsigned long long NREG = h_ctl[10];
 		// ---- stage 5: per-pair dedup + rescue. every rescue call adds at most one region: sum of caps <= 3 * regions
@@ -433,6 +435,7 @@ public:
 		be.k_pair(b, n_pairs); launches += 2;
 		be.ev_record(7);
 		read_ctl();
+		if (launch_broken) { err = "a CUDA kernel launch failed in the pair stage"; return LC_ECUDA; }
 		if (h_ctl_ovf) { err = "internal pool overflow in pair stage"; return LC_ENOMEM; }
 		const unsigned long long NC = h_ctl[7];
 		n_rescue_pairs = (unsigned long long)(uint32_t)h_ctl[27];
@@ -541,6 +544,11 @@ private:
 		be.d2h(h_ctl, d_ctl.p, sizeof(h_ctl));
 		be.sync();
 		h_ctl_ovf = (uint32_t)h_ctl[16];
+		if (be.launch_failed()) {      // a kernel was not launched: its outputs are garbage — make every caller stop (they all test the overflow word)
+			h_ctl_ovf = 0xffffffffu; launch_broken = true;
+			for (auto &w : h_ctl) w = 0;
+		}
 	}
+	bool launch_broken = false;
 };
 

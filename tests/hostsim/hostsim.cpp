@@ -34,6 +34,7 @@ struct HostBackend {
 	// each stage: items are dealt to `workers` scratch slots round-robin, like the grid-stride loops of the kernels
 	// the seeding state machine with a one-lane group (lc_seed.cuh), then the redo list through the one-thread-per-read body
 	int seed_pass_lanes(const LcBatch &, int) const { return 1; }
+	bool launch_failed() const { return false; }
 	void k_seed(const LcBatch &b, const int32_t *list, int n_items)
 	{
 		std::vector<uint32_t> lst((size_t)LC_SEED_ENT_WORDS * b.lst_cap + 4), q((size_t)lc_seed_q_words(b.lmax) + 4);
