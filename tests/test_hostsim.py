@@ -45,3 +45,26 @@ def test_chunked_call_equals_one_batch(hostsim_bin, tmp_path, chunk):
     subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out), "-K", chunk],
                           stderr=subprocess.DEVNULL)
     assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+
+
+def test_stage_bodies_on_fresh_repeat_rich_data(hostsim_bin, oracle_port, tmp_path):
+    """Fresh seeded data every run (not only the committed golden set): a small c4-shaped workload — repeat families, tandem
+    arrays, long molecules, degraded mates, repeat-biased sampling — through the kernels' stage bodies on the CPU, with idle ticks
+    before every housekeeping step and 64-bit interval arithmetic, against the oracle replay."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from lariat_b200 import index_build, iofmt, synth
+    g = synth.GenomeSpec(1_200_000, 6, 4711, segdup_frac=0.03, segdup_len=(1000, 6000),
+                         families=[(300, 400, 0.10, 0.15), (3000, 40, 0.02, 0.08)], n_tandem=30, name="fchr")
+    r = synth.ReadSpec(1500, 15, mol_len=200_000, mols_per_barcode=20, degraded_frac=0.30, repeat_bias=0.8, seed=4712)
+    contigs, loci = synth.make_genome(g)
+    fa = str(tmp_path / "f.fa")
+    synth.write_fasta(fa, contigs)
+    index_build.build_index(fa, contigs)
+    sim = synth.simulate_pairs(contigs, loci, r)
+    pairs = str(tmp_path / "f.pairs")
+    iofmt.write_pairs(pairs, sim["r1"], sim["r2"])
+    want, got = tmp_path / "want.out", tmp_path / "got.out"
+    subprocess.check_call([os.path.join(oracle_port, "replay_port"), fa, pairs, str(want), "-t", "4"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([hostsim_bin, fa, pairs, str(got), "-I", "2", "-W", "-J", "6"], stderr=subprocess.DEVNULL)
+    assert got.read_bytes() == want.read_bytes()
