@@ -686,12 +686,36 @@ LC_HDN int lc_patch_reg(const LcBatch &b, const uint8_t *query, const lc_alnreg_
 }
 
 // mem_sort_dedup_patch (B/bwamem.c:437-489); query == null disables patching (the call from mem_matesw, B/bwamem_pair.c:175)
-LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E)
+// The reference's introsort over regions, run on 4-byte handles when `h` (h_cap ints of scratch) can hold them: the algorithm sees the
+// same comparisons in the same order, so the permutation — ties included — is the one ks_introsort leaves on the structs themselves;
+// it is then applied in place, one 88-byte move per region instead of one or two per swap.  (In repeats the rescue stage re-sorts
+// lists of hundreds of regions after every insertion, by a single lane: profiles/r01y, 29 % of matesw_kernel's samples.)
+template <class Lt> LC_HD void lc_sort_regs(lc_alnreg_t *a, int n, Lt lt, int *h, int h_cap)
+{
+	if (n < 12 || !h || n > h_cap) { lc_introsort(a, (long)n, lt); return; }
+	for (int i = 0; i < n; ++i) h[i] = i;
+	lc_introsort(h, (long)n, [a, lt](int x, int y) { return lt(a[x], a[y]); });
+	for (int i = 0; i < n; ++i) {                          // position j receives the region that was at h[j]; visited positions are marked h[j] = j
+		if (h[i] == i) continue;
+		const lc_alnreg_t first = a[i];
+		int j = i;
+		for (;;) {
+			const int k = h[j];
+			h[j] = j;
+			if (k == i) { a[j] = first; break; }
+			a[j] = a[k];
+			j = k;
+		}
+	}
+}
+
+// h/h_cap: scratch for lc_sort_regs (may overlap H and E: the sorts and the patching never run at the same time)
+LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0)
 {
 	const lc_opt_t &opt = b.opt;
 	int m, i, j;
 	if (n <= 1) return n;
-	lc_introsort(a, (long)n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; });
+	lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; }, h, h_cap);
 	for (i = 0; i < n; ++i) a[i].n_comp = 1;
 	for (i = 1; i < n; ++i) {
 		lc_alnreg_t &p = a[i];
@@ -722,8 +746,8 @@ LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc
 	}
 	for (i = 0, m = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
 	n = m;
-	lc_introsort(a, (long)n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
-		return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb))); });
+	lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
+		return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb))); }, h, h_cap);
 	for (i = 1; i < n; ++i)
 		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
 	for (i = 1, m = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
@@ -795,7 +819,8 @@ LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const ui
 			for (int i = n - 1; i > at; --i) ma[i] = ma[i - 1];
 			ma[at] = nb;
 		}
-		n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0);   // :175 (n == 1 here); no patching without a query
+		// :175; no patching without a query.  The sub-optimal-row list of the SW just done is dead by now: its memory holds the sort handles
+		n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0, (int *)ex.bl, ex.bl ? 2 * b.w_u64_n : 0);
 	}
 	n_ma = (int)ex.bcast((unsigned long long)n);
 	ex.sync();
@@ -814,7 +839,7 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 		const int r = 2 * p + e;
 		len[e] = (int)(b.off[r + 1] - b.off[r]);
 		src[e] = b.reg + b.r_reg_off[r];
-		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], b.r_n_reg[r], src[e], H, E);      // tail of mem_align1_core (B/bwamem.c:1070)
+		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], b.r_n_reg[r], src[e], H, E, H, 2 * (b.lmax + 18));      // tail of mem_align1_core (B/bwamem.c:1070)
 		for (int i = 0; i < n[e]; ++i) {
 			if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
 			best[e] = lc_max(best[e], src[e][i].score);                                         // G/gobwa.go:264-283
