@@ -107,6 +107,12 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 		for (int i = 0, k = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) chk.mat[k++] = (i == 4 || j == 4) ? -1 : (i == j ? o.a : -o.b);
 		if (memcmp(chk.mat, o.mat, 25) != 0) { fail(LC_EARG, "opt->mat must equal bwa_fill_scmat(a, b)"); return nullptr; }
 		if (o.e_del <= 0 || o.e_ins <= 0 || o.a <= 0 || o.b < 0 || o.min_seed_len < 1 || o.max_occ < 1) { fail(LC_EARG, "unsupported scoring options"); return nullptr; }
+		// the extension / rescue / CIGAR kernels keep H and E in packed 16-bit halves (DPX s16x2): every score and every
+		// score-minus-penalty of a read of up to LC_MAX_READ_LEN bases must stay inside int16, or results would wrap silently
+		const long long pen = std::max<long long>(std::max<long long>((long long)o.o_del + o.e_del, (long long)o.o_ins + o.e_ins), std::max<long long>(o.b, std::max(o.pen_clip5, o.pen_clip3)));
+		if (o.o_del < 0 || o.o_ins < 0 || o.pen_clip5 < 0 || o.pen_clip3 < 0 || pen > 4096 || (long long)LC_MAX_READ_LEN * o.a + pen > 32767) {
+			fail(LC_EARG, "scoring options out of the supported range: LC_MAX_READ_LEN*a + max penalty must be <= 32767 and penalties <= 4096 (16-bit DP cells)"); return nullptr;
+		}
 	}
 	lc_ctx *c = new lc_ctx(device);
 	std::string err;
@@ -140,7 +146,8 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	{
 		const char *env = getenv("LC_DENSE_SA");
 		const bool want = !(env && env[0] == '0');
-		const bool wide = h.seq_len >= 0xffffffffull;
+		const char *fw = getenv("LC_FORCE_WIDE");      // tests: the 64-bit paths (interval arithmetic, sa64) on a small index
+		const bool wide = h.seq_len >= 0xffffffffull || (fw && fw[0] == '1');
 		const size_t bytes = (size_t)(h.seq_len + 1) * (wide ? 8 : 4);
 		size_t free_b = 0, total_b = 0;
 		cudaMemGetInfo(&free_b, &total_b);

@@ -67,7 +67,9 @@ struct LcAnn { int64_t offset; int32_t len; int32_t is_alt; };
 //                                          of the 64 symbols, first symbol in bit 63
 // Same bytes per base (0.5), but a lookup is ONE sector and at most three 64-bit popcounts.  Results are identical:
 // occ(k, c) is a property of the BWT string, not of its packing.
+#ifndef LC_SB_SHIFT              // tests/hostsim builds a second binary with a small value: several superblocks on a small index
 #define LC_SB_SHIFT 26          // blocks per superblock = 2^26 (2^32 symbols)
+#endif
 #define LC_MAX_SB 4             // up to 2^34 symbols (the 3.1 Gb reference doubled is 6.2e9)
 struct LcIndex {
 	uint64_t primary, L2[5], seq_len;

@@ -113,7 +113,7 @@ static inline bool lc_index_scalars(const LcHostIndex &h, LcIndex &ix, std::stri
 }
 // tests/hostsim only: the device layout built with host loops (the product builds it with kernels, lc_kernels.cu)
 struct LcHostDevIndex { std::vector<uint4> occ; std::vector<uint32_t> sa32; std::vector<uint64_t> sa64; };
-static inline bool lc_host_dev_index(const LcHostIndex &h, LcHostDevIndex &d, LcIndex &ix, bool dense, std::string &err)
+static inline bool lc_host_dev_index(const LcHostIndex &h, LcHostDevIndex &d, LcIndex &ix, bool dense, std::string &err, bool wide_sa = false)
 {
 	if (!lc_index_scalars(h, ix, err)) return false;
 	const uint64_t nb = lc_occ_blocks(h.seq_len);
@@ -122,7 +122,7 @@ static inline bool lc_host_dev_index(const LcHostIndex &h, LcHostDevIndex &d, Lc
 	ix.occ = d.occ.data(); ix.sa = h.sa.data(); ix.pac = h.pac.data(); ix.anns = h.anns.data();
 	if (dense) {
 		const uint64_t n_samples = h.sa.size();
-		if (h.seq_len < 0xffffffffull) { d.sa32.assign(h.seq_len + 1, 0); for (uint64_t j = 0; j < n_samples; ++j) lc_sa_fill_sample(ix, j, d.sa32.data()); ix.sa32 = d.sa32.data(); }
+		if (h.seq_len < 0xffffffffull && !wide_sa) { d.sa32.assign(h.seq_len + 1, 0); for (uint64_t j = 0; j < n_samples; ++j) lc_sa_fill_sample(ix, j, d.sa32.data()); ix.sa32 = d.sa32.data(); }
 		else { d.sa64.assign(h.seq_len + 1, 0); for (uint64_t j = 0; j < n_samples; ++j) lc_sa_fill_sample(ix, j, d.sa64.data()); ix.sa64 = d.sa64.data(); }
 	}
 	return true;
@@ -236,8 +236,12 @@ public:
 		const int R = 2 * n_pairs;
 		const int64_t off0 = off[0], total = off[R] - off0;     // off0 != 0: the batch is a slice of a larger packed array
 		int lmax = 1;
-		for (int r = 0; r < R; ++r) lmax = std::max<int>(lmax, (int)(off[r + 1] - off[r]));
-		if (lmax > LC_MAX_READ_LEN) { err = "read longer than LC_MAX_READ_LEN"; return LC_EARG; }
+		for (int r = 0; r < R; ++r) {      // the caller's offsets are not trusted: lengths in int64, 0 <= len <= LC_MAX_READ_LEN
+			const int64_t len = off[r + 1] - off[r];
+			if (len < 0) { err = "read offsets must be non-decreasing"; return LC_EARG; }
+			if (len > LC_MAX_READ_LEN) { err = "read longer than LC_MAX_READ_LEN"; return LC_EARG; }
+			lmax = std::max<int>(lmax, (int)len);
+		}
 		be.ev_record(0);
 		if (!d_seq.ensure(be, (size_t)total + 16) || !d_off.ensure(be, sizeof(int64_t) * (R + 1))) return nomem();
 		if (total) be.h2d(d_seq.p, bases + off0, (size_t)total);
@@ -454,8 +458,10 @@ public:
 				be.k_cigar_fallback(b, NC); ++launches;
 			}
 			read_ctl();
+			if (launch_broken) { err = "a CUDA kernel launch failed in the cigar stage"; return LC_ECUDA; }
 			n_cig_fallback = (unsigned long long)(uint32_t)(h_ctl[24 + LC_CIG_FALLBACK / 2] >> (32 * (LC_CIG_FALLBACK & 1)));
 			if (!h_ctl_ovf) break;
+			if (h_ctl_ovf & ~(uint32_t)(LC_OVF_CIGAR | LC_OVF_Z)) { err = "internal pool overflow in the cigar stage (flags " + std::to_string(h_ctl_ovf) + ")"; return LC_ENOMEM; }
 			if (attempt > 12) { err = "cigar pools keep overflowing"; return LC_ENOMEM; }
 			if (h_ctl_ovf & LC_OVF_CIGAR) cigar_per_cand = std::max(cigar_per_cand * 2, (double)h_ctl[8] / std::max<double>(NC, 1) * 1.25);
 			if (h_ctl_ovf & LC_OVF_Z) { z_pool_bytes = std::max<size_t>(z_pool_bytes * 2, (size_t)(h_ctl[9] * 1.25)); z_per_cand = std::max(z_per_cand, (double)h_ctl[9] / std::max<double>(NC, 1) * 1.25); }

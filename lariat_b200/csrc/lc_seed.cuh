@@ -47,17 +47,23 @@ template <> struct LcPkOps<uint32_t> {
 	static LC_HD int e1(const LcPk &p) { return (int)(p.m & 0xffff); }
 	static LC_HD int e2(const LcPk &p) { return (int)(p.m >> 16); }
 };
+// LC_PK_LOW_BITS: how many bits of a 64-bit interval value stay in its 32-bit word; the rest (2 bits) go to the shared word.  32 in the
+// product; tests/hostsim builds a second binary with 18 so that the high fields are non-zero on a small index (same code path).
+#ifndef LC_PK_LOW_BITS
+#define LC_PK_LOW_BITS 32
+#endif
+#define LC_PK_LOW_MASK ((uint32_t)((1ull << LC_PK_LOW_BITS) - 1))
 template <> struct LcPkOps<uint64_t> {      // x < 2^34, positions < 4096
 	static LC_HD LcPk pack(uint64_t x0, uint64_t x1, uint64_t x2, int e1, int e2)
 	{
 		LcPk p;
-		p.a = (uint32_t)x0; p.b = (uint32_t)x1; p.c = (uint32_t)x2;
-		p.m = (uint32_t)(x0 >> 32) | (uint32_t)(x1 >> 32) << 2 | (uint32_t)(x2 >> 32) << 4 | (uint32_t)e1 << 8 | (uint32_t)e2 << 20;
+		p.a = (uint32_t)x0 & LC_PK_LOW_MASK; p.b = (uint32_t)x1 & LC_PK_LOW_MASK; p.c = (uint32_t)x2 & LC_PK_LOW_MASK;
+		p.m = (uint32_t)(x0 >> LC_PK_LOW_BITS) | (uint32_t)(x1 >> LC_PK_LOW_BITS) << 2 | (uint32_t)(x2 >> LC_PK_LOW_BITS) << 4 | (uint32_t)e1 << 8 | (uint32_t)e2 << 20;
 		return p;
 	}
-	static LC_HD uint64_t x0(const LcPk &p) { return (uint64_t)(p.m & 3) << 32 | p.a; }
-	static LC_HD uint64_t x1(const LcPk &p) { return (uint64_t)((p.m >> 2) & 3) << 32 | p.b; }
-	static LC_HD uint64_t x2(const LcPk &p) { return (uint64_t)((p.m >> 4) & 3) << 32 | p.c; }
+	static LC_HD uint64_t x0(const LcPk &p) { return (uint64_t)(p.m & 3) << LC_PK_LOW_BITS | p.a; }
+	static LC_HD uint64_t x1(const LcPk &p) { return (uint64_t)((p.m >> 2) & 3) << LC_PK_LOW_BITS | p.b; }
+	static LC_HD uint64_t x2(const LcPk &p) { return (uint64_t)((p.m >> 4) & 3) << LC_PK_LOW_BITS | p.c; }
 	static LC_HD int e1(const LcPk &p) { return (int)((p.m >> 8) & 0xfff); }
 	static LC_HD int e2(const LcPk &p) { return (int)(p.m >> 20); }
 };
@@ -150,9 +156,9 @@ template <> struct LcEntOps<uint32_t> {
 };
 template <> struct LcEntOps<uint64_t> {      // x < 2^34
 	static LC_HD void pack(uint64_t x0, uint64_t x2, int e, uint32_t &w0, uint32_t &w1, uint32_t &w2)
-	{ w0 = (uint32_t)x0; w1 = (uint32_t)x2; w2 = (uint32_t)(x0 >> 32) | (uint32_t)(x2 >> 32) << 2 | (uint32_t)e << 4; }
+	{ w0 = (uint32_t)x0 & LC_PK_LOW_MASK; w1 = (uint32_t)x2 & LC_PK_LOW_MASK; w2 = (uint32_t)(x0 >> LC_PK_LOW_BITS) | (uint32_t)(x2 >> LC_PK_LOW_BITS) << 2 | (uint32_t)e << 4; }
 	static LC_HD void unpack(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t &x0, uint64_t &x2, int &e)
-	{ x0 = (uint64_t)(w2 & 3) << 32 | w0; x2 = (uint64_t)((w2 >> 2) & 3) << 32 | w1; e = (int)(w2 >> 4); }
+	{ x0 = (uint64_t)(w2 & 3) << LC_PK_LOW_BITS | w0; x2 = (uint64_t)((w2 >> 2) & 3) << LC_PK_LOW_BITS | w1; e = (int)(w2 >> 4); }
 };
 
 template <typename U, bool COUNT = true, int STRIDE = 1> struct LcSeedLane {      // COUNT = false: the work counters are compiled out; STRIDE: words between

@@ -34,6 +34,21 @@ def hostsim_bin():
 
 
 @pytest.fixture(scope="session")
+def hostsim_sb_bin():
+    """The same harness with 2^12-block superblocks and an 18-bit low word in the packed 64-bit interval entries: on the tiny golden
+    index (8e5 symbols) the superblock index runs 0..3 and the 2-bit high fields are non-zero — the arithmetic a >= 2^32-symbol
+    index exercises in the product build (LC_SB_SHIFT 26, LC_PK_LOW_BITS 32)."""
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, "hostsim_sb")
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    deps = [src] + [os.path.join(ROOT, "lariat_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "lariat_b200", "csrc"))
+                    if f.endswith((".cuh", ".hpp"))]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-DLC_SB_SHIFT=12", "-DLC_PK_LOW_BITS=18", "-o", out, src])
+    return out
+
+
+@pytest.fixture(scope="session")
 def lib_path():
     p = os.path.join(ROOT, "lariat_b200", "libcuda_lariat.so")
     if not os.path.exists(p):

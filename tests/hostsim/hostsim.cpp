@@ -137,7 +137,7 @@ int main(int argc, char **argv)
 
 	LcIndex ix;
 	LcHostDevIndex dix;
-	if (!lc_host_dev_index(hix, dix, ix, dense != 0, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+	if (!lc_host_dev_index(hix, dix, ix, dense != 0, err, wide != 0))  /* -W: 64-bit intervals AND the 64-bit dense suffix array */ { fprintf(stderr, "%s\n", err.c_str()); return 1; }
 	lc_opt_t opt; lc_default_opt(&opt);
 	LcPipeline<HostBackend> pl(be);
 	pl.counting = count;

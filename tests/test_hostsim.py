@@ -68,3 +68,14 @@ def test_stage_bodies_on_fresh_repeat_rich_data(hostsim_bin, oracle_port, tmp_pa
     subprocess.check_call([os.path.join(oracle_port, "replay_port"), fa, pairs, str(want), "-t", "4"], stderr=subprocess.DEVNULL)
     subprocess.check_call([hostsim_bin, fa, pairs, str(got), "-I", "2", "-W", "-J", "6"], stderr=subprocess.DEVNULL)
     assert got.read_bytes() == want.read_bytes()
+
+
+@pytest.mark.parametrize("extra", [["-W"], ["-W", "-S"], ["-W", "-C", "6", "-M", "4", "-D", "9", "-E", "7"], ["-W", "-I", "2", "-K", "101"]])
+def test_multi_superblock_and_high_interval_bits(hostsim_sb_bin, tmp_path, extra):
+    """What an index of >= 2^32 symbols exercises and a small one never does: superblock index >= 1 in every occ lookup and LF step,
+    non-zero high bits in the packed 64-bit interval entries (LcPkOps / LcEntOps), the 64-bit dense suffix array.  The harness is
+    rebuilt with 2^12-block superblocks and an 18-bit low word, so the tiny golden index has 4 superblocks and 20-bit intervals."""
+    out = tmp_path / "sim.out"
+    subprocess.check_call([hostsim_sb_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out)] + extra,
+                          stderr=subprocess.DEVNULL)
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
