@@ -187,6 +187,13 @@ int64_t lc_collect_intv_batch(lc_ctx *ctx, int n, const uint8_t *codes, const in
 /* bwt_sa (B/bwt.c:86-96) for n BWT rows */
 int lc_sa_batch(lc_ctx *ctx, int64_t n, const uint64_t *rows, uint64_t *out, float *ms);
 
+/* `bwa index` = bwa_idx_build (B/bwtindex.c:251-316) for an N-free reference, on the GPU: writes <prefix>.pac/.ann/.amb/.bwt/.sa,
+ * byte for byte the files the reference writes (pack: B/bntseq.c:275-328; BWT of forward + reverse complement: B/bwtindex.c:84-121;
+ * occ interleave: B/bwtindex.c:151-173; SA sampled every 32 rows: B/bwt.c:62-84; dump formats: B/bwt.c:385-407).
+ * codes[i]: the lens[i] bases of contig i as 2-bit codes 0..3, one per byte (ambiguous bases are rejected: the reference draws them
+ * from lrand48).  Sized for the 3.1 Gb reference: 6.2e9 suffixes are sorted in lexicographic chunks that fit one GPU's HBM. */
+int lc_index_build(const char *prefix, int n_contigs, const char *const *names, const uint8_t *const *codes, const int64_t *lens, int device);
+
 void lc_set_counting(lc_ctx *ctx, int on);
 /* Calls of more than 1.5 x n_pairs pairs are cut into chunks of about n_pairs pairs that alternate between two CUDA streams, so that the
  * H2D / D2H copies of one chunk run under the kernels of the other (the reference's analogue: barcode groups flowing through the

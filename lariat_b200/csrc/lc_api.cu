@@ -14,6 +14,7 @@
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+void lc_api_set_error(const std::string &msg) { g_err = msg; }      // for the other translation units of the library (lc_index_build.cu)
 
 // A growable pinned host buffer (cudaHostAlloc): D2H into it runs at PCIe speed and overlaps with kernels of the other lane.
 struct LcPinned {

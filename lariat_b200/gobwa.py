@@ -78,7 +78,7 @@ class lc_alnreg_v(C.Structure):
 EXPORTS = ["lc_opt_init", "lc_init", "lc_destroy", "lc_last_error", "lc_contigs", "lc_align_pairs", "lc_align_packed",
            "lc_batch_upload", "lc_batch_run", "lc_batch_fetch", "lc_free_result", "lc_fetch_seq", "lc_mem_align1_core",
            "lc_mem_matesw", "lc_mem_reg2aln", "lc_ksw_extend_batch", "lc_ksw_align_batch", "lc_collect_intv_batch",
-           "lc_sa_batch", "lc_set_counting", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
+           "lc_sa_batch", "lc_index_build", "lc_set_counting", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
 
 _lib = None
 
@@ -114,6 +114,7 @@ def load_library(path: str = LIB_PATH):
     lib.lc_ksw_align_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, f32p, u64p]
     lib.lc_collect_intv_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int64, f32p]; lib.lc_collect_intv_batch.restype = C.c_int64
     lib.lc_sa_batch.argtypes = [vp, C.c_int64, vp, vp, f32p]
+    lib.lc_index_build.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), i64p, C.c_int]
     lib.lc_set_counting.argtypes = [vp, C.c_int]; lib.lc_set_counting.restype = None
     lib.lc_set_chunk_pairs.argtypes = [vp, C.c_int]; lib.lc_set_chunk_pairs.restype = C.c_int
     lib.lc_timer_start.argtypes = [vp]
@@ -229,6 +230,45 @@ class BatchResult:
                 out.append(np.array([a["rid"], a["is_rev"], a["NM"], a["n_cigar"]], dtype="<i4").tobytes())
                 out.append(self.cigar_of(i).astype("<u4").tobytes())
         return b"".join(out)
+
+
+    def dump_fast(self, n_pairs: int | None = None) -> bytes:
+        """dump() of the first n_pairs pairs without per-read Python work (numpy scatter): bench.py verifies 10^5-pair prefixes with it."""
+        R = self.n_reads if n_pairs is None else min(self.n_reads, 2 * n_pairs)
+        ro = np.asarray(self.reg_off[:R + 1], dtype=np.int64)
+        c0, c1 = int(ro[0]), int(ro[R])
+        k = np.diff(ro)                                           # candidates per read
+        aln = self.aln[c0:c1]
+        nc = aln["n_cigar"].astype(np.int64)
+        cand_sz = 24 + 4 * nc
+        csum = np.concatenate([[0], np.cumsum(cand_sz)])
+        read_sz = 4 + 88 * k + (csum[ro[1:] - c0] - csum[ro[:-1] - c0])
+        read_off = 8 + np.concatenate([[0], np.cumsum(read_sz)])
+        buf = np.zeros(int(read_off[-1]), dtype=np.uint8)
+        buf[:4] = np.frombuffer(b"LRO1", dtype=np.uint8)
+        buf[4:8] = np.frombuffer(np.int32(R // 2).tobytes(), dtype=np.uint8)
+        hdr = read_off[:-1, None] + np.arange(4)[None, :]
+        buf[hdr.reshape(-1)] = k.astype("<i4").view(np.uint8)
+        n = c1 - c0
+        if n:
+            rd = np.repeat(np.arange(R), k)                       # read of each candidate
+            j = np.arange(n) - (ro[rd] - c0)                      # its index inside the read
+            reg_dst = read_off[rd] + 4 + 88 * j
+            buf[(reg_dst[:, None] + np.arange(88)[None, :]).reshape(-1)] = self.regs[c0:c1].view(np.uint8).reshape(-1)
+            aln_dst = read_off[rd] + 4 + 88 * k[rd] + (csum[:-1] - csum[ro[rd] - c0])
+            fixed = np.zeros((n, 24), dtype=np.uint8)
+            fixed[:, :8] = aln["pos"].astype("<i8").view(np.uint8).reshape(n, 8)
+            for t, f in enumerate(("rid", "is_rev", "NM", "n_cigar")):
+                fixed[:, 8 + 4 * t:12 + 4 * t] = aln[f].astype("<i4").view(np.uint8).reshape(n, 4)
+            buf[(aln_dst[:, None] + np.arange(24)[None, :]).reshape(-1)] = fixed.reshape(-1)
+            tot = int(nc.sum())
+            if tot:
+                cand = np.repeat(np.arange(n), nc)
+                t = np.arange(tot) - np.repeat(np.concatenate([[0], np.cumsum(nc)])[:-1], nc)
+                src = aln["cigar_off"].astype(np.int64)[cand] + t
+                dst = aln_dst[cand] + 24 + 4 * t
+                buf[(dst[:, None] + np.arange(4)[None, :]).reshape(-1)] = self.cigars[src].astype("<u4").view(np.uint8)
+        return buf.tobytes()
 
 
 class GoBwaReference:           # gobwa.go:21-24

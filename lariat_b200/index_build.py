@@ -1,4 +1,4 @@
-"""BWA-compatible index construction on the GPU.
+"""BWA-compatible index construction.
 
 Produces, byte for byte, the five files `bwa index` writes for an N-free reference
 (reference: go/src/gobwa/bwa/bwtindex.c:151-173,262-316, bwt.c:62-84,385-407, bntseq.c:66-96,275-328):
@@ -7,21 +7,42 @@ Produces, byte for byte, the five files `bwa index` writes for an N-free referen
     <prefix>.bwt   BWT of forward+reverse-complement text with the occ counts interleaved every 128 symbols
     <prefix>.sa    suffix array sampled every 32 rows
 
-The reference builds the BWT single-threaded (IS below 50 Mbp, rope/RLE above: ~6 min for 100 Mb, hours for 3.1 Gb)
-and then walks the whole text through invPsi for the SA samples.  Here the suffix array of the doubled text is built
-by prefix doubling with device-wide radix sorts (torch.sort on the current CUDA device; plain CPU tensors work for
-small genomes), the BWT and the SA samples are gathers.  Index construction is input preparation, not the hot path.
+`build_index` is the product path: `lc_index_build` of libcuda_lariat.so (lariat_b200/csrc/lc_index_build.{hpp,cu}) —
+chunked suffix sorting with device-wide radix sorts, sized for the 3.1 Gb reference (6.2e9 suffixes) in one GPU's HBM.
+It needs a GPU and fails loudly without one.
+
+`build_index_torch` is a small-genome helper for the CPU test-suite only (prefix doubling on torch.sort, ~64 B/base):
+tests that need an index for fresh synthetic data on a machine without a GPU use it; nothing in the product does.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import numpy as np
-import torch
 
 
-def _suffix_array(T: torch.Tensor) -> torch.Tensor:
+def build_index(prefix: str, contigs, device=0) -> dict:
+    """contigs: list of (name, uint8 code array 0..3).  Writes <prefix>.{pac,ann,amb,bwt,sa} with the CUDA builder."""
+    from . import gobwa
+    lib = gobwa.load_library()
+    if isinstance(device, str):      # "cuda:1" / "cuda"
+        device = int(device.split(":")[1]) if ":" in device else 0
+    arrs = [np.ascontiguousarray(c, dtype=np.uint8) for _, c in contigs]
+    n = len(arrs)
+    names = (C.c_char_p * n)(*[nm.encode() for nm, _ in contigs])
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * n)(*[a.size for a in arrs])
+    rc = lib.lc_index_build(prefix.encode(), n, names, ptrs, lens, int(device))
+    if rc != 0:
+        raise RuntimeError(f"lc_index_build failed ({rc}): {gobwa.last_error()}")
+    L = int(sum(a.size for a in arrs))
+    return dict(l_pac=L, seq_len=2 * L)
+
+
+def _suffix_array(T):
     """Ranks (1-based, unique) of all suffixes of T (uint8 codes 0..3), '$' < A."""
+    import torch
     n = T.numel()
     dev = T.device
     k0 = 24 if n > 1 << 22 else 12
@@ -67,10 +88,9 @@ def _suffix_array(T: torch.Tensor) -> torch.Tensor:
     return rank
 
 
-def build_index(prefix: str, contigs, device: str | None = None, sa_intv: int = 32) -> dict:
-    """contigs: list of (name, uint8 code array 0..3).  Writes <prefix>.{pac,ann,amb,bwt,sa}."""
-    if device is None:
-        device = "cuda" if torch.cuda.is_available() else "cpu"
+def build_index_torch(prefix: str, contigs, device: str = "cpu", sa_intv: int = 32) -> dict:
+    """TEST HELPER (small genomes, CPU tensors): same files as build_index, by prefix doubling on torch.sort."""
+    import torch
     fwd_np = np.concatenate([np.asarray(c, dtype=np.uint8) for _, c in contigs])
     if fwd_np.max(initial=0) > 3:
         raise ValueError("ambiguous bases are not supported by this builder (the reference randomises them with lrand48)")
@@ -148,8 +168,8 @@ def build_index(prefix: str, contigs, device: str | None = None, sa_intv: int = 
     return dict(l_pac=L, seq_len=n, primary=primary)
 
 
-def build_index_from_fasta(fa: str, device: str | None = None) -> dict:
-    """Index an (N-free, ACGT upper-case) FASTA in place: <fa>.{pac,ann,amb,bwt,sa} like `bwa index <fa>`."""
+def build_index_from_fasta(fa: str, device=0) -> dict:
+    """Index an (N-free, ACGT) FASTA in place: <fa>.{pac,ann,amb,bwt,sa} like `bwa index <fa>` (CUDA builder)."""
     lut = np.full(256, 255, dtype=np.uint8)
     for ch, v in ((b"Aa", 0), (b"Cc", 1), (b"Gg", 2), (b"Tt", 3)):
         for c in ch:

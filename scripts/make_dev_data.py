@@ -22,7 +22,7 @@ t = time.time()
 contigs, loci = synth.make_genome(g)
 fa = os.path.join(d, name + ".fa")
 synth.write_fasta(fa, contigs)
-index_build.build_index(fa, contigs)
+index_build.build_index_torch(fa, contigs)
 sim = synth.simulate_pairs(contigs, loci, r)
 iofmt.write_pairs(os.path.join(d, name + ".pairs"), sim["r1"], sim["r2"])
 print(f"{name}: {bp} bp, {n} pairs in {time.time() - t:.1f}s -> {fa}")

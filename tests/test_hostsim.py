@@ -60,7 +60,7 @@ def test_stage_bodies_on_fresh_repeat_rich_data(hostsim_bin, oracle_port, tmp_pa
     contigs, loci = synth.make_genome(g)
     fa = str(tmp_path / "f.fa")
     synth.write_fasta(fa, contigs)
-    index_build.build_index(fa, contigs)
+    index_build.build_index_torch(fa, contigs)
     sim = synth.simulate_pairs(contigs, loci, r)
     pairs = str(tmp_path / "f.pairs")
     iofmt.write_pairs(pairs, sim["r1"], sim["r2"])
