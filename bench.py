@@ -330,6 +330,7 @@ def main():
         log(f"[bench] verified {sample} pairs bit-exact vs the CPU {kind} ({hashlib.md5(want).hexdigest()}); CPU {j['pairs_per_s']:.0f} pairs/s on {ncores} threads")
     lib.lc_set_counting(ctx, 0)
     del br
+    lib.lc_free_result(ctx, res)      # results belong to the caller until it frees them (the reference: arena.Free(), lariat.go:546)
 
     # ---- device-resident arm: value
     # (the device-resident arm keeps one batch and its pools in HBM: on repeat-rich data the pools of 1 M pairs may not fit, then the
@@ -374,38 +375,44 @@ def main():
         check(lib.lc_set_chunk_pairs(ctx, cp))
         for _ in range(2):
             check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+            lib.lc_free_result(ctx, res)
         tw = time.perf_counter()
         for _ in range(args.steps):
             check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
+            last = {k: round(float(getattr(res.contents, k)), 2) for k in all_keys}
+            lib.lc_free_result(ctx, res)
         tw = (time.perf_counter() - tw) / args.steps
-        log(f"[bench] e2e sweep chunk_pairs={cp}: {1e3 * tw:.2f} ms/step wall, {n_pairs / tw:.0f} pairs/s; last call " +
-            json.dumps({k: round(float(getattr(res.contents, k)), 2) for k in all_keys}))
+        log(f"[bench] e2e sweep chunk_pairs={cp}: {1e3 * tw:.2f} ms/step wall, {n_pairs / tw:.0f} pairs/s; last call " + json.dumps(last))
     if args.chunk_pairs >= 0:
         check(lib.lc_set_chunk_pairs(ctx, args.chunk_pairs))
 
     def time_e2e(b_ptr, o_ptr):
+        """K calls, each followed by lc_free_result (the result is the caller's until then); returns (seconds, facts of the last call)"""
         for _ in range(max(1, args.warmup - 1)):
             check(lib.lc_align_packed(ctx, n_pairs, b_ptr, o_ptr, 25, C.byref(res)))
+            lib.lc_free_result(ctx, res)
         sync_all()
         t0 = time.perf_counter()
         check(lib.lc_timer_start(ctx))
+        facts = None
         for _ in range(args.steps):
             check(lib.lc_align_packed(ctx, n_pairs, b_ptr, o_ptr, 25, C.byref(res)))
+            rr = res.contents
+            facts = (int(rr.n_regs), int(rr.n_cigar_words), int(rr.n_reads), {k: float(getattr(rr, k)) for k in all_keys})
+            lib.lc_free_result(ctx, res)
         check(lib.lc_timer_stop(ctx, C.byref(ms_dev)))
         sync_all()
         wall = time.perf_counter() - t0
         # the call returns with the results on the host, so device events and the host clock bracket the same work; report the larger
-        return max(ms_dev.value * 1e-3, wall)
+        return max(ms_dev.value * 1e-3, wall), facts
 
-    dte = time_e2e(hb.data_ptr(), ho.data_ptr())
+    dte, (n_regs, n_cw, n_rd, e2e_ms) = time_e2e(hb.data_ptr(), ho.data_ptr())      # stage times are sums over the chunks of the call (chunks of the two lanes overlap)
     e2e = total_pairs * args.steps / sharding.max_over_ranks(dte, device="cuda")
-    rr = res.contents
     h2d = int(bases.nbytes + off.nbytes)
-    d2h = int(rr.n_regs * (88 + 32) + rr.n_cigar_words * 4 + (rr.n_reads + 1) * 8)
-    e2e_ms = {k: float(getattr(rr, k)) for k in all_keys}     # stage times are sums over the chunks of the call (chunks of the two lanes overlap)
+    d2h = int(n_regs * (88 + 32) + n_cw * 4 + (n_rd + 1) * 8)
     # the same call fed from pageable memory (what a cgo caller hands over: a Go slice)
     pb, po = np.array(bases, copy=True), np.array(off, copy=True)
-    dtp = time_e2e(pb.ctypes.data, po.ctypes.data)
+    dtp, _ = time_e2e(pb.ctypes.data, po.ctypes.data)
     e2e_pageable = total_pairs * args.steps / sharding.max_over_ranks(dtp, device="cuda")
     sampler.stop_flag = True
 

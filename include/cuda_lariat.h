@@ -6,8 +6,17 @@
  * no torch / CUDA types.  Each entry point names the reference interface it replaces ("G/" =
  * go/src/gobwa/, "B/" = go/src/gobwa/bwa/ in the reference tree).  See INTEGRATION.md for the cgo stub.
  *
- * Threading: an lc_ctx is bound to one GPU; calls on one lc_ctx are serialised internally.  Use one lc_ctx
- * per GPU (lc_init per device) and any number of host threads.
+ * Threading and ownership (what Lariat's worker pool needs: I/lariat.go:348-376,473,546; G/gobwa.go:107-126):
+ *   - An lc_ctx may be used by ANY number of host threads at once.  Calls of up to a few thousand pairs (one barcode group is ~100)
+ *     are merged across threads into device batches and cut apart again (lc_set_coalescing); larger calls run one at a time per
+ *     context, chunked over two CUDA streams.  lc_clone gives further contexts on the SAME index for callers that want several
+ *     large calls in flight: the index (FM-index, dense suffix array, packed reference) is in HBM once per lc_init, never per context.
+ *   - A result (*out of lc_align_packed / lc_align_pairs) belongs to the CALLER from the moment the call returns until
+ *     lc_free_result: no later call — on this context, a clone, or another thread — touches it.  This is the reference's Arena:
+ *     ChainedHit pointers alias the result arrays until the barcode's arena.Free().
+ *   - lc_destroy of the last context of an index frees the index; results already handed out stay valid until freed.
+ * Supported scoring options: the reference's defaults and anything with LC_MAX_READ_LEN * a + max(penalty) <= 32767 and every
+ *   penalty <= 4096 (the DP kernels keep H and E in 16-bit cells); mat must be bwa_fill_scmat(a, b).  lc_init rejects the rest.
  * Errors: functions return 0 on success, a negative LC_E* code otherwise; lc_last_error() gives the text.
  * Nothing here ever calls exit() (the reference does: B/malloc_wrap.c, B/utils.c).
  * There is NO CPU fallback: without a CUDA device lc_init fails with LC_ENODEV.
@@ -144,7 +153,7 @@ const lc_contigs_t *lc_contigs(const lc_ctx *ctx);
  * GoBwaSmithWaterman / mem_reg2aln (G/gobwa.go:400-415) on every candidate — one call, a fixed number of launches.
  * seq1[p]/seq2[p]: ASCII bases (ACGTacgt, anything else = N) of length len1[p]/len2[p]; a zero length end is
  * skipped exactly as the Go code does (G/gobwa.go:243,252,287,311).  score_delta: Lariat passes 25 (I/lariat.go:475).
- * *out stays valid until the next call on ctx that produces a result, or lc_free_result. */
+ * *out is owned by the caller until lc_free_result(ctx, *out) (see "Threading and ownership" above). */
 int lc_align_pairs(lc_ctx *ctx, int n_pairs, const uint8_t *const *seq1, const int32_t *len1,
                    const uint8_t *const *seq2, const int32_t *len2, int score_delta, lc_result_t **out);
 
@@ -156,7 +165,17 @@ int lc_align_packed(lc_ctx *ctx, int n_pairs, const uint8_t *bases, const int64_
 int lc_batch_upload(lc_ctx *ctx, int n_pairs, const uint8_t *bases, const int64_t *off);
 int lc_batch_run(lc_ctx *ctx, int score_delta);
 int lc_batch_fetch(lc_ctx *ctx, lc_result_t **out);
+/* (the result of lc_batch_fetch and the arrays of the single-read forms live in the context and are recycled by the next such call) */
+/* Arena.Free (G/gobwa.go:119-126): gives a result of lc_align_packed / lc_align_pairs back.  Safe from any thread. */
 void lc_free_result(lc_ctx *ctx, lc_result_t *res);
+/* Another context on the index of `ctx` (same device): own CUDA stream, pools and lock, no second copy of the index.  Destroy each
+ * with lc_destroy.  Replaces nothing in the reference (its bwaidx_t is read-only shared memory, G/gobwa.go:128-147) — this is how the
+ * same sharing is expressed for device memory. */
+lc_ctx *lc_clone(lc_ctx *ctx);
+/* Merging of small calls: calls of at most max_call_pairs pairs (0 = never merge) from all threads and contexts of the index are
+ * run as batches of at most max_batch_pairs pairs, up to `lanes` batches in flight; a leader may wait linger_us for company.
+ * Defaults 4096 / 65536 / 3 / 0 (env LC_COALESCE_MAX, LC_COALESCE_BATCH, LC_COALESCE_LANES, LC_COALESCE_LINGER_US).  Results do not depend on it. */
+int lc_set_coalescing(lc_ctx *ctx, int max_call_pairs, int max_batch_pairs, int lanes, int linger_us);
 
 /* bns_fetch_seq as used by GoBwaReference.GetSeq (G/gobwa.go:50-80): 2-bit codes of contig `rid`, [start,end) on the
  * forward strand, clamped to the contig like the reference; returns the number of codes written to out (<= end-start). */

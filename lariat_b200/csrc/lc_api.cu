@@ -2,7 +2,9 @@
 // Index load + upload to HBM, the batched alignment call, the split upload/run/fetch form used for timing,
 // single-read source-compatible forms, and the kernel-level entry points of the microbenchmark config.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -33,39 +35,95 @@ struct LcPinned {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// A second stream + pool set: large calls are cut into chunks of barcode groups that alternate between two lanes, so that one
-// chunk's H2D / D2H and kernel tails overlap the other's kernels.
+// A stream + pool set of its own: large calls are cut into chunks of barcode groups that alternate between two lanes, so that one
+// chunk's H2D / D2H and kernel tails overlap the other's kernels; the coalescer (below) runs merged small calls on lanes, too.
 struct LcLane {
 	LcCudaBackend be;
 	LcPipeline<LcCudaBackend> pl;
+	LcPinned in_bases, in_off, out_off, out_regs, out_aln, out_cig;      // pinned staging of a coalesced batch
 	explicit LcLane(int dev) : be(dev), pl(be) {}
+	~LcLane() { pl.release(); in_bases.release(); in_off.release(); out_off.release(); out_regs.release(); out_aln.release(); out_cig.release(); }
 };
 
-struct lc_ctx {
+// The result of one call.  It belongs to the CALLER from the moment the call returns until lc_free_result: nothing the library does
+// afterwards (on this ctx, a clone, or another thread) touches it — what Lariat needs, whose ChainedHit pointers alias the result arrays
+// until the barcode's arena.Free() while other goroutines keep aligning (I/lariat.go:348-350,473,546; G/gobwa.go:107-126).
+// Large calls land directly in pinned arrays (D2H at PCIe speed, recycled through a free list); the per-call results of merged small
+// calls are ordinary heap arrays cut out of the merged batch's staging.
+#define LC_RESULT_MAGIC 0x4c435253u
+struct LcResultBlock {
+	lc_result_t res;                 // first member: the lc_result_t* handed to the caller IS the block
+	uint32_t magic = LC_RESULT_MAGIC;
+	bool pinned = false;
+	LcPinned p_off, p_regs, p_aln, p_cig;
+	std::vector<int64_t> v_off; std::vector<lc_alnreg_t> v_regs; std::vector<lc_aln_t> v_aln; std::vector<uint32_t> v_cig;
+	LcResultBlock() { memset(&res, 0, sizeof(res)); }
+	~LcResultBlock() { p_off.release(); p_regs.release(); p_aln.release(); p_cig.release(); }
+};
+
+struct LcRequest {                   // one small call waiting in the coalescer
+	const uint8_t *bases; const int64_t *off; int n_pairs, score_delta;
+	enum { QUEUED, TAKEN, DONE } state = QUEUED;
+	int rc = LC_OK; std::string err;
+	LcResultBlock *blk = nullptr;
+};
+
+// Everything the contexts of one lc_init share: the index in HBM (one copy per device, however many host threads / cloned contexts
+// use it), the contig table, the free list of pinned result blocks and the coalescer of small calls.
+struct LcSharedIndex {
 	int device = 0;
 	LcHostIndex hix;
 	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_anns = nullptr, *d_sa_dense = nullptr;
 	LcIndex ix;
 	lc_opt_t opt;
-	LcCudaBackend be;
-	LcPipeline<LcCudaBackend> pl;
-	LcHostResult hres;
-	lc_result_t res;
-	std::mutex mu;
 	lc_contigs_t contigs;
 	std::vector<const char *> name_ptrs;
 	std::vector<int32_t> lens;
 	std::vector<int64_t> offsets;
+	// tuning copied into every pipeline (lc_init reads the environment once)
+	int lst_cap = 0, pk_cap = 64, lst_cap2 = 40, pk_cap2 = 256, lst_cap3 = 150, pk_cap3 = 2048, ext_heavy_seeds = 32, ext_heavy_chains = 8;
+	bool force_wide = false;
+	// pinned result blocks given back by lc_free_result
+	std::mutex blk_mu;
+	std::vector<LcResultBlock *> free_blocks;
+	// coalescer: calls of at most co_call_max pairs from any thread / context are merged into batches of at most co_batch_max pairs;
+	// up to co_lanes_max batches are in flight (each on a lane of its own), led by whichever waiting caller finds a free lane
+	std::mutex co_mu;
+	std::condition_variable co_cv;
+	std::deque<LcRequest *> co_q;
+	std::vector<std::unique_ptr<LcLane> > co_lanes;
+	std::vector<LcLane *> co_free;
+	int co_call_max = 4096, co_batch_max = 65536, co_lanes_max = 3, co_linger_us = 0;
+	uint64_t co_batches = 0, co_requests = 0;
+	~LcSharedIndex()
+	{
+		cudaSetDevice(device);
+		co_lanes.clear();
+		for (auto *b : free_blocks) delete b;
+		cudaFree(d_bwt); cudaFree(d_sa); cudaFree(d_pac); cudaFree(d_anns); cudaFree(d_sa_dense);
+	}
+	void tune(LcPipeline<LcCudaBackend> &pl) const
+	{
+		pl.lst_cap = lst_cap; pl.pk_cap = pk_cap; pl.lst_cap2 = lst_cap2; pl.pk_cap2 = pk_cap2; pl.lst_cap3 = lst_cap3; pl.pk_cap3 = pk_cap3;
+		pl.ext_heavy_seeds = ext_heavy_seeds; pl.ext_heavy_chains = ext_heavy_chains; pl.force_wide = force_wide;
+	}
+};
+
+struct lc_ctx {
+	int device = 0;
+	std::shared_ptr<LcSharedIndex> sh;
+	LcCudaBackend be;
+	LcPipeline<LcCudaBackend> pl;
+	LcHostResult hres;
+	lc_result_t res;                // result of the split upload/run/fetch form and the single-read forms (valid until the next such call)
+	std::mutex mu;
 	std::vector<uint8_t> stage;
 	std::vector<int64_t> stage_off;
 	bool have_batch = false;
-	int last_delta = 25;
-	// results of the batched calls: pinned host arrays, valid until the next call on this ctx
-	LcPinned h_off, h_regs, h_aln, h_cig;
 	std::vector<std::unique_ptr<LcLane> > lanes;      // lanes 2..n of chunked calls (lane 1 is be/pl above): own stream, pools and host thread
 	int max_lanes = 2;              // LC_LANES
 	int chunk_pairs = 500000;       // LC_CHUNK_PAIRS; calls of more than 1.5 chunks run chunked over two lanes, 0 = never
-	explicit lc_ctx(int dev) : device(dev), be(dev), pl(be) {}
+	explicit lc_ctx(int dev) : device(dev), be(dev), pl(be) { memset(&res, 0, sizeof(res)); }
 };
 
 struct DevTmp {
@@ -96,6 +154,14 @@ const char *lc_last_error(void) { return g_err.c_str(); }
 const char *lc_build_info(void) { return "libcuda_lariat 0.1.0 (sm_100a; CUDA kernels: smem, sa_lookup, chain, extend, matesw, global_cigar)"; }
 void lc_opt_init(lc_opt_t *opt) { lc_default_opt(opt); }
 
+static int env_int(const char *name, int lo, int hi, int dflt)
+{
+	const char *e = getenv(name);
+	if (!e) return dflt;
+	const int v = atoi(e);
+	return v >= lo && v <= hi ? v : dflt;
+}
+
 lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 {
 	int ndev = 0;
@@ -115,92 +181,114 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 			fail(LC_EARG, "scoring options out of the supported range: LC_MAX_READ_LEN*a + max penalty must be <= 32767 and penalties <= 4096 (16-bit DP cells)"); return nullptr;
 		}
 	}
-	lc_ctx *c = new lc_ctx(device);
+	std::shared_ptr<LcSharedIndex> sh(new LcSharedIndex);
+	sh->device = device;
 	std::string err;
-	if (!lc_load_index(idx_prefix, c->hix, err)) { fail(LC_EINDEX, err); delete c; return nullptr; }
+	if (!lc_load_index(idx_prefix, sh->hix, err)) { fail(LC_EINDEX, err); return nullptr; }
 	cudaSetDevice(device);
-	LcHostIndex &h = c->hix;
-	LcIndex &ix = c->ix;
+	lc_ctx *c = new lc_ctx(device);
+	c->sh = sh;
+	LcHostIndex &h = sh->hix;
+	LcIndex &ix = sh->ix;
 	if (!lc_index_scalars(h, ix, err)) { fail(LC_EINDEX, err); delete c; return nullptr; }
 	// upload the file payloads, then re-lay the BWT on the device as 32-byte blocks (lc_fmindex.cuh) and drop the file layout
 	const uint64_t n_blocks = lc_occ_blocks(h.seq_len);
 	size_t nb = h.bwt.size() * 4, ns = h.sa.size() * 8, np = h.pac.size(), na = h.anns.size() * sizeof(LcAnn);
 	void *d_file = nullptr;
-	if (cudaMalloc(&d_file, nb) != cudaSuccess || cudaMalloc(&c->d_bwt, 32 * (size_t)n_blocks) != cudaSuccess || cudaMalloc(&c->d_sa, ns) != cudaSuccess ||
-		cudaMalloc(&c->d_pac, np) != cudaSuccess || cudaMalloc(&c->d_anns, na ? na : 1) != cudaSuccess) {
-		cudaGetLastError(); if (d_file) cudaFree(d_file); fail(LC_ENOMEM, "cannot allocate the index in HBM"); lc_destroy(c); return nullptr;
+	if (cudaMalloc(&d_file, nb) != cudaSuccess || cudaMalloc(&sh->d_bwt, 32 * (size_t)n_blocks) != cudaSuccess || cudaMalloc(&sh->d_sa, ns) != cudaSuccess ||
+		cudaMalloc(&sh->d_pac, np) != cudaSuccess || cudaMalloc(&sh->d_anns, na ? na : 1) != cudaSuccess) {
+		cudaGetLastError(); if (d_file) cudaFree(d_file); fail(LC_ENOMEM, "cannot allocate the index in HBM"); delete c; return nullptr;
 	}
 	cudaMemcpy(d_file, h.bwt.data(), nb, cudaMemcpyHostToDevice);
-	cudaMemcpy(c->d_sa, h.sa.data(), ns, cudaMemcpyHostToDevice);
-	cudaMemcpy(c->d_pac, h.pac.data(), np, cudaMemcpyHostToDevice);
-	cudaMemcpy(c->d_anns, h.anns.data(), na, cudaMemcpyHostToDevice);
-	ix.occ = (const uint4 *)c->d_bwt; ix.sa = (const uint64_t *)c->d_sa;
-	ix.pac = (const uint8_t *)c->d_pac; ix.anns = (const LcAnn *)c->d_anns;
-	c->be.k_occ_convert((const uint32_t *)d_file, (uint4 *)c->d_bwt, n_blocks, ix);
+	cudaMemcpy(sh->d_sa, h.sa.data(), ns, cudaMemcpyHostToDevice);
+	cudaMemcpy(sh->d_pac, h.pac.data(), np, cudaMemcpyHostToDevice);
+	cudaMemcpy(sh->d_anns, h.anns.data(), na, cudaMemcpyHostToDevice);
+	ix.occ = (const uint4 *)sh->d_bwt; ix.sa = (const uint64_t *)sh->d_sa;
+	ix.pac = (const uint8_t *)sh->d_pac; ix.anns = (const LcAnn *)sh->d_anns;
+	c->be.k_occ_convert((const uint32_t *)d_file, (uint4 *)sh->d_bwt, n_blocks, ix);
 	{
 		std::string e;
-		if (c->be.check(e)) { cudaFree(d_file); fail(LC_ECUDA, e); lc_destroy(c); return nullptr; }
+		if (c->be.check(e)) { cudaFree(d_file); fail(LC_ECUDA, e); delete c; return nullptr; }
 	}
 	cudaFree(d_file);
+	sh->force_wide = env_int("LC_FORCE_WIDE", 0, 1, 0) != 0;      // tests: the 64-bit paths (interval arithmetic, sa64) on a small index
 	// dense suffix array: one entry per BWT row, built from the sampled one with one LF step per row.  Optional: if HBM is
 	// short (or LC_DENSE_SA=0) the kernels fall back to the reference's sampled array + LF walks; results are identical.
 	{
-		const char *env = getenv("LC_DENSE_SA");
-		const bool want = !(env && env[0] == '0');
-		const char *fw = getenv("LC_FORCE_WIDE");      // tests: the 64-bit paths (interval arithmetic, sa64) on a small index
-		const bool wide = h.seq_len >= 0xffffffffull || (fw && fw[0] == '1');
+		const bool want = env_int("LC_DENSE_SA", 0, 1, 1) != 0;
+		const bool wide = h.seq_len >= 0xffffffffull || sh->force_wide;
 		const size_t bytes = (size_t)(h.seq_len + 1) * (wide ? 8 : 4);
 		size_t free_b = 0, total_b = 0;
 		cudaMemGetInfo(&free_b, &total_b);
-		if (want && bytes < free_b / 2 && cudaMalloc(&c->d_sa_dense, bytes) == cudaSuccess) {
-			c->be.k_sa_fill(ix, (unsigned long long)h.sa.size(), c->d_sa_dense, wide);
+		if (want && bytes < free_b / 2 && cudaMalloc(&sh->d_sa_dense, bytes) == cudaSuccess) {
+			c->be.k_sa_fill(ix, (unsigned long long)h.sa.size(), sh->d_sa_dense, wide);
 			std::string e;
-			if (c->be.check(e)) { fail(LC_ECUDA, e); lc_destroy(c); return nullptr; }
-			if (wide) ix.sa64 = (const uint64_t *)c->d_sa_dense; else ix.sa32 = (const uint32_t *)c->d_sa_dense;
+			if (c->be.check(e)) { fail(LC_ECUDA, e); delete c; return nullptr; }
+			if (wide) ix.sa64 = (const uint64_t *)sh->d_sa_dense; else ix.sa32 = (const uint32_t *)sh->d_sa_dense;
 		} else cudaGetLastError();
 	}
-	c->opt = o;
-	c->pl.set_index(ix, o);
+	sh->opt = o;
 	// tuning knobs of the seeding state machine (tests use tiny values to force the redo path)
-	if (const char *e = getenv("LC_SEED_LST_CAP")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap = v; }
-	if (const char *e = getenv("LC_SEED_PK_CAP")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap = v; }
-	if (const char *e = getenv("LC_SEED_LST_CAP2")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap2 = v; }
-	if (const char *e = getenv("LC_SEED_PK_CAP2")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap2 = v; }
-	if (const char *e = getenv("LC_SEED_LST_CAP3")) { int v = atoi(e); if (v >= 2 && v <= 2048) c->pl.lst_cap3 = v; }
-	if (const char *e = getenv("LC_SEED_PK_CAP3")) { int v = atoi(e); if (v >= 1 && v <= 4096) c->pl.pk_cap3 = v; }
-	if (const char *e = getenv("LC_EXT_HEAVY_SEEDS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_seeds = v; }
-	if (const char *e = getenv("LC_EXT_HEAVY_CHAINS")) { int v = atoi(e); if (v >= 0) c->pl.ext_heavy_chains = v; }
-	if (const char *e = getenv("LC_FORCE_WIDE")) c->pl.force_wide = e[0] == '1';
-	if (const char *e = getenv("LC_CHUNK_PAIRS")) { int v = atoi(e); if (v >= 0) c->chunk_pairs = v; }
-	if (const char *e = getenv("LC_LANES")) { int v = atoi(e); if (v >= 1 && v <= 8) c->max_lanes = v; }
+	sh->lst_cap = env_int("LC_SEED_LST_CAP", 2, 2048, sh->lst_cap); sh->pk_cap = env_int("LC_SEED_PK_CAP", 1, 4096, sh->pk_cap);
+	sh->lst_cap2 = env_int("LC_SEED_LST_CAP2", 2, 2048, sh->lst_cap2); sh->pk_cap2 = env_int("LC_SEED_PK_CAP2", 1, 4096, sh->pk_cap2);
+	sh->lst_cap3 = env_int("LC_SEED_LST_CAP3", 2, 2048, sh->lst_cap3); sh->pk_cap3 = env_int("LC_SEED_PK_CAP3", 1, 4096, sh->pk_cap3);
+	sh->ext_heavy_seeds = env_int("LC_EXT_HEAVY_SEEDS", 0, 1 << 30, sh->ext_heavy_seeds);
+	sh->ext_heavy_chains = env_int("LC_EXT_HEAVY_CHAINS", 0, 1 << 30, sh->ext_heavy_chains);
+	sh->co_call_max = env_int("LC_COALESCE_MAX", 0, 1 << 20, sh->co_call_max);          // 0: small calls are not merged
+	sh->co_batch_max = env_int("LC_COALESCE_BATCH", 1, 1 << 22, sh->co_batch_max);
+	sh->co_lanes_max = env_int("LC_COALESCE_LANES", 1, 16, sh->co_lanes_max);
+	sh->co_linger_us = env_int("LC_COALESCE_LINGER_US", 0, 100000, sh->co_linger_us);
+	c->pl.set_index(ix, o);
+	sh->tune(c->pl);
+	c->chunk_pairs = env_int("LC_CHUNK_PAIRS", 0, 1 << 30, c->chunk_pairs);
+	c->max_lanes = env_int("LC_LANES", 1, 8, c->max_lanes);
 	// host copies of the big FM-index arrays are not needed any more (pac stays for lc_fetch_seq)
 	std::vector<uint32_t>().swap(h.bwt);
 	std::vector<uint64_t>().swap(h.sa);
-	for (size_t i = 0; i < h.names.size(); ++i) { c->name_ptrs.push_back(h.names[i].c_str()); c->lens.push_back(h.anns[i].len); c->offsets.push_back(h.anns[i].offset); }
-	c->contigs.n_seqs = (int32_t)h.names.size(); c->contigs.l_pac = h.l_pac;
-	c->contigs.names = c->name_ptrs.data(); c->contigs.lens = c->lens.data(); c->contigs.offsets = c->offsets.data();
-	memset(&c->res, 0, sizeof(c->res));
+	for (size_t i = 0; i < h.names.size(); ++i) { sh->name_ptrs.push_back(h.names[i].c_str()); sh->lens.push_back(h.anns[i].len); sh->offsets.push_back(h.anns[i].offset); }
+	sh->contigs.n_seqs = (int32_t)h.names.size(); sh->contigs.l_pac = h.l_pac;
+	sh->contigs.names = sh->name_ptrs.data(); sh->contigs.lens = sh->lens.data(); sh->contigs.offsets = sh->offsets.data();
 	return c;
 }
 
-void lc_destroy(lc_ctx *c)
+// A second context on the same index: its own stream, pools and lock, NO second copy of the index in HBM.  For callers that want
+// several large calls in flight at once (one clone per worker); small calls do not need it — they are merged across threads anyway.
+lc_ctx *lc_clone(lc_ctx *src)
+{
+	if (!src) { fail(LC_EARG, "null ctx"); return nullptr; }
+	cudaSetDevice(src->device);
+	lc_ctx *c = new lc_ctx(src->device);
+	c->sh = src->sh;
+	c->pl.set_index(c->sh->ix, c->sh->opt);
+	c->sh->tune(c->pl);
+	c->pl.counting = src->pl.counting;
+	c->chunk_pairs = src->chunk_pairs; c->max_lanes = src->max_lanes;
+	return c;
+}
+
+void lc_destroy(lc_ctx *c)      // the index leaves HBM when its last context is destroyed; results already handed out stay valid
 {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	c->pl.release();
 	c->lanes.clear();
-	c->h_off.release(); c->h_regs.release(); c->h_aln.release(); c->h_cig.release();
-	cudaFree(c->d_bwt); cudaFree(c->d_sa); cudaFree(c->d_pac); cudaFree(c->d_anns); cudaFree(c->d_sa_dense);
 	delete c;
 }
 
-const lc_contigs_t *lc_contigs(const lc_ctx *c) { return c ? &c->contigs : nullptr; }
+const lc_contigs_t *lc_contigs(const lc_ctx *c) { return c ? &c->sh->contigs : nullptr; }
 void lc_set_counting(lc_ctx *c, int on) { if (c) c->pl.counting = on != 0; }
 int lc_set_chunk_pairs(lc_ctx *c, int n_pairs)
 {
 	if (!c || n_pairs < 0) return fail(LC_EARG, "bad arguments");
 	std::lock_guard<std::mutex> g(c->mu);
 	c->chunk_pairs = n_pairs;
+	return LC_OK;
+}
+int lc_set_coalescing(lc_ctx *c, int max_call_pairs, int max_batch_pairs, int lanes, int linger_us)
+{
+	if (!c || max_call_pairs < 0 || max_batch_pairs < 1 || lanes < 1 || lanes > 16 || linger_us < 0) return fail(LC_EARG, "bad arguments");
+	std::lock_guard<std::mutex> g(c->sh->co_mu);
+	c->sh->co_call_max = max_call_pairs; c->sh->co_batch_max = max_batch_pairs; c->sh->co_lanes_max = lanes; c->sh->co_linger_us = linger_us;
 	return LC_OK;
 }
 int lc_timer_start(lc_ctx *c)
@@ -272,6 +360,43 @@ static int do_fetch(lc_ctx *c, lc_result_t **out)
 	return LC_OK;
 }
 
+// ---- result blocks ---------------------------------------------------------------------------------------------------------
+static LcResultBlock *take_pinned_block(LcSharedIndex &S)
+{
+	{
+		std::lock_guard<std::mutex> g(S.blk_mu);
+		if (!S.free_blocks.empty()) { LcResultBlock *b = S.free_blocks.back(); S.free_blocks.pop_back(); return b; }
+	}
+	LcResultBlock *b = new LcResultBlock;
+	b->pinned = true;
+	return b;
+}
+static void give_block(LcSharedIndex &S, LcResultBlock *b)
+{
+	if (!b) return;
+	if (!b->pinned) { delete b; return; }
+	memset(&b->res, 0, sizeof(b->res));
+	std::lock_guard<std::mutex> g(S.blk_mu);
+	if (S.free_blocks.size() < 4) S.free_blocks.push_back(b); else { cudaSetDevice(S.device); delete b; }
+}
+static void set_counters(lc_result_t &r, const LcCounters &k)
+{
+	r.cnt_occ_blocks = k.occ_blocks; r.cnt_extend_calls = k.extend_calls; r.cnt_sa_calls = k.sa_calls; r.cnt_lf_steps = k.lf_steps;
+	r.cnt_ext_calls = k.ext_calls; r.cnt_ext_cells = k.ext_cells; r.cnt_sw_calls = k.sw_calls; r.cnt_sw_cells = k.sw_cells;
+	r.cnt_glb_calls = k.glb_calls; r.cnt_glb_cells = k.glb_cells;
+}
+static void set_stage_ms(lc_result_t &r, const float ms[10])
+{
+	r.ms_h2d = ms[0]; r.ms_seed = ms[1]; r.ms_sa = ms[2]; r.ms_chain = ms[3]; r.ms_extend = ms[4]; r.ms_dedup = ms[5];
+	r.ms_pair = ms[6]; r.ms_cigar = ms[7]; r.ms_d2h = ms[8]; r.ms_total = ms[9];
+}
+// every read 0 <= len <= LC_MAX_READ_LEN, in int64 (the caller's offsets are not trusted)
+static bool offsets_ok(int n_pairs, const int64_t *off)
+{
+	for (size_t r = 0; r < 2 * (size_t)n_pairs; ++r) { const int64_t l = off[r + 1] - off[r]; if (l < 0 || l > LC_MAX_READ_LEN) return false; }
+	return true;
+}
+
 // ---- the batched call: upload -> stages -> pack -> D2H into the pinned result arrays; large calls chunked over two lanes -----
 struct LcChunkShared {
 	std::mutex mu;
@@ -285,6 +410,7 @@ struct LcChunkShared {
 	float ms[10] = {0};
 	int64_t launches = 0;
 	LcCounters cnt;
+	LcResultBlock *blk = nullptr;
 	void fail_with(int code, const std::string &e) { std::lock_guard<std::mutex> g(mu); if (rc == LC_OK) { rc = code; err = e; } }
 };
 
@@ -300,6 +426,7 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 						const uint8_t *bases, const int64_t *off, int score_delta)
 {
 	cudaSetDevice(c->device);
+	LcResultBlock &B = *sh->blk;
 	for (int k = first; k < n_chunks; k += stride) {
 		const int p0 = (int)((int64_t)n_pairs * k / n_chunks), p1 = (int)((int64_t)n_pairs * (k + 1) / n_chunks);
 		int rc = LC_OK;
@@ -322,20 +449,20 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 		rc = pl->run_pack(reg_base, (uint32_t)cig_base);
 		if (rc) { sh->fail_with(rc, pl->err); continue; }
 		const size_t need_reg = (size_t)(reg_base + (int64_t)pl->n_cand), need_cig = (size_t)(cig_base + (int64_t)pl->n_cigar_words);
-		if (need_reg * sizeof(lc_alnreg_t) > c->h_regs.cap || need_reg * sizeof(lc_aln_t) > c->h_aln.cap || need_cig * 4 > c->h_cig.cap) {
-			// regrow (rare: capacities persist across calls): extrapolate from the chunks seen so far, wait out in-flight copies, keep what is there
+		if (need_reg * sizeof(lc_alnreg_t) > B.p_regs.cap || need_reg * sizeof(lc_aln_t) > B.p_aln.cap || need_cig * 4 > B.p_cig.cap) {
+			// regrow (rare: blocks are recycled with their capacities): extrapolate from the chunks seen so far, wait out in-flight copies, keep what is there
 			std::unique_lock<std::shared_mutex> g(sh->res_mu);
 			const double f = 1.2 * n_chunks / (double)(k + 1);
 			const size_t want_reg = (size_t)(need_reg * f) + 1024, want_cig = (size_t)(need_cig * f) + 1024;
-			if (!c->h_regs.ensure(want_reg * sizeof(lc_alnreg_t), c->h_regs.cap) || !c->h_aln.ensure(want_reg * sizeof(lc_aln_t), c->h_aln.cap) ||
-				!c->h_cig.ensure(want_cig * 4, c->h_cig.cap)) { sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue; }
+			if (!B.p_regs.ensure(want_reg * sizeof(lc_alnreg_t), B.p_regs.cap) || !B.p_aln.ensure(want_reg * sizeof(lc_aln_t), B.p_aln.cap) ||
+				!B.p_cig.ensure(want_cig * 4, B.p_cig.cap)) { sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue; }
 		}
 		float ms[10]; LcCounters cn;
 		{
 			std::shared_lock<std::shared_mutex> g(sh->res_mu);
 			const size_t n_off = 2 * (size_t)(p1 - p0) + (k == n_chunks - 1 ? 1 : 0);
-			pl->fetch_into((int64_t *)c->h_off.p + 2 * (size_t)p0, n_off, (lc_alnreg_t *)c->h_regs.p + reg_base, (lc_aln_t *)c->h_aln.p + reg_base,
-						   (uint32_t *)c->h_cig.p + cig_base);
+			pl->fetch_into((int64_t *)B.p_off.p + 2 * (size_t)p0, n_off, (lc_alnreg_t *)B.p_regs.p + reg_base, (lc_aln_t *)B.p_aln.p + reg_base,
+						   (uint32_t *)B.p_cig.p + cig_base);
 			be->sync();
 		}
 		std::string e;
@@ -355,7 +482,6 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 // chunking), and the smaller chunk size is kept for the calls that follow.
 static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out)
 {
-	if (!c || n_pairs < 0 || !off || (n_pairs && !bases && off[2 * (size_t)n_pairs] > off[0])) return fail(LC_EARG, "bad arguments");
 	cudaSetDevice(c->device);
 	int n_chunks = 1;
 	if (c->chunk_pairs > 0 && (double)n_pairs > 1.5 * c->chunk_pairs) n_chunks = (n_pairs + c->chunk_pairs - 1) / c->chunk_pairs;
@@ -372,18 +498,19 @@ static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 
 static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out, int n_chunks)
 {
+	LcSharedIndex &S = *c->sh;
 	const int n_lanes = std::max(1, std::min(n_chunks, c->max_lanes));
 	while ((int)c->lanes.size() < n_lanes - 1) {
 		std::unique_ptr<LcLane> l(new LcLane(c->device));
-		l->pl.set_index(c->ix, c->opt);
-		l->pl.lst_cap = c->pl.lst_cap; l->pl.pk_cap = c->pl.pk_cap; l->pl.force_wide = c->pl.force_wide;
-		l->pl.lst_cap2 = c->pl.lst_cap2; l->pl.pk_cap2 = c->pl.pk_cap2; l->pl.lst_cap3 = c->pl.lst_cap3; l->pl.pk_cap3 = c->pl.pk_cap3;
-		l->pl.ext_heavy_seeds = c->pl.ext_heavy_seeds; l->pl.ext_heavy_chains = c->pl.ext_heavy_chains;
+		l->pl.set_index(S.ix, S.opt);
+		S.tune(l->pl);
 		c->lanes.push_back(std::move(l));
 	}
 	for (auto &l : c->lanes) l->pl.counting = c->pl.counting;
-	if (!c->h_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results");
+	LcResultBlock *blk = take_pinned_block(S);
+	if (!blk->p_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) { give_block(S, blk); return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results"); }
 	LcChunkShared sh;
+	sh.blk = blk;
 	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.ready.assign(n_chunks + 1, 0); sh.ready[0] = 1;
 	memset(&sh.cnt, 0, sizeof(sh.cnt));
 	c->be.ev_record(12);
@@ -397,21 +524,145 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 	c->be.ev_record(13);
 	c->be.sync();
 	c->have_batch = n_lanes == 1;      // lc_batch_run / lc_batch_fetch continue from a single-lane call only
-	if (sh.rc) return fail(sh.rc, sh.err);
-	lc_result_t &r = c->res;
+	if (sh.rc) { give_block(S, blk); return fail(sh.rc, sh.err); }
+	lc_result_t &r = blk->res;
 	memset(&r, 0, sizeof(r));
 	r.n_reads = 2 * n_pairs; r.n_regs = sh.cum_reg[n_chunks]; r.n_cigar_words = sh.cum_cig[n_chunks];
-	r.reg_off = (const int64_t *)c->h_off.p; r.regs = (const lc_alnreg_t *)c->h_regs.p; r.aln = (const lc_aln_t *)c->h_aln.p; r.cigars = (const uint32_t *)c->h_cig.p;
-	if (r.reg_off[r.n_reads] != r.n_regs) return fail(LC_ECUDA, "result size mismatch");
+	r.reg_off = (const int64_t *)blk->p_off.p; r.regs = (const lc_alnreg_t *)blk->p_regs.p; r.aln = (const lc_aln_t *)blk->p_aln.p; r.cigars = (const uint32_t *)blk->p_cig.p;
+	if (r.reg_off[r.n_reads] != r.n_regs) { give_block(S, blk); return fail(LC_ECUDA, "result size mismatch"); }
 	// stage times: summed over the chunks (chunks of the two lanes overlap); ms_total: the whole call on the device clock, copies included when chunked
-	r.ms_h2d = sh.ms[0]; r.ms_seed = sh.ms[1]; r.ms_sa = sh.ms[2]; r.ms_chain = sh.ms[3]; r.ms_extend = sh.ms[4]; r.ms_dedup = sh.ms[5];
-	r.ms_pair = sh.ms[6]; r.ms_cigar = sh.ms[7]; r.ms_d2h = sh.ms[8]; r.ms_total = n_chunks > 1 ? c->be.ev_ms(12, 13) : sh.ms[9];
+	set_stage_ms(r, sh.ms);
+	if (n_chunks > 1) r.ms_total = c->be.ev_ms(12, 13);
 	r.gpu_launches = sh.launches;
-	const LcCounters &k = sh.cnt;
-	r.cnt_occ_blocks = k.occ_blocks; r.cnt_extend_calls = k.extend_calls; r.cnt_sa_calls = k.sa_calls; r.cnt_lf_steps = k.lf_steps;
-	r.cnt_ext_calls = k.ext_calls; r.cnt_ext_cells = k.ext_cells; r.cnt_sw_calls = k.sw_calls; r.cnt_sw_cells = k.sw_cells;
-	r.cnt_glb_calls = k.glb_calls; r.cnt_glb_cells = k.glb_cells;
-	if (out) *out = &c->res;
+	set_counters(r, sh.cnt);
+	if (out) *out = &blk->res; else give_block(S, blk);
+	return LC_OK;
+}
+
+// ---- small calls: merged across threads ----------------------------------------------------------------------------------------
+// Lariat's loop hands BWA one barcode group (~100 pairs) at a time from each of its worker goroutines (I/lariat.go:348-376).  One such
+// call cannot fill a GPU, and the pipeline's latency (a read's seeding alone is ~700 dependent FM-index steps) does not shrink with the
+// batch: so calls of up to co_call_max pairs, from ANY thread and ANY context of the index, are queued, and whichever waiting caller
+// finds a free lane takes everything queued (up to co_batch_max pairs), runs it as ONE batch and cuts the results apart again.
+// Results are identical to separate calls (reads are independent; test_coalesced_calls_equal_separate_calls).
+static void run_coalesced(LcSharedIndex &S, LcLane *lane, std::vector<LcRequest *> &batch, int score_delta)
+{
+	cudaSetDevice(S.device);
+	int tot = 0; int64_t nb = 0;
+	for (auto *r : batch) { tot += r->n_pairs; nb += r->off[2 * (size_t)r->n_pairs] - r->off[0]; }
+	auto fail_all = [&](int rc, const std::string &e) { for (auto *r : batch) { r->rc = rc; r->err = e; } };
+	if (!lane->in_bases.ensure((size_t)nb + 64, 0) || !lane->in_off.ensure(8 * (2 * (size_t)tot + 1), 0)) return fail_all(LC_ENOMEM, "cannot allocate pinned staging for a merged batch");
+	uint8_t *hb = (uint8_t *)lane->in_bases.p; int64_t *ho = (int64_t *)lane->in_off.p;
+	{
+		int64_t o = 0; size_t rr = 0;
+		for (auto *r : batch) {
+			const int64_t o0 = r->off[0], n = r->off[2 * (size_t)r->n_pairs] - o0;
+			if (n) memcpy(hb + o, r->bases + o0, (size_t)n);
+			for (size_t k = 0; k < 2 * (size_t)r->n_pairs; ++k) ho[rr++] = o + (r->off[k] - o0);
+			o += n;
+		}
+		ho[rr] = o;
+	}
+	LcPipeline<LcCudaBackend> &pl = lane->pl;
+	int rc = pl.upload(tot, hb, ho, true);
+	if (!rc) rc = pl.run_stages(score_delta);
+	if (!rc) rc = pl.run_pack(0, 0);
+	if (rc) return fail_all(rc, pl.err);
+	const size_t NC = (size_t)pl.n_cand, NW = (size_t)pl.n_cigar_words;
+	if (!lane->out_off.ensure(8 * (2 * (size_t)tot + 1), 0) || !lane->out_regs.ensure(sizeof(lc_alnreg_t) * (NC + 1), 0) ||
+		!lane->out_aln.ensure(sizeof(lc_aln_t) * (NC + 1), 0) || !lane->out_cig.ensure(4 * (NW + 1), 0)) return fail_all(LC_ENOMEM, "cannot allocate pinned staging for a merged batch");
+	pl.fetch_into((int64_t *)lane->out_off.p, 2 * (size_t)tot + 1, (lc_alnreg_t *)lane->out_regs.p, (lc_aln_t *)lane->out_aln.p, (uint32_t *)lane->out_cig.p);
+	lane->be.sync();
+	std::string e;
+	if (lane->be.check(e)) return fail_all(LC_ECUDA, e);
+	float ms[10]; LcCounters cn;
+	pl.fetch_done(ms, cn);
+	const int64_t *roff = (const int64_t *)lane->out_off.p;
+	const lc_alnreg_t *regs = (const lc_alnreg_t *)lane->out_regs.p;
+	const lc_aln_t *aln = (const lc_aln_t *)lane->out_aln.p;
+	const uint32_t *cig = (const uint32_t *)lane->out_cig.p;
+	if ((size_t)roff[2 * (size_t)tot] != NC) return fail_all(LC_ECUDA, "result size mismatch");
+	size_t r0 = 0;
+	for (auto *rq : batch) {      // cut the merged result apart: each request gets arrays of its own
+		const size_t R = 2 * (size_t)rq->n_pairs;
+		const int64_t c0 = roff[r0], c1 = roff[r0 + R];
+		LcResultBlock *b = new LcResultBlock;
+		b->v_off.resize(R + 1);
+		for (size_t k = 0; k <= R; ++k) b->v_off[k] = roff[r0 + k] - c0;
+		b->v_regs.assign(regs + c0, regs + c1);
+		b->v_aln.assign(aln + c0, aln + c1);
+		size_t nw = 0;
+		for (auto &a : b->v_aln) nw += (size_t)a.n_cigar;
+		b->v_cig.resize(nw + 1);
+		nw = 0;
+		for (auto &a : b->v_aln) {      // CIGARs are carved from the batch's pool in no particular order: gather them per candidate
+			if (a.n_cigar) memcpy(&b->v_cig[nw], cig + a.cigar_off, 4 * (size_t)a.n_cigar);
+			a.cigar_off = (uint32_t)nw; nw += (size_t)a.n_cigar;
+		}
+		lc_result_t &r = b->res;
+		r.n_reads = (int32_t)R; r.n_regs = c1 - c0; r.n_cigar_words = (int64_t)nw;
+		r.reg_off = b->v_off.data(); r.regs = b->v_regs.data(); r.aln = b->v_aln.data(); r.cigars = b->v_cig.data();
+		set_stage_ms(r, ms);      // times and launches are those of the merged batch the call rode in
+		r.gpu_launches = pl.launches;
+		rq->blk = b;
+		r0 += R;
+	}
+}
+
+static int coalesced_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out)
+{
+	LcSharedIndex &S = *c->sh;
+	LcRequest rq;
+	rq.bases = bases; rq.off = off; rq.n_pairs = n_pairs; rq.score_delta = score_delta;
+	std::unique_lock<std::mutex> g(S.co_mu);
+	S.co_q.push_back(&rq);
+	++S.co_requests;
+	for (;;) {
+		if (rq.state == LcRequest::DONE) break;
+		const bool lane_free = !S.co_free.empty() || (int)S.co_lanes.size() < S.co_lanes_max;
+		if (rq.state == LcRequest::QUEUED && lane_free) {
+			// lead one batch: everything queued with the head's score_delta, up to co_batch_max pairs
+			LcLane *lane = nullptr;
+			if (!S.co_free.empty()) { lane = S.co_free.back(); S.co_free.pop_back(); }
+			else {
+				S.co_lanes.emplace_back(nullptr);      // reserve the slot under the lock, build the lane outside it
+				const size_t slot = S.co_lanes.size() - 1;
+				g.unlock();
+				cudaSetDevice(S.device);
+				std::unique_ptr<LcLane> l(new LcLane(S.device));
+				l->pl.set_index(S.ix, S.opt);
+				S.tune(l->pl);
+				g.lock();
+				lane = l.get();
+				S.co_lanes[slot] = std::move(l);
+			}
+			if (S.co_linger_us > 0 && (int)S.co_q.size() < 2) {      // optional: give other callers a moment to join
+				g.unlock(); std::this_thread::sleep_for(std::chrono::microseconds(S.co_linger_us)); g.lock();
+			}
+			std::vector<LcRequest *> batch;
+			int tot = 0;
+			if (!S.co_q.empty()) {
+				const int delta = S.co_q.front()->score_delta;
+				for (auto it = S.co_q.begin(); it != S.co_q.end();) {
+					if ((*it)->score_delta == delta && (batch.empty() || tot + (*it)->n_pairs <= S.co_batch_max)) {
+						batch.push_back(*it); tot += (*it)->n_pairs; (*it)->state = LcRequest::TAKEN; it = S.co_q.erase(it);
+					} else ++it;
+				}
+				++S.co_batches;
+				g.unlock();
+				run_coalesced(S, lane, batch, delta);
+				g.lock();
+				for (auto *r : batch) r->state = LcRequest::DONE;
+			}
+			S.co_free.push_back(lane);
+			S.co_cv.notify_all();
+			continue;
+		}
+		S.co_cv.wait(g);
+	}
+	g.unlock();
+	if (rq.rc) { if (rq.blk) delete rq.blk; return fail(rq.rc, rq.err); }
+	if (out) *out = &rq.blk->res; else delete rq.blk;
 	return LC_OK;
 }
 
@@ -433,11 +684,21 @@ int lc_batch_fetch(lc_ctx *c, lc_result_t **out)
 	std::lock_guard<std::mutex> g(c->mu);
 	return do_fetch(c, out);
 }
-void lc_free_result(lc_ctx *c, lc_result_t *res) { (void)c; (void)res; /* results live in the ctx and are recycled by the next call */ }
+void lc_free_result(lc_ctx *c, lc_result_t *res)
+{
+	if (!c || !res || res == &c->res) return;      // the split / single-read forms hand out the context's own block: nothing to free
+	LcResultBlock *b = (LcResultBlock *)res;
+	if (b->magic != LC_RESULT_MAGIC) return;
+	give_block(*c->sh, b);
+}
 
 int lc_align_packed(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out)
 {
-	if (!c) return fail(LC_EARG, "null ctx");
+	if (!c || n_pairs < 0 || !off || (n_pairs && !bases && off[2 * (size_t)n_pairs] > off[0])) return fail(LC_EARG, "bad arguments");
+	if (!offsets_ok(n_pairs, off)) return fail(LC_EARG, "read offsets must be non-decreasing and no read longer than LC_MAX_READ_LEN");
+	// small calls are merged across threads — unless the work counters are on (they are per call) or the caller asked for chunks this small
+	if (n_pairs > 0 && n_pairs <= c->sh->co_call_max && !c->pl.counting && !(c->chunk_pairs > 0 && (double)n_pairs > 1.5 * c->chunk_pairs))
+		return coalesced_align(c, n_pairs, bases, off, score_delta, out);
 	std::lock_guard<std::mutex> g(c->mu);
 	return do_align(c, n_pairs, bases, off, score_delta, out);
 }
@@ -446,32 +707,32 @@ int lc_align_pairs(lc_ctx *c, int n_pairs, const uint8_t *const *seq1, const int
 				   int score_delta, lc_result_t **out)
 {
 	if (!c || n_pairs < 0 || (n_pairs && (!seq1 || !seq2 || !len1 || !len2))) return fail(LC_EARG, "bad arguments");
-	std::lock_guard<std::mutex> g(c->mu);
-	c->stage_off.assign(2 * (size_t)n_pairs + 1, 0);
+	// the packed copy is the calling thread's own (the call may be merged with other threads' calls)
+	std::vector<int64_t> off(2 * (size_t)n_pairs + 1, 0);
 	for (int p = 0; p < n_pairs; ++p) {
 		if (len1[p] < 0 || len2[p] < 0) return fail(LC_EARG, "negative read length");
-		c->stage_off[2 * p + 1] = c->stage_off[2 * p] + len1[p];
-		c->stage_off[2 * p + 2] = c->stage_off[2 * p + 1] + len2[p];
+		off[2 * p + 1] = off[2 * p] + len1[p];
+		off[2 * p + 2] = off[2 * p + 1] + len2[p];
 	}
-	c->stage.resize((size_t)c->stage_off[2 * (size_t)n_pairs] + 16);
+	std::vector<uint8_t> stage((size_t)off[2 * (size_t)n_pairs] + 16);
 	for (int p = 0; p < n_pairs; ++p) {
-		if (len1[p]) memcpy(&c->stage[c->stage_off[2 * p]], seq1[p], len1[p]);
-		if (len2[p]) memcpy(&c->stage[c->stage_off[2 * p + 1]], seq2[p], len2[p]);
+		if (len1[p]) memcpy(&stage[off[2 * p]], seq1[p], len1[p]);
+		if (len2[p]) memcpy(&stage[off[2 * p + 1]], seq2[p], len2[p]);
 	}
-	return do_align(c, n_pairs, c->stage.data(), c->stage_off.data(), score_delta, out);
+	return lc_align_packed(c, n_pairs, stage.data(), off.data(), score_delta, out);
 }
 
 int64_t lc_fetch_seq(const lc_ctx *c, int rid, int64_t start, int64_t end, uint8_t *out)
 {
-	if (!c || rid < 0 || rid >= (int)c->hix.anns.size() || !out) return fail(LC_EARG, "bad arguments");
+	if (!c || rid < 0 || rid >= (int)c->sh->hix.anns.size() || !out) return fail(LC_EARG, "bad arguments");
 	// bns_fetch_seq clamps [beg,end) to the contig (B/bntseq.c:430-438); GetSeq passes contig-relative coordinates (G/gobwa.go:56-59)
-	const LcAnn &a = c->hix.anns[rid];
+	const LcAnn &a = c->sh->hix.anns[rid];
 	int64_t b = start + a.offset, e = end + a.offset;
 	if (e < b) { int64_t t = b; b = e; e = t; }
 	if (b < a.offset) b = a.offset;
 	if (e > a.offset + a.len) e = a.offset + a.len;
 	int64_t n = 0;
-	for (int64_t p = b; p < e; ++p) out[n++] = (c->hix.pac[p >> 2] >> ((~p & 3) << 1)) & 3;
+	for (int64_t p = b; p < e; ++p) out[n++] = (c->sh->hix.pac[p >> 2] >> ((~p & 3) << 1)) & 3;
 	return n;
 }
 
@@ -565,7 +826,7 @@ int lc_ksw_extend_batch(lc_ctx *c, int n, const uint8_t *q, const int64_t *qoff,
 	DevTmp d;
 	LcExtJobs j;
 	j.n = n; j.q = d.up(q, (size_t)qoff[n] + 1); j.qoff = d.up(qoff, (size_t)n + 1); j.t = d.up(t, (size_t)toff[n] + 1); j.toff = d.up(toff, (size_t)n + 1);
-	j.h0 = d.up(h0, n); j.w = w; j.end_bonus = end_bonus; j.zdrop = zdrop; j.sc = score_of(c->opt);
+	j.h0 = d.up(h0, n); j.w = w; j.end_bonus = end_bonus; j.zdrop = zdrop; j.sc = score_of(c->sh->opt);
 	j.out = d.alloc<int32_t>(6 * (size_t)n);
 	j.qmax = qmax;
 	j.ctr = d.alloc<unsigned int>(1);
@@ -596,7 +857,7 @@ int lc_ksw_align_batch(lc_ctx *c, int n, const uint8_t *q, const int64_t *qoff, 
 	DevTmp d;
 	LcSwJobs j;
 	j.n = n; j.q = d.up(q, (size_t)qoff[n] + 1); j.qoff = d.up(qoff, (size_t)n + 1); j.t = d.up(t, (size_t)toff[n] + 1); j.toff = d.up(toff, (size_t)n + 1);
-	j.sc = score_of(c->opt); j.min_seed_len = c->opt.min_seed_len;
+	j.sc = score_of(c->sh->opt); j.min_seed_len = c->sh->opt.min_seed_len;
 	j.out = d.alloc<int32_t>(7 * (size_t)n);
 	j.qmax = qmax;
 	j.ctr = d.alloc<unsigned int>(1);
@@ -654,12 +915,12 @@ int lc_sa_batch(lc_ctx *c, int64_t n, const uint64_t *rows, uint64_t *out, float
 	if (!c || n < 0 || !rows || !out) return fail(LC_EARG, "bad arguments");
 	std::lock_guard<std::mutex> g(c->mu);
 	cudaSetDevice(c->device);
-	for (int64_t i = 0; i < n; ++i) if (rows[i] > c->ix.seq_len) return fail(LC_EARG, "BWT row out of range");
+	for (int64_t i = 0; i < n; ++i) if (rows[i] > c->sh->ix.seq_len) return fail(LC_EARG, "BWT row out of range");
 	DevTmp d;
 	uint64_t *dr = d.up(rows, (size_t)n), *dout = d.alloc<uint64_t>((size_t)n);
 	c->be.sync();
 	c->be.ev_record(12);
-	c->be.k_sa_batch(c->ix, dr, dout, n, nullptr);
+	c->be.k_sa_batch(c->sh->ix, dr, dout, n, nullptr);
 	c->be.ev_record(13);
 	std::string e;
 	if (c->be.check(e)) return fail(LC_ECUDA, e);

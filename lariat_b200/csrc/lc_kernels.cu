@@ -373,6 +373,8 @@ __global__ void __launch_bounds__(256) sa_batch_kernel(const LcIndex ix, const u
 }
 
 // ---- backend -------------------------------------------------------------------------------------------------
+static std::once_flag lc_attr_once[64];
+static void lc_set_kernel_attrs(int device);
 struct LcCastI64 { __host__ __device__ int64_t operator()(const int32_t &x) const { return (int64_t)x; } };
 
 LcCudaBackend::LcCudaBackend(int device_) : device(device_)
@@ -381,6 +383,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties(&prop, device);
 	n_sm = prop.multiProcessorCount;
+	if (device >= 0 && device < 64) std::call_once(lc_attr_once[device], lc_set_kernel_attrs, device);
 	cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventCreate(&ev[i]);
 	cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
@@ -423,20 +426,27 @@ void LcCudaBackend::k_convert(uint8_t *p, unsigned long long n, bool ascii)
 	convert_kernel<<<grid_for((n + 15) / 16, 256, 8), 256, 0, stream>>>(p, n, ascii ? 1 : 0);
 }
 static bool lc_wide(const LcBatch &b) { return b.ix.seq_len >= 0xffffffffull || b.force_wide; }
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is state of the FUNCTION, not of a stream or a launch, and the lanes of a
-// chunked call launch the same kernels from several host threads with different sizes (seeding passes, chunks with different
-// read lengths): without this lock one thread can lower the limit between another thread's set and its launch, the launch then
-// fails and the stage's outputs stay uninitialised.  Every "set the limit, then launch" pair runs under it.
-static std::recursive_mutex lc_launch_mu;
-#define LC_LAUNCH_GUARD std::lock_guard<std::recursive_mutex> lc_launch_guard_(lc_launch_mu)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is state of the FUNCTION (per device), not of a stream or a launch, and lanes,
+// cloned contexts and coalescer leaders launch the same kernels from many host threads with different sizes.  Round 1 serialised
+// every "set the limit, then launch" pair under one process-wide lock; now the limit of every kernel with dynamic shared memory is
+// raised ONCE per device to the device's opt-in maximum (it is only a permission: the carve-out of a launch follows its own size),
+// and launches need no lock at all.
+static void lc_set_kernel_attrs(int device)
+{
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return; }
+	const int mx = (int)prop.sharedMemPerBlockOptin;
+	auto set = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); };
+	set(smem_kernel<uint32_t, true>); set(smem_kernel<uint32_t, false>); set(smem_kernel<uint64_t, true>); set(smem_kernel<uint64_t, false>);
+	set(extend_kernel<LcCells8<32> >); set(extend_kernel<LcCells16<32> >);
+	set(extend_heavy_kernel); set(matesw_kernel); set(global_cigar_kernel); set(ksw_extend_kernel); set(ksw_align_kernel);
+	cudaGetLastError();
+}
 int LcCudaBackend::seed_grid(const LcBatch &b, int n_items)
 {
 	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
 	int per_sm = 1;
-	auto prep = [&](auto kern) {
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC_SEED_TPB, smem);
-	};
+	auto prep = [&](auto kern) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC_SEED_TPB, smem); };
 	if (lc_wide(b)) { if (b.cnt) prep(smem_kernel<uint64_t, true>); else prep(smem_kernel<uint64_t, false>); }
 	else { if (b.cnt) prep(smem_kernel<uint32_t, true>); else prep(smem_kernel<uint32_t, false>); }
 	if (per_sm < 1) per_sm = 1;
@@ -444,10 +454,9 @@ int LcCudaBackend::seed_grid(const LcBatch &b, int n_items)
 	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
 	return (int)(need < cap ? (need ? need : 1) : cap);
 }
-int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { LC_LAUNCH_GUARD; return seed_grid(b, n_items) * LC_SEED_TPB; }
+int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { return seed_grid(b, n_items) * LC_SEED_TPB; }
 void LcCudaBackend::k_seed(const LcBatch &b, const int32_t *list, int n_items)
 {
-	LC_LAUNCH_GUARD;
 	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4, grid = seed_grid(b, n_items);
 	cudaMemsetAsync(b.work_ctr + 3, 0, 4, stream);
 	const unsigned gm = (unsigned)seed_gate_mask;
@@ -483,10 +492,8 @@ void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_ker
 void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
 template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
 {
-	LC_LAUNCH_GUARD;
 	const int smem = ((LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) + LC_EXT_MTAB_WORDS) * 4;
 	int per_sm = 1;
-	cudaFuncSetAttribute(extend_kernel<CELLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<CELLS>, LC_EXT_TPB, smem);
 	if (per_sm < 1) per_sm = 1;
 	const long long need = ((long long)b.n_reads + LC_EXT_TPB - 1) / LC_EXT_TPB, cap = (long long)n_sm * per_sm;
@@ -501,9 +508,7 @@ void LcCudaBackend::k_extend(const LcBatch &b)
 	unsigned int n = 0;
 	const uint64_t *list = sort_worklist(b, b.ext_heavy_n, n);
 	if (n) {
-		LC_LAUNCH_GUARD;
-		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
-		cudaFuncSetAttribute(extend_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
 		extend_heavy_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
 	}
 }
@@ -529,17 +534,13 @@ void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 	unsigned int n = 0;
 	const uint64_t *list = sort_worklist(b, b.resc_n, n);      // pairs that need a Smith-Waterman, heaviest first
 	if (n) {
-		LC_LAUNCH_GUARD;
-		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
-		cudaFuncSetAttribute(matesw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax, 3);
 		matesw_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
 	}
 }
 void LcCudaBackend::k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 {
-	LC_LAUNCH_GUARD;
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
-	cudaFuncSetAttribute(global_cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	cudaMemsetAsync(b.work_ctr + 2, 0, 4, stream);      // the stage may be re-launched after a pool regrow
 	global_cigar_kernel<<<grid_for(n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n, n_dev);
 }
@@ -576,16 +577,12 @@ void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)
 }
 void LcCudaBackend::k_ksw_extend(const LcExtJobs &j)
 {
-	LC_LAUNCH_GUARD;
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(j.qmax);
-	cudaFuncSetAttribute(ksw_extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	ksw_extend_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 8), LC_TPB, smem, stream>>>(j);
 }
 void LcCudaBackend::k_ksw_align(const LcSwJobs &j)
 {
-	LC_LAUNCH_GUARD;
 	const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(j.qmax, 3);
-	cudaFuncSetAttribute(ksw_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	ksw_align_kernel<<<grid_for((unsigned long long)j.n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(j);
 }
 void LcCudaBackend::k_sa_batch(const LcIndex &ix, const uint64_t *rows, uint64_t *out, long long n, LcCounters *cnt)

@@ -75,7 +75,7 @@ class lc_alnreg_v(C.Structure):
 
 
 # every symbol include/cuda_lariat.h declares
-EXPORTS = ["lc_opt_init", "lc_init", "lc_destroy", "lc_last_error", "lc_contigs", "lc_align_pairs", "lc_align_packed",
+EXPORTS = ["lc_opt_init", "lc_init", "lc_clone", "lc_set_coalescing", "lc_destroy", "lc_last_error", "lc_contigs", "lc_align_pairs", "lc_align_packed",
            "lc_batch_upload", "lc_batch_run", "lc_batch_fetch", "lc_free_result", "lc_fetch_seq", "lc_mem_align1_core",
            "lc_mem_matesw", "lc_mem_reg2aln", "lc_ksw_extend_batch", "lc_ksw_align_batch", "lc_collect_intv_batch",
            "lc_sa_batch", "lc_index_build", "lc_set_counting", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
@@ -96,6 +96,8 @@ def load_library(path: str = LIB_PATH):
     lib.lc_opt_init.argtypes = [C.POINTER(lc_opt_t)]; lib.lc_opt_init.restype = None
     lib.lc_init.argtypes = [C.c_char_p, C.c_int, C.POINTER(lc_opt_t)]; lib.lc_init.restype = vp
     lib.lc_destroy.argtypes = [vp]; lib.lc_destroy.restype = None
+    lib.lc_clone.argtypes = [vp]; lib.lc_clone.restype = vp
+    lib.lc_set_coalescing.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.lc_last_error.argtypes = []; lib.lc_last_error.restype = C.c_char_p
     lib.lc_build_info.argtypes = []; lib.lc_build_info.restype = C.c_char_p
     lib.lc_contigs.argtypes = [vp]; lib.lc_contigs.restype = C.POINTER(lc_contigs_t)
@@ -163,7 +165,12 @@ class SingleReadAlignment:      # gobwa.go:417-433
     ReadE: int = 0
 
 
-class Arena:                    # gobwa.go:107-126 — the GPU build returns numpy-owned memory, so there is nothing to free
+class Arena:                    # gobwa.go:107-126
+    """The reference's Arena collects the C arrays BWA malloc'd for one barcode and C.free()s them at the end of
+    DoRFAForOneBarcode (lariat.go:494,546).  Here it collects the result handles of the batched calls: the arrays a
+    BatchResult(copy=False) views stay valid — whatever other threads or later calls do — until Free() gives them back
+    to the library (lc_free_result)."""
+
     def __init__(self):
         self.Pointers = []
 
@@ -171,6 +178,9 @@ class Arena:                    # gobwa.go:107-126 — the GPU build returns num
         self.Pointers.append(p)
 
     def Free(self):
+        for p in self.Pointers:
+            if hasattr(p, "free"):
+                p.free()
         self.Pointers = []
 
 
@@ -191,7 +201,10 @@ def GoBwaAllocSettings() -> GoBwaSettings:
 class BatchResult:
     """Flat views of one lc_result_t (copied out of the library's buffers so they survive the next call)."""
 
-    def __init__(self, res: lc_result_t, copy: bool = True):
+    def __init__(self, res: lc_result_t, copy: bool = True, owner=None):
+        """owner = (lib, ctx, pointer): the library-side block these arrays live in; free() (or Arena.Free) releases it.
+        With copy=True the arrays are numpy-owned copies and the block is released right away."""
+        self._owner = owner
         n = int(res.n_reads)
         nr = int(res.n_regs)
         self.n_reads = n
@@ -206,12 +219,20 @@ class BatchResult:
         self.cigars = np.ctypeslib.as_array(res.cigars, shape=(nc,)) if nc else np.zeros(0, dtype=np.uint32)
         if copy:
             self.reg_off, self.regs, self.aln, self.cigars = self.reg_off.copy(), self.regs.copy(), self.aln.copy(), self.cigars.copy()
+            self.free()
         self.timing = {k: float(getattr(res, k)) for k in ("ms_h2d", "ms_seed", "ms_sa", "ms_chain", "ms_extend", "ms_dedup",
                                                            "ms_pair", "ms_cigar", "ms_d2h", "ms_total")}
         self.gpu_launches = int(res.gpu_launches)
         self.counters = {k[4:]: int(getattr(res, k)) for k in ("cnt_occ_blocks", "cnt_extend_calls", "cnt_sa_calls", "cnt_lf_steps",
                                                                "cnt_ext_calls", "cnt_ext_cells", "cnt_sw_calls", "cnt_sw_cells",
                                                                "cnt_glb_calls", "cnt_glb_cells")}
+
+    def free(self):
+        """lc_free_result: the caller owns a result until it says so (views made with copy=False are dead afterwards)."""
+        if self._owner is not None:
+            lib, ctx, ptr = self._owner
+            lib.lc_free_result(ctx, ptr)
+            self._owner = None
 
     def cigar_of(self, i: int) -> np.ndarray:
         a = self.aln[i]
@@ -311,7 +332,14 @@ class GoBwaReference:           # gobwa.go:21-24
         rc = self._lib.lc_align_packed(self.BWTData, n_pairs, bases.ctypes.data, off.ctypes.data, score_delta, C.byref(res))
         if rc != 0:
             raise RuntimeError(f"lc_align_packed failed ({rc}): {last_error()}")
-        return BatchResult(res.contents, copy=copy)
+        return BatchResult(res.contents, copy=copy, owner=(self._lib, self.BWTData, res))
+
+    def clone(self) -> "GoBwaReference":
+        """A second context on the same device index (own stream and pools, no second copy of the index): lc_clone."""
+        ctx = self._lib.lc_clone(self.BWTData)
+        if not ctx:
+            raise RuntimeError("lc_clone failed: " + last_error())
+        return GoBwaReference(ctx, self._lib)
 
 
 def GoBwaLoadReference(path: str, device: int = 0, settings: GoBwaSettings | None = None):

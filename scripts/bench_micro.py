@@ -44,6 +44,7 @@ with tempfile.TemporaryDirectory() as td:
             lib.lc_set_counting(ctx, 1)
             assert lib.lc_align_packed(ctx, n, bases.ctypes.data, off.ctypes.data, 25, C.byref(res)) == 0, gobwa.last_error()
             cnt = gobwa.BatchResult(res.contents, copy=False).counters
+            lib.lc_free_result(ctx, res)
             lib.lc_set_counting(ctx, 0)
             assert lib.lc_batch_upload(ctx, n, bases.ctypes.data, off.ctypes.data) == 0
             ms = {"ms_seed": [], "ms_extend": [], "ms_total": []}
