@@ -104,6 +104,23 @@ typedef struct {
 	int32_t n_mismatch; /* number of mismatching aligned bases (== NM - gap bases), for GetAlignments (I/lariat.go:1633) */
 } lc_aln_t;
 
+/* ---- what inference.GetAlignments computes per candidate AFTER mem_reg2aln (I/lariat.go:1573-1637,1645-1650): the Go loop fetches the
+ * reference span with GetSeq (one cgo call per candidate), walks the CIGAR and compares bases.  With lc_set_alnx(ctx, 1) a kernel does
+ * the same walk on the device and the result carries the outcome, so the shim needs no further BWA call per candidate.
+ * Read and reference are compared byte for byte like the two Go slices ('A' 'C' 'G' 'T' against the read as given: a lower-case or
+ * ambiguous read base differs from everything), so the lists are the Go lists. */
+typedef struct {
+	int64_t pos, aend;           /* Alignment.pos / .aend: contig-relative, swapped (+1) on the reverse strand (I/lariat.go:1645-1650) */
+	int32_t matches;             /* M bases minus mismatches (I/lariat.go:1633-1634) */
+	int32_t mismatches;          /* EditDistance - indel_length, floored at 0 (I/lariat.go:1633-1637) */
+	int32_t indels;              /* number of I and D operations */
+	int32_t indel_length;
+	int32_t soft_clipped;        /* number of S operations */
+	int32_t soft_clipped_length;
+	int32_t n_mm;                /* len(mismatchLocs) == len(mismatchReadLocs) */
+	uint32_t mm_off;             /* first entry of this candidate in lc_result.mm_ref_pos / mm_read_pos */
+} lc_alnx_t;
+
 /* ---- insert-size model: mem_pestat_t (B/bwamem.h:81-85). Lariat hard-codes FR, low=-35, high=500 (G/gobwa.go:229-237) ---- */
 typedef struct { int low, high, failed; double avg, std; } lc_pestat_t;
 
@@ -133,6 +150,11 @@ typedef struct {
 	/* algorithmic work counters, filled when lc_set_counting(ctx, 1) */
 	uint64_t cnt_occ_blocks, cnt_extend_calls, cnt_sa_calls, cnt_lf_steps;
 	uint64_t cnt_ext_calls, cnt_ext_cells, cnt_sw_calls, cnt_sw_cells, cnt_glb_calls, cnt_glb_cells;
+	/* GetAlignments post-processing, when lc_set_alnx(ctx, 1) was called (else null / 0): alnx[i] belongs to regs[i] */
+	const lc_alnx_t *alnx;        /* [n_regs] */
+	const int32_t *mm_ref_pos;    /* mismatchLocs: contig-relative reference positions, in the order the Go loop appends them */
+	const int32_t *mm_read_pos;   /* mismatchReadLocs: positions on the read as given */
+	int64_t n_mm;                 /* entries of the two arrays */
 } lc_result_t;
 
 typedef struct lc_ctx lc_ctx;
@@ -214,6 +236,8 @@ int lc_sa_batch(lc_ctx *ctx, int64_t n, const uint64_t *rows, uint64_t *out, flo
 int lc_index_build(const char *prefix, int n_contigs, const char *const *names, const uint8_t *const *codes, const int64_t *lens, int device);
 
 void lc_set_counting(lc_ctx *ctx, int on);
+/* GetAlignments post-processing on the device (lc_alnx_t above): off by default; applies to this context and its later clones */
+void lc_set_alnx(lc_ctx *ctx, int on);
 /* Calls of more than 1.5 x n_pairs pairs are cut into chunks of about n_pairs pairs that alternate between two CUDA streams, so that the
  * H2D / D2H copies of one chunk run under the kernels of the other (the reference's analogue: barcode groups flowing through the
  * goroutine pool of I/lariat.go:348-350 while the BAM thread drains results).  0 = never chunk.  Default 500000 (env LC_CHUNK_PAIRS).

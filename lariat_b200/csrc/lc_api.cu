@@ -40,9 +40,13 @@ struct LcPinned {
 struct LcLane {
 	LcCudaBackend be;
 	LcPipeline<LcCudaBackend> pl;
-	LcPinned in_bases, in_off, out_off, out_regs, out_aln, out_cig;      // pinned staging of a coalesced batch
+	LcPinned in_bases, in_off, out_off, out_regs, out_aln, out_cig, out_alnx, out_mmr, out_mmd;      // pinned staging of a coalesced batch
 	explicit LcLane(int dev) : be(dev), pl(be) {}
-	~LcLane() { pl.release(); in_bases.release(); in_off.release(); out_off.release(); out_regs.release(); out_aln.release(); out_cig.release(); }
+	~LcLane()
+	{
+		pl.release(); in_bases.release(); in_off.release(); out_off.release(); out_regs.release(); out_aln.release(); out_cig.release();
+		out_alnx.release(); out_mmr.release(); out_mmd.release();
+	}
 };
 
 // The result of one call.  It belongs to the CALLER from the moment the call returns until lc_free_result: nothing the library does
@@ -55,10 +59,11 @@ struct LcResultBlock {
 	lc_result_t res;                 // first member: the lc_result_t* handed to the caller IS the block
 	uint32_t magic = LC_RESULT_MAGIC;
 	bool pinned = false;
-	LcPinned p_off, p_regs, p_aln, p_cig;
+	LcPinned p_off, p_regs, p_aln, p_cig, p_alnx, p_mmr, p_mmd;
 	std::vector<int64_t> v_off; std::vector<lc_alnreg_t> v_regs; std::vector<lc_aln_t> v_aln; std::vector<uint32_t> v_cig;
+	std::vector<lc_alnx_t> v_alnx; std::vector<int32_t> v_mmr, v_mmd;
 	LcResultBlock() { memset(&res, 0, sizeof(res)); }
-	~LcResultBlock() { p_off.release(); p_regs.release(); p_aln.release(); p_cig.release(); }
+	~LcResultBlock() { p_off.release(); p_regs.release(); p_aln.release(); p_cig.release(); p_alnx.release(); p_mmr.release(); p_mmd.release(); }
 };
 
 struct LcRequest {                   // one small call waiting in the coalescer
@@ -83,6 +88,7 @@ struct LcSharedIndex {
 	// tuning copied into every pipeline (lc_init reads the environment once)
 	int lst_cap = 0, pk_cap = 64, lst_cap2 = 40, pk_cap2 = 256, lst_cap3 = 150, pk_cap3 = 2048, ext_heavy_seeds = 32, ext_heavy_chains = 8;
 	bool force_wide = false;
+	bool want_alnx = false;       // lc_set_alnx: GetAlignments post-processing in every pipeline of the index
 	// pinned result blocks given back by lc_free_result
 	std::mutex blk_mu;
 	std::vector<LcResultBlock *> free_blocks;
@@ -105,7 +111,7 @@ struct LcSharedIndex {
 	void tune(LcPipeline<LcCudaBackend> &pl) const
 	{
 		pl.lst_cap = lst_cap; pl.pk_cap = pk_cap; pl.lst_cap2 = lst_cap2; pl.pk_cap2 = pk_cap2; pl.lst_cap3 = lst_cap3; pl.pk_cap3 = pk_cap3;
-		pl.ext_heavy_seeds = ext_heavy_seeds; pl.ext_heavy_chains = ext_heavy_chains; pl.force_wide = force_wide;
+		pl.ext_heavy_seeds = ext_heavy_seeds; pl.ext_heavy_chains = ext_heavy_chains; pl.force_wide = force_wide; pl.want_alnx = want_alnx;
 	}
 };
 
@@ -277,6 +283,14 @@ void lc_destroy(lc_ctx *c)      // the index leaves HBM when its last context is
 
 const lc_contigs_t *lc_contigs(const lc_ctx *c) { return c ? &c->sh->contigs : nullptr; }
 void lc_set_counting(lc_ctx *c, int on) { if (c) c->pl.counting = on != 0; }
+void lc_set_alnx(lc_ctx *c, int on)
+{
+	if (!c) return;
+	std::lock_guard<std::mutex> g(c->mu);
+	std::lock_guard<std::mutex> g2(c->sh->co_mu);      // no merged batch is being assembled while the switch flips
+	c->sh->want_alnx = on != 0;
+	c->pl.want_alnx = on != 0;
+}
 int lc_set_chunk_pairs(lc_ctx *c, int n_pairs)
 {
 	if (!c || n_pairs < 0) return fail(LC_EARG, "bad arguments");
@@ -319,6 +333,8 @@ static void fill_result(lc_ctx *c)
 	r.n_regs = (int64_t)h.regs.size();
 	r.reg_off = h.reg_off.data(); r.regs = h.regs.data(); r.aln = h.aln.data(); r.cigars = h.cigars.data();
 	r.n_cigar_words = (int64_t)h.cigars.size();
+	r.alnx = h.alnx.empty() ? nullptr : h.alnx.data(); r.mm_ref_pos = h.mm_ref.data(); r.mm_read_pos = h.mm_read.data(); r.n_mm = (int64_t)h.mm_ref.size();
+	if (!r.alnx) { r.mm_ref_pos = r.mm_read_pos = nullptr; r.n_mm = 0; }
 	r.ms_h2d = h.ms[0]; r.ms_seed = h.ms[1]; r.ms_sa = h.ms[2]; r.ms_chain = h.ms[3]; r.ms_extend = h.ms[4]; r.ms_dedup = h.ms[5];
 	r.ms_pair = h.ms[6]; r.ms_cigar = h.ms[7]; r.ms_d2h = h.ms[8]; r.ms_total = h.ms[9];
 	r.gpu_launches = h.launches;
@@ -402,7 +418,7 @@ struct LcChunkShared {
 	std::mutex mu;
 	std::condition_variable cv;
 	std::vector<int64_t> cum_reg;       // [n_chunks + 1] candidates before chunk k, valid once ready[k]
-	std::vector<int64_t> cum_cig;
+	std::vector<int64_t> cum_cig, cum_mm;
 	std::vector<char> ready;
 	std::shared_mutex res_mu;           // shared: a D2H into the pinned arrays is in flight; exclusive: the arrays are being regrown
 	int rc = LC_OK;
@@ -434,11 +450,12 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 		if (!rc) rc = pl->upload(p1 - p0, bases, off + 2 * (size_t)p0, true);
 		if (!rc) rc = pl->run_stages(score_delta);
 		if (rc) sh->fail_with(rc, pl->err);
-		int64_t reg_base, cig_base;
+		int64_t reg_base, cig_base, mm_base;
 		{   // chunk k's place in the call's arrays = totals of the chunks before it (known when their CIGAR stage is done)
 			std::unique_lock<std::mutex> g(sh->mu);
 			sh->cv.wait(g, [&] { return sh->ready[k] != 0; });
-			reg_base = sh->cum_reg[k]; cig_base = sh->cum_cig[k];
+			reg_base = sh->cum_reg[k]; cig_base = sh->cum_cig[k]; mm_base = sh->cum_mm[k];
+			sh->cum_mm[k + 1] = mm_base + (rc ? 0 : (int64_t)pl->n_mm);
 			sh->cum_reg[k + 1] = reg_base + (rc ? 0 : (int64_t)pl->n_cand);
 			sh->cum_cig[k + 1] = cig_base + (rc ? 0 : (int64_t)pl->n_cigar_words);
 			sh->ready[k + 1] = 1;
@@ -446,23 +463,32 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 		}
 		sh->cv.notify_all();
 		if (rc) continue;
-		rc = pl->run_pack(reg_base, (uint32_t)cig_base);
+		if (sh->cum_mm[k + 1] > 0xffffffffll) { sh->fail_with(LC_ENOMEM, "more than 2^32 mismatch positions in one call"); continue; }
+		rc = pl->run_pack(reg_base, (uint32_t)cig_base, (uint32_t)mm_base);
 		if (rc) { sh->fail_with(rc, pl->err); continue; }
 		const size_t need_reg = (size_t)(reg_base + (int64_t)pl->n_cand), need_cig = (size_t)(cig_base + (int64_t)pl->n_cigar_words);
-		if (need_reg * sizeof(lc_alnreg_t) > B.p_regs.cap || need_reg * sizeof(lc_aln_t) > B.p_aln.cap || need_cig * 4 > B.p_cig.cap) {
+		const bool ax = pl->want_alnx;
+		const size_t need_mm = ax ? (size_t)(mm_base + (int64_t)pl->n_mm) : 0;
+		if (need_reg * sizeof(lc_alnreg_t) > B.p_regs.cap || need_reg * sizeof(lc_aln_t) > B.p_aln.cap || need_cig * 4 > B.p_cig.cap ||
+			(ax && (need_reg * sizeof(lc_alnx_t) > B.p_alnx.cap || need_mm * 4 > B.p_mmr.cap || need_mm * 4 > B.p_mmd.cap))) {
 			// regrow (rare: blocks are recycled with their capacities): extrapolate from the chunks seen so far, wait out in-flight copies, keep what is there
 			std::unique_lock<std::shared_mutex> g(sh->res_mu);
 			const double f = 1.2 * n_chunks / (double)(k + 1);
 			const size_t want_reg = (size_t)(need_reg * f) + 1024, want_cig = (size_t)(need_cig * f) + 1024;
 			if (!B.p_regs.ensure(want_reg * sizeof(lc_alnreg_t), B.p_regs.cap) || !B.p_aln.ensure(want_reg * sizeof(lc_aln_t), B.p_aln.cap) ||
 				!B.p_cig.ensure(want_cig * 4, B.p_cig.cap)) { sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue; }
+			const size_t want_mm = (size_t)(need_mm * f) + 1024;
+			if (ax && (!B.p_alnx.ensure(want_reg * sizeof(lc_alnx_t), B.p_alnx.cap) || !B.p_mmr.ensure(want_mm * 4, B.p_mmr.cap) || !B.p_mmd.ensure(want_mm * 4, B.p_mmd.cap))) {
+				sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue;
+			}
 		}
 		float ms[10]; LcCounters cn;
 		{
 			std::shared_lock<std::shared_mutex> g(sh->res_mu);
 			const size_t n_off = 2 * (size_t)(p1 - p0) + (k == n_chunks - 1 ? 1 : 0);
 			pl->fetch_into((int64_t *)B.p_off.p + 2 * (size_t)p0, n_off, (lc_alnreg_t *)B.p_regs.p + reg_base, (lc_aln_t *)B.p_aln.p + reg_base,
-						   (uint32_t *)B.p_cig.p + cig_base);
+						   (uint32_t *)B.p_cig.p + cig_base, ax ? (lc_alnx_t *)B.p_alnx.p + reg_base : nullptr,
+						   ax ? (int32_t *)B.p_mmr.p + mm_base : nullptr, ax ? (int32_t *)B.p_mmd.p + mm_base : nullptr);
 			be->sync();
 		}
 		std::string e;
@@ -506,12 +532,12 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 		S.tune(l->pl);
 		c->lanes.push_back(std::move(l));
 	}
-	for (auto &l : c->lanes) l->pl.counting = c->pl.counting;
+	for (auto &l : c->lanes) { l->pl.counting = c->pl.counting; l->pl.want_alnx = c->pl.want_alnx; }
 	LcResultBlock *blk = take_pinned_block(S);
 	if (!blk->p_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) { give_block(S, blk); return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results"); }
 	LcChunkShared sh;
 	sh.blk = blk;
-	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.ready.assign(n_chunks + 1, 0); sh.ready[0] = 1;
+	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.cum_mm.assign(n_chunks + 1, 0); sh.ready.assign(n_chunks + 1, 0); sh.ready[0] = 1;
 	memset(&sh.cnt, 0, sizeof(sh.cnt));
 	c->be.ev_record(12);
 	{
@@ -530,6 +556,7 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 	r.n_reads = 2 * n_pairs; r.n_regs = sh.cum_reg[n_chunks]; r.n_cigar_words = sh.cum_cig[n_chunks];
 	r.reg_off = (const int64_t *)blk->p_off.p; r.regs = (const lc_alnreg_t *)blk->p_regs.p; r.aln = (const lc_aln_t *)blk->p_aln.p; r.cigars = (const uint32_t *)blk->p_cig.p;
 	if (r.reg_off[r.n_reads] != r.n_regs) { give_block(S, blk); return fail(LC_ECUDA, "result size mismatch"); }
+	if (c->pl.want_alnx) { r.alnx = (const lc_alnx_t *)blk->p_alnx.p; r.mm_ref_pos = (const int32_t *)blk->p_mmr.p; r.mm_read_pos = (const int32_t *)blk->p_mmd.p; r.n_mm = sh.cum_mm[n_chunks]; }
 	// stage times: summed over the chunks (chunks of the two lanes overlap); ms_total: the whole call on the device clock, copies included when chunked
 	set_stage_ms(r, sh.ms);
 	if (n_chunks > 1) r.ms_total = c->be.ev_ms(12, 13);
@@ -564,14 +591,19 @@ static void run_coalesced(LcSharedIndex &S, LcLane *lane, std::vector<LcRequest 
 		ho[rr] = o;
 	}
 	LcPipeline<LcCudaBackend> &pl = lane->pl;
+	pl.want_alnx = S.want_alnx;
 	int rc = pl.upload(tot, hb, ho, true);
 	if (!rc) rc = pl.run_stages(score_delta);
 	if (!rc) rc = pl.run_pack(0, 0);
 	if (rc) return fail_all(rc, pl.err);
-	const size_t NC = (size_t)pl.n_cand, NW = (size_t)pl.n_cigar_words;
+	const size_t NC = (size_t)pl.n_cand, NW = (size_t)pl.n_cigar_words, NM = (size_t)pl.n_mm;
+	const bool ax = pl.want_alnx;
 	if (!lane->out_off.ensure(8 * (2 * (size_t)tot + 1), 0) || !lane->out_regs.ensure(sizeof(lc_alnreg_t) * (NC + 1), 0) ||
-		!lane->out_aln.ensure(sizeof(lc_aln_t) * (NC + 1), 0) || !lane->out_cig.ensure(4 * (NW + 1), 0)) return fail_all(LC_ENOMEM, "cannot allocate pinned staging for a merged batch");
-	pl.fetch_into((int64_t *)lane->out_off.p, 2 * (size_t)tot + 1, (lc_alnreg_t *)lane->out_regs.p, (lc_aln_t *)lane->out_aln.p, (uint32_t *)lane->out_cig.p);
+		!lane->out_aln.ensure(sizeof(lc_aln_t) * (NC + 1), 0) || !lane->out_cig.ensure(4 * (NW + 1), 0) ||
+		(ax && (!lane->out_alnx.ensure(sizeof(lc_alnx_t) * (NC + 1), 0) || !lane->out_mmr.ensure(4 * (NM + 1), 0) || !lane->out_mmd.ensure(4 * (NM + 1), 0))))
+		return fail_all(LC_ENOMEM, "cannot allocate pinned staging for a merged batch");
+	pl.fetch_into((int64_t *)lane->out_off.p, 2 * (size_t)tot + 1, (lc_alnreg_t *)lane->out_regs.p, (lc_aln_t *)lane->out_aln.p, (uint32_t *)lane->out_cig.p,
+				  ax ? (lc_alnx_t *)lane->out_alnx.p : nullptr, ax ? (int32_t *)lane->out_mmr.p : nullptr, ax ? (int32_t *)lane->out_mmd.p : nullptr);
 	lane->be.sync();
 	std::string e;
 	if (lane->be.check(e)) return fail_all(LC_ECUDA, e);
@@ -581,6 +613,8 @@ static void run_coalesced(LcSharedIndex &S, LcLane *lane, std::vector<LcRequest 
 	const lc_alnreg_t *regs = (const lc_alnreg_t *)lane->out_regs.p;
 	const lc_aln_t *aln = (const lc_aln_t *)lane->out_aln.p;
 	const uint32_t *cig = (const uint32_t *)lane->out_cig.p;
+	const lc_alnx_t *alnx = (const lc_alnx_t *)lane->out_alnx.p;
+	const int32_t *mmr = (const int32_t *)lane->out_mmr.p, *mmd = (const int32_t *)lane->out_mmd.p;
 	if ((size_t)roff[2 * (size_t)tot] != NC) return fail_all(LC_ECUDA, "result size mismatch");
 	size_t r0 = 0;
 	for (auto *rq : batch) {      // cut the merged result apart: each request gets arrays of its own
@@ -600,6 +634,18 @@ static void run_coalesced(LcSharedIndex &S, LcLane *lane, std::vector<LcRequest 
 			a.cigar_off = (uint32_t)nw; nw += (size_t)a.n_cigar;
 		}
 		lc_result_t &r = b->res;
+		if (ax) {      // likewise the mismatch position lists
+			b->v_alnx.assign(alnx + c0, alnx + c1);
+			size_t nm = 0;
+			for (auto &x : b->v_alnx) nm += (size_t)x.n_mm;
+			b->v_mmr.resize(nm + 1); b->v_mmd.resize(nm + 1);
+			nm = 0;
+			for (auto &x : b->v_alnx) {
+				if (x.n_mm) { memcpy(&b->v_mmr[nm], mmr + x.mm_off, 4 * (size_t)x.n_mm); memcpy(&b->v_mmd[nm], mmd + x.mm_off, 4 * (size_t)x.n_mm); }
+				x.mm_off = (uint32_t)nm; nm += (size_t)x.n_mm;
+			}
+			r.alnx = b->v_alnx.data(); r.mm_ref_pos = b->v_mmr.data(); r.mm_read_pos = b->v_mmd.data(); r.n_mm = (int64_t)nm;
+		}
 		r.n_reads = (int32_t)R; r.n_regs = c1 - c0; r.n_cigar_words = (int64_t)nw;
 		r.reg_off = b->v_off.data(); r.regs = b->v_regs.data(); r.aln = b->v_aln.data(); r.cigars = b->v_cig.data();
 		set_stage_ms(r, ms);      // times and launches are those of the merged batch the call rode in

@@ -58,6 +58,7 @@ struct LcCudaBackend {
 	void k_cigar_plan(const LcBatch &b, unsigned long long n);
 	int k_cigar_band(const LcBatch &b, unsigned long long n_max);
 	void k_cigar_fallback(const LcBatch &b, unsigned long long n_max);
+	void k_alnx(const LcBatch &b, unsigned long long n);
 	void k_pack(const LcBatch &b, const LcPackArgs &pa);
 	void k_rebase(int64_t *off, int n, int64_t off0);
 	void scan_exclusive(const int32_t *in, int64_t *out, int n);

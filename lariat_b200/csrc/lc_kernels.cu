@@ -303,6 +303,13 @@ __global__ void __launch_bounds__(LC_TPB) global_cigar_kernel(const LcBatch b, c
 	}
 }
 
+// Stage 6b (lc_post.cuh): one thread per candidate — the CIGAR walk of inference.GetAlignments (I/lariat.go:1573-1650)
+__global__ void __launch_bounds__(256) alnx_kernel(const LcBatch b, unsigned long long n)
+{
+	unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (; c < n; c += stride) lc_stage_alnx(b, b.cand[c]);
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const LcBatch b, const LcPackArgs pa)
 {
 	const int stride = gridDim.x * blockDim.x;
@@ -565,6 +572,7 @@ void LcCudaBackend::k_cigar_fallback(const LcBatch &b, unsigned long long n_max)
 	// sized for a small list (the usual case); the warps pull candidates from a counter, so a long list only takes longer
 	k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, n_max < 65536 ? n_max : 65536, b.cig_n + LC_CIG_FALLBACK);
 }
+void LcCudaBackend::k_alnx(const LcBatch &b, unsigned long long n) { alnx_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
 void LcCudaBackend::k_pack(const LcBatch &b, const LcPackArgs &pa) { pack_kernel<<<grid_for((unsigned long long)b.n_reads + 1, 256, 8), 256, 0, stream>>>(b, pa); }
 void LcCudaBackend::k_rebase(int64_t *off, int n, int64_t off0) { rebase_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(off, n, off0); }
 void LcCudaBackend::scan_exclusive(const int32_t *in, int64_t *out, int n)

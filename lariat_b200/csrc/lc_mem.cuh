@@ -21,7 +21,7 @@ struct LcChainRec { int64_t pos; int32_t rid, n, head, tail; uint32_t w; int32_t
 struct LcBtNode { int32_t n, internal; int32_t key[LC_BT_MAXK]; int32_t child[LC_BT_MAXK + 1]; };
 
 enum { LC_OVF_INTV = 1, LC_OVF_SEED = 2, LC_OVF_SCRATCH = 4, LC_OVF_CSEED = 8, LC_OVF_REG = 16, LC_OVF_FINAL = 32,
-	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512, LC_OVF_PK = 1024 };
+	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512, LC_OVF_PK = 1024, LC_OVF_MM = 2048 };
 
 // packed 16x2 constants of the extension tick (lc_extsm.cuh), derived from the scoring options once on the host: as kernel
 // parameters they are constant-bank operands, not per-tick arithmetic
@@ -94,6 +94,11 @@ struct LcBatch {
 	uint64_t *wl_in, *wl_out;                            // work lists of the warp-per-item kernels (heavy reads of stage 4, rescue pairs of stage 5):
 	                                                     //   entries weight << 32 | id, appended to wl_in; the backend sorts them by weight,
 	                                                     //   heaviest first, into wl_out so that the long items do not start last
+	// ---- stage 6b (optional): GetAlignments post-processing (lc_post.cuh)
+	lc_alnx_t *alnx;                                     // parallel to fin / aln
+	const uint8_t *raw;                                  // the reads as given (ASCII), kept beside the 2-bit codes: the Go loop compares BYTES
+	                                                     //   (a lower-case read mismatches everywhere); null = compare codes
+	int32_t *mm_ref, *mm_read; unsigned long long mm_cap, *mm_cur;   // mismatch position lists, carved per candidate
 	unsigned int *ext_heavy_n;                           // stage 4: reads listed (in `redo`) for the warp-per-read extension kernel, then its work counter
 	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read is "heavy" above this many chained seeds / chains (0 = never)
 };
@@ -785,8 +790,14 @@ LC_HD bool lc_matesw_wants_sw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, 
 }
 
 // mem_matesw (B/bwamem_pair.c:111-180)
+// `fixed` (state of the LIST, kept by the caller across calls, meaningful in the leader lane): the list is the output of a
+// mem_sort_dedup_patch that inserted nothing and removed nothing.  Such a list is sorted by the strict order (score, rb, qb) with
+// every n_comp == 1, so running mem_sort_dedup_patch on it again (B/bwamem_pair.c:175 does, after EVERY Smith-Waterman, accepted or
+// not) sees the same array, makes the same comparisons and leaves the same array: the call is skipped.  In repeats most rescue
+// attempts are rejected (score < min_seed_len) and the lists hold hundreds of regions; the re-sort by a single lane after each of
+// them was the largest part of matesw_kernel (profiles/r01y: 29 % of its samples).  Any insertion or removal clears the flag.
 template <class Exec>
-LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const Exec &ex)
+LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const Exec &ex, bool &fixed)
 {
 	const lc_opt_t &opt = b.opt;
 	const int64_t l_pac = b.ix.l_pac;
@@ -800,8 +811,10 @@ LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const ui
 	ex.sync();
 	int n = n_ma;
 	if (ex.leader()) {
+		bool inserted = false;
 		if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
 			lc_alnreg_t nb;
+			inserted = true;
 			memset(&nb, 0, sizeof(nb));
 			nb.rid = anchor.rid;
 			nb.is_alt = anchor.is_alt;
@@ -820,7 +833,11 @@ LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const ui
 			ma[at] = nb;
 		}
 		// :175; no patching without a query.  The sub-optimal-row list of the SW just done is dead by now: its memory holds the sort handles
-		n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0, (int *)ex.bl, ex.bl ? 2 * b.w_u64_n : 0);
+		if (inserted || !fixed) {
+			const int n_in = n;
+			n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0, (int *)ex.bl, ex.bl ? 2 * b.w_u64_n : 0);
+			fixed = !inserted && n == n_in;
+		}
 	}
 	n_ma = (int)ex.bcast((unsigned long long)n);
 	ex.sync();
@@ -885,16 +902,17 @@ LC_HD void lc_pair_rescue_t(const LcBatch &b, int p, const Exec &ex)
 	for (int e = 0; e < 2; ++e) { const int r = 2 * p + e; len[e] = (int)(b.off[r + 1] - b.off[r]); q[e] = b.seq + b.off[r]; }
 	lc_alnreg_t *f0 = b.fin + b.r_fin_off[2 * p], *f1 = b.fin + b.r_fin_off[2 * p + 1];
 	int n0 = b.r_n_fin[2 * p], n1 = b.r_n_fin[2 * p + 1], num = 0;
+	bool fixed0 = false, fixed1 = false;      // see lc_matesw_t
 	for (int i = 0; i < n0; ++i) best[0] = lc_max(best[0], f0[i].score);      // the pre-rescue best scores (G/gobwa.go:264-283)
 	for (int i = 0; i < n1; ++i) best[1] = lc_max(best[1], f1[i].score);
 	ex.sync();
 	// phase 1: rescue read 1 from read 2's hits (G/gobwa.go:286-300). read 2's list is not touched in this phase.
 	for (int i = 0; i < n1 && num < b.max_anchors && len[0] > 0; ++i)
-		if (f1[i].score >= best[1] - b.score_delta) { ++num; lc_matesw_t(b, f1[i], len[0], q[0], f0, n0, ex); }
+		if (f1[i].score >= best[1] - b.score_delta) { ++num; lc_matesw_t(b, f1[i], len[0], q[0], f0, n0, ex, fixed0); }
 	// phase 2: rescue read 2 from read 1's post-rescue list, gated by the pre-rescue best (G/gobwa.go:302-324)
 	num = 0;
 	for (int i = 0; i < n0 && num < b.max_anchors && len[1] > 0; ++i)
-		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw_t(b, f0[i], len[1], q[1], f1, n1, ex); }
+		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw_t(b, f0[i], len[1], q[1], f1, n1, ex, fixed1); }
 	if (ex.leader()) {
 		b.r_n_fin[2 * p] = n0; b.r_n_fin[2 * p + 1] = n1;
 		unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));
@@ -918,7 +936,8 @@ LC_HDN int lc_matesw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uin
 {
 	LcExecThreadSw ex;
 	ex.H = ws.H; ex.E = ws.E; ex.Hmax = ws.Hmax; ex.bl = ws.b;
-	return lc_matesw_t(b, a, l_ms, ms, ma, n_ma, ex);
+	bool fixed = false;
+	return lc_matesw_t(b, a, l_ms, ms, ma, n_ma, ex, fixed);
 }
 
 // thread forms of the two halves of stage 5 (tests/hostsim; the device runs lc_pair_rescue_t with a warp)

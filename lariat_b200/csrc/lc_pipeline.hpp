@@ -14,6 +14,7 @@
 #include "lc_mem.cuh"
 #include "lc_seed.cuh"
 #include "lc_cigar.cuh"
+#include "lc_post.cuh"
 
 struct LcHostIndex {
 	uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0}, seq_len = 0;
@@ -154,6 +155,7 @@ struct LcPackArgs {            // stage 7: dense result arrays
 	// a batch that is one chunk of a larger call (lc_api.cu): its candidates / CIGAR words start at these positions of the call's arrays
 	int64_t *off_final;        // [n_reads+1] out_off + reg_base
 	int64_t reg_base; uint32_t cig_base;
+	lc_alnx_t *out_alnx; uint32_t mm_base;      // stage 6b outputs (null when off)
 };
 
 // r in [0, n_reads]: entry n_reads only carries the total
@@ -169,6 +171,7 @@ LC_HD void lc_stage_pack(const LcBatch &b, const LcPackArgs &pa, int r)
 		lc_aln_t a = b.aln[src + i];
 		a.cigar_off += pa.cig_base;
 		pa.out_aln[dst + i] = a;
+		if (pa.out_alnx) { lc_alnx_t x = b.alnx[src + i]; x.mm_off += pa.mm_base; pa.out_alnx[dst + i] = x; }
 	}
 }
 
@@ -177,6 +180,7 @@ struct LcHostResult {
 	std::vector<lc_alnreg_t> regs;
 	std::vector<lc_aln_t> aln;
 	std::vector<uint32_t> cigars;
+	std::vector<lc_alnx_t> alnx; std::vector<int32_t> mm_ref, mm_read;      // stage 6b (empty when off)
 	float ms[10] = {0};        // h2d, seed, sa, chain, extend, (dedup: folded into pair), pair, cigar, d2h, total
 	int64_t launches = 0;
 	LcCounters counters;
@@ -217,6 +221,8 @@ public:
 	int lst_cap3 = 150, pk_cap3 = 2048;
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
 	bool force_wide = false;
+	bool want_alnx = false;             // stage 6b: GetAlignments post-processing (lc_post.cuh)
+	double mm_per_cand = 4;
 
 	explicit LcPipeline(BE &be_) : be(be_) { memset(&b, 0, sizeof(b)); }
 	~LcPipeline() { release(); }
@@ -245,6 +251,12 @@ public:
 		be.ev_record(0);
 		if (!d_seq.ensure(be, (size_t)total + 16) || !d_off.ensure(be, sizeof(int64_t) * (R + 1))) return nomem();
 		if (total) be.h2d(d_seq.p, bases + off0, (size_t)total);
+		b.raw = nullptr;
+		if (want_alnx && is_ascii) {      // stage 6b compares the reads byte for byte, as the Go loop does: keep them beside the codes
+			if (!d_raw.ensure(be, (size_t)total + 16)) return nomem();
+			if (total) be.d2d(d_raw.p, d_seq.p, (size_t)total);
+			b.raw = (const uint8_t *)d_raw.p;
+		}
 		be.h2d(d_off.p, off, sizeof(int64_t) * (R + 1));
 		if (off0) be.k_rebase((int64_t *)d_off.p, R + 1, off0);
 		be.k_convert((uint8_t *)d_seq.p, (unsigned long long)total, is_ascii);   // ASCII -> 2-bit codes on the device (G/gobwa.go:159-167)
@@ -282,7 +294,7 @@ public:
 			unsigned long long *c = (unsigned long long *)d_ctl.p;
 			b.intv_cur = c + 0; b.seed_cur = c + 1; b.scratch_cur = c + 2; b.chain_cur = c + 3; b.cseed_cur = c + 4;
 			b.reg_cur = c + 5; b.fin_cur = c + 6; b.cand_cur = c + 7; b.cigar_cur = c + 8; b.z_cur = c + 9;
-			b.reg_total = c + 10; b.pk_cur = c + 11;
+			b.reg_total = c + 10; b.pk_cur = c + 11; b.mm_cur = c + 12;
 			b.overflow = (uint32_t *)(c + 16);
 			b.work_ctr = (unsigned int *)(c + 20);
 			b.redo_cur = (unsigned int *)(c + 22);
@@ -387,7 +399,7 @@ public:
 		const unsigned long long need = (unsigned long long)(b.lmax + 2) * (unsigned long long)(ar.re > ar.rb ? ar.re - ar.rb : 1) + 4096;
 		b.cigar_cap = 4 * (unsigned long long)b.lmax + 64; b.z_cap = need;
 		if (!d_cigar.ensure(be, 4 * b.cigar_cap) || !d_z.ensure(be, b.z_cap)) return nomem();
-		b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p;
+		b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p; b.alnx = nullptr;
 		be.k_cigar(b, b.cand, 1, nullptr); ++launches;
 		read_ctl();
 		if (h_ctl_ovf) { err = "overflow in single cigar"; return LC_ENOMEM; }
@@ -447,34 +459,46 @@ public:
 		b.cig_jobs_cap = NC + 1;
 		if (!d_cigjobs.ensure(be, 8 * (size_t)LC_CIG_NLIST * b.cig_jobs_cap)) return nomem();
 		b.cig_jobs = (uint64_t *)d_cigjobs.p;
+		b.alnx = nullptr; b.mm_ref = b.mm_read = nullptr; b.mm_cap = 0;
+		if (want_alnx) {
+			if (!d_alnx.ensure(be, sizeof(lc_alnx_t) * b.fin_cap)) return nomem();
+			b.alnx = (lc_alnx_t *)d_alnx.p;
+		}
 		for (int attempt = 0;; ++attempt) {
 			b.cigar_cap = (unsigned long long)(cigar_per_cand * NC) + 1024;
 			b.z_cap = std::max<unsigned long long>(z_pool_bytes, (unsigned long long)(z_per_cand * NC));
 			if (!d_cigar.ensure(be, 4 * b.cigar_cap) || !d_z.ensure(be, b.z_cap)) return nomem();
 			b.cigar = (uint32_t *)d_cigar.p; b.zpool = (uint8_t *)d_z.p;
+			if (want_alnx) {
+				b.mm_cap = (unsigned long long)(mm_per_cand * NC) + 1024;
+				if (!d_mmref.ensure(be, 4 * b.mm_cap) || !d_mmread.ensure(be, 4 * b.mm_cap)) return nomem();
+				b.mm_ref = (int32_t *)d_mmref.p; b.mm_read = (int32_t *)d_mmread.p;
+			}
 			if (NC) {
 				be.k_cigar_plan(b, NC); ++launches;
 				launches += be.k_cigar_band(b, NC);
 				be.k_cigar_fallback(b, NC); ++launches;
+				if (want_alnx) { be.k_alnx(b, NC); ++launches; }      // reads the CIGARs: a no-op if the stage above overflowed
 			}
 			read_ctl();
 			if (launch_broken) { err = "a CUDA kernel launch failed in the cigar stage"; return LC_ECUDA; }
 			n_cig_fallback = (unsigned long long)(uint32_t)(h_ctl[24 + LC_CIG_FALLBACK / 2] >> (32 * (LC_CIG_FALLBACK & 1)));
 			if (!h_ctl_ovf) break;
-			if (h_ctl_ovf & ~(uint32_t)(LC_OVF_CIGAR | LC_OVF_Z)) { err = "internal pool overflow in the cigar stage (flags " + std::to_string(h_ctl_ovf) + ")"; return LC_ENOMEM; }
+			if (h_ctl_ovf & ~(uint32_t)(LC_OVF_CIGAR | LC_OVF_Z | LC_OVF_MM)) { err = "internal pool overflow in the cigar stage (flags " + std::to_string(h_ctl_ovf) + ")"; return LC_ENOMEM; }
 			if (attempt > 12) { err = "cigar pools keep overflowing"; return LC_ENOMEM; }
 			if (h_ctl_ovf & LC_OVF_CIGAR) cigar_per_cand = std::max(cigar_per_cand * 2, (double)h_ctl[8] / std::max<double>(NC, 1) * 1.25);
 			if (h_ctl_ovf & LC_OVF_Z) { z_pool_bytes = std::max<size_t>(z_pool_bytes * 2, (size_t)(h_ctl[9] * 1.25)); z_per_cand = std::max(z_per_cand, (double)h_ctl[9] / std::max<double>(NC, 1) * 1.25); }
-			be.dzero_words(b.cigar_cur, 1); be.dzero_words(b.z_cur, 1); be.dzero_words((unsigned long long *)b.overflow, 1);
+			if (h_ctl_ovf & LC_OVF_MM) mm_per_cand = std::max(mm_per_cand * 2, (double)h_ctl[12] / std::max<double>(NC, 1) * 1.25);
+			be.dzero_words(b.cigar_cur, 1); be.dzero_words(b.z_cur, 1); be.dzero_words(b.mm_cur, 1); be.dzero_words((unsigned long long *)b.overflow, 1);
 			be.dzero(b.cig_n, 4 * LC_CIG_NLIST);
 		}
 		be.ev_record(8);
-		n_cand = NC; n_cigar_words = h_ctl[8];
+		n_cand = NC; n_cigar_words = h_ctl[8]; n_mm = want_alnx ? h_ctl[12] : 0;
 		return LC_OK;
 	}
 
 	// ---- stage 7: pack into dense arrays (candidate indices offset by reg_base, CIGAR indices by cig_base)
-	int run_pack(int64_t reg_base, uint32_t cig_base)
+	int run_pack(int64_t reg_base, uint32_t cig_base, uint32_t mm_base = 0)
 	{
 		const int R = b.n_reads;
 		const unsigned long long NC = n_cand;
@@ -483,6 +507,8 @@ public:
 		be.scan_exclusive(b.r_n_fin, (int64_t *)d_outoff.p, R + 1); ++launches;   // r_n_fin[R] == 0, so out[R] = total
 		LcPackArgs pa; pa.out_off = (const int64_t *)d_outoff.p; pa.out_reg = (lc_alnreg_t *)d_outreg.p; pa.out_aln = (lc_aln_t *)d_outaln.p;
 		pa.off_final = (int64_t *)d_outoff2.p; pa.reg_base = reg_base; pa.cig_base = cig_base;
+		pa.out_alnx = nullptr; pa.mm_base = mm_base;
+		if (b.alnx) { if (!d_outalnx.ensure(be, sizeof(lc_alnx_t) * (NC + 1))) return nomem(); pa.out_alnx = (lc_alnx_t *)d_outalnx.p; }
 		be.k_pack(b, pa); ++launches;
 		be.ev_record(9);
 		return LC_OK;
@@ -490,8 +516,13 @@ public:
 
 	// D2H of the packed arrays into caller-provided host memory (pinned in lc_api.cu); n_off = how many offsets to copy
 	// (n_reads for an inner chunk, n_reads + 1 for the last).  Asynchronous: call fetch_done() after be.sync().
-	void fetch_into(int64_t *h_off, size_t n_off, lc_alnreg_t *h_regs, lc_aln_t *h_aln, uint32_t *h_cig)
+	void fetch_into(int64_t *h_off, size_t n_off, lc_alnreg_t *h_regs, lc_aln_t *h_aln, uint32_t *h_cig,
+					lc_alnx_t *h_alnx = nullptr, int32_t *h_mmref = nullptr, int32_t *h_mmread = nullptr)
 	{
+		if (b.alnx && h_alnx) {
+			if (n_cand) be.d2h(h_alnx, d_outalnx.p, sizeof(lc_alnx_t) * n_cand);
+			if (n_mm) { be.d2h(h_mmref, d_mmref.p, 4 * n_mm); be.d2h(h_mmread, d_mmread.p, 4 * n_mm); }
+		}
 		be.d2h(h_off, d_outoff2.p, 8 * n_off);
 		if (n_cand) { be.d2h(h_regs, d_outreg.p, sizeof(lc_alnreg_t) * n_cand); be.d2h(h_aln, d_outaln.p, sizeof(lc_aln_t) * n_cand); }
 		if (n_cigar_words) be.d2h(h_cig, d_cigar.p, 4 * n_cigar_words);
@@ -514,6 +545,9 @@ public:
 		be.d2h(res.reg_off.data(), d_outoff2.p, 8 * ((size_t)R + 1));
 		if (n_cand) { be.d2h(res.regs.data(), d_outreg.p, sizeof(lc_alnreg_t) * n_cand); be.d2h(res.aln.data(), d_outaln.p, sizeof(lc_aln_t) * n_cand); }
 		if (n_cigar_words) be.d2h(res.cigars.data(), d_cigar.p, 4 * n_cigar_words);
+		res.alnx.resize(b.alnx ? n_cand : 0); res.mm_ref.resize(b.alnx ? n_mm : 0); res.mm_read.resize(b.alnx ? n_mm : 0);
+		if (b.alnx && n_cand) be.d2h(res.alnx.data(), d_outalnx.p, sizeof(lc_alnx_t) * n_cand);
+		if (b.alnx && n_mm) { be.d2h(res.mm_ref.data(), d_mmref.p, 4 * n_mm); be.d2h(res.mm_read.data(), d_mmread.p, 4 * n_mm); }
 		be.ev_record(10);
 		be.sync();
 		if ((unsigned long long)res.reg_off[R] != n_cand) { err = "result size mismatch"; return LC_ECUDA; }
@@ -529,18 +563,20 @@ public:
 	void release()
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
-							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_redo3, &d_wl };
+							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_redo3, &d_wl,
+							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw };
 		for (auto *x : all) x->release(be);
 	}
 
 	int64_t launches = 0;
 	int n_redo = 0, n_redo_pass1 = 0;
 	unsigned long long n_cig_fallback = 0, n_rescue_pairs = 0;
-	unsigned long long n_cand = 0, n_cigar_words = 0;
+	unsigned long long n_cand = 0, n_cigar_words = 0, n_mm = 0;
 
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
-		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_redo3, d_wl;
+		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_redo3, d_wl,
+		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

@@ -37,7 +37,9 @@ ALNREG_DTYPE = np.dtype([
     ("n_comp_is_alt", "<u4"), ("frac_rep", "<f4"), ("hash", "<u8")])
 ALN_DTYPE = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("NM", "<i4"), ("n_cigar", "<i4"),
                       ("cigar_off", "<u4"), ("n_mismatch", "<i4")])
-assert ALNREG_DTYPE.itemsize == 88 and ALN_DTYPE.itemsize == 32
+ALNX_DTYPE = np.dtype([("pos", "<i8"), ("aend", "<i8"), ("matches", "<i4"), ("mismatches", "<i4"), ("indels", "<i4"), ("indel_length", "<i4"),
+                       ("soft_clipped", "<i4"), ("soft_clipped_length", "<i4"), ("n_mm", "<i4"), ("mm_off", "<u4")])
+assert ALNREG_DTYPE.itemsize == 88 and ALN_DTYPE.itemsize == 32 and ALNX_DTYPE.itemsize == 48
 
 
 class lc_opt_t(C.Structure):
@@ -63,7 +65,8 @@ class lc_result_t(C.Structure):
                                          "ms_cigar", "ms_d2h", "ms_total")] + \
                [("gpu_launches", C.c_int64)] + \
                [(n, C.c_uint64) for n in ("cnt_occ_blocks", "cnt_extend_calls", "cnt_sa_calls", "cnt_lf_steps", "cnt_ext_calls",
-                                          "cnt_ext_cells", "cnt_sw_calls", "cnt_sw_cells", "cnt_glb_calls", "cnt_glb_cells")]
+                                          "cnt_ext_cells", "cnt_sw_calls", "cnt_sw_cells", "cnt_glb_calls", "cnt_glb_cells")] + \
+               [("alnx", C.c_void_p), ("mm_ref_pos", C.POINTER(C.c_int32)), ("mm_read_pos", C.POINTER(C.c_int32)), ("n_mm", C.c_int64)]
 
 
 class lc_pestat_t(C.Structure):
@@ -78,7 +81,7 @@ class lc_alnreg_v(C.Structure):
 EXPORTS = ["lc_opt_init", "lc_init", "lc_clone", "lc_set_coalescing", "lc_destroy", "lc_last_error", "lc_contigs", "lc_align_pairs", "lc_align_packed",
            "lc_batch_upload", "lc_batch_run", "lc_batch_fetch", "lc_free_result", "lc_fetch_seq", "lc_mem_align1_core",
            "lc_mem_matesw", "lc_mem_reg2aln", "lc_ksw_extend_batch", "lc_ksw_align_batch", "lc_collect_intv_batch",
-           "lc_sa_batch", "lc_index_build", "lc_set_counting", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
+           "lc_sa_batch", "lc_index_build", "lc_set_counting", "lc_set_alnx", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
 
 _lib = None
 
@@ -118,6 +121,7 @@ def load_library(path: str = LIB_PATH):
     lib.lc_sa_batch.argtypes = [vp, C.c_int64, vp, vp, f32p]
     lib.lc_index_build.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), i64p, C.c_int]
     lib.lc_set_counting.argtypes = [vp, C.c_int]; lib.lc_set_counting.restype = None
+    lib.lc_set_alnx.argtypes = [vp, C.c_int]; lib.lc_set_alnx.restype = None
     lib.lc_set_chunk_pairs.argtypes = [vp, C.c_int]; lib.lc_set_chunk_pairs.restype = C.c_int
     lib.lc_timer_start.argtypes = [vp]
     lib.lc_timer_stop.argtypes = [vp, f32p]
@@ -217,8 +221,17 @@ class BatchResult:
             self.aln = np.zeros(0, dtype=ALN_DTYPE)
         nc = int(res.n_cigar_words)
         self.cigars = np.ctypeslib.as_array(res.cigars, shape=(nc,)) if nc else np.zeros(0, dtype=np.uint32)
+        # GetAlignments post-processing (lc_set_alnx): per candidate counts + the two mismatch position lists
+        self.alnx = self.mm_ref = self.mm_read = None
+        if res.alnx:
+            self.alnx = np.frombuffer((C.c_char * (48 * nr)).from_address(res.alnx), dtype=ALNX_DTYPE) if nr else np.zeros(0, dtype=ALNX_DTYPE)
+            nm = int(res.n_mm)
+            self.mm_ref = np.ctypeslib.as_array(res.mm_ref_pos, shape=(nm,)) if nm else np.zeros(0, dtype=np.int32)
+            self.mm_read = np.ctypeslib.as_array(res.mm_read_pos, shape=(nm,)) if nm else np.zeros(0, dtype=np.int32)
         if copy:
             self.reg_off, self.regs, self.aln, self.cigars = self.reg_off.copy(), self.regs.copy(), self.aln.copy(), self.cigars.copy()
+            if self.alnx is not None:
+                self.alnx, self.mm_ref, self.mm_read = self.alnx.copy(), self.mm_ref.copy(), self.mm_read.copy()
             self.free()
         self.timing = {k: float(getattr(res, k)) for k in ("ms_h2d", "ms_seed", "ms_sa", "ms_chain", "ms_extend", "ms_dedup",
                                                            "ms_pair", "ms_cigar", "ms_d2h", "ms_total")}
@@ -252,6 +265,21 @@ class BatchResult:
                 out.append(self.cigar_of(i).astype("<u4").tobytes())
         return b"".join(out)
 
+
+    def dump_alnx(self) -> bytes:
+        """The GetAlignments records in the LRX1 layout (lariat_b200/iofmt.py), byte-comparable with `replay_* -x`."""
+        out = [b"LRX1", np.int32(self.n_reads // 2).tobytes()]
+        for r in range(self.n_reads):
+            s, e = int(self.reg_off[r]), int(self.reg_off[r + 1])
+            out.append(np.int32(e - s).tobytes())
+            for i in range(s, e):
+                a = self.alnx[i]
+                out.append(np.array([a["pos"], a["aend"]], dtype="<i8").tobytes())
+                out.append(np.array([a[k] for k in ("matches", "mismatches", "indels", "indel_length", "soft_clipped", "soft_clipped_length", "n_mm")], dtype="<i4").tobytes())
+                o, n = int(a["mm_off"]), int(a["n_mm"])
+                out.append(self.mm_ref[o:o + n].astype("<i4").tobytes())
+                out.append(self.mm_read[o:o + n].astype("<i4").tobytes())
+        return b"".join(out)
 
     def dump_fast(self, n_pairs: int | None = None) -> bytes:
         """dump() of the first n_pairs pairs without per-read Python work (numpy scatter): bench.py verifies 10^5-pair prefixes with it."""

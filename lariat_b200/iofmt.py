@@ -1,6 +1,9 @@
 """Small binary formats shared with the checker-side replay harnesses, tests and bench.
 
 pairs file ("LRP1"): int32 n_pairs, int32 len[2n] (r1,r2 interleaved), ASCII bases back to back.
+alnx file ("LRX1"): int32 n_pairs, then per read end: int32 n; n x {int64 pos, aend; int32 matches, mismatches, indels,
+    indel_length, soft_clipped, soft_clipped_length, n_mm; int32 mismatchLocs[n_mm]; int32 mismatchReadLocs[n_mm]}
+    (what inference.GetAlignments computes per candidate after mem_reg2aln, lariat.go:1573-1650).
 result file ("LRO1"): int32 n_pairs, then per read end: int32 n; n x 88-byte alnreg; n x
     {int64 pos; int32 rid, is_rev, NM, n_cigar; uint32 cigar[n_cigar]}.
 """
@@ -72,3 +75,28 @@ def parse_results(buf):
 
 def cigar_str(cig):
     return "".join(f"{int(c) >> 4}{'MIDSH'[int(c) & 15]}" for c in cig)
+
+
+def parse_alnx(buf):
+    """-> list (len 2*n_pairs) of lists of dicts, one per candidate (LRX1)."""
+    assert buf[:4] == b"LRX1"
+    n = int(np.frombuffer(buf, dtype="<i4", count=1, offset=4)[0])
+    off = 8
+    out = []
+    names = ("matches", "mismatches", "indels", "indel_length", "soft_clipped", "soft_clipped_length", "n_mm")
+    for _ in range(2 * n):
+        k = int(np.frombuffer(buf, dtype="<i4", count=1, offset=off)[0])
+        off += 4
+        recs = []
+        for _j in range(k):
+            pos, aend = (int(x) for x in np.frombuffer(buf, dtype="<i8", count=2, offset=off))
+            h = [int(x) for x in np.frombuffer(buf, dtype="<i4", count=7, offset=off + 16)]
+            off += 44
+            nm = h[6]
+            d = dict(zip(names, h), pos=pos, aend=aend, mm_ref=np.frombuffer(buf, dtype="<i4", count=nm, offset=off).tolist(),
+                     mm_read=np.frombuffer(buf, dtype="<i4", count=nm, offset=off + 4 * nm).tolist())
+            off += 8 * nm
+            recs.append(d)
+        out.append(recs)
+    assert off == len(buf)
+    return out

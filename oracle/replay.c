@@ -18,7 +18,12 @@
  * Both produce the same binary dump, so `cmp` of the two files is the port's parity check and either
  * file is a golden vector for the CUDA path.
  *
- * usage: replay_{ref,port} <index-prefix> <pairs.bin> <out.bin> [-t threads] [-d score_delta] [-r repeat] [-n max_pairs]
+ *   - the rest of inference.GetAlignments per candidate (CIGAR walk against GetSeq's reference span: matches, mismatches, indels,
+ *     soft clips, mismatch positions, pos/aend)                         lariat.go:1573-1650, gobwa.go:50-80,339-371   [-x file]
+ *
+ * usage: replay_{ref,port} <index-prefix> <pairs.bin> <out.bin> [-t threads] [-d score_delta] [-r repeat] [-n max_pairs] [-x alnx.bin]
+ * alnx.bin  : "LRX1" int32 n_pairs, then per read end: int32 n; n x {int64 pos, aend; int32 matches, mismatches, indels, indel_length,
+ *             soft_clipped, soft_clipped_length, n_mm; int32 mismatchLocs[n_mm]; int32 mismatchReadLocs[n_mm]}
  * pairs.bin : "LRP1" int32 n_pairs, int32 len[2*n_pairs] (r1,r2 interleaved), then the ASCII bases back to back
  * out.bin   : "LRO1" int32 n_pairs, then per read end: int32 n; n x 88-byte alnreg; n x aln records
  *             {int64 pos; int32 rid, is_rev, NM, n_cigar; uint32 cigar[n_cigar]}
@@ -49,6 +54,9 @@ typedef mem_aln_t aln_t;
 #define REG2ALN(o, x, l, s, ar) mem_reg2aln((o), (x)->bns, (x)->pac, (l), (const char*)(s), (ar))
 #define NT4(c) nst_nt4_table[(int)(c)]
 #define KIND "reference"
+#define L_PAC(x) ((x)->bns->l_pac)
+#define ANN_OFFSET(x, rid) ((x)->bns->anns[rid].offset)
+#define FETCH_SEQ(x, beg, mid, end, rid) bns_fetch_seq((x)->bns, (x)->pac, (beg), (mid), (end), (rid))
 #else
 #include "port.h"
 typedef port_idx_t idx_t;
@@ -64,6 +72,9 @@ typedef port_aln_t aln_t;
 #define REG2ALN(o, x, l, s, ar) port_reg2aln((o), (x), (l), (s), (ar))
 #define NT4(c) port_nt4_table[(int)(c)]
 #define KIND "port"
+#define L_PAC(x) ((x)->l_pac)
+#define ANN_OFFSET(x, rid) ((x)->anns[rid].offset)
+#define FETCH_SEQ(x, beg, mid, end, rid) port_fetch_seq((x), (beg), (mid), (end), (rid))
 #endif
 
 typedef struct { uint8_t *buf; size_t n, m; } obuf_t;
@@ -79,6 +90,7 @@ static const char *g_bases;
 static idx_t *g_idx;
 static opt_t *g_opt;
 static obuf_t *g_out;         /* one per pair */
+static obuf_t *g_xout;        /* one per pair: the GetAlignments post-processing records (-x) */
 static volatile int g_next;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static double g_stage[4];     /* align, matesw, reg2aln (thread 0 only, single-thread runs) */
@@ -94,10 +106,72 @@ static uint8_t *convert(const char *s, int l) /* gobwa.go:159-167 */
 
 static int best_of(const regv_t *v) { int b = 0; for (size_t i = 0; i < v->n; ++i) if (v->a[i].score > b) b = v->a[i].score; return b; }
 
-static void dump_end(obuf_t *o, const regv_t *v, int l, const uint8_t *seq_codes_unused, const char *ascii)
+/* inference.GetAlignments after GoBwaSmithWaterman, for one candidate (lariat.go:1573-1650).  `a` = mem_reg2aln's result,
+ * ascii = the read as given (chain.read).  GetSeq = gobwa.go:50-80 (bns_fetch_seq of the contig-relative span, reverse-complemented
+ * when `reversed`, zero bytes where the fetch was clamped); pos/aend = InterpretAlign (gobwa.go:352-363). */
+static void getalignments_tail(obuf_t *xo, const reg_t *reg, const aln_t *a, int l, const char *ascii)
+{
+	static const char twoBitToSeq[4] = { 'A', 'C', 'G', 'T' }, twoBitToSeqComp[4] = { 'T', 'G', 'C', 'A' };
+	int64_t l_pac = L_PAC(g_idx), coff = ANN_OFFSET(g_idx, reg->rid);
+	int64_t chain_pos = reg->rb < l_pac ? reg->rb - coff : l_pac * 2 - 1 - reg->rb - coff;          /* gobwa.go:352-358 */
+	int64_t chain_aend = reg->re < l_pac ? (int64_t)reg->re - coff : l_pac * 2 - 1 - reg->re - coff;   /* gobwa.go:359-363 */
+	int reversed = a->is_rev;
+	int matches = 0, indels = 0, indel_length = 0, soft_clipping = 0, soft_clipping_length = 0;
+	int64_t refStart = chain_pos, refEnd = chain_aend;
+	if (reversed) { refStart = chain_aend + 1; refEnd = chain_pos + 1; }
+	/* GetSeq */
+	int64_t n_ref = refEnd - refStart;
+	char *refSeq = calloc(n_ref > 0 ? n_ref : 1, 1);
+	if (n_ref > 0) {
+		int64_t offstart = refStart + coff, offend = refEnd + coff;
+		int rid = reg->rid;
+		uint8_t *res = FETCH_SEQ(g_idx, &offstart, (offstart + offend) >> 1, &offend, &rid);
+		int64_t got = offend - offstart;
+		for (int64_t i = 0; i < got; ++i) {
+			if (reversed) refSeq[got - i - 1] = twoBitToSeqComp[res[i]];
+			else refSeq[i] = twoBitToSeq[res[i]];
+		}
+		free(res);
+	}
+	int32_t *mismatchLocs = malloc(4 * (size_t)(l + 1)), *mismatchReadLocs = malloc(4 * (size_t)(l + 1));
+	int n_mm = 0;
+	int64_t refSeqOffset = 0; int readOffset = 0;
+	int n = a->n_cigar;
+	for (int t = 0; t < n; ++t) {                              /* k from cigarStart in steps of cigarIncrement (lariat.go:1590-1596) */
+		uint32_t c = a->cigar[reversed ? n - 1 - t : t];
+		int op = c & 0xf, len = c >> 4;
+		if (op == 0) {
+			matches += len;
+			for (int match = 0; match < len; ++match) {
+				if (refSeqOffset + match >= n_ref) continue;
+				if (readOffset + match >= l) continue;           /* the Go code panics here */
+				if (refSeq[refSeqOffset + match] != ascii[readOffset + match]) {
+					mismatchLocs[n_mm] = (int32_t)(reversed ? refEnd - (refSeqOffset + match) : refSeqOffset + refStart + match);
+					mismatchReadLocs[n_mm] = readOffset + match;
+					++n_mm;
+				}
+			}
+			refSeqOffset += len; readOffset += len;
+		} else if (op == 1) { indels += 1; indel_length += len; readOffset += len; }
+		else if (op == 2) { indels += 1; indel_length += len; refSeqOffset += len; }
+		else if (op == 3) { soft_clipping += 1; soft_clipping_length += len; readOffset += len; }
+	}
+	int mismatches = (int)a->NM - indel_length;                /* lariat.go:1633-1637 */
+	matches -= mismatches;
+	if (mismatches < 0) mismatches = 0;
+	int64_t pos = chain_pos, aend = chain_aend;
+	if (pos != -1 && reversed) { pos = chain_aend + 1; aend = chain_pos + 1; }      /* lariat.go:1645-1650 */
+	int32_t h[7] = { matches, mismatches, indels, indel_length, soft_clipping, soft_clipping_length, n_mm };
+	ob_put(xo, &pos, 8); ob_put(xo, &aend, 8); ob_put(xo, h, 28);
+	ob_put(xo, mismatchLocs, 4 * (size_t)n_mm); ob_put(xo, mismatchReadLocs, 4 * (size_t)n_mm);
+	free(mismatchLocs); free(mismatchReadLocs); free(refSeq);
+}
+
+static void dump_end(obuf_t *o, obuf_t *xo, const regv_t *v, int l, const uint8_t *seq_codes_unused, const char *ascii)
 {
 	int32_t n = (int32_t)v->n;
 	ob_put(o, &n, 4);
+	if (xo) ob_put(xo, &n, 4);
 	if (n) ob_put(o, v->a, (size_t)n * sizeof(reg_t));
 	for (int i = 0; i < n; ++i) {
 		/* GoBwaSmithWaterman re-converts the ASCII read for every candidate (gobwa.go:401) */
@@ -106,11 +180,12 @@ static void dump_end(obuf_t *o, const regv_t *v, int l, const uint8_t *seq_codes
 		int64_t pos = a.pos; int32_t h[4] = { a.rid, (int32_t)a.is_rev, (int32_t)a.NM, a.n_cigar };
 		ob_put(o, &pos, 8); ob_put(o, h, 16);
 		if (a.n_cigar) ob_put(o, a.cigar, 4 * (size_t)a.n_cigar);
+		if (xo) getalignments_tail(xo, &v->a[i], &a, l, ascii);
 		free(a.cigar); free(q);
 	}
 }
 
-static void do_pair(int p, obuf_t *o, int timed)
+static void do_pair(int p, obuf_t *o, obuf_t *xo, int timed)
 {
 	int l1 = g_len[2*p], l2 = g_len[2*p+1];
 	const char *s1 = g_bases + g_off[2*p], *s2 = g_bases + g_off[2*p+1];
@@ -137,9 +212,9 @@ static void do_pair(int p, obuf_t *o, int timed)
 	for (size_t i = 0; i < r1.n && num < 50 && l2 > 0; ++i)
 		if (r1.a[i].score >= best1 - g_delta) { ++num; MATESW(g_opt, g_idx, pes, &r1.a[i], l2, c2, &r2); }
 	double t2 = timed ? now() : 0;
-	if (o) { dump_end(o, &r1, l1, c1, s1); dump_end(o, &r2, l2, c2, s2); }
+	if (o) { dump_end(o, xo, &r1, l1, c1, s1); dump_end(o, xo, &r2, l2, c2, s2); }
 	else { /* timing-only pass still does the reg2aln work */
-		obuf_t tmp = {0,0,0}; dump_end(&tmp, &r1, l1, c1, s1); dump_end(&tmp, &r2, l2, c2, s2); free(tmp.buf);
+		obuf_t tmp = {0,0,0}; dump_end(&tmp, 0, &r1, l1, c1, s1); dump_end(&tmp, 0, &r2, l2, c2, s2); free(tmp.buf);
 	}
 	double t3 = timed ? now() : 0;
 	if (timed) { g_stage[0] += t1 - t0; g_stage[1] += t2 - t1; g_stage[2] += t3 - t2; }
@@ -156,17 +231,19 @@ static void *worker(void *arg)
 		pthread_mutex_unlock(&g_mu);
 		if (s >= g_n_pairs) break;
 		e = s + 64 < g_n_pairs ? s + 64 : g_n_pairs;
-		for (int p = s; p < e; ++p) do_pair(p, g_out ? &g_out[p] : 0, g_threads == 1 && tid == 0);
+		for (int p = s; p < e; ++p) do_pair(p, g_out ? &g_out[p] : 0, g_out && g_xout ? &g_xout[p] : 0, g_threads == 1 && tid == 0);
 	}
 	return 0;
 }
 
 int main(int argc, char **argv)
 {
-	if (argc < 4) { fprintf(stderr, "usage: %s <idx-prefix> <pairs.bin> <out.bin|-> [-t threads] [-d delta] [-r repeat] [-n max_pairs]\n", argv[0]); return 2; }
+	if (argc < 4) { fprintf(stderr, "usage: %s <idx-prefix> <pairs.bin> <out.bin|-> [-t threads] [-d delta] [-r repeat] [-n max_pairs] [-x alnx.bin]\n", argv[0]); return 2; }
 	int maxp = -1;
+	const char *xpath = 0;
 	for (int i = 4; i + 1 < argc; i += 2) {
 		if (!strcmp(argv[i], "-t")) g_threads = atoi(argv[i+1]);
+		else if (!strcmp(argv[i], "-x")) xpath = argv[i+1];
 		else if (!strcmp(argv[i], "-d")) g_delta = atoi(argv[i+1]);
 		else if (!strcmp(argv[i], "-r")) g_repeat = atoi(argv[i+1]);
 		else if (!strcmp(argv[i], "-n")) maxp = atoi(argv[i+1]);
@@ -194,6 +271,7 @@ int main(int argc, char **argv)
 	double best = 1e30;
 	for (int rep = 0; rep < g_repeat; ++rep) {
 		if (want_out && rep == 0) g_out = calloc(g_n_pairs, sizeof(obuf_t)); else g_out = 0;
+		if (want_out && rep == 0 && xpath) g_xout = calloc(g_n_pairs, sizeof(obuf_t)); else g_xout = 0;
 		g_next = 0;
 		memset(g_stage, 0, sizeof(g_stage));
 		double t1 = now();
@@ -209,6 +287,12 @@ int main(int argc, char **argv)
 			fwrite("LRO1", 1, 4, o); fwrite(&np, 4, 1, o);
 			for (int p = 0; p < g_n_pairs; ++p) { fwrite(g_out[p].buf, 1, g_out[p].n, o); free(g_out[p].buf); }
 			fclose(o); free(g_out); g_out = 0;
+			if (g_xout) {
+				FILE *x = fopen(xpath, "wb");
+				fwrite("LRX1", 1, 4, x); fwrite(&np, 4, 1, x);
+				for (int p = 0; p < g_n_pairs; ++p) { fwrite(g_xout[p].buf, 1, g_xout[p].n, x); free(g_xout[p].buf); }
+				fclose(x); free(g_xout); g_xout = 0;
+			}
 		}
 	}
 	fprintf(stderr, "{\"kind\": \"%s\", \"pairs\": %d, \"threads\": %d, \"seconds\": %.4f, \"pairs_per_s\": %.1f, \"index_load_s\": %.2f, "

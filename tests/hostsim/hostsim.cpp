@@ -92,6 +92,7 @@ struct HostBackend {
 	}
 	unsigned long long n_band[LC_CIG_NCLASS] = {0, 0, 0, 0};
 	void k_cigar_fallback(const LcBatch &b, unsigned long long) { k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, 0, b.cig_n + LC_CIG_FALLBACK); }
+	void k_alnx(const LcBatch &b, unsigned long long n) { for (unsigned long long c = n; c-- > 0;) lc_stage_alnx(b, b.cand[c]); }
 	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r <= b.n_reads; ++r) lc_stage_pack(b, pa, r); }
 	void k_rebase(int64_t *off, int n, int64_t off0) { for (int i = 0; i < n; ++i) off[i] -= off0; }
 	void scan_exclusive(const int32_t *in, int64_t *out, int n) { int64_t s = 0; for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; } }
@@ -100,6 +101,7 @@ struct HostBackend {
 int main(int argc, char **argv)
 {
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
+	const char *xpath = 0;
 	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
@@ -118,6 +120,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
 		else if (!strcmp(argv[i], "-K") && i + 1 < argc) chunk = atoi(argv[++i]);       // run the batch as chunks of this many pairs (the way lc_align_packed splits large calls)
+		else if (!strcmp(argv[i], "-x") && i + 1 < argc) xpath = argv[++i];             // stage 6b on: write the GetAlignments records (LRX1) here
 		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
 	}
 	LcHostIndex hix; std::string err;
@@ -147,22 +150,26 @@ int main(int argc, char **argv)
 	if (heavy_seeds >= 0) pl.ext_heavy_seeds = heavy_seeds;
 	if (pk_cap2 > 0) { pl.pk_cap2 = pk_cap2; pl.pk_cap3 = pk_cap2 + 2; }
 	pl.force_wide = wide != 0;
+	pl.want_alnx = xpath != 0;
 	pl.set_index(ix, opt);
 	LcHostResult res;
 	int rc = 0;
 	if (chunk > 0 && chunk < n) {
 		// chunked form: slices of the packed arrays, results appended at the running candidate / CIGAR-word totals
 		res.reg_off.assign(2 * (size_t)n + 1, 0);
-		int64_t reg_base = 0; uint32_t cig_base = 0;
+		int64_t reg_base = 0; uint32_t cig_base = 0, mm_base = 0;
 		std::vector<uint8_t> raw(bases);          // every chunk converts its own slice in place on its own copy
 		for (int p0 = 0; p0 < n && !rc; p0 += chunk) {
 			const int np = std::min(chunk, n - p0);
 			rc = pl.upload(np, raw.data(), off.data() + 2 * (size_t)p0, true);
 			if (!rc) rc = pl.run_stages(delta);
-			if (!rc) rc = pl.run_pack(reg_base, cig_base);
+			if (!rc) rc = pl.run_pack(reg_base, cig_base, mm_base);
 			if (rc) break;
 			res.regs.resize((size_t)reg_base + pl.n_cand); res.aln.resize((size_t)reg_base + pl.n_cand); res.cigars.resize((size_t)cig_base + pl.n_cigar_words);
-			pl.fetch_into(res.reg_off.data() + 2 * (size_t)p0, 2 * (size_t)np + 1, res.regs.data() + reg_base, res.aln.data() + reg_base, res.cigars.data() + cig_base);
+			if (xpath) { res.alnx.resize((size_t)reg_base + pl.n_cand); res.mm_ref.resize((size_t)mm_base + pl.n_mm + 1); res.mm_read.resize((size_t)mm_base + pl.n_mm + 1); }
+			pl.fetch_into(res.reg_off.data() + 2 * (size_t)p0, 2 * (size_t)np + 1, res.regs.data() + reg_base, res.aln.data() + reg_base, res.cigars.data() + cig_base,
+						  xpath ? res.alnx.data() + reg_base : nullptr, xpath ? res.mm_ref.data() + mm_base : nullptr, xpath ? res.mm_read.data() + mm_base : nullptr);
+			mm_base += (uint32_t)pl.n_mm;
 			float ms[10]; LcCounters cn; pl.fetch_done(ms, cn);
 			res.launches += pl.launches;
 			reg_base += (int64_t)pl.n_cand; cig_base += (uint32_t)pl.n_cigar_words;
@@ -187,6 +194,21 @@ int main(int argc, char **argv)
 		}
 	}
 	fclose(o);
+	if (xpath) {
+		FILE *x = fopen(xpath, "wb");
+		fwrite("LRX1", 1, 4, x); fwrite(&n, 4, 1, x);
+		for (int r = 0; r < 2 * n; ++r) {
+			int32_t k = (int32_t)(res.reg_off[r + 1] - res.reg_off[r]);
+			fwrite(&k, 4, 1, x);
+			for (int i = 0; i < k; ++i) {
+				const lc_alnx_t &a = res.alnx[res.reg_off[r] + i];
+				int32_t h[7] = { a.matches, a.mismatches, a.indels, a.indel_length, a.soft_clipped, a.soft_clipped_length, a.n_mm };
+				fwrite(&a.pos, 8, 1, x); fwrite(&a.aend, 8, 1, x); fwrite(h, 4, 7, x);
+				if (a.n_mm) { fwrite(&res.mm_ref[a.mm_off], 4, a.n_mm, x); fwrite(&res.mm_read[a.mm_off], 4, a.n_mm, x); }
+			}
+		}
+		fclose(x);
+	}
 	if (count) {
 		const LcCounters &c = res.counters;
 		fprintf(stderr, "{\"occ_blocks\": %llu, \"extend_calls\": %llu, \"sa_calls\": %llu, \"lf_steps\": %llu, \"ext_calls\": %llu, \"ext_cells\": %llu, "

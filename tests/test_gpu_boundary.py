@@ -232,3 +232,44 @@ def test_mem_matesw_export_vs_oracle(tiny_ref, oracle_port):
             n_sw += want_n; n_grown += int(wv.n > len(ma0))
             libc.free(wv.a); libc.free(gv.a)
     assert n_sw > 20 and n_grown > 5          # the test really exercised Smith-Watermans and insertions
+
+
+def test_getalignments_post_processing_on_device(lib_path, oracle_port, tmp_path):
+    """lc_set_alnx: per candidate matches / mismatches / indels / soft clips / pos, aend and the two mismatch position lists, exactly
+    what inference.GetAlignments computes with one GetSeq call per candidate (I/lariat.go:1573-1650) — against the golden records
+    (written from the compiled reference), through the direct path, the merged-small-call path, chunks over lanes, and on fresh
+    repeat-rich data against the oracle.  n_mismatch of lc_aln_t is checked on the way."""
+    lib = gobwa.load_library()
+    want = open(os.path.join(GOLDEN, "tiny", "tiny.ref.x"), "rb").read()
+    bases, off = _load_pairs(TINY_PAIRS)
+    ref = gobwa.GoBwaLoadReference(TINY)
+    lib.lc_set_alnx(ref.BWTData, 1)
+    br = ref.align_packed(bases, off, 25)                      # 605 pairs: the merged-small-call path
+    assert br.dump() == open(WANT, "rb").read() and br.dump_alnx() == want
+    # lc_aln_t.n_mismatch == NM - gap bases (B/bwa.c:169-199)
+    for i in range(len(br.aln)):
+        gaps = sum(int(c) >> 4 for c in br.cigar_of(i) if (int(c) & 0xf) in (1, 2))
+        assert int(br.aln[i]["n_mismatch"]) == int(br.aln[i]["NM"]) - gaps
+    assert lib.lc_set_coalescing(ref.BWTData, 0, 65536, 1, 0) == 0
+    assert ref.align_packed(bases, off, 25).dump_alnx() == want                         # the direct path
+    assert lib.lc_set_chunk_pairs(ref.BWTData, 97) == 0
+    assert ref.align_packed(bases, off, 25).dump_alnx() == want                         # chunks over two lanes
+    lib.lc_set_alnx(ref.BWTData, 0)
+    assert ref.align_packed(bases, off, 25).alnx is None
+    ref.close()
+    # fresh data
+    from lariat_b200 import synth
+    from test_gpu_parity import _fresh_dataset, _oracle_replay
+    g = synth.GenomeSpec(1_500_000, 3, 2025, segdup_frac=0.10, segdup_len=(1000, 8000), segdup_div=0.005,
+                         families=[(300, 700, 0.03, 0.10), (2500, 40, 0.01, 0.03)], n_tandem=50, name="xchr")
+    r = synth.ReadSpec(2500, 25, degraded_frac=0.3, repeat_bias=0.8, indel_rate=0.004, seed=10)
+    fa, pairs = _fresh_dataset(tmp_path, "alnx", g, r)
+    w_out, w_x = str(tmp_path / "want.out"), str(tmp_path / "want.x")
+    subprocess.check_call([_oracle_replay(oracle_port), fa, pairs, w_out, "-t", "8", "-x", w_x], stderr=subprocess.DEVNULL)
+    ref = gobwa.GoBwaLoadReference(fa)
+    lib.lc_set_alnx(ref.BWTData, 1)
+    b2, o2 = _load_pairs(pairs)
+    br = ref.align_packed(b2, o2, 25)
+    assert br.dump() == open(w_out, "rb").read()
+    assert br.dump_alnx() == open(w_x, "rb").read()
+    ref.close()

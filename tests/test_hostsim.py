@@ -79,3 +79,14 @@ def test_multi_superblock_and_high_interval_bits(hostsim_sb_bin, tmp_path, extra
     subprocess.check_call([hostsim_sb_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out)] + extra,
                           stderr=subprocess.DEVNULL)
     assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+
+
+@pytest.mark.parametrize("extra", [[], ["-K", "101", "-W"], ["-w", "7"]])
+def test_getalignments_stage_matches_reference_golden(hostsim_bin, tmp_path, extra):
+    """Stage 6b (lc_post.cuh: the CIGAR walk of inference.GetAlignments, lariat.go:1573-1650) against the golden records the
+    compiled reference + the C restatement of the Go loop wrote (tests/golden/tiny/tiny.ref.x), whole and chunked."""
+    out, x = tmp_path / "sim.out", tmp_path / "sim.x"
+    subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out), "-x", str(x)] + extra,
+                          stderr=subprocess.DEVNULL)
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+    assert x.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.x"), "rb").read()

@@ -21,6 +21,22 @@ def test_port_replay_matches_reference_golden(oracle_port, tmp_path):
     assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
 
 
+def test_getalignments_restatement_port_equals_reference_golden(oracle_port, tmp_path):
+    """oracle/replay.c -x: the CIGAR walk of inference.GetAlignments (lariat.go:1573-1650) restated in C; the golden file was written by
+    the build linked against the unmodified reference library, the port build must reproduce it."""
+    out, x = tmp_path / "port.out", tmp_path / "port.x"
+    subprocess.check_call([os.path.join(oracle_port, "replay_port"), os.path.join(GOLDEN, "tiny", "tiny.fa"),
+                           os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out), "-x", str(x)], stderr=subprocess.DEVNULL)
+    want = open(os.path.join(GOLDEN, "tiny", "tiny.ref.x"), "rb").read()
+    assert x.read_bytes() == want
+    recs = iofmt.parse_alnx(want)
+    flat = [a for r in recs for a in r]
+    assert len(flat) == 5684
+    assert max(a["n_mm"] for a in flat) == 150          # the golden set has a lower-case read: the Go loop compares bytes
+    assert sum(1 for a in flat if a["indels"]) > 20 and sum(1 for a in flat if a["soft_clipped"]) > 20
+    assert all(a["pos"] < a["aend"] for a in flat)                   # after the reverse-strand swap (+1) of lariat.go:1645-1650
+
+
 def test_golden_is_not_trivial():
     res = iofmt.read_results(os.path.join(GOLDEN, "tiny", "tiny.ref.out"))
     n = [len(r["regs"]) for r in res]
