@@ -27,6 +27,7 @@ static lc_ctx **g_ctx;
 static lc_result_t **g_res;          /* per group (kept when an output file is wanted) */
 static uint64_t *g_sum;              /* per group: checksum taken right after the call ... */
 static float *g_lat;                 /* per call latency (ms) */
+static double g_dev[8];              /* sums over calls of the device-side stage times of the (merged) batch each call rode in */
 static volatile int g_next, g_fail;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 
@@ -62,6 +63,10 @@ static void *worker(void *arg)
 		g_lat[g] = (float)(1e3 * (now_s() - t0));
 		if (rc) { fprintf(stderr, "lc_align_packed failed (%d): %s\n", rc, lc_last_error()); g_fail = 1; break; }
 		if (res->n_reads != 2 * np) { fprintf(stderr, "wrong n_reads\n"); g_fail = 1; break; }
+		pthread_mutex_lock(&g_mu);
+		g_dev[0] += res->ms_total; g_dev[1] += res->ms_seed; g_dev[2] += res->ms_chain; g_dev[3] += res->ms_extend; g_dev[4] += res->ms_pair;
+		g_dev[5] += res->ms_cigar; g_dev[6] += res->ms_h2d; g_dev[7] += res->ms_d2h;
+		pthread_mutex_unlock(&g_mu);
 		if (g_keep) { g_res[gi] = res; g_sum[gi] = checksum(res); continue; }
 		/* keep it while the next calls run; before freeing the oldest, check that nothing has touched it in the meantime */
 		if (g < g_groups) g_sum[gi] = checksum(res);
@@ -124,6 +129,7 @@ int main(int argc, char **argv)
 		for (int t = 0; t < g_threads; ++t) pthread_create(&th[t], 0, worker, (void *)(intptr_t)t);
 		for (int t = 0; t < g_threads; ++t) pthread_join(th[t], 0);
 		g_groups = save_groups; g_repeat = save_rep; g_keep = save_keep; g_next = 0;
+		memset(g_dev, 0, sizeof(g_dev));
 	}
 	const double t0 = now_s();
 	for (int t = 0; t < g_threads; ++t) pthread_create(&th[t], 0, worker, (void *)(intptr_t)t);
@@ -155,8 +161,11 @@ int main(int argc, char **argv)
 	const int calls = g_groups * g_repeat;
 	qsort(g_lat, (size_t)calls, 4, cmp_f);
 	fprintf(stderr, "{\"pairs\": %d, \"calls\": %d, \"threads\": %d, \"pairs_per_call\": %d, \"clones\": %d, \"hold\": %d, \"seconds\": %.4f, \"pairs_per_s\": %.1f, "
-			"\"call_ms_p50\": %.3f, \"call_ms_p90\": %.3f, \"call_ms_p99\": %.3f, \"call_ms_max\": %.3f}\n", n, calls, g_threads, g_call, g_clones, g_hold, dt,
-			(double)n * g_repeat / dt, g_lat[calls / 2], g_lat[(int)(calls * 0.9)], g_lat[(int)(calls * 0.99)], g_lat[calls - 1]);
+			"\"call_ms_p50\": %.3f, \"call_ms_p90\": %.3f, \"call_ms_p99\": %.3f, \"call_ms_max\": %.3f, "
+			"\"batch_device_ms_mean\": {\"total\": %.3f, \"seed\": %.3f, \"chain\": %.3f, \"extend\": %.3f, \"pair\": %.3f, \"cigar\": %.3f, \"h2d\": %.3f, \"d2h\": %.3f}}\n",
+			n, calls, g_threads, g_call, g_clones, g_hold, dt,
+			(double)n * g_repeat / dt, g_lat[calls / 2], g_lat[(int)(calls * 0.9)], g_lat[(int)(calls * 0.99)], g_lat[calls - 1],
+			g_dev[0] / calls, g_dev[1] / calls, g_dev[2] / calls, g_dev[3] / calls, g_dev[4] / calls, g_dev[5] / calls, g_dev[6] / calls, g_dev[7] / calls);
 	for (int k = g_clones - 1; k >= 0; --k) lc_destroy(g_ctx[k]);
 	return 0;
 }

@@ -32,6 +32,8 @@ def num(r, k, scale=None):
         v = float(r[col[k]].replace(",", ""))
     except ValueError:
         return None
+    if v != v:      # "nan": the metric was not collected for this launch
+        return None
     if scale is not None:
         v *= scale.get(units[col[k]], 1)
     return v
@@ -55,7 +57,11 @@ for r in rows[h + 2:]:
     ms = num(r, "gpu__time_duration.sum", scale_t) or 0.0
     k["launches"] += 1
     k["ms"] += ms
-    k["warp_instr"] += num(r, "sm__inst_executed.sum") or 0.0
+    wi = num(r, "sm__inst_executed.sum")
+    if wi is None:      # the full set reports the rate: warp instructions per cycle per SM x elapsed cycles x SMs
+        ipc, cyc = num(r, "sm__inst_executed.avg.per_cycle_elapsed"), num(r, "sm__cycles_elapsed.avg")
+        wi = ipc * cyc * n_sm if ipc is not None and cyc is not None else 0.0
+    k["warp_instr"] += wi
     k["dram_bytes"] += (num(r, "dram__bytes_read.sum", scale_b) or 0.0) + (num(r, "dram__bytes_write.sum", scale_b) or 0.0)
     k["_at"] += ms * (num(r, "smsp__thread_inst_executed_per_inst_executed.ratio") or 0.0)
     k["_occ"] += ms * (num(r, "sm__warps_active.avg.pct_of_peak_sustained_active") or 0.0)
