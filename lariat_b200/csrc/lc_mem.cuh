@@ -327,18 +327,21 @@ struct LcChainer {
 };
 
 LC_HD size_t lc_align8(size_t x) { return (x + 7) & ~(size_t)7; }
+// what mem_chain_flt's pairwise loop reads of a chain, by position in the weight-sorted order: 16 contiguous bytes instead of the
+// head/tail seeds behind four pointers (in repeats the loop is quadratic in the chains of a read and was the tail of chain_kernel)
+struct LcChainFlt { int32_t beg, end; int32_t w; int32_t first_alt; };      // first_alt: bit 31 = is_alt, low bits = `first` + 1 (0 = none)
 LC_HD size_t lc_chain_scratch_bytes(int S)
 {
 	return lc_align8(sizeof(LcChainRec) * (size_t)S) + lc_align8(sizeof(LcBtNode) * ((size_t)S / (LC_BT_T - 1) + 2)) +
-		   lc_align8(4 * (size_t)S) * 6 /* s_q, s_len, s_next, order, srt, kept_idx */ + 64;
+		   lc_align8(4 * (size_t)S) * 6 /* s_q, s_len, s_next, order, srt, kept_idx */ + lc_align8(sizeof(LcChainFlt) * (size_t)S) + 64;
 }
 
 #define LC_CHAIN_SMALL 12
-#define LC_CHAIN_SMALL_BYTES 1408       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in lc_stage_chain)
+#define LC_CHAIN_SMALL_BYTES 1616       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in lc_stage_chain)
 LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 {
-	static_assert(sizeof(LcChainRec) * LC_CHAIN_SMALL + 8 + sizeof(LcBtNode) * (LC_CHAIN_SMALL / (LC_BT_T - 1) + 2) + 8 + (4 * LC_CHAIN_SMALL + 8) * 6 + 64 + 8
-				  <= LC_CHAIN_SMALL_BYTES, "LC_CHAIN_SMALL_BYTES too small");
+	static_assert(sizeof(LcChainRec) * LC_CHAIN_SMALL + 8 + sizeof(LcBtNode) * (LC_CHAIN_SMALL / (LC_BT_T - 1) + 2) + 8 + (4 * LC_CHAIN_SMALL + 8) * 6 +
+				  sizeof(LcChainFlt) * LC_CHAIN_SMALL + 8 + 64 + 8 <= LC_CHAIN_SMALL_BYTES, "LC_CHAIN_SMALL_BYTES too small");
 	const lc_opt_t &opt = b.opt;
 	const int S = b.r_n_seed[r], NI = b.r_n_intv[r];
 	const int len = (int)(b.off[r + 1] - b.off[r]);
@@ -375,7 +378,8 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 	c.s_next = (int32_t *)p; p += lc_align8(4 * (size_t)S);
 	int32_t *order = (int32_t *)p; p += lc_align8(4 * (size_t)S);
 	int32_t *srt = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	int32_t *kept_idx = (int32_t *)p;
+	int32_t *kept_idx = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+	LcChainFlt *flt = (LcChainFlt *)p;
 	c.s_rbeg = (int64_t *)(b.seed_row + b.r_seed_off[r]);
 	c.n_ch = 0; c.n_nd = 0; c.n_keys = 0;
 	c.root = c.new_node(0);
@@ -429,28 +433,33 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 		const LcChainRec *ch = c.ch;
 		lc_introsort(srt, (long)n, [ch](int a, int d) { return ch[a].w > ch[d].w; });      // flt_lt (B/bwamem.c:324-325,341)
 	}
-#define LC_CBEG(id) (c.s_q[c.ch[id].head])
-#define LC_CEND(id) (c.s_q[c.ch[id].tail] + c.s_len[c.ch[id].tail])
+	for (int i = 0; i < n; ++i) {      // the loop's view of chain srt[i]
+		const LcChainRec &cc = c.ch[srt[i]];
+		flt[i].beg = c.s_q[cc.head]; flt[i].end = c.s_q[cc.tail] + c.s_len[cc.tail]; flt[i].w = (int32_t)cc.w;
+		flt[i].first_alt = cc.is_alt ? (int32_t)0x80000000u : 0;
+	}
 	int n_kept = 0;
 	c.ch[srt[0]].kept = 3; kept_idx[n_kept++] = 0;
 	for (int i = 1; i < n; ++i) {
-		const int ai = srt[i];
+		const LcChainFlt fi = flt[i];
+		const int li = fi.end - fi.beg;
 		int large_ovlp = 0;
 		for (k = 0; k < n_kept; ++k) {
-			const int j = kept_idx[k], aj = srt[j];
-			int b_max = lc_max(LC_CBEG(aj), LC_CBEG(ai)), e_min = lc_min(LC_CEND(aj), LC_CEND(ai));
-			if (e_min > b_max && (!c.ch[aj].is_alt || c.ch[ai].is_alt)) {
-				int li = LC_CEND(ai) - LC_CBEG(ai), lj = LC_CEND(aj) - LC_CBEG(aj), min_l = lc_min(li, lj);
+			const int j = kept_idx[k];
+			const LcChainFlt fj = flt[j];
+			int b_max = lc_max(fj.beg, fi.beg), e_min = lc_min(fj.end, fi.end);
+			if (e_min > b_max && (fj.first_alt >= 0 || fi.first_alt < 0)) {      // (!a[j].is_alt || a[i].is_alt)
+				int lj = fj.end - fj.beg, min_l = lc_min(li, lj);
 				if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
 					large_ovlp = 1;
-					if (c.ch[aj].first < 0) c.ch[aj].first = i;
-					if ((int)c.ch[ai].w < (int)c.ch[aj].w * opt.drop_ratio && (int)c.ch[aj].w - (int)c.ch[ai].w >= opt.min_seed_len << 1) break;
+					if ((fj.first_alt & 0x7fffffff) == 0) flt[j].first_alt = fj.first_alt | (i + 1);
+					if (fi.w < fj.w * opt.drop_ratio && fj.w - fi.w >= opt.min_seed_len << 1) break;
 				}
 			}
 		}
-		if (k == n_kept) { kept_idx[n_kept++] = i; c.ch[ai].kept = large_ovlp ? 2 : 3; }
+		if (k == n_kept) { kept_idx[n_kept++] = i; c.ch[srt[i]].kept = large_ovlp ? 2 : 3; }
 	}
-	for (int i = 0; i < n_kept; ++i) { const LcChainRec &cc = c.ch[srt[kept_idx[i]]]; if (cc.first >= 0) c.ch[srt[cc.first]].kept = 1; }
+	for (int i = 0; i < n_kept; ++i) { const int f = flt[kept_idx[i]].first_alt & 0x7fffffff; if (f) c.ch[srt[f - 1]].kept = 1; }
 	{
 		int i;
 		for (i = k = 0; i < n; ++i) {

@@ -428,7 +428,7 @@ public:
 		if (rc0) return rc0;
 		const unsigned long long S = h_ctl[1];
 		// ---- stage 2-4 pools, sized exactly from the seed count
-		b.scratch_cap = 96ull * S + 320ull * R + 4096;     // chain scratch (<= 85 B/seed + 280 B/read) + extension sort keys (8 B/seed + 16 B/read)
+		b.scratch_cap = 112ull * S + 320ull * R + 4096;    // chain scratch (<= 101 B/seed + 280 B/read) + extension sort keys (8 B/seed + 16 B/read)
 		b.chain_cap = S + 16; b.cseed_cap = S + 16; b.reg_cap = S + 16;
 		if (!d_scratch.ensure(be, b.scratch_cap) || !d_chain.ensure(be, sizeof(LcChainOut) * b.chain_cap) ||
 			!d_cseed.ensure(be, sizeof(LcSeed) * b.cseed_cap) || !d_reg.ensure(be, sizeof(lc_alnreg_t) * b.reg_cap)) return nomem();
