@@ -235,6 +235,27 @@ int lc_sa_batch(lc_ctx *ctx, int64_t n, const uint64_t *rows, uint64_t *out, flo
  * from lrand48).  Sized for the 3.1 Gb reference: 6.2e9 suffixes are sorted in lexicographic chunks that fit one GPU's HBM. */
 int lc_index_build(const char *prefix, int n_contigs, const char *const *names, const uint8_t *const *codes, const int64_t *lens, int device);
 
+/* ---- the 9-line barcode-sorted FASTQ reader (go/src/fastqreader/reader.go:91-149 ReadOneLine, :190-260 ReadBarcodeSet; zipread.go:63-85),
+ * producing barcode sets already packed for lc_align_packed.  gzip or plain text.  Grouping rules are the reference's: a set ends when
+ * Barcode10X changes, after 30000 records, after 200 records of a barcode without '-' (not on the whitelist), or after 200 records of a
+ * set that continues the previous set's barcode. */
+enum { LC_RD_INFO = 0, LC_RD_RGID, LC_RD_BARCODE10X, LC_RD_RAWBARCODE10X, LC_RD_BARCODE10X_QUAL, LC_RD_SAMPLE_INDEX, LC_RD_SAMPLE_INDEX_QUAL,
+       LC_RD_TRIM_BASES, LC_RD_TRIM_QUALS, LC_RD_NFIELDS };
+typedef struct {
+	int32_t n_records;        /* FastQRecords (read pairs) of the set */
+	int32_t complete;         /* the bool ReadBarcodeSet returns: the set closes its barcode (or the file) */
+	const uint8_t *bases;     /* read 2i = Read1 of record i AFTER trimming `trim` leading bases, read 2i + 1 = Read2: the arrays lc_align_packed takes */
+	const uint8_t *quals;     /* same layout */
+	const int64_t *off;       /* [2 * n_records + 1] */
+	const char *text;         /* field f of record i = text[text_off[i * LC_RD_NFIELDS + f] .. text_off[i * LC_RD_NFIELDS + f + 1]) */
+	const int64_t *text_off;  /* [n_records * LC_RD_NFIELDS + 1] */
+} lc_readset_t;
+typedef struct lc_reader lc_reader;
+lc_reader *lc_reader_open(const char *path);
+/* 1 = a set (valid until the next call on this reader), 0 = end of file, < 0 = error */
+int lc_reader_next_set(lc_reader *rd, int trim, lc_readset_t *out);
+void lc_reader_close(lc_reader *rd);
+
 void lc_set_counting(lc_ctx *ctx, int on);
 /* GetAlignments post-processing on the device (lc_alnx_t above): off by default; applies to this context and its later clones */
 void lc_set_alnx(lc_ctx *ctx, int on);

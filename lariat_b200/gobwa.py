@@ -81,7 +81,7 @@ class lc_alnreg_v(C.Structure):
 EXPORTS = ["lc_opt_init", "lc_init", "lc_clone", "lc_set_coalescing", "lc_destroy", "lc_last_error", "lc_contigs", "lc_align_pairs", "lc_align_packed",
            "lc_batch_upload", "lc_batch_run", "lc_batch_fetch", "lc_free_result", "lc_fetch_seq", "lc_mem_align1_core",
            "lc_mem_matesw", "lc_mem_reg2aln", "lc_ksw_extend_batch", "lc_ksw_align_batch", "lc_collect_intv_batch",
-           "lc_sa_batch", "lc_index_build", "lc_set_counting", "lc_set_alnx", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
+           "lc_sa_batch", "lc_index_build", "lc_reader_open", "lc_reader_next_set", "lc_reader_close", "lc_set_counting", "lc_set_alnx", "lc_set_chunk_pairs", "lc_build_info", "lc_timer_start", "lc_timer_stop"]
 
 _lib = None
 
