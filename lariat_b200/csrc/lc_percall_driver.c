@@ -6,7 +6,9 @@
  * `bench.py --mode percall` (pairs/s and call latency in the drop-in regime).
  *
  * usage: lc_percall_driver <index-prefix> <pairs.bin> <out.bin|-> [-t threads] [-c pairs_per_call] [-n max_pairs] [-r repeat]
- *                          [-g device] [-k clones] [-h hold]
+ *                          [-g device] [-G n_devices] [-k clones] [-h hold]
+ *   -G n      : ONE process driving n GPUs (devices 0..n-1), the way a single Lariat process would: one lc_init per device (the index
+ *               is replicated per GPU), worker t uses device t % n.  No process-wide state is shared between the devices' contexts.
  *   -k clones : number of contexts (lc_clone of the first) the threads are spread over; the index is in HBM once either way
  *   -h hold   : results a worker keeps alive before freeing the oldest (default 1: the previous barcode's result is still
  *               alive while the next call runs).  With an output file every result is kept until the dump is written.
@@ -21,7 +23,7 @@
 
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
-static int g_threads = 32, g_call = 100, g_repeat = 1, g_hold = 1, g_clones = 1, g_n, g_groups, g_keep;
+static int g_threads = 32, g_call = 100, g_repeat = 1, g_hold = 1, g_clones = 1, g_ndev = 1, g_n, g_groups, g_keep;
 static const uint8_t *g_bases; static const int64_t *g_off;
 static lc_ctx **g_ctx;
 static lc_result_t **g_res;          /* per group (kept when an output file is wanted) */
@@ -48,7 +50,7 @@ static uint64_t checksum(const lc_result_t *r)
 static void *worker(void *arg)
 {
 	const int tid = (int)(intptr_t)arg;
-	lc_ctx *ctx = g_ctx[tid % g_clones];
+	lc_ctx *ctx = g_ctx[(tid % g_ndev) * g_clones + (tid / g_ndev) % g_clones];
 	lc_result_t **held = (lc_result_t **)calloc((size_t)g_hold + 1, sizeof(*held));
 	int *held_g = (int *)calloc((size_t)g_hold + 1, sizeof(int));
 	int nh = 0;
@@ -96,9 +98,10 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-r")) g_repeat = atoi(argv[i + 1]);
 		else if (!strcmp(argv[i], "-g")) device = atoi(argv[i + 1]);
 		else if (!strcmp(argv[i], "-k")) g_clones = atoi(argv[i + 1]);
+		else if (!strcmp(argv[i], "-G")) g_ndev = atoi(argv[i + 1]);
 		else if (!strcmp(argv[i], "-h")) g_hold = atoi(argv[i + 1]);
 	}
-	if (g_threads < 1 || g_call < 1 || g_repeat < 1 || g_clones < 1 || g_hold < 0) return 2;
+	if (g_threads < 1 || g_call < 1 || g_repeat < 1 || g_clones < 1 || g_hold < 0 || g_ndev < 1) return 2;
 	FILE *f = fopen(argv[2], "rb");
 	if (!f) { perror(argv[2]); return 1; }
 	char magic[4]; int32_t n;
@@ -115,10 +118,13 @@ int main(int argc, char **argv)
 	g_n = n; g_bases = bases; g_off = off; g_groups = (n + g_call - 1) / g_call;
 	g_keep = strcmp(argv[3], "-") != 0;
 	if (g_keep) g_repeat = 1;
-	g_ctx = (lc_ctx **)calloc((size_t)g_clones, sizeof(*g_ctx));
-	g_ctx[0] = lc_init(argv[1], device, 0);
-	if (!g_ctx[0]) { fprintf(stderr, "lc_init failed: %s\n", lc_last_error()); return 1; }
-	for (int k = 1; k < g_clones; ++k) if (!(g_ctx[k] = lc_clone(g_ctx[0]))) { fprintf(stderr, "lc_clone failed: %s\n", lc_last_error()); return 1; }
+	g_ctx = (lc_ctx **)calloc((size_t)g_clones * g_ndev, sizeof(*g_ctx));
+	for (int d = 0; d < g_ndev; ++d) {
+		lc_ctx **c = g_ctx + (size_t)d * g_clones;
+		c[0] = lc_init(argv[1], g_ndev > 1 ? d : device, 0);
+		if (!c[0]) { fprintf(stderr, "lc_init failed on device %d: %s\n", d, lc_last_error()); return 1; }
+		for (int k = 1; k < g_clones; ++k) if (!(c[k] = lc_clone(c[0]))) { fprintf(stderr, "lc_clone failed: %s\n", lc_last_error()); return 1; }
+	}
 	g_res = (lc_result_t **)calloc((size_t)g_groups, sizeof(*g_res));
 	g_sum = (uint64_t *)calloc((size_t)g_groups, 8);
 	g_lat = (float *)calloc((size_t)g_groups * g_repeat, 4);
@@ -156,16 +162,16 @@ int main(int argc, char **argv)
 			}
 		}
 		fclose(o);
-		for (int g = 0; g < g_groups; ++g) lc_free_result(g_ctx[0], g_res[g]);
+		for (int g = 0; g < g_groups; ++g) lc_free_result(g_ctx[0], g_res[g]);      /* (a result may be freed through any context) */
 	}
 	const int calls = g_groups * g_repeat;
 	qsort(g_lat, (size_t)calls, 4, cmp_f);
-	fprintf(stderr, "{\"pairs\": %d, \"calls\": %d, \"threads\": %d, \"pairs_per_call\": %d, \"clones\": %d, \"hold\": %d, \"seconds\": %.4f, \"pairs_per_s\": %.1f, "
+	fprintf(stderr, "{\"pairs\": %d, \"calls\": %d, \"threads\": %d, \"pairs_per_call\": %d, \"clones\": %d, \"devices\": %d, \"hold\": %d, \"seconds\": %.4f, \"pairs_per_s\": %.1f, "
 			"\"call_ms_p50\": %.3f, \"call_ms_p90\": %.3f, \"call_ms_p99\": %.3f, \"call_ms_max\": %.3f, "
 			"\"batch_device_ms_mean\": {\"total\": %.3f, \"seed\": %.3f, \"chain\": %.3f, \"extend\": %.3f, \"pair\": %.3f, \"cigar\": %.3f, \"h2d\": %.3f, \"d2h\": %.3f}}\n",
-			n, calls, g_threads, g_call, g_clones, g_hold, dt,
+			n, calls, g_threads, g_call, g_clones, g_ndev, g_hold, dt,
 			(double)n * g_repeat / dt, g_lat[calls / 2], g_lat[(int)(calls * 0.9)], g_lat[(int)(calls * 0.99)], g_lat[calls - 1],
 			g_dev[0] / calls, g_dev[1] / calls, g_dev[2] / calls, g_dev[3] / calls, g_dev[4] / calls, g_dev[5] / calls, g_dev[6] / calls, g_dev[7] / calls);
-	for (int k = g_clones - 1; k >= 0; --k) lc_destroy(g_ctx[k]);
+	for (int k = g_clones * g_ndev - 1; k >= 0; --k) lc_destroy(g_ctx[k]);
 	return 0;
 }

@@ -17,9 +17,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 DRIVER = os.path.join(_HERE, "lc_percall_driver")
 
 
-def run_driver(fa, pairs, out, threads, call_pairs, n_pairs, repeat=1, clones=1, hold=1, device=0, env=None):
+def run_driver(fa, pairs, out, threads, call_pairs, n_pairs, repeat=1, clones=1, hold=1, device=0, env=None, devices=1):
     cmd = [DRIVER, fa, pairs, out, "-t", str(threads), "-c", str(call_pairs), "-n", str(n_pairs), "-r", str(repeat), "-k", str(clones),
-           "-h", str(hold), "-g", str(device)]
+           "-h", str(hold), "-g", str(device), "-G", str(devices)]
     r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
     if r.returncode != 0:
         raise SystemExit(f"lc_percall_driver failed: {r.stderr[-2000:]}")
