@@ -182,6 +182,31 @@ __global__ void __launch_bounds__(LC_TPB) chain_kernel(const LcBatch b)
 	for (int r = worker; r < b.n_reads; r += stride) lc_stage_chain(b, r);
 }
 
+// Stage 3b: the reads chain_kernel listed (very many seeds: repeats), one warp each (LcChainJob::run, lc_mem.cuh)
+struct LcChainExecWarp {
+	int ln;
+	__device__ __forceinline__ int lane() const { return ln; }
+	__device__ __forceinline__ int width() const { return 32; }
+	__device__ __forceinline__ bool leader() const { return ln == 0; }
+	__device__ __forceinline__ void sync() const { __syncwarp(); }
+	__device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(LC_FULL, p); }
+	__device__ __forceinline__ int bcast(int v) const { return __shfl_sync(LC_FULL, v, 0); }
+};
+__global__ void __launch_bounds__(LC_TPB) chain_heavy_kernel(const LcBatch b)
+{
+	LcChainExecWarp ex;
+	ex.ln = threadIdx.x & 31;
+	const unsigned int n = b.chain_heavy_n[0];      // written by chain_kernel, which finished before this launch started
+	for (;;) {
+		unsigned int t = 0;
+		if (ex.ln == 0) t = atomicAdd(b.chain_heavy_n + 1, 1u);
+		t = __shfl_sync(LC_FULL, t, 0);
+		if (t >= n) break;
+		lc_stage_chain_heavy_t(b, b.chain_list[t], ex);
+		__syncwarp();
+	}
+}
+
 // Stage 4: one lane per read, mem_chain2aln + ksw_extend2 as a state machine (lc_extsm.cuh).  Per warp the shared memory holds
 // the 32 H/E rows ([column][lane], packed by CELLS) and the 32 reads (4 bits per base, [word][lane], one spare word in front).
 template <class CELLS> __host__ __device__ inline int lc_ext_warp_words(int lmax) { return (CELLS::words(lc_ext_he_cols(lmax)) + lc_ext_q_words(lmax)) * 32; }
@@ -496,7 +521,12 @@ void LcCudaBackend::k_sa_fill(const LcIndex &ix, unsigned long long n_samples, v
 	else sa_fill_kernel<uint32_t><<<grid_for(n_samples, 256, 8), 256, 0, stream>>>(ix, n_samples, (uint32_t *)out);
 }
 void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
-void LcCudaBackend::k_chain(const LcBatch &b) { chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b); }
+void LcCudaBackend::k_chain(const LcBatch &b)
+{
+	chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b);
+	// the list length is only known on the device: a resident-size grid whose warps pull listed reads from a counter (no host round trip)
+	if (b.chain_heavy > 0) chain_heavy_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 4), LC_TPB, 0, stream>>>(b);
+}
 template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
 {
 	const int smem = ((LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) + LC_EXT_MTAB_WORDS) * 4;

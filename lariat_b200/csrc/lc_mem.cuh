@@ -99,6 +99,8 @@ struct LcBatch {
 	const uint8_t *raw;                                  // the reads as given (ASCII), kept beside the 2-bit codes: the Go loop compares BYTES
 	                                                     //   (a lower-case read mismatches everywhere); null = compare codes
 	int32_t *mm_ref, *mm_read; unsigned long long mm_cap, *mm_cur;   // mismatch position lists, carved per candidate
+	int32_t chain_heavy; int32_t *chain_list; unsigned int *chain_heavy_n;   // stage 3: reads with more than chain_heavy seeds are listed for the
+	                                                     //   warp-per-read kernel ([0] = list length, [1] = its work counter); 0 = never
 	unsigned int *ext_heavy_n;                           // stage 4: reads listed (in `redo`) for the warp-per-read extension kernel, then its work counter
 	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read is "heavy" above this many chained seeds / chains (0 = never)
 };
@@ -337,77 +339,95 @@ LC_HD size_t lc_chain_scratch_bytes(int S)
 }
 
 #define LC_CHAIN_SMALL 12
-#define LC_CHAIN_SMALL_BYTES 1616       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in lc_stage_chain)
-LC_HDN void lc_stage_chain(const LcBatch &b, int r)
-{
-	static_assert(sizeof(LcChainRec) * LC_CHAIN_SMALL + 8 + sizeof(LcBtNode) * (LC_CHAIN_SMALL / (LC_BT_T - 1) + 2) + 8 + (4 * LC_CHAIN_SMALL + 8) * 6 +
-				  sizeof(LcChainFlt) * LC_CHAIN_SMALL + 8 + 64 + 8 <= LC_CHAIN_SMALL_BYTES, "LC_CHAIN_SMALL_BYTES too small");
-	const lc_opt_t &opt = b.opt;
-	const int S = b.r_n_seed[r], NI = b.r_n_intv[r];
-	const int len = (int)(b.off[r + 1] - b.off[r]);
-	b.r_n_chain[r] = 0; b.r_chain_off[r] = 0; b.r_frac_rep[r] = 0.f; b.r_n_cseed[r] = 0;
-	if (S == 0 && NI == 0) return;
-	const LcIntvOut *iv = b.intv + b.r_intv_off[r];
-	// frac_rep: span covered by intervals more frequent than max_occ (B/bwamem.c:265-272,310)
-	int rb = 0, re = 0, l_rep = 0;
-	for (int i = 0; i < NI; ++i) {
-		int sb = (int)iv[i].qbeg, se = (int)iv[i].qend;
-		if (iv[i].x2 <= (uint64_t)opt.max_occ) continue;
-		if (sb > re) { l_rep += re - rb; rb = sb; re = se; } else re = lc_max(re, se);
-	}
-	l_rep += re - rb;
-	const float frac_rep = (float)l_rep / len;
-	b.r_frac_rep[r] = frac_rep;
-	if (S == 0) return;
-	// A read with a handful of seeds (the usual case outside repeats) keeps the chainer's arrays in thread-local memory: the pool is
-	// cold global memory, and chaining is a string of dependent accesses to it (ncu: the kernel is latency, not work).
-	uint64_t small[LC_CHAIN_SMALL_BYTES / 8];
-	uint8_t *p;
-	if (S <= LC_CHAIN_SMALL) p = (uint8_t *)small;
-	else {
-		unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, lc_chain_scratch_bytes(S), LC_OVF_SCRATCH);
-		if (so == (unsigned long long)-1) return;
-		p = b.scratch + so;
-	}
-	p = (uint8_t *)lc_align8((size_t)p);
+#define LC_CHAIN_SMALL_BYTES 1616       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in LcChainJob::init)
+
+// Who runs lc_chain_job: one thread (chain_kernel, tests/hostsim) ...
+struct LcChainExec1 {
+	LC_HD int lane() const { return 0; }
+	LC_HD int width() const { return 1; }
+	LC_HD bool leader() const { return true; }
+	LC_HD void sync() const {}
+	LC_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+	LC_HD int bcast(int v) const { return v; }
+};
+// ... or the 32 lanes of a warp (chain_heavy_kernel, lc_kernels.cu: LcChainExecWarp), for reads with thousands of seeds: in repeats
+// mem_chain_flt's pairwise loop is quadratic in the chains of a read (none shadows the others: they all weigh the same), the seed lists
+// are walked three times, and one thread doing it all was the tail of chain_kernel (profiles/r2b: 255 ms of the C3 step at 1.4 active
+// threads per warp).  The lanes split everything that is independent per chain and the kept-chain scan of the filter; what is
+// inherently ordered (the B-tree insertions, the introsort) stays with lane 0.  Same statements, same order of side effects.
+
+struct LcChainJob {
+	const LcBatch &b; int r, S, NI, n, n_kept;
 	LcChainer c;
-	c.ch = (LcChainRec *)p; p += lc_align8(sizeof(LcChainRec) * (size_t)S);
-	c.nd = (LcBtNode *)p; p += lc_align8(sizeof(LcBtNode) * ((size_t)S / (LC_BT_T - 1) + 2));
-	c.s_q = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	c.s_len = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	c.s_next = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	int32_t *order = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	int32_t *srt = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	int32_t *kept_idx = (int32_t *)p; p += lc_align8(4 * (size_t)S);
-	LcChainFlt *flt = (LcChainFlt *)p;
-	c.s_rbeg = (int64_t *)(b.seed_row + b.r_seed_off[r]);
-	c.n_ch = 0; c.n_nd = 0; c.n_keys = 0;
-	c.root = c.new_node(0);
-	for (int i = 0; i < NI; ++i) {
-		const int slen = (int)(iv[i].qend - iv[i].qbeg);
-		const int cnt = (i + 1 < NI ? (int)iv[i + 1].soff : S) - (int)iv[i].soff;
-		for (int t = 0; t < cnt; ++t) {
-			const int si = (int)iv[i].soff + t;
-			c.s_q[si] = (int)iv[i].qbeg; c.s_len[si] = slen; c.s_next[si] = -1;
-			const int64_t rbeg = c.s_rbeg[si];
-			const int rid = lc_intv2rid(b.ix, rbeg, rbeg + slen);
-			if (rid < 0) continue;                       // spans contigs or the strand boundary (B/bwamem.c:286-287)
-			bool add = true;
-			if (c.n_keys) {
-				int low = c.lower(rbeg);
-				if (low >= 0 && c.merge(opt, b.ix.l_pac, low, si, rid)) add = false;
-			}
-			if (add) {
-				LcChainRec &n = c.ch[c.n_ch];
-				n.pos = rbeg; n.rid = rid; n.n = 1; n.head = n.tail = si; n.w = 0; n.kept = 0; n.first = -1;
-				n.is_alt = b.ix.anns[rid].is_alt ? 1 : 0;
-				c.put(c.n_ch++);
+	int32_t *order, *srt, *kept_idx;
+	LcChainFlt *flt;
+	const LcIntvOut *iv;
+	LC_HD LcChainJob(const LcBatch &b_, int r_) : b(b_), r(r_), S(b_.r_n_seed[r_]), NI(b_.r_n_intv[r_]), n(0), n_kept(0) {}
+
+	// frac_rep: span covered by intervals more frequent than max_occ (B/bwamem.c:265-272,310); false = nothing to chain
+	LC_HD bool prologue()
+	{
+		const int len = (int)(b.off[r + 1] - b.off[r]);
+		b.r_n_chain[r] = 0; b.r_chain_off[r] = 0; b.r_frac_rep[r] = 0.f; b.r_n_cseed[r] = 0;
+		if (S == 0 && NI == 0) return false;
+		iv = b.intv + b.r_intv_off[r];
+		int rb = 0, re = 0, l_rep = 0;
+		for (int i = 0; i < NI; ++i) {
+			int sb = (int)iv[i].qbeg, se = (int)iv[i].qend;
+			if (iv[i].x2 <= (uint64_t)b.opt.max_occ) continue;
+			if (sb > re) { l_rep += re - rb; rb = sb; re = se; } else re = lc_max(re, se);
+		}
+		l_rep += re - rb;
+		b.r_frac_rep[r] = (float)l_rep / len;
+		return S != 0;
+	}
+	LC_HD void init(uint8_t *p)
+	{
+		static_assert(sizeof(LcChainRec) * LC_CHAIN_SMALL + 8 + sizeof(LcBtNode) * (LC_CHAIN_SMALL / (LC_BT_T - 1) + 2) + 8 + (4 * LC_CHAIN_SMALL + 8) * 6 +
+					  sizeof(LcChainFlt) * LC_CHAIN_SMALL + 8 + 64 + 8 <= LC_CHAIN_SMALL_BYTES, "LC_CHAIN_SMALL_BYTES too small");
+		p = (uint8_t *)lc_align8((size_t)p);
+		c.ch = (LcChainRec *)p; p += lc_align8(sizeof(LcChainRec) * (size_t)S);
+		c.nd = (LcBtNode *)p; p += lc_align8(sizeof(LcBtNode) * ((size_t)S / (LC_BT_T - 1) + 2));
+		c.s_q = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+		c.s_len = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+		c.s_next = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+		order = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+		srt = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+		kept_idx = (int32_t *)p; p += lc_align8(4 * (size_t)S);
+		flt = (LcChainFlt *)p;
+		c.s_rbeg = (int64_t *)(b.seed_row + b.r_seed_off[r]);
+	}
+	// mem_chain (B/bwamem.c:273-307): every seed joins the chain below it in the tree or opens a new one; then the in-order walk
+	// (__kb_traverse, B/kbtree.h:336-358).  Ordered work: one thread.
+	LC_HD void build()
+	{
+		const lc_opt_t &opt = b.opt;
+		c.n_ch = 0; c.n_nd = 0; c.n_keys = 0;
+		c.root = c.new_node(0);
+		for (int i = 0; i < NI; ++i) {
+			const int slen = (int)(iv[i].qend - iv[i].qbeg);
+			const int cnt = (i + 1 < NI ? (int)iv[i + 1].soff : S) - (int)iv[i].soff;
+			for (int t = 0; t < cnt; ++t) {
+				const int si = (int)iv[i].soff + t;
+				c.s_q[si] = (int)iv[i].qbeg; c.s_len[si] = slen; c.s_next[si] = -1;
+				const int64_t rbeg = c.s_rbeg[si];
+				const int rid = lc_intv2rid(b.ix, rbeg, rbeg + slen);
+				if (rid < 0) continue;                       // spans contigs or the strand boundary (B/bwamem.c:286-287)
+				bool add = true;
+				if (c.n_keys) {
+					int low = c.lower(rbeg);
+					if (low >= 0 && c.merge(opt, b.ix.l_pac, low, si, rid)) add = false;
+				}
+				if (add) {
+					LcChainRec &nn = c.ch[c.n_ch];
+					nn.pos = rbeg; nn.rid = rid; nn.n = 1; nn.head = nn.tail = si; nn.w = 0; nn.kept = 0; nn.first = -1;
+					nn.is_alt = b.ix.anns[rid].is_alt ? 1 : 0;
+					c.put(c.n_ch++);
+				}
 			}
 		}
-	}
-	int n = 0;
-	{   // in-order walk (__kb_traverse, B/kbtree.h:336-358) with an explicit stack; step t of an internal node:
-		// even t = descend into child t/2, odd t = emit key t/2
+		n = 0;
+		// step t of an internal node: even t = descend into child t/2, odd t = emit key t/2
 		int st_node[24], st_t[24], top = 0;
 		st_node[0] = c.root; st_t[0] = 0;
 		while (top >= 0) {
@@ -419,49 +439,79 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 			else { ++top; st_node[top] = x.child[t >> 1]; st_t[top] = 0; }
 		}
 	}
-	// ---- mem_chain_flt
-	int k = 0;
-	for (int i = 0; i < n; ++i) {
-		LcChainRec &cc = c.ch[order[i]];
-		cc.first = -1; cc.kept = 0;
-		cc.w = (uint32_t)c.weight(order[i]);
-		if ((int)cc.w >= opt.min_chain_weight) srt[k++] = order[i];
-	}
-	n = k;
-	if (n == 0) return;
+	// ---- mem_chain_flt (B/bwamem.c:327-385)
+	template <class EX> LC_HD void weights(const EX &ex)      // independent per chain
 	{
+		for (int i = ex.lane(); i < n; i += ex.width()) {
+			LcChainRec &cc = c.ch[order[i]];
+			cc.first = -1; cc.kept = 0;
+			cc.w = (uint32_t)c.weight(order[i]);
+		}
+		ex.sync();
+	}
+	LC_HD void sort_by_weight()                               // one thread: the permutation of ks_introsort is observable (ties)
+	{
+		int k = 0;
+		for (int i = 0; i < n; ++i) if ((int)c.ch[order[i]].w >= b.opt.min_chain_weight) srt[k++] = order[i];
+		n = k;
+		if (n == 0) return;
 		const LcChainRec *ch = c.ch;
 		lc_introsort(srt, (long)n, [ch](int a, int d) { return ch[a].w > ch[d].w; });      // flt_lt (B/bwamem.c:324-325,341)
 	}
-	for (int i = 0; i < n; ++i) {      // the loop's view of chain srt[i]
-		const LcChainRec &cc = c.ch[srt[i]];
-		flt[i].beg = c.s_q[cc.head]; flt[i].end = c.s_q[cc.tail] + c.s_len[cc.tail]; flt[i].w = (int32_t)cc.w;
-		flt[i].first_alt = cc.is_alt ? (int32_t)0x80000000u : 0;
-	}
-	int n_kept = 0;
-	c.ch[srt[0]].kept = 3; kept_idx[n_kept++] = 0;
-	for (int i = 1; i < n; ++i) {
-		const LcChainFlt fi = flt[i];
-		const int li = fi.end - fi.beg;
-		int large_ovlp = 0;
-		for (k = 0; k < n_kept; ++k) {
-			const int j = kept_idx[k];
-			const LcChainFlt fj = flt[j];
-			int b_max = lc_max(fj.beg, fi.beg), e_min = lc_min(fj.end, fi.end);
-			if (e_min > b_max && (fj.first_alt >= 0 || fi.first_alt < 0)) {      // (!a[j].is_alt || a[i].is_alt)
-				int lj = fj.end - fj.beg, min_l = lc_min(li, lj);
-				if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
-					large_ovlp = 1;
-					if ((fj.first_alt & 0x7fffffff) == 0) flt[j].first_alt = fj.first_alt | (i + 1);
-					if (fi.w < fj.w * opt.drop_ratio && fj.w - fi.w >= opt.min_seed_len << 1) break;
-				}
-			}
-		}
-		if (k == n_kept) { kept_idx[n_kept++] = i; c.ch[srt[i]].kept = large_ovlp ? 2 : 3; }
-	}
-	for (int i = 0; i < n_kept; ++i) { const int f = flt[kept_idx[i]].first_alt & 0x7fffffff; if (f) c.ch[srt[f - 1]].kept = 1; }
+	// the pairwise loop: chain i (in weight order) against the chains kept so far, in order, until one of them shadows it.  A group of
+	// `width` lanes tests `width` kept chains at a time; the first lane that would `break` cuts the scan exactly where the loop does.
+	template <class EX> LC_HD void filter(const EX &ex)
 	{
-		int i;
+		const lc_opt_t &opt = b.opt;
+		for (int i = ex.lane(); i < n; i += ex.width()) {      // the loop's view of chain srt[i]
+			const LcChainRec &cc = c.ch[srt[i]];
+			flt[i].beg = c.s_q[cc.head]; flt[i].end = c.s_q[cc.tail] + c.s_len[cc.tail]; flt[i].w = (int32_t)cc.w;
+			flt[i].first_alt = cc.is_alt ? (int32_t)0x80000000u : 0;
+		}
+		if (ex.leader()) { c.ch[srt[0]].kept = 3; kept_idx[0] = 0; }
+		n_kept = 1;
+		ex.sync();
+		for (int i = 1; i < n; ++i) {
+			const LcChainFlt fi = flt[i];
+			const int li = fi.end - fi.beg;
+			int large_ovlp = 0;
+			bool broke = false;
+			for (int k0 = 0; k0 < n_kept && !broke; k0 += ex.width()) {
+				const int k = k0 + ex.lane();
+				bool sig = false, brk = false;
+				int j = 0;
+				LcChainFlt fj; fj.beg = fj.end = fj.w = fj.first_alt = 0;
+				if (k < n_kept) {
+					j = kept_idx[k];
+					fj = flt[j];
+					const int b_max = lc_max(fj.beg, fi.beg), e_min = lc_min(fj.end, fi.end);
+					if (e_min > b_max && (fj.first_alt >= 0 || fi.first_alt < 0)) {      // (!a[j].is_alt || a[i].is_alt)
+						const int lj = fj.end - fj.beg, min_l = lc_min(li, lj);
+						if (e_min - b_max >= min_l * opt.mask_level && min_l < opt.max_chain_gap) {
+							sig = true;
+							brk = fi.w < fj.w * opt.drop_ratio && fj.w - fi.w >= opt.min_seed_len << 1;
+						}
+					}
+				}
+				const uint32_t mb = ex.ballot(brk), ms = ex.ballot(sig);
+				const int cut = mb ? lc_ctz(mb) : 31;                    // lanes up to and including `cut` are the iterations the loop runs
+				const uint32_t upto = cut >= 31 ? 0xffffffffu : ((2u << cut) - 1u);
+				if (sig && ex.lane() <= cut && (fj.first_alt & 0x7fffffff) == 0) flt[j].first_alt = fj.first_alt | (i + 1);
+				if (ms & upto) large_ovlp = 1;
+				broke = mb != 0;
+			}
+			if (!broke) {
+				if (ex.leader()) { kept_idx[n_kept] = i; c.ch[srt[i]].kept = large_ovlp ? 2 : 3; }
+				++n_kept;
+			}
+			ex.sync();
+		}
+	}
+	LC_HD void mark()                                         // B/bwamem.c:369-383
+	{
+		const lc_opt_t &opt = b.opt;
+		for (int i = 0; i < n_kept; ++i) { const int f = flt[kept_idx[i]].first_alt & 0x7fffffff; if (f) c.ch[srt[f - 1]].kept = 1; }
+		int i, k;
 		for (i = k = 0; i < n; ++i) {
 			int kp = c.ch[srt[i]].kept;
 			if (kp == 0 || kp == 3) continue;
@@ -469,21 +519,80 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 		}
 		for (; i < n; ++i) if (c.ch[srt[i]].kept < 3) c.ch[srt[i]].kept = 0;
 	}
-	// ---- emit kept chains in filter order with their seeds compacted
-	int nk = 0; unsigned long long ns = 0;
-	for (int i = 0; i < n; ++i) if (c.ch[srt[i]].kept) { ++nk; ns += c.ch[srt[i]].n; }
-	unsigned long long co = lc_carve(b, b.chain_cur, b.chain_cap, nk, LC_OVF_CHAIN);
-	unsigned long long eo = lc_carve(b, b.cseed_cur, b.cseed_cap, ns, LC_OVF_CSEED);
-	if (co == (unsigned long long)-1 || eo == (unsigned long long)-1) return;
-	nk = 0; ns = 0;
-	for (int i = 0; i < n; ++i) {
-		const LcChainRec &cc = c.ch[srt[i]];
-		if (!cc.kept) continue;
-		LcChainOut o; o.rid = cc.rid; o.n = cc.n; o.seed_off = (int64_t)(eo + ns); o.w = cc.w; o.is_alt = cc.is_alt;
-		b.chain[co + nk++] = o;
-		for (int s = cc.head; s >= 0; s = c.s_next[s]) { LcSeed sd; sd.rbeg = c.s_rbeg[s]; sd.qbeg = c.s_q[s]; sd.len = c.s_len[s]; b.cseed[eo + ns++] = sd; }
+	// kept chains in filter order with their seeds compacted: offsets by one thread, the copies by all
+	template <class EX> LC_HD void emit(const EX &ex)
+	{
+		int nk = 0; unsigned long long ns = 0;
+		long long co = 0, eo = 0;
+		if (ex.leader()) {
+			for (int i = 0; i < n; ++i) if (c.ch[srt[i]].kept) { order[nk] = (int32_t)ns; kept_idx[nk] = srt[i]; ++nk; ns += c.ch[srt[i]].n; }      // order / kept_idx are free by now
+			const unsigned long long co_ = lc_carve(b, b.chain_cur, b.chain_cap, nk, LC_OVF_CHAIN);
+			const unsigned long long eo_ = lc_carve(b, b.cseed_cur, b.cseed_cap, ns, LC_OVF_CSEED);
+			if (co_ == (unsigned long long)-1 || eo_ == (unsigned long long)-1) nk = -1;
+			else { co = (long long)co_; eo = (long long)eo_; b.r_chain_off[r] = co; b.r_n_chain[r] = nk; b.r_n_cseed[r] = (int32_t)ns; }
+		}
+		ex.sync();
+		nk = ex.bcast(nk);
+		if (nk <= 0) return;
+		co = ((long long)ex.bcast((int)(co >> 32)) << 32) | (unsigned)ex.bcast((int)co);
+		eo = ((long long)ex.bcast((int)(eo >> 32)) << 32) | (unsigned)ex.bcast((int)eo);
+		for (int t = ex.lane(); t < nk; t += ex.width()) {
+			const LcChainRec &cc = c.ch[kept_idx[t]];
+			unsigned long long so = (unsigned long long)eo + (unsigned)order[t];
+			LcChainOut o; o.rid = cc.rid; o.n = cc.n; o.seed_off = (int64_t)so; o.w = cc.w; o.is_alt = cc.is_alt;
+			b.chain[co + t] = o;
+			for (int sd_ = cc.head; sd_ >= 0; sd_ = c.s_next[sd_]) { LcSeed sd; sd.rbeg = c.s_rbeg[sd_]; sd.qbeg = c.s_q[sd_]; sd.len = c.s_len[sd_]; b.cseed[so++] = sd; }
+		}
 	}
-	b.r_chain_off[r] = (int64_t)co; b.r_n_chain[r] = nk; b.r_n_cseed[r] = (int32_t)ns;
+	// the whole of stage 3 for one read
+	template <class EX> LC_HD void run(const EX &ex)
+	{
+		if (ex.leader()) build();
+		ex.sync();
+		n = ex.bcast(n);
+		weights(ex);
+		if (ex.leader()) sort_by_weight();
+		ex.sync();
+		n = ex.bcast(n);
+		if (n == 0) return;
+		filter(ex);
+		if (ex.leader()) mark();
+		ex.sync();
+		emit(ex);
+	}
+};
+
+// one thread per read (chain_kernel): reads with more than b.chain_heavy seeds are listed for chain_heavy_kernel instead
+LC_HDN void lc_stage_chain(const LcBatch &b, int r)
+{
+	LcChainJob job(b, r);
+	if (!job.prologue()) return;
+	const int S = job.S;
+	if (b.chain_heavy > 0 && S > b.chain_heavy) { b.chain_list[lc_atomic_add(b.chain_heavy_n, 1u)] = r; return; }
+	// A read with a handful of seeds (the usual case outside repeats) keeps the chainer's arrays in thread-local memory: the pool is
+	// cold global memory, and chaining is a string of dependent accesses to it (ncu: the kernel is latency, not work).
+	uint64_t small[LC_CHAIN_SMALL_BYTES / 8];
+	uint8_t *p;
+	if (S <= LC_CHAIN_SMALL) p = (uint8_t *)small;
+	else {
+		unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, lc_chain_scratch_bytes(S), LC_OVF_SCRATCH);
+		if (so == (unsigned long long)-1) return;
+		p = b.scratch + so;
+	}
+	job.init(p);
+	job.run(LcChainExec1());
+}
+// one warp (or, in tests/hostsim, one thread) per listed read
+template <class EX> LC_HD void lc_stage_chain_heavy_t(const LcBatch &b, int r, const EX &ex)
+{
+	LcChainJob job(b, r);
+	job.iv = b.intv + b.r_intv_off[r];      // prologue() ran in lc_stage_chain
+	long long so = 0;
+	if (ex.leader()) so = (long long)lc_carve(b, b.scratch_cur, b.scratch_cap, lc_chain_scratch_bytes(job.S), LC_OVF_SCRATCH);
+	so = ((long long)ex.bcast((int)(so >> 32)) << 32) | (unsigned)ex.bcast((int)so);
+	if (so == -1) return;
+	job.init(b.scratch + so);
+	job.run(ex);
 }
 
 // ============================================================================================================

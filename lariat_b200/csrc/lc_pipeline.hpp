@@ -217,6 +217,7 @@ public:
 	int memcap = 256;
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
 	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
+	int chain_heavy = 192;                               // chaining: reads with more seeds than this go to the warp-per-read kernel (0 = never)
 	int lst_cap2 = 40, pk_cap2 = 256;     // the second and third pass' capacities; overflow of the third -> the one-thread-per-read redo kernel
 	int lst_cap3 = 150, pk_cap3 = 2048;
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
@@ -301,6 +302,8 @@ public:
 			b.cig_n = (unsigned int *)(c + 24);
 			b.resc_n = (unsigned int *)(c + 27);
 			b.ext_heavy_n = (unsigned int *)(c + 28);
+			b.chain_heavy_n = (unsigned int *)(c + 29);
+			b.chain_heavy = chain_heavy;
 			b.ext_heavy_seeds = ext_heavy_seeds; b.ext_heavy_chains = ext_heavy_chains;
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
@@ -315,6 +318,7 @@ public:
 		} b.force_wide = force_wide ? 1 : 0;
 		if (!d_wpk.ensure(be, sizeof(LcPk) * (size_t)be.seed_lanes() * b.pk_cap) || !d_redo.ensure(be, 4 * ((size_t)R + 1))) return nomem();
 		b.w_pk = (LcPk *)d_wpk.p; b.redo = (int32_t *)d_redo.p;
+		b.chain_list = (int32_t *)d_redo.p;      // the seeding stage is done with its redo list when chaining starts
 		if (!d_wl.ensure(be, 16 * ((size_t)R + 1))) return nomem();
 		b.wl_in = (uint64_t *)d_wl.p; b.wl_out = b.wl_in + (R + 1);
 		b.w_int_n = std::max(3 * (b.lmax + 18), 2 * (b.lmax + 2) + 2 * b.lmax + 8) + 8;
@@ -435,7 +439,7 @@ public:
 		b.scratch = (uint8_t *)d_scratch.p; b.chain = (LcChainOut *)d_chain.p; b.cseed = (LcSeed *)d_cseed.p; b.reg = (lc_alnreg_t *)d_reg.p;
 		if (S && !(b.ix.sa32 || b.ix.sa64)) { be.k_sa(b, S); ++launches; }     // with the dense suffix array the seeding kernels wrote positions already
 		be.ev_record(4);
-		be.k_chain(b); ++launches;
+		be.k_chain(b); launches += chain_heavy > 0 ? 2 : 1;      // one thread per read, then a warp per read with very many seeds
 		be.ev_record(5);
 		be.k_extend(b); launches += 2;          // lanes (one read each), then a warp per read for the heavy ones
 		be.ev_record(6);

@@ -51,7 +51,11 @@ struct HostBackend {
 	}
 	void k_seed_redo(const LcBatch &b, int n_redo) { for (int t = 0; t < n_redo; ++t) lc_stage_seed(b, b.redo[t], t % workers); }
 	void k_sa(const LcBatch &b, unsigned long long n) { for (unsigned long long g = 0; g < n; ++g) lc_stage_sa(b, g); }
-	void k_chain(const LcBatch &b) { for (int r = 0; r < b.n_reads; ++r) lc_stage_chain(b, r); }
+	void k_chain(const LcBatch &b)
+	{
+		for (int r = 0; r < b.n_reads; ++r) lc_stage_chain(b, r);
+		for (unsigned int t = 0; t < b.chain_heavy_n[0]; ++t) lc_stage_chain_heavy_t(b, b.chain_list[t], LcChainExec1());      // the listed reads' kernel
+	}
 	// the extension state machine with stride-1 rows (lc_extsm.cuh); -X runs the older one-call-per-read body instead
 	bool old_extend = false;
 	void k_extend(const LcBatch &b)
@@ -102,6 +106,7 @@ int main(int argc, char **argv)
 {
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
 	const char *xpath = 0;
+	int chain_heavy = -1;
 	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
@@ -116,6 +121,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-W")) wide = 1;                                      // 64-bit interval arithmetic (as for indexes >= 2^32 symbols)
 		else if (!strcmp(argv[i], "-I") && i + 1 < argc) be.idle_ticks = atoi(argv[++i]);  // idle ticks before every housekeeping step of the state machines
 		else if (!strcmp(argv[i], "-J") && i + 1 < argc) heavy_seeds = atoi(argv[++i]);   // extension: reads above this many chained seeds take the per-read body
+		else if (!strcmp(argv[i], "-Q") && i + 1 < argc) chain_heavy = atoi(argv[++i]);   // chaining: reads above this many seeds take the listed-read body (0 = never)
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
@@ -148,6 +154,7 @@ int main(int argc, char **argv)
 	if (pk_cap > 0) pl.pk_cap = pk_cap;
 	if (lst_cap2 > 0) { pl.lst_cap2 = lst_cap2; pl.lst_cap3 = lst_cap2 + 2; }      // (third pass: barely larger, so that the last fallback still gets reads)
 	if (heavy_seeds >= 0) pl.ext_heavy_seeds = heavy_seeds;
+	if (chain_heavy >= 0) pl.chain_heavy = chain_heavy;
 	if (pk_cap2 > 0) { pl.pk_cap2 = pk_cap2; pl.pk_cap3 = pk_cap2 + 2; }
 	pl.force_wide = wide != 0;
 	pl.want_alnx = xpath != 0;

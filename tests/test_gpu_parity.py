@@ -41,10 +41,12 @@ def test_golden_tiny_bit_exact(tiny_ref):
     assert br.gpu_launches >= 6
 
 
-@pytest.mark.parametrize("env", [{"LC_DENSE_SA": "0"}, {"LC_SEED_LST_CAP": "10", "LC_SEED_PK_CAP": "6"}, {"LC_SEED_LST_CAP": "6", "LC_SEED_PK_CAP": "4", "LC_SEED_LST_CAP2": "9", "LC_SEED_PK_CAP2": "7", "LC_SEED_LST_CAP3": "12", "LC_SEED_PK_CAP3": "9"}, {"LC_DENSE_SA": "0", "LC_SEED_LST_CAP": "16"}, {"LC_FORCE_WIDE": "1"}, {"LC_EXT_HEAVY_SEEDS": "2", "LC_EXT_HEAVY_CHAINS": "1"}, {"LC_EXT_HEAVY_SEEDS": "0", "LC_EXT_HEAVY_CHAINS": "0"}])
+@pytest.mark.parametrize("env", [{"LC_DENSE_SA": "0"}, {"LC_SEED_LST_CAP": "10", "LC_SEED_PK_CAP": "6"}, {"LC_SEED_LST_CAP": "6", "LC_SEED_PK_CAP": "4", "LC_SEED_LST_CAP2": "9", "LC_SEED_PK_CAP2": "7", "LC_SEED_LST_CAP3": "12", "LC_SEED_PK_CAP3": "9"}, {"LC_DENSE_SA": "0", "LC_SEED_LST_CAP": "16"}, {"LC_FORCE_WIDE": "1"}, {"LC_EXT_HEAVY_SEEDS": "2", "LC_EXT_HEAVY_CHAINS": "1"}, {"LC_EXT_HEAVY_SEEDS": "0", "LC_EXT_HEAVY_CHAINS": "0"},
+                                 {"LC_CHAIN_HEAVY": "3"}, {"LC_CHAIN_HEAVY": "40", "LC_FORCE_WIDE": "1"}, {"LC_CHAIN_HEAVY": "0"}])
 def test_golden_tiny_fallback_paths(env, lib_path, monkeypatch):
     """Same golden through the optional paths: sampled suffix array + LF walks instead of the dense array, and the
-    one-thread-per-read redo kernel for reads that outgrow the state machine's fixed-size lists."""
+    one-thread-per-read redo kernel for reads that outgrow the state machine's fixed-size lists; LC_CHAIN_HEAVY: nearly every read
+    through the warp-per-read chaining kernel (32 lanes sharing the filter's kept-chain scan), or none."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     ref = gobwa.GoBwaLoadReference(os.path.join(GOLDEN, "tiny", "tiny.fa"))
@@ -176,6 +178,8 @@ def test_fresh_synthetic_vs_oracle(kind, lib_path, oracle_port, tmp_path, monkey
             monkeypatch.setenv("LC_FORCE_WIDE", "1")
         else:
             r = synth.ReadSpec(8_000, 80, mol_len=200_000, mols_per_barcode=50, degraded_frac=0.30, repeat_bias=0.8, seed=780)
+    if kind in ("repeat", "c4like"):
+        monkeypatch.setenv("LC_CHAIN_HEAVY", "24")      # most repeat reads through the warp-per-read chaining kernel
     fa, pairs = _fresh_dataset(tmp_path, kind, g, r)
     want = str(tmp_path / "want.out")
     subprocess.check_call([_oracle_replay(oracle_port), fa, pairs, want, "-t", "8"], stderr=subprocess.DEVNULL)
