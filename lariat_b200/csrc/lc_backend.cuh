@@ -19,8 +19,8 @@ struct LcCudaBackend {
 	int device, n_sm = 0, workers = 0;
 	cudaStream_t stream = 0;
 	cudaEvent_t ev[LC_N_EVENTS];
-	cudaStream_t aux[4] = { 0, 0, 0, 0 };      // side streams: the four band classes of the CIGAR stage run concurrently (fork/join on events)
-	cudaEvent_t ev_fork = 0, ev_join[4] = { 0, 0, 0, 0 };
+	cudaStream_t aux[LC_CIG_NCLASS] = {};      // side streams: the band classes of the CIGAR stage run concurrently (fork/join on events)
+	cudaEvent_t ev_fork = 0, ev_join[LC_CIG_NCLASS] = {};
 	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
 	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
 	int seed_gate_mask = 3, seed_gate_n = 12, ext_gate_mask = 15, ext_row_mask = 1;

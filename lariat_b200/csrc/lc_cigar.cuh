@@ -14,7 +14,7 @@
 //     cell (the reference's byte holds three 2-bit fields of which only 4 bits carry information), one 32-bit word per 8
 //     cells, in a per-job slice of a global pool; the same thread walks it back, merges the ops, counts mismatches and
 //     writes the final CIGAR;
-//   * everything unusual — bands wider than 64 cells, the rare band-doubling retry of mem_reg2aln (B/bwamem.c:1111-1119),
+//   * everything unusual — bands wider than 80 cells, the rare band-doubling retry of mem_reg2aln (B/bwamem.c:1111-1119),
 //     CIGARs with more than LC_CIG_MAXOPS merged ops, degenerate regions — goes to a fallback list that the warp-per-candidate
 //     body (lc_stage_cigar_t) processes from scratch.
 // Values are plain int32 with the reference's own NEG_INF, so every comparison is the reference's comparison.
@@ -22,12 +22,15 @@
 #pragma once
 #include "lc_mem.cuh"
 
-#define LC_CIG_NCLASS 4
+#define LC_CIG_NCLASS 5
 #define LC_CIG_FALLBACK LC_CIG_NCLASS      // index of the fallback list
 #define LC_CIG_NLIST (LC_CIG_NCLASS + 1)
 #define LC_CIG_MAXOPS 24                   // merged CIGAR ops a thread keeps; longer CIGARs take the fallback
 
-LC_HD int lc_cig_class_cells(int c) { return c == 0 ? 24 : c == 1 ? 32 : c == 2 ? 48 : 64; }
+// 80 cells: a 150-base candidate whose score deficit comes from mismatches (diverged repeat copies) asks for w = 35-36 (B/bwa.c:152-157);
+// that band no longer fits the register file, the compiler keeps part of it in (thread-interleaved, L1-resident) local memory — still
+// an order of magnitude cheaper than the warp-per-candidate fallback (profiles/r2e: 139 ms of 166 on the 3.1 Gb config)
+LC_HD int lc_cig_class_cells(int c) { return c == 0 ? 24 : c == 1 ? 32 : c == 2 ? 48 : c == 3 ? 64 : 80; }
 
 struct LcCigJob {      // a candidate, decoded (B/bwamem.c:1086-1110)
 	int r, l_query, qb, qe, lq, rlen, w2, truesc;

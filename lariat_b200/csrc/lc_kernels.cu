@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, const u
 		if (lane == 0) t = atomicAdd(b.work_ctr + 1, 1u);
 		t = __shfl_sync(LC_FULL, t, 0);
 		if (t >= n) break;
-		lc_pair_rescue_t(b, (int)(uint32_t)list[t], ex);
+		lc_pair_rescue_t(b, (int)(uint32_t)list[t], (int)(list[t] >> 48) & 3, ex);
 		__syncwarp();
 	}
 }
@@ -419,7 +419,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventCreate(&ev[i]);
 	cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-	for (int i = 0; i < 4; ++i) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
+	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
 	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
 	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
 	env_int("LC_SEED_GATE_MASK", seed_gate_mask, 0, 255); env_int("LC_SEED_GATE_N", seed_gate_n, 1, 33);     // tuning knobs; mask must be 2^k - 1
@@ -430,7 +430,7 @@ LcCudaBackend::~LcCudaBackend()
 	cudaSetDevice(device);
 	if (scan_tmp) cudaFree(scan_tmp);
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventDestroy(ev[i]);
-	for (int i = 0; i < 4; ++i) { cudaEventDestroy(ev_join[i]); cudaStreamDestroy(aux[i]); }
+	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaEventDestroy(ev_join[i]); cudaStreamDestroy(aux[i]); }
 	cudaEventDestroy(ev_fork);
 	cudaStreamDestroy(stream);
 }
@@ -585,17 +585,18 @@ void LcCudaBackend::k_cigar_plan(const LcBatch &b, unsigned long long n) { cigar
 int LcCudaBackend::k_cigar_band(const LcBatch &b, unsigned long long n_max)
 {
 	// list lengths are only known on the device: grids are sized for the worst case (every candidate in one list) and stride over the real length
-	// The four classes are independent (separate job lists, atomically carved output): they run side by side on four streams so
+	// The classes are independent (separate job lists, atomically carved output): they run side by side on four streams so
 	// that the thin tail of one class (a few long jobs, one thread each) overlaps the bulk of the others.
 	const int grid = grid_for(n_max, 128, 8);
 	cudaEventRecord(ev_fork, stream);
-	for (int c = 0; c < 4; ++c) cudaStreamWaitEvent(aux[c], ev_fork, 0);
+	for (int c = 0; c < LC_CIG_NCLASS; ++c) cudaStreamWaitEvent(aux[c], ev_fork, 0);
+	cigar_band_kernel<80><<<grid, 128, 0, aux[4]>>>(b, 4);
 	cigar_band_kernel<64><<<grid, 128, 0, aux[3]>>>(b, 3);
 	cigar_band_kernel<48><<<grid, 128, 0, aux[2]>>>(b, 2);
 	cigar_band_kernel<32><<<grid, 128, 0, aux[1]>>>(b, 1);
 	cigar_band_kernel<24><<<grid, 128, 0, aux[0]>>>(b, 0);
-	for (int c = 0; c < 4; ++c) { cudaEventRecord(ev_join[c], aux[c]); cudaStreamWaitEvent(stream, ev_join[c], 0); }
-	return 4;
+	for (int c = 0; c < LC_CIG_NCLASS; ++c) { cudaEventRecord(ev_join[c], aux[c]); cudaStreamWaitEvent(stream, ev_join[c], 0); }
+	return LC_CIG_NCLASS;
 }
 void LcCudaBackend::k_cigar_fallback(const LcBatch &b, unsigned long long n_max)
 {

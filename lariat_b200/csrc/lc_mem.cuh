@@ -611,6 +611,13 @@ LC_HD int lc_cal_max_gap(const lc_opt_t &opt, int qlen)          // B/bwamem.c:6
 // Executors: who runs a stage body.  LcExecThread = one thread does everything (scalar SW, per-worker scratch in HBM).
 // LcExecWarp (lc_sw_warp.cuh, device only) = the 32 lanes of a warp run the control flow redundantly, lane 0 owns the
 // side effects, and the SW jobs are computed cooperatively with shared-memory rows and warp shuffles.
+#if defined(LC_STATS) && !defined(__CUDA_ARCH__)
+struct LcStats { unsigned long long sw, skipped, onepass, hazard, full_nofix, n_sum, nmax, hv_reads, hv_chains, hv_seeds, hv_scan, hv_ext, hv_regs, hv_maxchains; };
+static LcStats lc_stats;
+#define LC_STAT(x) (x)
+#else
+#define LC_STAT(x) ((void)0)
+#endif
 struct LcExecThread {
 	int *H, *E;
 	LC_HD bool leader() const { return true; }
@@ -643,6 +650,7 @@ LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
 	uint64_t *srt = (uint64_t *)lc_align8((size_t)(b.scratch + so));
 	const int64_t l_pac = b.ix.l_pac;
 	int n_av = 0;
+	LC_STAT((++lc_stats.hv_reads, lc_stats.hv_chains += NC, lc_stats.hv_seeds += T, lc_stats.hv_maxchains = lc_stats.hv_maxchains > (unsigned long long)NC ? lc_stats.hv_maxchains : NC));
 	for (int ci = 0; ci < NC; ++ci) {
 		const LcChainOut &c = b.chain[b.r_chain_off[r] + ci];
 		const LcSeed *seeds = b.cseed + c.seed_off;
@@ -669,6 +677,7 @@ LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
 			for (i = 0; i < n_av; ++i) {                    // seed already explained by an earlier region? (B/bwamem.c:671-687)
 				const lc_alnreg_t &p = av[i];
 				int64_t rd; int qd, w, g;
+				LC_STAT(++lc_stats.hv_scan);
 				if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
 				if (s.len - p.seedlen0 > .1 * l_query) continue;
 				qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
@@ -732,6 +741,7 @@ LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
 			a.frac_rep = b.r_frac_rep[r];
 			if (ex.leader()) av[n_av] = a;
 			++n_av;
+			LC_STAT(++lc_stats.hv_regs);
 			ex.sync();
 		}
 	}
@@ -833,11 +843,16 @@ template <class Lt> LC_HD void lc_sort_regs(lc_alnreg_t *a, int n, Lt lt, int *h
 }
 
 // h/h_cap: scratch for lc_sort_regs (may overlap H and E: the sorts and the patching never run at the same time)
-LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0)
+// *clean (optional) := the call excluded nothing and merged nothing (and saw at least two regions): its output is then a fixed point of the
+// query-less form — sorted by the strict order (score, rb, qb), every n_comp == 1, no redundant pair (see lc_matesw_t)
+LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0, bool *clean = nullptr)
 {
 	const lc_opt_t &opt = b.opt;
 	int m, i, j;
+	if (clean) *clean = false;
 	if (n <= 1) return n;
+	const int n_in = n;
+	bool merged = false;
 	lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; }, h, h_cap);
 	for (i = 0; i < n; ++i) a[i].n_comp = 1;
 	for (i = 1; i < n; ++i) {
@@ -864,6 +879,7 @@ LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc
 				p.truesc = p.score = score;
 				p.w = w;
 				q.qb = q.qe;
+				merged = true;
 			}
 		}
 	}
@@ -874,6 +890,7 @@ LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc
 	for (i = 1; i < n; ++i)
 		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
 	for (i = 1, m = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+	if (clean) *clean = !merged && m == n_in;
 	return m;
 }
 
@@ -888,15 +905,18 @@ LC_HD int lc_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t &dist)   /
 // The part of mem_matesw (B/bwamem_pair.c:118-147) that decides whether a Smith-Waterman is run for anchor `a`, with Lariat's
 // insert model: only orientation FR (index 1) is enabled (G/gobwa.go:229-237), so at most one SW is run per call.
 // Returns false when the call changes nothing; else [rb, re) is the reference window.
-LC_HD bool lc_matesw_wants_sw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const lc_alnreg_t *ma, int n_ma, int64_t &rb, int64_t &re)
+template <class Exec>
+LC_HD bool lc_matesw_wants_sw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const lc_alnreg_t *ma, int n_ma, int64_t &rb, int64_t &re, const Exec &ex)
 {
 	const int64_t l_pac = b.ix.l_pac;
 	const int low = b.pes_low, high = b.pes_high;
-	for (int i = 0; i < n_ma; ++i) {                       // an existing mate hit in range satisfies the orientation (:118-124)
+	bool found = false;
+	for (int i = ex.lane_id(); i < n_ma && !found; i += ex.n_lanes()) {      // an existing mate hit in range satisfies the orientation (:118-124)
 		int64_t dist;
 		int r = lc_infer_dir(l_pac, a.rb, ma[i].rb, dist);
-		if (r == 1 && dist >= low && dist <= high) return false;
+		if (r == 1 && dist >= low && dist <= high) found = true;
 	}
+	if (ex.any(found)) return false;
 	// r = 1: is_rev = 1 (mate is reverse-complemented), is_larger = 1 (:130-143)
 	rb = a.rb + low - l_ms; re = a.rb + high;
 	if (rb < 0) rb = 0;
@@ -906,58 +926,129 @@ LC_HD bool lc_matesw_wants_sw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, 
 	// (when rb >= re the reference compares against an uninitialised rid, :147; treated as "no window")
 	return a.rid == rid && re - rb >= b.opt.min_seed_len;
 }
+struct LcExecOne {      // the one-lane executor of the list scans (thread-per-pair callers)
+	LC_HD int lane_id() const { return 0; }
+	LC_HD int n_lanes() const { return 1; }
+	LC_HD bool any(bool v) const { return v; }
+};
+LC_HD bool lc_matesw_wants_sw(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const lc_alnreg_t *ma, int n_ma, int64_t &rb, int64_t &re)
+{
+	return lc_matesw_wants_sw_t(b, a, l_ms, ma, n_ma, rb, re, LcExecOne());
+}
+
+// one region against another in the redundancy test of mem_sort_dedup_patch (B/bwamem.c:451-456): p follows q in the order by `re`
+LC_HD bool lc_reg_redundant(const lc_opt_t &opt, const lc_alnreg_t &p, const lc_alnreg_t &q)
+{
+	const int64_t orr = q.re - p.rb;
+	const int64_t oq = q.qb < p.qb ? q.qe - p.qb : p.qe - q.qb;
+	const int64_t mr = lc_min(q.re - q.rb, p.re - p.rb);
+	const int64_t mq = lc_min((int64_t)(q.qe - q.qb), (int64_t)(p.qe - p.qb));
+	return orr > opt.mask_level_redun * mr && oq > opt.mask_level_redun * mq;
+}
+
+// a[at .. n) moves up by one slot, all lanes of the executor together (top chunk first: a chunk is read, then written)
+template <class Exec>
+LC_HD void lc_regs_shift_up(lc_alnreg_t *a, int at, int n, const Exec &ex)
+{
+	const int W = ex.n_lanes();
+	for (int hi = n; hi > at; hi -= W) {
+		const int i = hi - 1 - ex.lane_id();
+		lc_alnreg_t t;
+		if (i >= at) t = a[i];
+		ex.sync();
+		if (i >= at) a[i + 1] = t;
+		ex.sync();
+	}
+}
 
 // mem_matesw (B/bwamem_pair.c:111-180)
-// `fixed` (state of the LIST, kept by the caller across calls, meaningful in the leader lane): the list is the output of a
-// mem_sort_dedup_patch that inserted nothing and removed nothing.  Such a list is sorted by the strict order (score, rb, qb) with
-// every n_comp == 1, so running mem_sort_dedup_patch on it again (B/bwamem_pair.c:175 does, after EVERY Smith-Waterman, accepted or
-// not) sees the same array, makes the same comparisons and leaves the same array: the call is skipped.  In repeats most rescue
-// attempts are rejected (score < min_seed_len) and the lists hold hundreds of regions; the re-sort by a single lane after each of
-// them was the largest part of matesw_kernel (profiles/r01y: 29 % of its samples).  Any insertion or removal clears the flag.
+// `fixed` (state of the LIST, kept by the caller across calls, the same in every lane): the list is a fixed point of the query-less
+// mem_sort_dedup_patch — sorted by the strict order (score, rb, qb) with distinct keys, every n_comp == 1, at least two regions, and
+// no pair of regions that the redundancy test would remove.  The reference runs mem_sort_dedup_patch after EVERY Smith-Waterman,
+// accepted or not (B/bwamem_pair.c:175); in repeats the lists hold hundreds of regions and a pair makes up to a hundred calls, and those
+// two introsorts by a single lane were most of this stage (profiles/r01y, r2c).  On a fixed list they are not needed:
+//   * nothing inserted: the call sees the same array, makes the same comparisons and leaves the same array — skipped;
+//   * region x inserted: every test between two old regions comes out as it did before (the tests are pairwise; which pairs meet
+//     depends only on `re` and rid, and for two regions with equal `re` the test is symmetric, so the place introsort gives to ties
+//     does not matter).  What is new are the tests between x and each old region y.  If none of them fires, and x's key (score, rb, qb)
+//     differs from every old key, the call's result is the old list with x at its place in the key order: one pass over the list by
+//     all lanes (tests, key ties, rank of x), one cooperative shift.  The list is again a fixed point.
+//     If any test fires (or a key ties) the reference's statements are replayed as they stand, by the leader lane.
 template <class Exec>
 LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const uint8_t *ms, lc_alnreg_t *ma, int &n_ma, const Exec &ex, bool &fixed)
 {
 	const lc_opt_t &opt = b.opt;
 	const int64_t l_pac = b.ix.l_pac;
 	int64_t rb, re;
-	if (!lc_matesw_wants_sw(b, a, l_ms, ma, n_ma, rb, re)) return 0;
+	if (!lc_matesw_wants_sw_t(b, a, l_ms, ma, n_ma, rb, re, ex)) return 0;
 	const int xtra = LC_XSUBO | LC_XSTART | (l_ms * opt.a < 250 ? LC_XBYTE : 0) | (opt.min_seed_len * opt.a);
 	LcSeqRevComp qf = { ms, l_ms };
 	LcRefFwd tf = { &b.ix, rb };
-	const lc_alnreg_t anchor = a;      // `a` may alias the list that is about to be reshuffled
+	const int anchor_rid = a.rid, anchor_is_alt = a.is_alt;      // `a` may alias the list that is about to be reshuffled
 	LcSwResult aln = ex.sw_align2(l_ms, qf, (int)(re - rb), tf, b.sc, xtra, b.cnt);
 	ex.sync();
+	aln.score = (int)ex.bcast((unsigned long long)(unsigned)aln.score); aln.score2 = (int)ex.bcast((unsigned long long)(unsigned)aln.score2);
+	aln.qb = (int)ex.bcast((unsigned long long)(unsigned)aln.qb); aln.qe = (int)ex.bcast((unsigned long long)(unsigned)aln.qe);
+	aln.tb = (int)ex.bcast((unsigned long long)(unsigned)aln.tb); aln.te = (int)ex.bcast((unsigned long long)(unsigned)aln.te);
 	int n = n_ma;
-	if (ex.leader()) {
-		bool inserted = false;
-		if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
-			lc_alnreg_t nb;
-			inserted = true;
-			memset(&nb, 0, sizeof(nb));
-			nb.rid = anchor.rid;
-			nb.is_alt = anchor.is_alt;
-			nb.qb = l_ms - (aln.qe + 1);
-			nb.qe = l_ms - aln.qb;
-			nb.rb = (l_pac << 1) - (rb + aln.te + 1);
-			nb.re = (l_pac << 1) - (rb + aln.tb);
-			nb.score = aln.score;
-			nb.csub = aln.score2;
-			nb.secondary = -1;
-			nb.seedcov = (int)((nb.re - nb.rb < nb.qe - nb.qb ? nb.re - nb.rb : nb.qe - nb.qb) >> 1);
-			int at;
-			++n;
-			for (at = 0; at < n - 1; ++at) if (ma[at].score < nb.score) break;     // keep sorted by score (:165-171)
-			for (int i = n - 1; i > at; --i) ma[i] = ma[i - 1];
-			ma[at] = nb;
-		}
-		// :175; no patching without a query.  The sub-optimal-row list of the SW just done is dead by now: its memory holds the sort handles
-		if (inserted || !fixed) {
-			const int n_in = n;
-			n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0, (int *)ex.bl, ex.bl ? 2 * b.w_u64_n : 0);
-			fixed = !inserted && n == n_in;
-		}
+	const bool inserted = aln.score >= opt.min_seed_len && aln.qb >= 0;
+	lc_alnreg_t nb;
+	if (inserted) {
+		memset(&nb, 0, sizeof(nb));
+		nb.rid = anchor_rid;
+		nb.is_alt = anchor_is_alt;
+		nb.qb = l_ms - (aln.qe + 1);
+		nb.qe = l_ms - aln.qb;
+		nb.rb = (l_pac << 1) - (rb + aln.te + 1);
+		nb.re = (l_pac << 1) - (rb + aln.tb);
+		nb.score = aln.score;
+		nb.csub = aln.score2;
+		nb.secondary = -1;
+		nb.seedcov = (int)((nb.re - nb.rb < nb.qe - nb.qb ? nb.re - nb.rb : nb.qe - nb.qb) >> 1);
 	}
-	n_ma = (int)ex.bcast((unsigned long long)n);
+	bool done = !inserted && fixed;                        // the skipped call
+	LC_STAT((++lc_stats.sw, lc_stats.skipped += done, lc_stats.n_sum += n, lc_stats.nmax = lc_stats.nmax > (unsigned long long)n ? lc_stats.nmax : n));
+	if (inserted && fixed) {                               // the one-pass form (see above)
+		int below = 0;
+		bool hazard = false;
+		for (int i = ex.lane_id(); i < n; i += ex.n_lanes()) {
+			const lc_alnreg_t &y = ma[i];
+			const int64_t y_rb = y.rb, y_re = y.re;
+			const int y_qb = y.qb, y_score = y.score;
+			if (y_score > nb.score || (y_score == nb.score && (y_rb < nb.rb || (y_rb == nb.rb && y_qb < nb.qb)))) ++below;
+			else if (y_score == nb.score && y_rb == nb.rb && y_qb == nb.qb) hazard = true;
+			if (y.rid == nb.rid) {
+				if (y_re <= nb.re && nb.rb < y_re + opt.max_chain_gap && lc_reg_redundant(opt, nb, y)) hazard = true;
+				if (y_re >= nb.re && y_rb < nb.re + opt.max_chain_gap && lc_reg_redundant(opt, y, nb)) hazard = true;
+			}
+		}
+		if (!ex.any(hazard)) {
+			const int at = ex.sum(below);
+			lc_regs_shift_up(ma, at, n, ex);
+			if (ex.leader()) { nb.n_comp = 1; ma[at] = nb; }
+			++n;
+			done = true;
+			LC_STAT(++lc_stats.onepass);
+		} else LC_STAT(++lc_stats.hazard);
+	}
+	if (!done) {
+		bool fx = false;
+		LC_STAT(lc_stats.full_nofix += !fixed);
+		if (ex.leader()) {
+			if (inserted) {
+				int at;
+				++n;
+				for (at = 0; at < n - 1; ++at) if (ma[at].score < nb.score) break;     // keep sorted by score (:165-171)
+				for (int i = n - 1; i > at; --i) ma[i] = ma[i - 1];
+				ma[at] = nb;
+			}
+			// :175; no patching without a query.  The sub-optimal-row list of the SW just done is dead by now: its memory holds the sort handles
+			n = lc_sort_dedup_patch(b, (const uint8_t *)0, n, ma, (int *)0, (int *)0, (int *)ex.bl, ex.bl ? 2 * b.w_u64_n : 0, &fx);
+		}
+		n = (int)ex.bcast((unsigned long long)n);
+		fixed = ex.bcast(fx ? 1ull : 0ull) != 0;
+	}
+	n_ma = n;
 	ex.sync();
 	return 1;
 }
@@ -969,12 +1060,13 @@ LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const ui
 LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 {
 	int n[2], len[2], best[2] = { 0, 0 };
+	bool clean[2];
 	lc_alnreg_t *src[2];
 	for (int e = 0; e < 2; ++e) {
 		const int r = 2 * p + e;
 		len[e] = (int)(b.off[r + 1] - b.off[r]);
 		src[e] = b.reg + b.r_reg_off[r];
-		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], b.r_n_reg[r], src[e], H, E, H, 2 * (b.lmax + 18));      // tail of mem_align1_core (B/bwamem.c:1070)
+		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], b.r_n_reg[r], src[e], H, E, H, 2 * (b.lmax + 18), &clean[e]);      // tail of mem_align1_core (B/bwamem.c:1070)
 		for (int i = 0; i < n[e]; ++i) {
 			if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
 			best[e] = lc_max(best[e], src[e][i].score);                                         // G/gobwa.go:264-283
@@ -1001,9 +1093,9 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 	num = 0;
 	for (int i = 0; i < n[0] && num < b.max_anchors && len[1] > 0 && !need; ++i)
 		if (f0[i].score >= best[0] - b.score_delta) { ++num; need = lc_matesw_wants_sw(b, f0[i], len[1], f1, n[1], rb, re); }
-	if (need) {                                          // weight = candidates of the pair (anchors to try, lists to re-sort)
-		const int wgt = lc_min(n[0] + n[1], 0xffff);
-		b.wl_in[lc_atomic_add(b.resc_n, 1u)] = (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
+	if (need) {                                          // weight = candidates of the pair (anchors to try, lists to scan); bits 48, 49: the lists
+		const int wgt = lc_min(n[0] + n[1], 0xffff);     // are fixed points already (lc_matesw_t) — a clean mem_sort_dedup_patch just made them
+		b.wl_in[lc_atomic_add(b.resc_n, 1u)] = (uint64_t)((clean[0] ? 1 : 0) | (clean[1] ? 2 : 0)) << 48 | (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
 		return;
 	}
 	const unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
@@ -1013,14 +1105,14 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 
 // Stage 5b, one warp (or thread) per listed pair: the two rescue phases on the lists lc_pair_prepare filled
 template <class Exec>
-LC_HD void lc_pair_rescue_t(const LcBatch &b, int p, const Exec &ex)
+LC_HD void lc_pair_rescue_t(const LcBatch &b, int p, int fixed_bits, const Exec &ex)
 {
 	int len[2], best[2] = { 0, 0 };
 	const uint8_t *q[2];
 	for (int e = 0; e < 2; ++e) { const int r = 2 * p + e; len[e] = (int)(b.off[r + 1] - b.off[r]); q[e] = b.seq + b.off[r]; }
 	lc_alnreg_t *f0 = b.fin + b.r_fin_off[2 * p], *f1 = b.fin + b.r_fin_off[2 * p + 1];
 	int n0 = b.r_n_fin[2 * p], n1 = b.r_n_fin[2 * p + 1], num = 0;
-	bool fixed0 = false, fixed1 = false;      // see lc_matesw_t
+	bool fixed0 = (fixed_bits & 1) != 0, fixed1 = (fixed_bits & 2) != 0;      // see lc_matesw_t
 	for (int i = 0; i < n0; ++i) best[0] = lc_max(best[0], f0[i].score);      // the pre-rescue best scores (G/gobwa.go:264-283)
 	for (int i = 0; i < n1; ++i) best[1] = lc_max(best[1], f1[i].score);
 	ex.sync();
@@ -1031,18 +1123,22 @@ LC_HD void lc_pair_rescue_t(const LcBatch &b, int p, const Exec &ex)
 	num = 0;
 	for (int i = 0; i < n0 && num < b.max_anchors && len[1] > 0; ++i)
 		if (f0[i].score >= best[0] - b.score_delta) { ++num; lc_matesw_t(b, f0[i], len[1], q[1], f1, n1, ex, fixed1); }
+	unsigned long long co = 0;
 	if (ex.leader()) {
 		b.r_n_fin[2 * p] = n0; b.r_n_fin[2 * p + 1] = n1;
-		unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));
-		for (int i = 0; i < n0; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
-		for (int i = 0; i < n1; ++i) b.cand[co + n0 + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
+		co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));
 	}
+	co = ex.bcast(co);
+	for (int i = ex.lane_id(); i < n0; i += ex.n_lanes()) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
+	for (int i = ex.lane_id(); i < n1; i += ex.n_lanes()) b.cand[co + n0 + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
 }
 
 struct LcExecThreadSw : LcExecThread {     // thread executor with the extra rows the local SW needs
 	int *Hmax; unsigned long long *bl;
 	LC_HD int lane_id() const { return 0; }
 	LC_HD int n_lanes() const { return 1; }
+	LC_HD bool any(bool v) const { return v; }
+	LC_HD int sum(int v) const { return v; }
 	template <class QF, class TF>
 	LC_HD LcSwResult sw_align2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int xtra, LcCounters *cnt) const
 	{
@@ -1064,13 +1160,13 @@ LC_HDN void lc_stage_pair_prepare(const LcBatch &b, int p, int worker)
 	int *wi = b.w_int + (size_t)worker * b.w_int_n;
 	lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
 }
-LC_HDN void lc_stage_pair_rescue(const LcBatch &b, int p, int worker)
+LC_HDN void lc_stage_pair_rescue(const LcBatch &b, int p, int fixed_bits, int worker)
 {
 	int *wi = b.w_int + (size_t)worker * b.w_int_n;
 	LcExecThreadSw ex;
 	ex.H = wi; ex.E = wi + (b.lmax + 18); ex.Hmax = wi + 2 * (b.lmax + 18);
 	ex.bl = b.w_u64 + (size_t)worker * b.w_u64_n;
-	lc_pair_rescue_t(b, p, ex);
+	lc_pair_rescue_t(b, p, fixed_bits, ex);
 }
 
 // ============================================================================================================

@@ -69,7 +69,7 @@ struct HostBackend {
 	void k_pair(const LcBatch &b, int n_pairs)
 	{
 		for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair_prepare(b, p, p % workers);   // reversed: order must not matter
-		for (unsigned int t = 0; t < *b.resc_n; ++t) lc_stage_pair_rescue(b, (int)(uint32_t)b.wl_in[t], (int)(t % workers));
+		for (unsigned int t = 0; t < *b.resc_n; ++t) lc_stage_pair_rescue(b, (int)(uint32_t)b.wl_in[t], (int)(b.wl_in[t] >> 48) & 3, (int)(t % workers));
 	}
 	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
 	{
@@ -88,13 +88,13 @@ struct HostBackend {
 			const uint64_t *jobs = b.cig_jobs + (size_t)cls * b.cig_jobs_cap;
 			for (unsigned int t = 0; t < b.cig_n[cls]; ++t) {
 				if (cls == 0) lc_cig_band<24>(b, jobs[t]); else if (cls == 1) lc_cig_band<32>(b, jobs[t]);
-				else if (cls == 2) lc_cig_band<48>(b, jobs[t]); else lc_cig_band<64>(b, jobs[t]);
+				else if (cls == 2) lc_cig_band<48>(b, jobs[t]); else if (cls == 3) lc_cig_band<64>(b, jobs[t]); else lc_cig_band<80>(b, jobs[t]);
 			}
 			n_band[cls] += b.cig_n[cls];
 		}
-		return 4;
+		return LC_CIG_NCLASS;
 	}
-	unsigned long long n_band[LC_CIG_NCLASS] = {0, 0, 0, 0};
+	unsigned long long n_band[LC_CIG_NCLASS] = {};
 	void k_cigar_fallback(const LcBatch &b, unsigned long long) { k_cigar(b, b.cig_jobs + (size_t)LC_CIG_FALLBACK * b.cig_jobs_cap, 0, b.cig_n + LC_CIG_FALLBACK); }
 	void k_alnx(const LcBatch &b, unsigned long long n) { for (unsigned long long c = n; c-- > 0;) lc_stage_alnx(b, b.cand[c]); }
 	void k_pack(const LcBatch &b, const LcPackArgs &pa) { for (int r = 0; r <= b.n_reads; ++r) lc_stage_pack(b, pa, r); }
@@ -222,7 +222,13 @@ int main(int argc, char **argv)
 				"\"sw_calls\": %llu, \"sw_cells\": %llu, \"glb_calls\": %llu, \"glb_cells\": %llu}\n", c.occ_blocks, c.extend_calls, c.sa_calls, c.lf_steps,
 				c.ext_calls, c.ext_cells, c.sw_calls, c.sw_cells, c.glb_calls, c.glb_cells);
 	}
-	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu, fallback %llu; %llu pairs to the rescue kernel\n", n,
-			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], pl.n_cig_fallback, pl.n_rescue_pairs);
+	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu/%llu, fallback %llu; %llu pairs to the rescue kernel\n", n,
+			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], be.n_band[4], pl.n_cig_fallback, pl.n_rescue_pairs);
+#ifdef LC_STATS
+	fprintf(stderr, "rescue: %llu SW calls (mean list %.1f, max %llu): %llu skipped re-sorts, %llu one-pass inserts, %llu inserts with a hazard, %llu full calls on unfixed lists\n",
+			lc_stats.sw, lc_stats.sw ? (double)lc_stats.n_sum / lc_stats.sw : 0., lc_stats.nmax, lc_stats.skipped, lc_stats.onepass, lc_stats.hazard, lc_stats.full_nofix);
+	fprintf(stderr, "heavy extension: %llu reads, %llu chains (max %llu), %llu seeds, %llu regions, %llu containment tests\n", lc_stats.hv_reads, lc_stats.hv_chains,
+			lc_stats.hv_maxchains, lc_stats.hv_seeds, lc_stats.hv_regs, lc_stats.hv_scan);
+#endif
 	return 0;
 }
