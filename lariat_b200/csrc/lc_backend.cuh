@@ -51,7 +51,7 @@ struct LcCudaBackend {
 	void k_sa_fill(const LcIndex &ix, unsigned long long n_samples, void *out, bool wide);
 	void k_sa(const LcBatch &b, unsigned long long n);
 	void k_chain(const LcBatch &b);
-	void k_extend(const LcBatch &b);
+	int k_extend(const LcBatch &b);                 // returns the number of kernels launched
 	void k_pair(const LcBatch &b, int n_pairs);
 	const uint64_t *sort_worklist(const LcBatch &b, const unsigned int *n_dev, unsigned int &n);
 	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev);

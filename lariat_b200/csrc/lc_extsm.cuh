@@ -136,7 +136,9 @@ enum { LC_XP_FETCH = 0, LC_XP_AFTER_LEFT, LC_XP_AFTER_RIGHT, LC_XP_RIGHT_CHECK, 
 	   LC_XP_LEFT_SETUP, LC_XP_RIGHT_SETUP, LC_XP_READ_DONE,
 	   LC_XP_DP, LC_XP_ROWEND, LC_XP_DONE };   // states >= LC_XP_DP: a DP row is in progress or waits for its end-of-row work (or the lane is finished)
 
-template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
+// UNIT: the lane's work item is one unit of a read with very many chains (lc_ext_plan, lc_mem.cuh) instead of a whole read: the chains
+// are followed through LcChainAux::next, every chain records where its regions went, the read's region count is a sum over its units
+template <int STRIDE, class CELLS = LcCells16<STRIDE>, bool UNIT = false> struct LcExtLane {
 	const LcBatch &b;
 	uint32_t *he;            // H/E row of lmax + 2 columns, packed by CELLS
 	uint32_t *qw;            // the read: qw[w * STRIDE] holds bases 8w..8w+7, 4 bits each, first base in the low nibble; qw[-STRIDE] is
@@ -145,6 +147,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 	int phase;
 	// ---- read-level state (mem_chain2aln's locals)
 	int r, l_query, NC, ci, n_av, k, cn, tryi, prev;
+	long long cg; int n_av0;     // UNIT: the current chain (index into b.chain, < 0 = the unit is done), regions before it
 	unsigned long long ro;
 	lc_alnreg_t *av;
 	uint64_t *srt;
@@ -170,6 +173,7 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 		return (int)((pw >> ((((int)(fpos >> 2) & 3) << 3) + ((~(int)fpos & 3) << 1))) & 3) ^ comp;
 	}
 	LC_HD void begin_read(int r_) { r = r_; phase = LC_XP_READ_START; }
+	LC_HD void begin_unit(long long first_chain) { cg = first_chain; r = b.chain_aux[first_chain].r; phase = LC_XP_READ_START; }
 
 	// ---- ksw_extend2 prologue (B/ksw.c:385-412) and the first row's set-up
 	LC_HD void dp_setup(int qlen_, int q0_, int qdir_, int tlen_, int64_t t0_, int tdir_, int w_, int end_bonus, int h0_)
@@ -436,10 +440,18 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				l_query = (int)(b.off[r + 1] - b.off[r]);
 				NC = b.r_n_chain[r];
 				const int T = b.r_n_cseed[r];
-				b.r_n_reg[r] = 0; b.r_reg_off[r] = 0;
+				if (!UNIT) { b.r_n_reg[r] = 0; b.r_reg_off[r] = 0; }
 				n_av = 0; ci = 0; ro = 0;
 				phase = LC_XP_CHAIN_START;
-				if (NC == 0) phase = LC_XP_FETCH;
+				if (UNIT) {
+					const int TU = b.chain_aux[cg].unit_seeds;
+					n_av0 = 0;
+					ro = lc_carve(b, b.reg_cur, b.reg_cap, (unsigned long long)TU, LC_OVF_REG);
+					const unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * TU + 8, LC_OVF_SCRATCH);
+					if (ro == (unsigned long long)-1 || so == (unsigned long long)-1) phase = LC_XP_FETCH;
+					else { av = b.reg + ro; srt = (uint64_t *)lc_align8((size_t)(b.scratch + so)); }
+				}
+				else if (NC == 0) phase = LC_XP_FETCH;
 				else if ((b.ext_heavy_seeds > 0 && T > b.ext_heavy_seeds) || (b.ext_heavy_chains > 0 && NC > b.ext_heavy_chains)) {
 					// a read with very many chains (repeats) would keep this lane — and with it the kernel — busy long after the others are
 					// done: it goes to a list that a warp-per-read kernel works off (lc_stage_extend_t, cooperative rows)
@@ -453,9 +465,9 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				}
 			}
 			if (phase == LC_XP_CHAIN_START) {                     // B/bwamem.c:642-665
-				if (ci >= NC) phase = LC_XP_READ_DONE;
+				if (UNIT ? cg < 0 : ci >= NC) phase = LC_XP_READ_DONE;
 				else {
-					const LcChainOut &c = b.chain[b.r_chain_off[r] + ci];
+					const LcChainOut &c = b.chain[UNIT ? cg : (long long)b.r_chain_off[r] + ci];
 					seeds = b.cseed + c.seed_off; cn = c.n; c_rid = c.rid;
 					if (cn == 0) ++ci;                            // (stays in CHAIN_START: another sweep)
 					else {
@@ -479,7 +491,14 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				}
 			}
 			if (phase == LC_XP_SEED_NEXT) {                       // B/bwamem.c:667-713
-				if (k < 0) { ++ci; phase = LC_XP_CHAIN_START; }
+				if (k < 0) {
+					if (UNIT) {
+						LcChainAux &ax = b.chain_aux[cg];
+						ax.reg_off = (int64_t)(ro + (unsigned long long)n_av0); ax.n_reg = n_av - n_av0;
+						n_av0 = n_av; cg = ax.next;
+					} else ++ci;
+					phase = LC_XP_CHAIN_START;
+				}
 				else {
 					const LcSeed s = seeds[(uint32_t)srt[k]];
 					int t;
@@ -523,7 +542,8 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE> > struct LcExtLane {
 				dp_setup(l_query - qe0, qe0, 1, (int)(r1 - re0), re0, 1, aw1, opt.pen_clip3, sc0);
 			}
 			if (phase == LC_XP_READ_DONE) {
-				b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av;
+				if (!UNIT) { b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av; }
+				else if (n_av) lc_atomic_add(b.r_n_reg + r, (int32_t)n_av);
 				if (n_av) lc_atomic_add(b.reg_total, (unsigned long long)n_av);
 				phase = LC_XP_FETCH;
 			}
@@ -552,18 +572,20 @@ template <int STRIDE> LC_HD void lc_ext_load_read(const LcBatch &b, int r, uint3
 }
 
 // scalar driver (tests/hostsim): all reads, one after another, through the same state machine; cells8 selects the byte packing
-template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, uint32_t *he, uint32_t *qw, int idle_ticks = 0)
+template <class CELLS, bool UNIT> static inline void lc_ext_run_scalar_t(const LcBatch &b, uint32_t *he, uint32_t *qw, int idle_ticks = 0)
 {
 	uint32_t mtab[36];
 	lc_ext_fill_masks(mtab);
-	LcExtLane<1, CELLS> ex(b, he, qw + 1, mtab);
+	LcExtLane<1, CELLS, UNIT> ex(b, he, qw + 1, mtab);
 	int next = 0;
+	const int n_items = UNIT ? (int)b.ext_unit_n[0] : b.n_reads;
 	for (;;) {
 		while (ex.phase == LC_XP_FETCH) {
-			if (next >= b.n_reads) { ex.phase = LC_XP_DONE; break; }
-			const int r = next++;
+			if (next >= n_items) { ex.phase = LC_XP_DONE; break; }
+			const int it = next++;
+			const int r = UNIT ? b.chain_aux[b.ext_units[it]].r : it;
 			lc_ext_load_read<1>(b, r, qw + 1, lc_ext_q_words(b.lmax) - 1);
-			ex.begin_read(r);
+			if (UNIT) ex.begin_unit((long long)b.ext_units[it]); else ex.begin_read(r);
 			ex.resolve();
 		}
 		if (ex.phase == LC_XP_DONE) break;
@@ -577,7 +599,8 @@ template <class CELLS> static inline void lc_ext_run_scalar_t(const LcBatch &b, 
 	}
 }
 LC_HD bool lc_ext_cells8_ok(const LcBatch &b) { return b.lmax * b.opt.a <= 255 && b.opt.a > 0; }
-static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *qw, bool cells8, int idle_ticks = 0)
+static inline void lc_ext_run_scalar(const LcBatch &b, uint32_t *he, uint32_t *qw, bool cells8, int idle_ticks = 0, bool units = false)
 {
-	if (cells8) lc_ext_run_scalar_t<LcCells8<1> >(b, he, qw, idle_ticks); else lc_ext_run_scalar_t<LcCells16<1> >(b, he, qw, idle_ticks);
+	if (units) { if (cells8) lc_ext_run_scalar_t<LcCells8<1>, true>(b, he, qw, idle_ticks); else lc_ext_run_scalar_t<LcCells16<1>, true>(b, he, qw, idle_ticks); }
+	else if (cells8) lc_ext_run_scalar_t<LcCells8<1>, false>(b, he, qw, idle_ticks); else lc_ext_run_scalar_t<LcCells16<1>, false>(b, he, qw, idle_ticks);
 }

@@ -213,7 +213,8 @@ template <class CELLS> __host__ __device__ inline int lc_ext_warp_words(int lmax
 #define LC_EXT_MTAB_WORDS 64      // lc_ext_fill_masks table (36 words) in front of the per-warp areas
 // Gates (as in smem_kernel): the read fetch and resolve() run on ticks that are multiples of hk_mask + 1, the end-of-row work on
 // multiples of row_mask + 1; lanes that need either idle until then, so that the divergent code runs with several live lanes.
-template <class CELLS>
+// UNIT: the work items are the units lc_ext_plan made of the reads with very many chains (b.ext_units) instead of reads.
+template <class CELLS, bool UNIT>
 __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, const unsigned hk_mask, const unsigned row_mask)
 {
 	extern __shared__ uint32_t lc_ext_smem[];
@@ -222,23 +223,30 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 	uint32_t *qf = wbase + (CELLS::words(lc_ext_he_cols(b.lmax)) + 1) * 32;         // word 0 of the read copies; word -1 is the spare
 	if (threadIdx.x == 0) lc_ext_fill_masks(lc_ext_smem);
 	__syncthreads();
-	LcExtLane<32, CELLS> ex(b, wbase + lane, qf + lane, lc_ext_smem);
+	LcExtLane<32, CELLS, UNIT> ex(b, wbase + lane, qf + lane, lc_ext_smem);
+	const int n_items = UNIT ? (int)b.ext_unit_n[0] : b.n_reads;
+	unsigned int *ctr = UNIT ? b.ext_unit_n + 1 : b.work_ctr + 0;
 	for (unsigned it = 0;; ++it) {
 		if ((it & hk_mask) == 0) {                               // warp-uniform
 			const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
 			if (need) {
 				int base = 0;
-				if (lane == 0) base = (int)atomicAdd(b.work_ctr + 0, (unsigned)__popc(need));
+				if (lane == 0) base = (int)atomicAdd(ctr, (unsigned)__popc(need));
 				base = __shfl_sync(LC_FULL, base, 0);
-				int myr = -1;
-				if (need >> lane & 1) { myr = base + __popc(need & ((1u << lane) - 1)); if (myr >= b.n_reads) myr = -1; }
+				int myi = -1, myr = -1;
+				if (need >> lane & 1) { myi = base + __popc(need & ((1u << lane) - 1)); if (myi >= n_items) myi = -1; }
+				if (myi >= 0) myr = UNIT ? b.chain_aux[b.ext_units[myi]].r : myi;
 				for (unsigned m = need; m; m &= m - 1) {
 					const int L = __ffs(m) - 1;
 					const int rr = __shfl_sync(LC_FULL, myr, L);
 					if (rr >= 0 && b.r_n_chain[rr] > 0) lc_warp_pack_read(b, rr, lane, qf + L, 32);
 				}
 				__syncwarp();
-				if (need >> lane & 1) { if (myr < 0) ex.phase = LC_XP_DONE; else ex.begin_read(myr); }
+				if (need >> lane & 1) {
+					if (myi < 0) ex.phase = LC_XP_DONE;
+					else if (UNIT) ex.begin_unit((long long)b.ext_units[myi]);
+					else ex.begin_read(myr);
+				}
 			}
 			if (!__ballot_sync(LC_FULL, ex.phase != LC_XP_DONE)) break;
 			if (__any_sync(LC_FULL, ex.phase < LC_XP_DP && ex.phase != LC_XP_FETCH)) ex.resolve();
@@ -247,7 +255,13 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 	}
 }
 
-// Stage 4b: the reads extend_kernel set aside (very many chains): one warp per read, cooperative ksw_extend2 rows (lc_sw_warp.cuh)
+// Stage 4b: the reads extend_kernel set aside (very many chains) are cut into units (lc_ext_plan, one thread per listed read) ...
+__global__ void __launch_bounds__(LC_TPB) ext_plan_kernel(const LcBatch b, const unsigned int n)
+{
+	for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) lc_ext_plan(b, (int)(uint32_t)b.wl_in[t]);
+}
+// ... most of which go through extend_kernel<CELLS, true>; a unit that is itself very large (many overlapping chains: tandem arrays) gets
+// a warp: cooperative ksw_extend2 rows (lc_sw_warp.cuh)
 __global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
 {
 	extern __shared__ int lc_smem[];
@@ -257,10 +271,10 @@ __global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b, c
 	ex.Hmax = nullptr; ex.bl = nullptr; ex.cig = nullptr; ex.zloc = nullptr;
 	for (;;) {
 		unsigned int t = 0;
-		if (lane == 0) t = atomicAdd(b.ext_heavy_n + 1, 1u);
+		if (lane == 0) t = atomicAdd(b.ext_hvu_n + 1, 1u);
 		t = __shfl_sync(LC_FULL, t, 0);
 		if (t >= n) break;
-		lc_stage_extend_t(b, (int)(uint32_t)list[t], ex);
+		lc_stage_extend_t(b, -1, (long long)(uint32_t)list[t], ex);
 		__syncwarp();
 	}
 }
@@ -470,7 +484,7 @@ static void lc_set_kernel_attrs(int device)
 	const int mx = (int)prop.sharedMemPerBlockOptin;
 	auto set = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); };
 	set(smem_kernel<uint32_t, true>); set(smem_kernel<uint32_t, false>); set(smem_kernel<uint64_t, true>); set(smem_kernel<uint64_t, false>);
-	set(extend_kernel<LcCells8<32> >); set(extend_kernel<LcCells16<32> >);
+	set(extend_kernel<LcCells8<32>, false>); set(extend_kernel<LcCells16<32>, false>); set(extend_kernel<LcCells8<32>, true>); set(extend_kernel<LcCells16<32>, true>);
 	set(extend_heavy_kernel); set(matesw_kernel); set(global_cigar_kernel); set(ksw_extend_kernel); set(ksw_align_kernel);
 	cudaGetLastError();
 }
@@ -527,27 +541,51 @@ void LcCudaBackend::k_chain(const LcBatch &b)
 	// the list length is only known on the device: a resident-size grid whose warps pull listed reads from a counter (no host round trip)
 	if (b.chain_heavy > 0) chain_heavy_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 4), LC_TPB, 0, stream>>>(b);
 }
-template <class CELLS> static void lc_launch_extend(const LcBatch &b, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
+template <class CELLS, bool UNIT> static void lc_launch_extend(const LcBatch &b, long long n_items, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
 {
 	const int smem = ((LC_EXT_TPB / 32) * lc_ext_warp_words<CELLS>(b.lmax) + LC_EXT_MTAB_WORDS) * 4;
 	int per_sm = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<CELLS>, LC_EXT_TPB, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extend_kernel<CELLS, UNIT>, LC_EXT_TPB, smem);
 	if (per_sm < 1) per_sm = 1;
-	const long long need = ((long long)b.n_reads + LC_EXT_TPB - 1) / LC_EXT_TPB, cap = (long long)n_sm * per_sm;
-	extend_kernel<CELLS><<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b, hk_mask, row_mask);
+	const long long need = (n_items + LC_EXT_TPB - 1) / LC_EXT_TPB, cap = (long long)n_sm * per_sm;
+	extend_kernel<CELLS, UNIT><<<(int)(need < cap ? (need ? need : 1) : cap), LC_EXT_TPB, smem, stream>>>(b, hk_mask, row_mask);
 }
-void LcCudaBackend::k_extend(const LcBatch &b)
+int LcCudaBackend::k_extend(const LcBatch &b)
 {
 	// byte-packed H/E cells whenever no score of the batch can exceed 255 (half the shared memory per warp, twice the resident warps)
-	if (lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS")) lc_launch_extend<LcCells8<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
-	else lc_launch_extend<LcCells16<32> >(b, n_sm, stream, (unsigned)ext_gate_mask, (unsigned)ext_row_mask);
-	// the heavy reads, heaviest first; the warps pull them from a counter
+	const bool cells8 = lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS");
+	const unsigned hk = (unsigned)ext_gate_mask, rw = (unsigned)ext_row_mask;
+	if (cells8) lc_launch_extend<LcCells8<32>, false>(b, b.n_reads, n_sm, stream, hk, rw);
+	else lc_launch_extend<LcCells16<32>, false>(b, b.n_reads, n_sm, stream, hk, rw);
+	int launches = 1;
+	// the reads with very many chains: cut into units, the units through the same lane kernel, the few large units through a warp each
 	unsigned int n = 0;
-	const uint64_t *list = sort_worklist(b, b.ext_heavy_n, n);
-	if (n) {
-			const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
-		extend_heavy_kernel<<<grid_for((unsigned long long)n * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, n);
+	cudaMemcpyAsync(&n, b.ext_heavy_n, 4, cudaMemcpyDeviceToHost, stream);
+	cudaStreamSynchronize(stream);
+	if (!n) return launches;
+	ext_plan_kernel<<<grid_for(n, LC_TPB, 8), LC_TPB, 0, stream>>>(b, n); ++launches;
+	unsigned int cnt[4] = { 0, 0, 0, 0 };      // ext_unit_n[0..1], ext_hvu_n[0..1] are adjacent control words
+	cudaMemcpyAsync(cnt, b.ext_unit_n, 16, cudaMemcpyDeviceToHost, stream);
+	cudaStreamSynchronize(stream);
+	if (cnt[0]) {
+		if (cells8) lc_launch_extend<LcCells8<32>, true>(b, cnt[0], n_sm, stream, hk, rw);
+		else lc_launch_extend<LcCells16<32>, true>(b, cnt[0], n_sm, stream, hk, rw);
+		++launches;
 	}
+	unsigned int nh = cnt[2] < b.ext_hvu_cap ? cnt[2] : (unsigned int)b.ext_hvu_cap;
+	if (nh) {
+		const uint64_t *list = b.ext_hvu_in;      // heaviest first; the warps pull them from a counter
+		if (nh > 1) {
+			size_t need = 0;
+			cub::DeviceRadixSort::SortKeysDescending(nullptr, need, b.ext_hvu_in, b.ext_hvu_out, (int)nh, 32, 48, stream);
+			if (need > scan_tmp_bytes) { if (scan_tmp) cudaFree(scan_tmp); cudaMalloc(&scan_tmp, need + 256); scan_tmp_bytes = need + 256; }
+			cub::DeviceRadixSort::SortKeysDescending(scan_tmp, need, b.ext_hvu_in, b.ext_hvu_out, (int)nh, 32, 48, stream);
+			list = b.ext_hvu_out;
+		}
+		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+		extend_heavy_kernel<<<grid_for((unsigned long long)nh * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, list, nh); ++launches;
+	}
+	return launches;
 }
 // Length of a device work list (one small D2H + stream sync), and the list sorted by weight, heaviest first (LPT order): the
 // kernels that give a whole warp to an item finish when their slowest item does, so the slow ones must not start last.

@@ -15,6 +15,10 @@ struct LcIntvOut { uint64_t x0, x2; uint32_t qbeg, qend; uint32_t soff, step; };
 struct LcPk { uint32_t a, b, c, m; };     // 16 B packed bi-interval of the seeding state machine (lc_seed.cuh): x0, x1, x2 < 2^34 + two read positions
 struct LcSeed { int64_t rbeg; int32_t qbeg, len; };                                 // mem_seed_t (B/bwamem.c:168-172); score == len here
 struct LcChainOut { int32_t rid, n; int64_t seed_off; uint32_t w; int32_t is_alt; }; // a kept chain; seeds in cseed[seed_off..+n)
+// Stage 4 on reads with very many chains (repeats): the chains of a read are split into UNITS — clusters of chains whose reference
+// windows overlap (lc_ext_plan) — and every unit is extended on its own.  Per chain: the next chain of its unit, its read, and
+// where the regions it produced went.
+struct LcChainAux { int32_t next, r, n_reg, unit_seeds; int64_t reg_off; };
 struct LcChainRec { int64_t pos; int32_t rid, n, head, tail; uint32_t w; int32_t kept, first, is_alt; };
 #define LC_BT_T 5
 #define LC_BT_MAXK (2 * LC_BT_T - 1)
@@ -101,8 +105,13 @@ struct LcBatch {
 	int32_t *mm_ref, *mm_read; unsigned long long mm_cap, *mm_cur;   // mismatch position lists, carved per candidate
 	int32_t chain_heavy; int32_t *chain_list; unsigned int *chain_heavy_n;   // stage 3: reads with more than chain_heavy seeds are listed for the
 	                                                     //   warp-per-read kernel ([0] = list length, [1] = its work counter); 0 = never
-	unsigned int *ext_heavy_n;                           // stage 4: reads listed (in `redo`) for the warp-per-read extension kernel, then its work counter
-	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read is "heavy" above this many chained seeds / chains (0 = never)
+	unsigned int *ext_heavy_n;                           // stage 4: [0] = reads with very many chains, listed in wl_in for lc_ext_plan
+	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read — and then a unit — is "heavy" above this many chained seeds / chains (0 = never)
+	LcChainAux *chain_aux;                               // parallel to `chain`; filled for the chains of listed reads only
+	uint32_t *ext_units; unsigned int *ext_unit_n;       // units for the lane kernel (first chain of each, index into `chain`): [0] = count, [1] = work counter
+	uint64_t *ext_hvu_in, *ext_hvu_out;                  // heavy units for the warp-per-unit kernel: weight << 32 | first chain; sorted like wl_in -> wl_out
+	unsigned int *ext_hvu_n;                             // [0] = count, [1] = work counter
+	unsigned long long ext_hvu_cap;
 };
 
 LC_HD void lc_raise(const LcBatch &b, uint32_t flag)
@@ -630,15 +639,23 @@ struct LcExecThread {
 	}
 };
 
+// `unit` < 0: all chains of read r, in order (the regions land in one slice of `reg`: r_reg_off / r_n_reg).
+// `unit` >= 0: the chains of one unit (index of its first chain in `chain`; the read and the links come from chain_aux): the regions
+// of the unit land in a slice of their own, every chain records where its regions are, and r_n_reg[r] is the sum over the read's units
+// (r_reg_off[r] = -1 tells lc_pair_prepare to collect them chain by chain).
 template <class Exec>
-LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
+LC_HD void lc_stage_extend_t(const LcBatch &b, int r, long long unit, const Exec &ex)
 {
 	const lc_opt_t &opt = b.opt;
+	const bool whole = unit < 0;
+	if (!whole) r = b.chain_aux[unit].r;
 	const int l_query = (int)(b.off[r + 1] - b.off[r]);
 	const uint8_t *query = b.seq + b.off[r];
-	const int NC = b.r_n_chain[r], T = b.r_n_cseed[r];
-	if (ex.leader()) { b.r_n_reg[r] = 0; b.r_reg_off[r] = 0; }
-	if (NC == 0) return;
+	const int NC = b.r_n_chain[r], T = whole ? b.r_n_cseed[r] : b.chain_aux[unit].unit_seeds;
+	if (whole) {
+		if (ex.leader()) { b.r_n_reg[r] = 0; b.r_reg_off[r] = 0; }
+		if (NC == 0) return;
+	}
 	unsigned long long ro = 0, so = 0;
 	if (ex.leader()) {
 		ro = lc_carve(b, b.reg_cur, b.reg_cap, T, LC_OVF_REG);
@@ -649,10 +666,18 @@ LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
 	lc_alnreg_t *av = b.reg + ro;
 	uint64_t *srt = (uint64_t *)lc_align8((size_t)(b.scratch + so));
 	const int64_t l_pac = b.ix.l_pac;
-	int n_av = 0;
+	int n_av = 0, n_av0 = 0;
 	LC_STAT((++lc_stats.hv_reads, lc_stats.hv_chains += NC, lc_stats.hv_seeds += T, lc_stats.hv_maxchains = lc_stats.hv_maxchains > (unsigned long long)NC ? lc_stats.hv_maxchains : NC));
-	for (int ci = 0; ci < NC; ++ci) {
-		const LcChainOut &c = b.chain[b.r_chain_off[r] + ci];
+	long long cg = whole ? (long long)b.r_chain_off[r] : unit;
+	for (int ci = 0;; ++ci) {
+		if (ci > 0 && !whole) {                             // the chain just done: where its regions are; on to the next chain of the unit
+			if (ex.leader()) { b.chain_aux[cg].reg_off = (int64_t)(ro + n_av0); b.chain_aux[cg].n_reg = n_av - n_av0; }
+			cg = b.chain_aux[cg].next;
+		}
+		if (whole) { if (ci >= NC) break; cg = (long long)b.r_chain_off[r] + ci; }
+		else if (cg < 0) break;
+		n_av0 = n_av;
+		const LcChainOut &c = b.chain[cg];
 		const LcSeed *seeds = b.cseed + c.seed_off;
 		if (c.n == 0) continue;
 		int64_t r0 = l_pac << 1, r1 = 0;
@@ -746,16 +771,83 @@ LC_HD void lc_stage_extend_t(const LcBatch &b, int r, const Exec &ex)
 		}
 	}
 	if (ex.leader()) {
-		b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av;
+		if (whole) { b.r_reg_off[r] = (int64_t)ro; b.r_n_reg[r] = n_av; }
+		else if (n_av) lc_atomic_add(b.r_n_reg + r, (int32_t)n_av);
 		if (n_av) lc_atomic_add(b.reg_total, (unsigned long long)n_av);
 	}
 }
 
-LC_HDN void lc_stage_extend(const LcBatch &b, int r, int worker)
+LC_HDN void lc_stage_extend(const LcBatch &b, int r, long long unit, int worker)
 {
 	LcExecThread ex;
 	ex.H = b.w_int + (size_t)worker * b.w_int_n; ex.E = ex.H + (b.lmax + 2);
-	lc_stage_extend_t(b, r, ex);
+	lc_stage_extend_t(b, r, unit, ex);
+}
+
+// ---- units of a read with very many chains (one thread per listed read)
+// mem_chain2aln lets a chain see the regions of the chains before it only through the containment test (B/bwamem.c:671-687): a seed is
+// skipped when it lies inside an earlier region.  A region never leaves the reference window of its chain (the extensions run on the
+// window's sequence, B/bwamem.c:642-659), and neither does a seed, so two chains whose windows share no base cannot influence each
+// other: the connected groups of overlapping windows — the UNITS — can be extended independently, each one running its chains in the
+// read's chain order against the regions of that unit alone.  In repeats a read has hundreds of chains at hundreds of loci, i.e.
+// hundreds of one-chain units: work for many lanes instead of one warp.  The regions come back chain by chain (LcChainAux), so the
+// read's list is rebuilt in the reference's order whatever order the units finished in.
+// Windows are taken before the strand / contig clamps (a superset: merging two units is always safe).
+LC_HD unsigned long long lc_ext_plan_scratch_bytes(int NC) { return 40ull * NC + 16; }
+LC_HD void lc_ext_plan(const LcBatch &b, int r)
+{
+	const lc_opt_t &opt = b.opt;
+	const int l_query = (int)(b.off[r + 1] - b.off[r]), NC = b.r_n_chain[r];
+	const long long c0 = (long long)b.r_chain_off[r];
+	b.r_reg_off[r] = -1; b.r_n_reg[r] = 0;
+	const unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, lc_ext_plan_scratch_bytes(NC), LC_OVF_SCRATCH);
+	if (so == (unsigned long long)-1) return;
+	uint64_t *key = (uint64_t *)lc_align8((size_t)(b.scratch + so));      // window start << 24 | chain
+	int64_t *wend = (int64_t *)(key + NC);                                // window end
+	int32_t *unit_of = (int32_t *)(wend + NC), *first = unit_of + NC, *last = first + NC, *tot = last + NC, *cnt = tot + NC;
+	int n_used = 0;
+	for (int ci = 0; ci < NC; ++ci) {
+		const LcChainOut &c = b.chain[c0 + ci];
+		LcChainAux &ax = b.chain_aux[c0 + ci];
+		ax.next = -1; ax.r = r; ax.n_reg = 0; ax.unit_seeds = 0; ax.reg_off = 0;
+		if (c.n == 0) continue;
+		const LcSeed *seeds = b.cseed + c.seed_off;
+		int64_t x0 = b.ix.l_pac << 1, x1 = 0;
+		for (int t = 0; t < c.n; ++t) {
+			const LcSeed &sd = seeds[t];
+			const int tail = l_query - sd.qbeg - sd.len;
+			x0 = lc_min(x0, sd.rbeg - (sd.qbeg + lc_cal_max_gap(opt, sd.qbeg)));
+			x1 = lc_max(x1, sd.rbeg + sd.len + (tail + lc_cal_max_gap(opt, tail)));
+		}
+		key[n_used] = (uint64_t)(x0 + (1ll << 20)) << 24 | (uint32_t)ci;      // windows start above -2^20 (read length + gap allowance)
+		wend[ci] = x1;
+		++n_used;
+	}
+	lc_introsort(key, (long)n_used, [](uint64_t x, uint64_t y) { return x < y; });
+	int n_units = 0;
+	int64_t cur_end = -(1ll << 40);
+	for (int t = 0; t < n_used; ++t) {
+		const int ci = (int)(key[t] & 0xffffffu);
+		const int64_t x0 = (int64_t)(key[t] >> 24) - (1ll << 20);
+		if (x0 >= cur_end) { first[n_units] = last[n_units] = -1; tot[n_units] = 0; cnt[n_units] = 0; ++n_units; cur_end = wend[ci]; }
+		else cur_end = lc_max(cur_end, wend[ci]);
+		unit_of[ci] = n_units - 1;
+	}
+	for (int ci = 0; ci < NC; ++ci) {                                    // chains of a unit linked in the read's chain order
+		if (b.chain[c0 + ci].n == 0) continue;
+		const int u = unit_of[ci];
+		if (last[u] < 0) first[u] = ci; else b.chain_aux[c0 + last[u]].next = (int32_t)(c0 + ci);
+		last[u] = ci; tot[u] += b.chain[c0 + ci].n; ++cnt[u];
+	}
+	for (int u = 0; u < n_units; ++u) {
+		const long long fc = c0 + first[u];
+		b.chain_aux[fc].unit_seeds = tot[u];
+		if ((b.ext_heavy_seeds > 0 && tot[u] > b.ext_heavy_seeds) || (b.ext_heavy_chains > 0 && cnt[u] > b.ext_heavy_chains)) {
+			const unsigned int at = lc_atomic_add(b.ext_hvu_n, 1u);
+			if (at < b.ext_hvu_cap) b.ext_hvu_in[at] = (uint64_t)(uint32_t)lc_min(tot[u], 0xffff) << 32 | (uint32_t)fc;
+			else lc_raise(b, LC_OVF_CHAIN);
+		} else b.ext_units[lc_atomic_add(b.ext_unit_n, 1u)] = (uint32_t)fc;
+	}
 }
 
 // ============================================================================================================
@@ -1061,28 +1153,35 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 {
 	int n[2], len[2], best[2] = { 0, 0 };
 	bool clean[2];
-	lc_alnreg_t *src[2];
-	for (int e = 0; e < 2; ++e) {
-		const int r = 2 * p + e;
-		len[e] = (int)(b.off[r + 1] - b.off[r]);
-		src[e] = b.reg + b.r_reg_off[r];
-		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], b.r_n_reg[r], src[e], H, E, H, 2 * (b.lmax + 18), &clean[e]);      // tail of mem_align1_core (B/bwamem.c:1070)
-		for (int i = 0; i < n[e]; ++i) {
-			if (src[e][i].rid >= 0 && b.ix.anns[src[e][i].rid].is_alt) src[e][i].is_alt = 1;   // B/bwamem.c:1078-1082
-			best[e] = lc_max(best[e], src[e][i].score);                                         // G/gobwa.go:264-283
-		}
-	}
-	// capacity of the final lists: every rescue call adds at most one region
-	int a2 = 0;
-	if (len[0] > 0) for (int i = 0; i < n[1] && a2 < b.max_anchors; ++i) if (src[1][i].score >= best[1] - b.score_delta) ++a2;
-	const int cap0 = n[0] + a2;
+	for (int e = 0; e < 2; ++e) { const int r = 2 * p + e; len[e] = (int)(b.off[r + 1] - b.off[r]); n[e] = b.r_n_reg[r]; }
+	// capacity of the final lists: what stage 4 produced (the dedup can only shrink it) plus one region per rescue call
+	const int cap0 = n[0] + (len[0] > 0 ? lc_min(b.max_anchors, n[1]) : 0);
 	const int cap1 = n[1] + (len[1] > 0 ? lc_min(b.max_anchors, cap0) : 0);
 	b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
 	const unsigned long long fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
 	if (fo == (unsigned long long)-1) return;
 	lc_alnreg_t *f0 = b.fin + fo, *f1 = b.fin + fo + cap0;
-	for (int i = 0; i < n[0]; ++i) f0[i] = src[0][i];
-	for (int i = 0; i < n[1]; ++i) f1[i] = src[1][i];
+	for (int e = 0; e < 2; ++e) {
+		const int r = 2 * p + e;
+		lc_alnreg_t *dst = e ? f1 : f0;
+		if (b.r_reg_off[r] >= 0) {                            // one slice of `reg`, in the reference's order
+			const lc_alnreg_t *src = b.reg + b.r_reg_off[r];
+			for (int i = 0; i < n[e]; ++i) dst[i] = src[i];
+		} else {                                             // extended unit by unit (lc_ext_plan): chain by chain, which IS that order
+			const long long c0 = (long long)b.r_chain_off[r];
+			int m = 0;
+			for (int ci = 0; ci < b.r_n_chain[r]; ++ci) {
+				const LcChainAux &ax = b.chain_aux[c0 + ci];
+				const lc_alnreg_t *src = b.reg + ax.reg_off;
+				for (int i = 0; i < ax.n_reg; ++i) dst[m++] = src[i];
+			}
+		}
+		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], n[e], dst, H, E, H, 2 * (b.lmax + 18), &clean[e]);      // tail of mem_align1_core (B/bwamem.c:1070)
+		for (int i = 0; i < n[e]; ++i) {
+			if (dst[i].rid >= 0 && b.ix.anns[dst[i].rid].is_alt) dst[i].is_alt = 1;   // B/bwamem.c:1078-1082
+			best[e] = lc_max(best[e], dst[i].score);                                 // G/gobwa.go:264-283
+		}
+	}
 	b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n[0];
 	b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n[1];
 	bool need = false;

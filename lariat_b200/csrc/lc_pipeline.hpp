@@ -303,6 +303,7 @@ public:
 			b.resc_n = (unsigned int *)(c + 27);
 			b.ext_heavy_n = (unsigned int *)(c + 28);
 			b.chain_heavy_n = (unsigned int *)(c + 29);
+			b.ext_unit_n = (unsigned int *)(c + 30); b.ext_hvu_n = (unsigned int *)(c + 31);      // adjacent: the backend reads both with one copy
 			b.chain_heavy = chain_heavy;
 			b.ext_heavy_seeds = ext_heavy_seeds; b.ext_heavy_chains = ext_heavy_chains;
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
@@ -432,16 +433,27 @@ public:
 		if (rc0) return rc0;
 		const unsigned long long S = h_ctl[1];
 		// ---- stage 2-4 pools, sized exactly from the seed count
-		b.scratch_cap = 112ull * S + 320ull * R + 4096;    // chain scratch (<= 101 B/seed + 280 B/read) + extension sort keys (8 B/seed + 16 B/read)
+		// chain scratch (<= 101 B/seed + 280 B/read) + extension sort keys (8 B/seed + 16 B/read) + unit planning (40 B/chain + 16 B/read)
+		b.scratch_cap = 152ull * S + 336ull * R + 4096;
 		b.chain_cap = S + 16; b.cseed_cap = S + 16; b.reg_cap = S + 16;
+		{
+			// a heavy unit has more than ext_heavy_seeds seeds or more than ext_heavy_chains chains (each at least one seed)
+			unsigned long long m = 0;
+			if (ext_heavy_seeds > 0) m = (unsigned long long)ext_heavy_seeds + 1;
+			if (ext_heavy_chains > 0 && (m == 0 || (unsigned long long)ext_heavy_chains + 1 < m)) m = (unsigned long long)ext_heavy_chains + 1;
+			b.ext_hvu_cap = m ? S / m + 16 : 16;
+		}
 		if (!d_scratch.ensure(be, b.scratch_cap) || !d_chain.ensure(be, sizeof(LcChainOut) * b.chain_cap) ||
-			!d_cseed.ensure(be, sizeof(LcSeed) * b.cseed_cap) || !d_reg.ensure(be, sizeof(lc_alnreg_t) * b.reg_cap)) return nomem();
+			!d_cseed.ensure(be, sizeof(LcSeed) * b.cseed_cap) || !d_reg.ensure(be, sizeof(lc_alnreg_t) * b.reg_cap) ||
+			!d_chainaux.ensure(be, sizeof(LcChainAux) * b.chain_cap) || !d_units.ensure(be, 4 * b.chain_cap) || !d_hvu.ensure(be, 16 * b.ext_hvu_cap)) return nomem();
 		b.scratch = (uint8_t *)d_scratch.p; b.chain = (LcChainOut *)d_chain.p; b.cseed = (LcSeed *)d_cseed.p; b.reg = (lc_alnreg_t *)d_reg.p;
+		b.chain_aux = (LcChainAux *)d_chainaux.p; b.ext_units = (uint32_t *)d_units.p;
+		b.ext_hvu_in = (uint64_t *)d_hvu.p; b.ext_hvu_out = b.ext_hvu_in + b.ext_hvu_cap;
 		if (S && !(b.ix.sa32 || b.ix.sa64)) { be.k_sa(b, S); ++launches; }     // with the dense suffix array the seeding kernels wrote positions already
 		be.ev_record(4);
 		be.k_chain(b); launches += chain_heavy > 0 ? 2 : 1;      // one thread per read, then a warp per read with very many seeds
 		be.ev_record(5);
-		be.k_extend(b); launches += 2;          // lanes (one read each), then a warp per read for the heavy ones
+		launches += be.k_extend(b);             // lanes (one read each); reads with very many chains: plan, lanes (one unit each), a warp per large unit
 		be.ev_record(6);
 		read_ctl();
 		if (launch_broken) { err = "a CUDA kernel launch failed in the chain/extend stages"; return LC_ECUDA; }
@@ -568,7 +580,7 @@ public:
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
 							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_redo3, &d_wl,
-							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw };
+							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw, &d_chainaux, &d_units, &d_hvu };
 		for (auto *x : all) x->release(be);
 	}
 
@@ -580,7 +592,7 @@ public:
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
 		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_redo3, d_wl,
-		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw;
+		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw, d_chainaux, d_units, d_hvu;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

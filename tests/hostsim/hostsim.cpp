@@ -58,13 +58,20 @@ struct HostBackend {
 	}
 	// the extension state machine with stride-1 rows (lc_extsm.cuh); -X runs the older one-call-per-read body instead
 	bool old_extend = false;
-	void k_extend(const LcBatch &b)
+	int k_extend(const LcBatch &b)
 	{
-		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, r % workers); return; }
+		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, -1, r % workers); return 1; }
 		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax));
-		lc_ext_run_scalar(b, he.data(), qw.data(), lc_ext_cells8_ok(b) && !wide_cells, idle_ticks);
-		for (unsigned int t = 0; t < *b.ext_heavy_n; ++t) lc_stage_extend(b, (int)(uint32_t)b.wl_in[t], (int)(t % workers));     // the heavy reads' kernel
+		const bool c8 = lc_ext_cells8_ok(b) && !wide_cells;
+		lc_ext_run_scalar(b, he.data(), qw.data(), c8, idle_ticks);
+		if (!*b.ext_heavy_n) return 1;
+		for (unsigned int t = *b.ext_heavy_n; t-- > 0;) lc_ext_plan(b, (int)(uint32_t)b.wl_in[t]);      // reversed: order must not matter
+		n_units += b.ext_unit_n[0]; n_heavy_units += b.ext_hvu_n[0];
+		lc_ext_run_scalar(b, he.data(), qw.data(), c8, idle_ticks, true);                                // the units' lane kernel
+		for (unsigned int t = b.ext_hvu_n[0]; t-- > 0;) lc_stage_extend(b, -1, (long long)(uint32_t)b.ext_hvu_in[t], (int)(t % workers));   // the large units' kernel
+		return 4;
 	}
+	unsigned long long n_units = 0, n_heavy_units = 0;
 	bool wide_cells = false;     // -H: 16-bit H/E cells even when the batch would fit the byte packing
 	void k_pair(const LcBatch &b, int n_pairs)
 	{
@@ -222,8 +229,8 @@ int main(int argc, char **argv)
 				"\"sw_calls\": %llu, \"sw_cells\": %llu, \"glb_calls\": %llu, \"glb_cells\": %llu}\n", c.occ_blocks, c.extend_calls, c.sa_calls, c.lf_steps,
 				c.ext_calls, c.ext_cells, c.sw_calls, c.sw_cells, c.glb_calls, c.glb_cells);
 	}
-	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu/%llu, fallback %llu; %llu pairs to the rescue kernel\n", n,
-			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], be.n_band[4], pl.n_cig_fallback, pl.n_rescue_pairs);
+	fprintf(stderr, "hostsim: %d pairs, %llu candidates, %lld launches, %d reads redone; cigar jobs by band class %llu/%llu/%llu/%llu/%llu, fallback %llu; %llu pairs to the rescue kernel; %llu + %llu extension units\n", n,
+			(unsigned long long)res.regs.size(), (long long)res.launches, pl.n_redo, be.n_band[0], be.n_band[1], be.n_band[2], be.n_band[3], be.n_band[4], pl.n_cig_fallback, pl.n_rescue_pairs, be.n_units, be.n_heavy_units);
 #ifdef LC_STATS
 	fprintf(stderr, "rescue: %llu SW calls (mean list %.1f, max %llu): %llu skipped re-sorts, %llu one-pass inserts, %llu inserts with a hazard, %llu full calls on unfixed lists\n",
 			lc_stats.sw, lc_stats.sw ? (double)lc_stats.n_sum / lc_stats.sw : 0., lc_stats.nmax, lc_stats.skipped, lc_stats.onepass, lc_stats.hazard, lc_stats.full_nofix);
