@@ -203,6 +203,7 @@ template <class BE> struct LcBuf {
 	void release(BE &be) { if (p) be.dfree(p); p = nullptr; cap = 0; }
 };
 
+static inline bool lc_verbose() { static const bool v = getenv("LC_VERBOSE") != nullptr; return v; }
 template <class BE> class LcPipeline {
 public:
 	BE &be;
@@ -363,9 +364,11 @@ public:
 				b2.w_pk = (LcPk *)d_wpk2.p; b2.redo = (int32_t *)out.p; b2.redo_cur = b.redo_cur + 2 + pass;
 				be.k_seed(b2, in_list, n_redo); ++launches;
 				read_ctl();
+				if (lc_verbose()) fprintf(stderr, "[lc] seeding pass %d (lists of %d entries, %d seeds) ran %d of %d reads\n", pass + 2, b2.lst_cap, b2.pk_cap, n_redo, R);
 				n_redo = (int)(uint32_t)(h_ctl[23] >> (32 * pass));
 				bf.redo = b2.redo; in_list = b2.redo;
 			}
+			if (lc_verbose() && n_redo) fprintf(stderr, "[lc] seeding: %d reads left for the one-thread-per-read kernel\n", n_redo);
 			if (!(h_ctl_ovf & LC_OVF_PK)) {
 				be.k_seed_finish(b); ++launches;    // sort + occurrence schedule + positions
 				if (n_redo) { be.k_seed_redo(bf, n_redo); ++launches; }
