@@ -86,7 +86,7 @@ struct LcSharedIndex {
 	std::vector<int32_t> lens;
 	std::vector<int64_t> offsets;
 	// tuning copied into every pipeline (lc_init reads the environment once)
-	int lst_cap = 0, pk_cap = 64, lst_cap2 = 40, pk_cap2 = 256, lst_cap3 = 150, pk_cap3 = 2048, ext_heavy_seeds = 32, ext_heavy_chains = 8, chain_heavy = 192;
+	int lst_cap = 0, pk_cap = 64, lst_cap2 = 64, pk_cap2 = 256, lst_cap3 = 0, pk_cap3 = 2048, ext_heavy_seeds = 32, ext_heavy_chains = 8, chain_heavy = 192;
 	bool force_wide = false;
 	bool want_alnx = false;       // lc_set_alnx: GetAlignments post-processing in every pipeline of the index
 	// pinned result blocks given back by lc_free_result
@@ -238,7 +238,7 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	// tuning knobs of the seeding state machine (tests use tiny values to force the redo path)
 	sh->lst_cap = env_int("LC_SEED_LST_CAP", 2, 2048, sh->lst_cap); sh->pk_cap = env_int("LC_SEED_PK_CAP", 1, 4096, sh->pk_cap);
 	sh->lst_cap2 = env_int("LC_SEED_LST_CAP2", 2, 2048, sh->lst_cap2); sh->pk_cap2 = env_int("LC_SEED_PK_CAP2", 1, 4096, sh->pk_cap2);
-	sh->lst_cap3 = env_int("LC_SEED_LST_CAP3", 2, 2048, sh->lst_cap3); sh->pk_cap3 = env_int("LC_SEED_PK_CAP3", 1, 4096, sh->pk_cap3);
+	sh->lst_cap3 = env_int("LC_SEED_LST_CAP3", 0, 2048, sh->lst_cap3); sh->pk_cap3 = env_int("LC_SEED_PK_CAP3", 1, 4096, sh->pk_cap3);
 	sh->ext_heavy_seeds = env_int("LC_EXT_HEAVY_SEEDS", 0, 1 << 30, sh->ext_heavy_seeds);
 	sh->ext_heavy_chains = env_int("LC_EXT_HEAVY_CHAINS", 0, 1 << 30, sh->ext_heavy_chains);
 	sh->chain_heavy = env_int("LC_CHAIN_HEAVY", 0, 1 << 30, sh->chain_heavy);

@@ -22,6 +22,7 @@ struct LcCudaBackend {
 	cudaStream_t aux[LC_CIG_NCLASS] = {};      // side streams: the band classes of the CIGAR stage run concurrently (fork/join on events)
 	cudaEvent_t ev_fork = 0, ev_join[LC_CIG_NCLASS] = {};
 	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+	void *seed_glists = nullptr; size_t seed_glists_bytes = 0;      // interval lists of the later seeding passes (smem_kernel<.., GL>)
 	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
 	int seed_gate_mask = 3, seed_gate_n = 12, ext_gate_mask = 15, ext_row_mask = 1;
 
@@ -42,7 +43,7 @@ struct LcCudaBackend {
 	int grid_for(unsigned long long items, int tpb, int ctas_per_sm) const;
 	void k_convert(uint8_t *p, unsigned long long n, bool ascii);
 	void k_seed(const LcBatch &b, const int32_t *list, int n_items);      // list: read ids of a second pass, null = reads 0..n_items-1
-	int seed_grid(const LcBatch &b, int n_items);
+	int seed_grid(const LcBatch &b, int n_items, bool listed);
 	int seed_pass_lanes(const LcBatch &b, int n_items);                   // threads k_seed would launch for this pass (sizes the per-lane seed lists)
 	int seed_lanes();
 	void k_seed_finish(const LcBatch &b);

@@ -205,57 +205,6 @@ LC_HD void lc_extend(const LcIndex &ix, const LcIntv &in, int c, int is_back, Lc
 	if (is_back) { out.x0 = s; out.x1 = o; } else { out.x1 = s; out.x0 = o; }
 }
 
-// All SMEMs through query position x (bwt_smem1a with max_intv = 0, B/bwt.c:289-351,353-356).
-// mem[] receives them sorted by start; prev/curr are scratch lists of capacity len + 1.  Returns the next x.
-LC_HDN int lc_smem1(const LcIndex &ix, int len, const uint8_t *q, int x, int min_intv, LcIntv *mem, int &n_mem,
-					LcIntv *prev, LcIntv *curr, LcCounters *cnt)
-{
-	LcIntv ik, ok;
-	int i, ret, n_prev, n_curr = 0;
-	n_mem = 0;
-	if (q[x] > 3) return x + 1;
-	if (min_intv < 1) min_intv = 1;
-	lc_set_intv(ix, q[x], ik);
-	ik.info = x + 1;
-	for (i = x + 1; i < len; ++i) {                 // forward: push the interval whenever its size changes
-		if (q[i] > 3) { curr[n_curr++] = ik; break; }
-		lc_extend(ix, ik, 3 - q[i], 0, ok, cnt);
-		if (ok.x2 != ik.x2) {
-			curr[n_curr++] = ik;
-			if (ok.x2 < (uint64_t)min_intv) break;
-		}
-		ok.info = i + 1;
-		ik = ok;
-	}
-	if (i == len) curr[n_curr++] = ik;
-	for (int a = 0, b = n_curr - 1; a < b; ++a, --b) { LcIntv t = curr[a]; curr[a] = curr[b]; curr[b] = t; }
-	ret = (int)curr[0].info;
-	{ LcIntv *t = curr; curr = prev; prev = t; }
-	n_prev = n_curr;
-	for (i = x - 1; i >= -1; --i) {                 // backward: shrink the list base by base
-		int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
-		n_curr = 0;
-		for (int j = 0; j < n_prev; ++j) {
-			const LcIntv p = prev[j];
-			if (c >= 0) lc_extend(ix, p, c, 1, ok, cnt);
-			if (c < 0 || ok.x2 < (uint64_t)min_intv) {
-				if (n_curr == 0 && (n_mem == 0 || (uint64_t)(i + 1) < (mem[n_mem - 1].info >> 32))) {
-					ik = p; ik.info |= (uint64_t)(i + 1) << 32;
-					mem[n_mem++] = ik;
-				}
-			} else if (n_curr == 0 || ok.x2 != curr[n_curr - 1].x2) {
-				ok.info = p.info;
-				curr[n_curr++] = ok;
-			}
-		}
-		if (n_curr == 0) break;
-		{ LcIntv *t = curr; curr = prev; prev = t; }
-		n_prev = n_curr;
-	}
-	for (int a = 0, b = n_mem - 1; a < b; ++a, --b) { LcIntv t = mem[a]; mem[a] = mem[b]; mem[b] = t; }
-	return ret;
-}
-
 // LAST-like forward seed (bwt_seed_strategy1, B/bwt.c:358-379)
 LC_HDN int lc_seed_strategy1(const LcIndex &ix, int len, const uint8_t *q, int x, int min_len, int max_intv, LcIntv &mem, LcCounters *cnt)
 {

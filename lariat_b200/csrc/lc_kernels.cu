@@ -26,6 +26,8 @@
 
 #define LC_TPB 128
 #define LC_SEED_TPB 64
+#define LC_SEED_GL_MIN 24      // list capacity above which a pass over listed reads keeps its lists in global memory
+#define LC_SEED_GL_CTAS 8      // resident CTAs per SM of such a pass (16 warps)
 #define LC_EXT_TPB 64
 
 __global__ void __launch_bounds__(256) convert_kernel(uint8_t *p, unsigned long long n, int is_ascii)
@@ -95,13 +97,24 @@ __device__ __forceinline__ void lc_warp_pack_read(const LcBatch &b, int rr, int 
 // tick — some lane of 32 nearly always wants it — made it a third of the kernel's instructions (profiles/r01m).  Lanes that
 // need it now wait (their tick() is a no-op on a stale interval) until `gate_n` lanes are waiting or the tick number is a
 // multiple of gate_mask + 1, and are then served together.
-template <typename U, bool COUNT>
-__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b, const unsigned gate_mask, const int gate_n, const int32_t *list, const int n_items)
+// GL (the later passes: reads in repeats whose lists need up to a read length of entries): the lists live in global memory — the same
+// [word][lane] layout per warp, so lanes at the same depth touch one 128-byte line — and only the reads stay in shared memory.  With
+// 150-entry lists in shared memory two warps fit an SM and the pass crawls at the latency of its dependent FM-index loads
+// (profiles/r2f: 59 ms for the third pass of the 3.1 Gb config); a list entry is written once and read once, sequentially, and is
+// not what a tick waits for.
+template <typename U, bool COUNT, bool GL>
+__global__ void __launch_bounds__(LC_SEED_TPB) smem_kernel(const LcBatch b, const unsigned gate_mask, const int gate_n, const int32_t *list, const int n_items, uint32_t *glists)
 {   // list: read ids of a second pass (the reads whose lists outgrew the first pass' slots), null: reads 0 .. n_items-1
 	extern __shared__ uint32_t lc_seed_smem[];
 	const int lane = threadIdx.x & 31;
-	uint32_t *wbase = lc_seed_smem + (size_t)(threadIdx.x >> 5) * lc_seed_warp_words(b.lmax, b.lst_cap);      // this warp's lists, then its reads
-	uint32_t *qbase = wbase + LC_SEED_ENT_WORDS * b.lst_cap * 32;
+	uint32_t *wbase, *qbase;
+	if (GL) {
+		wbase = glists + ((size_t)blockIdx.x * (LC_SEED_TPB / 32) + (threadIdx.x >> 5)) * (size_t)(LC_SEED_ENT_WORDS * b.lst_cap * 32);
+		qbase = lc_seed_smem + (size_t)(threadIdx.x >> 5) * lc_seed_q_words(b.lmax) * 32;
+	} else {
+		wbase = lc_seed_smem + (size_t)(threadIdx.x >> 5) * lc_seed_warp_words(b.lmax, b.lst_cap);      // this warp's lists, then its reads
+		qbase = wbase + LC_SEED_ENT_WORDS * b.lst_cap * 32;
+	}
 	LcPk *memv = b.w_pk + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * b.pk_cap;
 	LcSeedLane<U, COUNT, 32> sd(b, wbase + lane, b.lst_cap, qbase + lane, memv, b.pk_cap);
 	for (unsigned it = 0;; ++it) {
@@ -163,11 +176,30 @@ __global__ void __launch_bounds__(256) seed_finish_kernel(const LcBatch b)
 	for (int r = g; r < b.n_reads; r += ng) lc_seed_finish<U>(b, co, r);
 }
 
-// reads the state machine could not hold in its fixed-size slots: one thread per read, lists in global memory
+// reads the state machine could not hold in its slots — in practice the reads inside high-copy repeats, whose interval lists run to a
+// hundred entries: one WARP per read (lc_smem1_t: the backward phase extends the whole list in parallel), lists in global memory
+struct LcSeedExecWarp {
+	int ln;
+	__device__ __forceinline__ int lane_id() const { return ln; }
+	__device__ __forceinline__ int n_lanes() const { return 32; }
+	__device__ __forceinline__ bool leader() const { return ln == 0; }
+	__device__ __forceinline__ void sync() const { __syncwarp(); }
+	__device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(LC_FULL, p); }
+	__device__ __forceinline__ uint64_t shfl(uint64_t v, int src) const { return __shfl_sync(LC_FULL, (unsigned long long)v, src); }
+};
 __global__ void __launch_bounds__(LC_TPB) smem_redo_kernel(const LcBatch b, int n_redo)
 {
-	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-	for (int t = worker; t < n_redo; t += stride) lc_stage_seed(b, b.redo[t], worker);
+	LcSeedExecWarp ex;
+	ex.ln = threadIdx.x & 31;
+	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	for (;;) {
+		unsigned int t = 0;
+		if (ex.ln == 0) t = atomicAdd(b.work_ctr + 3, 1u);
+		t = __shfl_sync(LC_FULL, t, 0);
+		if (t >= (unsigned int)n_redo) break;
+		lc_stage_seed_t(b, b.redo[t], gwarp, ex);
+		__syncwarp();
+	}
 }
 
 __global__ void __launch_bounds__(256) sa_lookup_kernel(const LcBatch b, unsigned long long n)
@@ -443,6 +475,7 @@ LcCudaBackend::~LcCudaBackend()
 {
 	cudaSetDevice(device);
 	if (scan_tmp) cudaFree(scan_tmp);
+	if (seed_glists) cudaFree(seed_glists);
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventDestroy(ev[i]);
 	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaEventDestroy(ev_join[i]); cudaStreamDestroy(aux[i]); }
 	cudaEventDestroy(ev_fork);
@@ -483,37 +516,61 @@ static void lc_set_kernel_attrs(int device)
 	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return; }
 	const int mx = (int)prop.sharedMemPerBlockOptin;
 	auto set = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx); };
-	set(smem_kernel<uint32_t, true>); set(smem_kernel<uint32_t, false>); set(smem_kernel<uint64_t, true>); set(smem_kernel<uint64_t, false>);
+	set(smem_kernel<uint32_t, true, false>); set(smem_kernel<uint32_t, false, false>); set(smem_kernel<uint64_t, true, false>); set(smem_kernel<uint64_t, false, false>);
 	set(extend_kernel<LcCells8<32>, false>); set(extend_kernel<LcCells16<32>, false>); set(extend_kernel<LcCells8<32>, true>); set(extend_kernel<LcCells16<32>, true>);
 	set(extend_heavy_kernel); set(matesw_kernel); set(global_cigar_kernel); set(ksw_extend_kernel); set(ksw_align_kernel);
 	cudaGetLastError();
 }
-int LcCudaBackend::seed_grid(const LcBatch &b, int n_items)
+// a pass over listed reads with long lists keeps the lists in global memory (smem_kernel<.., GL>)
+static bool lc_seed_gl(const LcBatch &b, bool listed) { return listed && b.lst_cap > LC_SEED_GL_MIN; }
+template <bool GL> static int lc_seed_grid_t(const LcBatch &b, int n_items, int n_sm, int &smem)
 {
-	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
+	smem = GL ? (LC_SEED_TPB / 32) * lc_seed_q_words(b.lmax) * 32 * 4 : (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
 	int per_sm = 1;
 	auto prep = [&](auto kern) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC_SEED_TPB, smem); };
-	if (lc_wide(b)) { if (b.cnt) prep(smem_kernel<uint64_t, true>); else prep(smem_kernel<uint64_t, false>); }
-	else { if (b.cnt) prep(smem_kernel<uint32_t, true>); else prep(smem_kernel<uint32_t, false>); }
+	if (lc_wide(b)) { if (b.cnt) prep(smem_kernel<uint64_t, true, GL>); else prep(smem_kernel<uint64_t, false, GL>); }
+	else { if (b.cnt) prep(smem_kernel<uint32_t, true, GL>); else prep(smem_kernel<uint32_t, false, GL>); }
 	if (per_sm < 1) per_sm = 1;
+	if (GL && per_sm > LC_SEED_GL_CTAS) per_sm = LC_SEED_GL_CTAS;      // the per-lane seed and list scratch is sized by the resident lanes
 	const long long need = ((long long)n_items + LC_SEED_TPB - 1) / LC_SEED_TPB;
 	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
 	return (int)(need < cap ? (need ? need : 1) : cap);
 }
-int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { return seed_grid(b, n_items) * LC_SEED_TPB; }
+int LcCudaBackend::seed_grid(const LcBatch &b, int n_items, bool listed)
+{
+	int smem;
+	return lc_seed_gl(b, listed) ? lc_seed_grid_t<true>(b, n_items, n_sm, smem) : lc_seed_grid_t<false>(b, n_items, n_sm, smem);
+}
+int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { return seed_grid(b, n_items, true) * LC_SEED_TPB; }
+template <bool GL> static void lc_launch_seed(const LcBatch &b, const int32_t *list, int n_items, int n_sm, cudaStream_t stream, unsigned gm, int gn, uint32_t *glists)
+{
+	int smem;
+	const int grid = lc_seed_grid_t<GL>(b, n_items, n_sm, smem);
+	if (lc_wide(b)) {
+		if (b.cnt) smem_kernel<uint64_t, true, GL><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items, glists);
+		else smem_kernel<uint64_t, false, GL><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items, glists);
+	} else {
+		if (b.cnt) smem_kernel<uint32_t, true, GL><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items, glists);
+		else smem_kernel<uint32_t, false, GL><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items, glists);
+	}
+}
 void LcCudaBackend::k_seed(const LcBatch &b, const int32_t *list, int n_items)
 {
-	const int smem = (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4, grid = seed_grid(b, n_items);
 	cudaMemsetAsync(b.work_ctr + 3, 0, 4, stream);
 	const unsigned gm = (unsigned)seed_gate_mask;
 	const int gn = seed_gate_n;
-	if (lc_wide(b)) {
-		if (b.cnt) smem_kernel<uint64_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
-		else smem_kernel<uint64_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
-	} else {
-		if (b.cnt) smem_kernel<uint32_t, true><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
-		else smem_kernel<uint32_t, false><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items);
+	if (lc_seed_gl(b, list != nullptr)) {
+		const size_t need = (size_t)seed_grid(b, n_items, true) * (LC_SEED_TPB / 32) * (size_t)(LC_SEED_ENT_WORDS * b.lst_cap * 32) * 4;
+		if (need > seed_glists_bytes) {
+			if (seed_glists) { cudaStreamSynchronize(stream); cudaFree(seed_glists); }
+			seed_glists = nullptr; seed_glists_bytes = 0;
+			if (cudaMalloc(&seed_glists, need) != cudaSuccess) { cudaGetLastError(); seed_glists = nullptr; }
+			else seed_glists_bytes = need;
+		}
+		if (seed_glists) { lc_launch_seed<true>(b, list, n_items, n_sm, stream, gm, gn, (uint32_t *)seed_glists); return; }
+		// no memory for the lists: the shared-memory form below is slower but complete (seed_pass_lanes over-estimates its lanes, which is harmless)
 	}
+	lc_launch_seed<false>(b, list, n_items, n_sm, stream, gm, gn, nullptr);
 }
 void LcCudaBackend::k_seed_finish(const LcBatch &b)
 {
@@ -522,7 +579,11 @@ void LcCudaBackend::k_seed_finish(const LcBatch &b)
 	else seed_finish_kernel<uint32_t><<<grid, 256, 0, stream>>>(b);
 }
 int LcCudaBackend::seed_lanes() { return n_sm * 2048; }      // upper bound on resident lanes of smem_kernel
-void LcCudaBackend::k_seed_redo(const LcBatch &b, int n_redo) { smem_redo_kernel<<<grid_for(n_redo, LC_TPB, 1), LC_TPB, 0, stream>>>(b, n_redo); }
+void LcCudaBackend::k_seed_redo(const LcBatch &b, int n_redo)
+{
+	cudaMemsetAsync(b.work_ctr + 3, 0, 4, stream);
+	smem_redo_kernel<<<grid_for((unsigned long long)n_redo * 32, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_redo);      // at most n_sm * 16 warps = worker slots
+}
 void LcCudaBackend::k_occ_convert(const uint32_t *bwa, uint4 *occ, unsigned long long n_blocks, const LcIndex &ix)
 {
 	LcSbTable t;

@@ -133,81 +133,191 @@ LC_HD unsigned long long lc_carve(const LcBatch &b, unsigned long long *cur, uns
 // ============================================================================================================
 // Stage 1 — seeding: mem_collect_intv (B/bwamem.c:114-162) and the occurrence schedule of mem_chain (B/bwamem.c:273-279)
 // ============================================================================================================
+// Executors of the seeding bodies below: one thread, or the 32 lanes of a warp working on ONE read (lc_kernels.cu).
+struct LcSeedExec1 {
+	LC_HD int lane_id() const { return 0; }
+	LC_HD int n_lanes() const { return 1; }
+	LC_HD bool leader() const { return true; }
+	LC_HD void sync() const {}
+	LC_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+	LC_HD uint64_t shfl(uint64_t v, int) const { return v; }
+};
+
+// All SMEMs through query position x (bwt_smem1a with max_intv = 0, B/bwt.c:289-351,353-356), by all lanes of `ex` together.
+// mem[] receives them sorted by start; prev/curr are scratch lists of capacity len + 1 (memory every lane sees).  Returns the next x.
+// The forward phase is one dependent bwt_extend per base and runs the same in every lane (the leader writes the list).  The backward
+// phase extends EVERY interval of the list by the same base: those extensions are independent, one per lane, and what the reference
+// then does in list order has a closed form —
+//   * a hit is recorded only while the new list is empty, and the first recorded hit blocks the others of this base
+//     (its start equals theirs), so only the list's first entry can be recorded, and only if it ended here;
+//   * an interval that survives is pushed unless its size equals the size pushed last — and the size pushed last always equals the
+//     size of the previous SURVIVOR (pushed: by assignment; not pushed: by the test), so "pushed" is a comparison between neighbours.
+// In a high-copy repeat the list holds ~100 intervals for ~100 bases: ~10^4 dependent extensions per read in list order, a few
+// hundred rounds this way.
+template <class Exec>
+LC_HD int lc_smem1_t(const LcIndex &ix, int len, const uint8_t *q, int x, int min_intv, LcIntv *mem, int &n_mem,
+					 LcIntv *prev, LcIntv *curr, LcCounters *cnt, const Exec &ex)
+{
+	LcIntv ik, ok;
+	int i, ret, n_prev, n_curr = 0;
+	n_mem = 0;
+	if (q[x] > 3) return x + 1;
+	if (min_intv < 1) min_intv = 1;
+	LcCounters *cnt1 = ex.leader() ? cnt : nullptr;      // the forward extensions are the same call in every lane: counted once
+	lc_set_intv(ix, q[x], ik);
+	ik.info = x + 1;
+	for (i = x + 1; i < len; ++i) {                 // forward: push the interval whenever its size changes
+		if (q[i] > 3) { if (ex.leader()) curr[n_curr] = ik; ++n_curr; break; }
+		lc_extend(ix, ik, 3 - q[i], 0, ok, cnt1);
+		if (ok.x2 != ik.x2) {
+			if (ex.leader()) curr[n_curr] = ik;
+			++n_curr;
+			if (ok.x2 < (uint64_t)min_intv) break;
+		}
+		ok.info = i + 1;
+		ik = ok;
+	}
+	if (i == len) { if (ex.leader()) curr[n_curr] = ik; ++n_curr; }
+	ex.sync();
+	for (int a = ex.lane_id(); a < n_curr - 1 - a; a += ex.n_lanes()) { const int c2 = n_curr - 1 - a; LcIntv t = curr[a]; curr[a] = curr[c2]; curr[c2] = t; }
+	ex.sync();
+	ret = (int)curr[0].info;
+	{ LcIntv *t = curr; curr = prev; prev = t; }
+	n_prev = n_curr;
+	uint64_t last_start = 0;                        // start of the hit recorded last (mem[n_mem - 1].info >> 32)
+	for (i = x - 1; i >= -1; --i) {                 // backward: shrink the list base by base
+		const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
+		n_curr = 0;
+		uint64_t carry_x2 = 0;
+		bool have_carry = false;
+		for (int j0 = 0; j0 < n_prev; j0 += ex.n_lanes()) {
+			const int j = j0 + ex.lane_id();
+			const bool act = j < n_prev;
+			LcIntv p;
+			p.x0 = p.x1 = p.x2 = p.info = 0; ok = p;
+			if (act) { p = prev[j]; if (c >= 0) lc_extend(ix, p, c, 1, ok, cnt); }
+			const bool valid = act && c >= 0 && ok.x2 >= (uint64_t)min_intv;
+			if (j == 0 && !valid && (n_mem == 0 || (uint64_t)(i + 1) < last_start)) {      // (lane 0 of the first chunk)
+				ik = p; ik.info |= (uint64_t)(i + 1) << 32;
+				mem[n_mem] = ik;
+			}
+			if (j0 == 0) {
+				const bool rec = (ex.ballot(j == 0 && !valid && (n_mem == 0 || (uint64_t)(i + 1) < last_start)) & 1u) != 0;
+				if (rec) { ++n_mem; last_start = (uint64_t)(i + 1); }
+			}
+			const uint32_t vmask = ex.ballot(valid);
+			const uint32_t below = vmask & ((1u << ex.lane_id()) - 1u);
+			const int src = below ? 31 - lc_clz(below) : ex.lane_id();
+			const uint64_t nb_x2 = ex.shfl(ok.x2, src);
+			const bool push = valid && (below ? ok.x2 != nb_x2 : (!have_carry || ok.x2 != carry_x2));
+			const uint32_t pmask = ex.ballot(push);
+			if (push) { ok.info = p.info; curr[n_curr + lc_popc(pmask & ((1u << ex.lane_id()) - 1u))] = ok; }
+			n_curr += lc_popc(pmask);
+			if (vmask) { carry_x2 = ex.shfl(ok.x2, 31 - lc_clz(vmask)); have_carry = true; }
+		}
+		ex.sync();
+		if (n_curr == 0) break;
+		{ LcIntv *t = curr; curr = prev; prev = t; }
+		n_prev = n_curr;
+	}
+	for (int a = ex.lane_id(); a < n_mem - 1 - a; a += ex.n_lanes()) { const int c2 = n_mem - 1 - a; LcIntv t = mem[a]; mem[a] = mem[c2]; mem[c2] = t; }
+	ex.sync();
+	return ret;
+}
+
 // mem_collect_intv (B/bwamem.c:114-162): returns the number of intervals written to mem[] (sorted by info), or -1 if memcap is too small.
 // prev/curr/m1 are scratch lists of len + 1 entries.
-LC_HDN int lc_collect_intv(const LcIndex &ix, const lc_opt_t &opt, int len, const uint8_t *q, LcIntv *prev, LcIntv *curr, LcIntv *m1,
-						   LcIntv *mem, int memcap, LcCounters *cnt)
+template <class Exec>
+LC_HD int lc_collect_intv_t(const LcIndex &ix, const lc_opt_t &opt, int len, const uint8_t *q, LcIntv *prev, LcIntv *curr, LcIntv *m1,
+							LcIntv *mem, int memcap, LcCounters *cnt, const Exec &ex)
 {
 	int n = 0, n1, x;
 	const int split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
+	LcCounters *cnt1 = ex.leader() ? cnt : nullptr;
 	for (x = 0; x < len;) {                                                // pass 1: all SMEMs
 		if (q[x] > 3) { ++x; continue; }
-		x = lc_smem1(ix, len, q, x, 1, m1, n1, prev, curr, cnt);
+		x = lc_smem1_t(ix, len, q, x, 1, m1, n1, prev, curr, cnt, ex);
 		for (int i = 0; i < n1; ++i) {
 			int slen = (int)((uint32_t)m1[i].info - (uint32_t)(m1[i].info >> 32));
-			if (slen >= opt.min_seed_len) { if (n == memcap) return -1; mem[n++] = m1[i]; }
+			if (slen >= opt.min_seed_len) { if (n == memcap) return -1; if (ex.leader()) mem[n] = m1[i]; ++n; }
 		}
+		ex.sync();
 	}
 	const int old_n = n;
 	for (int k = 0; k < old_n; ++k) {                                      // pass 2: re-seed inside long near-unique SMEMs
 		const LcIntv p = mem[k];
 		int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
 		if (end - start < split_len || p.x2 > (uint64_t)opt.split_width) continue;
-		lc_smem1(ix, len, q, (start + end) >> 1, (int)p.x2 + 1, m1, n1, prev, curr, cnt);
+		lc_smem1_t(ix, len, q, (start + end) >> 1, (int)p.x2 + 1, m1, n1, prev, curr, cnt, ex);
 		for (int i = 0; i < n1; ++i)
 			if ((int)((uint32_t)m1[i].info - (uint32_t)(m1[i].info >> 32)) >= opt.min_seed_len) {
 				if (n == memcap) return -1;
-				mem[n++] = m1[i];
+				if (ex.leader()) mem[n] = m1[i];
+				++n;
 			}
+		ex.sync();
 	}
-	if (opt.max_mem_intv > 0)                                              // pass 3: LAST-like seeds
+	if (opt.max_mem_intv > 0)                                              // pass 3: LAST-like seeds (one dependent extension per base: every lane the same)
 		for (x = 0; x < len;) {
 			if (q[x] > 3) { ++x; continue; }
 			LcIntv m;
-			x = lc_seed_strategy1(ix, len, q, x, opt.min_seed_len, (int)opt.max_mem_intv, m, cnt);
-			if (m.x2 > 0) { if (n == memcap) return -1; mem[n++] = m; }
+			x = lc_seed_strategy1(ix, len, q, x, opt.min_seed_len, (int)opt.max_mem_intv, m, cnt1);
+			if (m.x2 > 0) { if (n == memcap) return -1; if (ex.leader()) mem[n] = m; ++n; }
 		}
+	ex.sync();
 	// elements with equal `info` are identical (same substring => same interval), so any correct sort reproduces B/bwamem.c:161
-	lc_introsort(mem, (long)n, [](const LcIntv &a, const LcIntv &c) { return a.info < c.info; });
+	if (ex.leader()) lc_introsort(mem, (long)n, [](const LcIntv &a, const LcIntv &c) { return a.info < c.info; });
+	ex.sync();
 	return n;
 }
 
-LC_HDN void lc_stage_seed(const LcBatch &b, int r, int worker)
+// Stage 1 for one read, whole: the fallback of the seeding state machine (lc_seed.cuh) for reads whose lists outgrow its slots
+template <class Exec>
+LC_HD void lc_stage_seed_t(const LcBatch &b, int r, int worker, const Exec &ex)
 {
 	const lc_opt_t &opt = b.opt;
 	const int len = (int)(b.off[r + 1] - b.off[r]);
 	const uint8_t *q = b.seq + b.off[r];
-	b.r_n_intv[r] = 0; b.r_n_seed[r] = 0; b.r_intv_off[r] = 0; b.r_seed_off[r] = 0;
+	if (ex.leader()) { b.r_n_intv[r] = 0; b.r_n_seed[r] = 0; b.r_intv_off[r] = 0; b.r_seed_off[r] = 0; }
 	if (len < opt.min_seed_len) return;                                    // B/bwamem.c:260
 	LcIntv *base = b.w_intv + (size_t)worker * (3 * (size_t)(b.lmax + 1) + b.memcap);
 	LcIntv *prev = base, *curr = base + (b.lmax + 1), *m1 = base + 2 * (size_t)(b.lmax + 1), *mem = base + 3 * (size_t)(b.lmax + 1);
-	const int n = lc_collect_intv(b.ix, opt, len, q, prev, curr, m1, mem, b.memcap, b.cnt);
-	if (n < 0) { lc_raise(b, LC_OVF_MEMLIST); return; }
+	const int n = lc_collect_intv_t(b.ix, opt, len, q, prev, curr, m1, mem, b.memcap, b.cnt, ex);
+	if (n < 0) { if (ex.leader()) lc_raise(b, LC_OVF_MEMLIST); return; }
 	// occurrence schedule: at most max_occ rows per interval, evenly strided (B/bwamem.c:278-279)
 	unsigned long long S = 0;
 	for (int i = 0; i < n; ++i) {
 		uint64_t step = mem[i].x2 > (uint64_t)opt.max_occ ? mem[i].x2 / opt.max_occ : 1;
 		uint64_t cnt = (mem[i].x2 + step - 1) / step;
 		if (cnt > (uint64_t)opt.max_occ) cnt = opt.max_occ;
-		mem[i].x1 = cnt;          // x1 is not needed past seeding; reuse it for the count
 		S += cnt;
 	}
-	unsigned long long io = lc_carve(b, b.intv_cur, b.intv_cap, n, LC_OVF_INTV);
-	unsigned long long so = lc_carve(b, b.seed_cur, b.seed_cap, S, LC_OVF_SEED);
+	unsigned long long io = 0, so = 0;
+	if (ex.leader()) {
+		io = lc_carve(b, b.intv_cur, b.intv_cap, n, LC_OVF_INTV);
+		so = lc_carve(b, b.seed_cur, b.seed_cap, S, LC_OVF_SEED);
+	}
+	io = ex.shfl(io, 0); so = ex.shfl(so, 0);
 	if (io == (unsigned long long)-1 || so == (unsigned long long)-1) return;
+	const bool dense = b.ix.sa32 || b.ix.sa64;     // with the dense suffix array resident the rows become positions right here
 	unsigned long long s = 0;
 	for (int i = 0; i < n; ++i) {
-		uint64_t step = mem[i].x2 > (uint64_t)opt.max_occ ? mem[i].x2 / opt.max_occ : 1;
-		LcIntvOut o;
-		o.x0 = mem[i].x0; o.x2 = mem[i].x2; o.qbeg = (uint32_t)(mem[i].info >> 32); o.qend = (uint32_t)mem[i].info;
-		o.soff = (uint32_t)s; o.step = (uint32_t)step;
-		b.intv[io + i] = o;
-		const bool dense = b.ix.sa32 || b.ix.sa64;     // with the dense suffix array resident the rows become positions right here
-		for (uint64_t t = 0; t < mem[i].x1; ++t) { const uint64_t row = mem[i].x0 + t * step; b.seed_row[so + s + t] = dense ? lc_sa(b.ix, row, b.cnt) : row; }
-		s += mem[i].x1;
+		const uint64_t x0 = mem[i].x0, x2 = mem[i].x2;
+		const uint64_t step = x2 > (uint64_t)opt.max_occ ? x2 / opt.max_occ : 1;
+		uint64_t cnt = (x2 + step - 1) / step;
+		if (cnt > (uint64_t)opt.max_occ) cnt = opt.max_occ;
+		if (ex.leader()) {
+			LcIntvOut o;
+			o.x0 = x0; o.x2 = x2; o.qbeg = (uint32_t)(mem[i].info >> 32); o.qend = (uint32_t)mem[i].info;
+			o.soff = (uint32_t)s; o.step = (uint32_t)step;
+			b.intv[io + i] = o;
+		}
+		for (uint64_t t = ex.lane_id(); t < cnt; t += ex.n_lanes()) { const uint64_t row = x0 + t * step; b.seed_row[so + s + t] = dense ? lc_sa(b.ix, row, b.cnt) : row; }
+		s += cnt;
 	}
-	b.r_intv_off[r] = (int64_t)io; b.r_n_intv[r] = n; b.r_seed_off[r] = (int64_t)so; b.r_n_seed[r] = (int32_t)S;
+	if (ex.leader()) { b.r_intv_off[r] = (int64_t)io; b.r_n_intv[r] = n; b.r_seed_off[r] = (int64_t)so; b.r_n_seed[r] = (int32_t)S; }
 }
+LC_HDN void lc_stage_seed(const LcBatch &b, int r, int worker) { lc_stage_seed_t(b, r, worker, LcSeedExec1()); }
 
 // ============================================================================================================
 // Stage 2 — suffix-array lookups, one BWT row each (bwt_sa inside mem_chain, B/bwamem.c:283)

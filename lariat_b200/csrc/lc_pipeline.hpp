@@ -219,8 +219,8 @@ public:
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
 	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
 	int chain_heavy = 192;                               // chaining: reads with more seeds than this go to the warp-per-read kernel (0 = never)
-	int lst_cap2 = 40, pk_cap2 = 256;     // the second and third pass' capacities; overflow of the third -> the one-thread-per-read redo kernel
-	int lst_cap3 = 150, pk_cap3 = 2048;
+	int lst_cap2 = 64, pk_cap2 = 256;     // the second and third pass' capacities; overflow of the third -> the one-thread-per-read redo kernel
+	int lst_cap3 = 0, pk_cap3 = 2048;       // third pass: off by default (0); what outgrows the second goes to the warp-per-read kernel
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
 	bool force_wide = false;
 	bool want_alnx = false;             // stage 6b: GetAlignments post-processing (lc_post.cuh)
@@ -356,6 +356,7 @@ public:
 			const int caps[2][2] = { { lst_cap2, pk_cap2 }, { lst_cap3, pk_cap3 } };
 			const int32_t *in_list = b.redo;
 			for (int pass = 0; pass < 2 && n_redo && !(h_ctl_ovf & LC_OVF_PK); ++pass) {
+				if (caps[pass][0] <= 0) continue;           // pass switched off
 				LcBatch b2 = b;
 				b2.lst_cap = std::min(caps[pass][0], b.lmax + 1); b2.pk_cap = caps[pass][1];
 				LcBuf<BE> &out = pass == 0 ? d_redo2 : d_redo3;
@@ -368,7 +369,7 @@ public:
 				n_redo = (int)(uint32_t)(h_ctl[23] >> (32 * pass));
 				bf.redo = b2.redo; in_list = b2.redo;
 			}
-			if (lc_verbose() && n_redo) fprintf(stderr, "[lc] seeding: %d reads left for the one-thread-per-read kernel\n", n_redo);
+			if (lc_verbose() && n_redo) fprintf(stderr, "[lc] seeding: %d reads left for the warp-per-read kernel\n", n_redo);
 			if (!(h_ctl_ovf & LC_OVF_PK)) {
 				be.k_seed_finish(b); ++launches;    // sort + occurrence schedule + positions
 				if (n_redo) { be.k_seed_redo(bf, n_redo); ++launches; }

@@ -314,6 +314,9 @@ template <typename U, bool COUNT = true, int STRIDE = 1> struct LcSeedLane {    
 			}
 			if (phase == LC_SP_FINISH) {                          // hand the unsorted seeds to lc_seed_finish
 				if (COUNT && b.cnt) { lc_atomic_add(&b.cnt->extend_calls, (unsigned long long)cnt_ext); lc_atomic_add(&b.cnt->occ_blocks, (unsigned long long)cnt_blk); }
+#if defined(LC_STATS) && !defined(__CUDA_ARCH__)
+				if (COUNT && b.cnt) fprintf(stderr, "SEEDEXT %d %u %d\n", r, cnt_ext, n_mem);
+#endif
 				unsigned long long po = n_mem ? lc_carve(b, b.pk_cur, b.pk_pool_cap, (unsigned long long)n_mem, LC_OVF_PK) : 0ull;
 				if (po == (unsigned long long)-1) { po = 0; n_mem = 0; }
 				for (int t = 0; t < n_mem; ++t) b.pk_pool[po + t] = memv[t];
