@@ -12,7 +12,7 @@ import json,sys; j=json.load(open('gpurun_out/${TAG}_c3.json')); print('C3', j['
 timeout 600 python bench.py --config c2 --steps 3 --warmup 3 > gpurun_out/${TAG}_c2.json 2> gpurun_out/${TAG}_c2.err
 python -c "
 import json,sys; j=json.load(open('gpurun_out/${TAG}_c2.json')); print('C2', j['value'], j['e2e']['value'], j['stage_ms_last_step'], j['verified_pairs'], j['gpu_launches'])"
-for V in "LC_SEED_LST_CAP2=64 LC_SEED_LST_CAP3=150" "LC_SEED_LST_CAP2=96 LC_SEED_LST_CAP3=150"; do
+for V in "LC_SEED_LST_CAP2=40" "LC_SEED_LST_CAP2=96"; do
 env $V LC_VERBOSE=1 timeout 600 python bench.py --config c3 --pairs $P --steps 2 --warmup 1 --no-cpu 2> gpurun_out/${TAG}_sweep.err | python -c "
 import json,sys; j=json.loads(sys.stdin.read()); print('$V', j['value'], j['stage_ms_last_step']['ms_seed'])"
 grep "\[lc\]" gpurun_out/${TAG}_sweep.err | sort | uniq -c | head -4
