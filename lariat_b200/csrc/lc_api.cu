@@ -86,7 +86,7 @@ struct LcSharedIndex {
 	std::vector<int32_t> lens;
 	std::vector<int64_t> offsets;
 	// tuning copied into every pipeline (lc_init reads the environment once)
-	int lst_cap = 0, pk_cap = 64, lst_cap2 = 64, pk_cap2 = 256, lst_cap3 = 0, pk_cap3 = 2048, ext_heavy_seeds = 32, ext_heavy_chains = 8, chain_heavy = 192;
+	int lst_cap = 0, pk_cap = 64, lst_cap2 = 64, pk_cap2 = 256, lst_cap3 = 0, pk_cap3 = 2048, ext_heavy_seeds = 32, ext_heavy_chains = 8, chain_heavy = 48, small_reads = 16384;
 	bool force_wide = false;
 	bool want_alnx = false;       // lc_set_alnx: GetAlignments post-processing in every pipeline of the index
 	// pinned result blocks given back by lc_free_result
@@ -112,7 +112,7 @@ struct LcSharedIndex {
 	{
 		pl.lst_cap = lst_cap; pl.pk_cap = pk_cap; pl.lst_cap2 = lst_cap2; pl.pk_cap2 = pk_cap2; pl.lst_cap3 = lst_cap3; pl.pk_cap3 = pk_cap3;
 		pl.ext_heavy_seeds = ext_heavy_seeds; pl.ext_heavy_chains = ext_heavy_chains; pl.force_wide = force_wide; pl.want_alnx = want_alnx;
-		pl.chain_heavy = chain_heavy;
+		pl.chain_heavy = chain_heavy; pl.small_reads = small_reads;
 	}
 };
 
@@ -241,6 +241,7 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 	sh->lst_cap3 = env_int("LC_SEED_LST_CAP3", 0, 2048, sh->lst_cap3); sh->pk_cap3 = env_int("LC_SEED_PK_CAP3", 1, 4096, sh->pk_cap3);
 	sh->ext_heavy_seeds = env_int("LC_EXT_HEAVY_SEEDS", 0, 1 << 30, sh->ext_heavy_seeds);
 	sh->ext_heavy_chains = env_int("LC_EXT_HEAVY_CHAINS", 0, 1 << 30, sh->ext_heavy_chains);
+	sh->small_reads = env_int("LC_SMALL_READS", 0, 1 << 30, sh->small_reads);      // batches up to this many reads: warp-per-read seeding and extension (0 = never)
 	sh->chain_heavy = env_int("LC_CHAIN_HEAVY", 0, 1 << 30, sh->chain_heavy);
 	sh->co_call_max = env_int("LC_COALESCE_MAX", 0, 1 << 20, sh->co_call_max);          // 0: small calls are not merged
 	sh->co_batch_max = env_int("LC_COALESCE_BATCH", 1, 1 << 22, sh->co_batch_max);

@@ -27,7 +27,6 @@
 #define LC_TPB 128
 #define LC_SEED_TPB 64
 #define LC_SEED_GL_MIN 24      // list capacity above which a pass over listed reads keeps its lists in global memory
-#define LC_SEED_GL_CTAS 8      // resident CTAs per SM of such a pass (16 warps)
 #define LC_EXT_TPB 64
 
 __global__ void __launch_bounds__(256) convert_kernel(uint8_t *p, unsigned long long n, int is_ascii)
@@ -294,6 +293,7 @@ __global__ void __launch_bounds__(LC_TPB) ext_plan_kernel(const LcBatch b, const
 }
 // ... most of which go through extend_kernel<CELLS, true>; a unit that is itself very large (many overlapping chains: tandem arrays) gets
 // a warp: cooperative ksw_extend2 rows (lc_sw_warp.cuh)
+// list == null: the items are the reads 0 .. n-1, whole (small batches: every read gets a warp)
 __global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
 {
 	extern __shared__ int lc_smem[];
@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(LC_TPB) extend_heavy_kernel(const LcBatch b, c
 		if (lane == 0) t = atomicAdd(b.ext_hvu_n + 1, 1u);
 		t = __shfl_sync(LC_FULL, t, 0);
 		if (t >= n) break;
-		lc_stage_extend_t(b, -1, (long long)(uint32_t)list[t], ex);
+		if (list) lc_stage_extend_t(b, -1, (long long)(uint32_t)list[t], ex);
+		else lc_stage_extend_t(b, (int)t, -1, ex);
 		__syncwarp();
 	}
 }
@@ -468,6 +469,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
 	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
 	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
+	env_int("LC_SEED_GL_CTAS", seed_gl_ctas, 1, 32); env_int("LC_CHAIN_CTAS", chain_ctas, 1, 16); env_int("LC_CHAIN_HEAVY_CTAS", chain_heavy_ctas, 1, 16);
 	env_int("LC_SEED_GATE_MASK", seed_gate_mask, 0, 255); env_int("LC_SEED_GATE_N", seed_gate_n, 1, 33);     // tuning knobs; mask must be 2^k - 1
 	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_ROW_MASK", ext_row_mask, 0, 255);
 }
@@ -484,6 +486,9 @@ LcCudaBackend::~LcCudaBackend()
 void *LcCudaBackend::dmalloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
 void LcCudaBackend::dfree(void *p) { cudaStreamSynchronize(stream); cudaFree(p); }
 void LcCudaBackend::dzero(void *p, size_t n) { cudaMemsetAsync(p, 0, n, stream); }
+void LcCudaBackend::dfill(void *p, int byte, size_t n) { cudaMemsetAsync(p, byte, n, stream); }
+__global__ void iota_kernel(int32_t *p, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i; }
+void LcCudaBackend::k_iota(int32_t *p, int n) { if (n > 0) iota_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(p, n); }
 void LcCudaBackend::dzero_words(unsigned long long *p, size_t n) { cudaMemsetAsync(p, 0, 8 * n, stream); }
 void LcCudaBackend::h2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream); }
 void LcCudaBackend::d2h(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); }
@@ -523,7 +528,7 @@ static void lc_set_kernel_attrs(int device)
 }
 // a pass over listed reads with long lists keeps the lists in global memory (smem_kernel<.., GL>)
 static bool lc_seed_gl(const LcBatch &b, bool listed) { return listed && b.lst_cap > LC_SEED_GL_MIN; }
-template <bool GL> static int lc_seed_grid_t(const LcBatch &b, int n_items, int n_sm, int &smem)
+template <bool GL> static int lc_seed_grid_t(const LcBatch &b, int n_items, int n_sm, int gl_ctas, int &smem)
 {
 	smem = GL ? (LC_SEED_TPB / 32) * lc_seed_q_words(b.lmax) * 32 * 4 : (LC_SEED_TPB / 32) * lc_seed_warp_words(b.lmax, b.lst_cap) * 4;
 	int per_sm = 1;
@@ -531,7 +536,7 @@ template <bool GL> static int lc_seed_grid_t(const LcBatch &b, int n_items, int 
 	if (lc_wide(b)) { if (b.cnt) prep(smem_kernel<uint64_t, true, GL>); else prep(smem_kernel<uint64_t, false, GL>); }
 	else { if (b.cnt) prep(smem_kernel<uint32_t, true, GL>); else prep(smem_kernel<uint32_t, false, GL>); }
 	if (per_sm < 1) per_sm = 1;
-	if (GL && per_sm > LC_SEED_GL_CTAS) per_sm = LC_SEED_GL_CTAS;      // the per-lane seed and list scratch is sized by the resident lanes
+	if (GL && per_sm > gl_ctas) per_sm = gl_ctas;      // the per-lane seed and list scratch is sized by the resident lanes
 	const long long need = ((long long)n_items + LC_SEED_TPB - 1) / LC_SEED_TPB;
 	const long long cap = (long long)n_sm * per_sm;      // persistent: one wave of resident CTAs, reads dealt by an atomic counter
 	return (int)(need < cap ? (need ? need : 1) : cap);
@@ -539,13 +544,13 @@ template <bool GL> static int lc_seed_grid_t(const LcBatch &b, int n_items, int 
 int LcCudaBackend::seed_grid(const LcBatch &b, int n_items, bool listed)
 {
 	int smem;
-	return lc_seed_gl(b, listed) ? lc_seed_grid_t<true>(b, n_items, n_sm, smem) : lc_seed_grid_t<false>(b, n_items, n_sm, smem);
+	return lc_seed_gl(b, listed) ? lc_seed_grid_t<true>(b, n_items, n_sm, seed_gl_ctas, smem) : lc_seed_grid_t<false>(b, n_items, n_sm, seed_gl_ctas, smem);
 }
 int LcCudaBackend::seed_pass_lanes(const LcBatch &b, int n_items) { return seed_grid(b, n_items, true) * LC_SEED_TPB; }
-template <bool GL> static void lc_launch_seed(const LcBatch &b, const int32_t *list, int n_items, int n_sm, cudaStream_t stream, unsigned gm, int gn, uint32_t *glists)
+template <bool GL> static void lc_launch_seed(const LcBatch &b, const int32_t *list, int n_items, int n_sm, int gl_ctas, cudaStream_t stream, unsigned gm, int gn, uint32_t *glists)
 {
 	int smem;
-	const int grid = lc_seed_grid_t<GL>(b, n_items, n_sm, smem);
+	const int grid = lc_seed_grid_t<GL>(b, n_items, n_sm, gl_ctas, smem);
 	if (lc_wide(b)) {
 		if (b.cnt) smem_kernel<uint64_t, true, GL><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items, glists);
 		else smem_kernel<uint64_t, false, GL><<<grid, LC_SEED_TPB, smem, stream>>>(b, gm, gn, list, n_items, glists);
@@ -567,10 +572,10 @@ void LcCudaBackend::k_seed(const LcBatch &b, const int32_t *list, int n_items)
 			if (cudaMalloc(&seed_glists, need) != cudaSuccess) { cudaGetLastError(); seed_glists = nullptr; }
 			else seed_glists_bytes = need;
 		}
-		if (seed_glists) { lc_launch_seed<true>(b, list, n_items, n_sm, stream, gm, gn, (uint32_t *)seed_glists); return; }
+		if (seed_glists) { lc_launch_seed<true>(b, list, n_items, n_sm, seed_gl_ctas, stream, gm, gn, (uint32_t *)seed_glists); return; }
 		// no memory for the lists: the shared-memory form below is slower but complete (seed_pass_lanes over-estimates its lanes, which is harmless)
 	}
-	lc_launch_seed<false>(b, list, n_items, n_sm, stream, gm, gn, nullptr);
+	lc_launch_seed<false>(b, list, n_items, n_sm, seed_gl_ctas, stream, gm, gn, nullptr);
 }
 void LcCudaBackend::k_seed_finish(const LcBatch &b)
 {
@@ -598,9 +603,9 @@ void LcCudaBackend::k_sa_fill(const LcIndex &ix, unsigned long long n_samples, v
 void LcCudaBackend::k_sa(const LcBatch &b, unsigned long long n) { sa_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(b, n); }
 void LcCudaBackend::k_chain(const LcBatch &b)
 {
-	chain_kernel<<<grid_for(b.n_reads, LC_TPB, 4), LC_TPB, 0, stream>>>(b);
+	chain_kernel<<<grid_for(b.n_reads, LC_TPB, chain_ctas), LC_TPB, 0, stream>>>(b);
 	// the list length is only known on the device: a resident-size grid whose warps pull listed reads from a counter (no host round trip)
-	if (b.chain_heavy > 0) chain_heavy_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 4), LC_TPB, 0, stream>>>(b);
+	if (b.chain_heavy > 0) chain_heavy_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, chain_heavy_ctas), LC_TPB, 0, stream>>>(b);
 }
 template <class CELLS, bool UNIT> static void lc_launch_extend(const LcBatch &b, long long n_items, int n_sm, cudaStream_t stream, unsigned hk_mask, unsigned row_mask)
 {
@@ -614,6 +619,11 @@ template <class CELLS, bool UNIT> static void lc_launch_extend(const LcBatch &b,
 int LcCudaBackend::k_extend(const LcBatch &b)
 {
 	// byte-packed H/E cells whenever no score of the batch can exceed 255 (half the shared memory per warp, twice the resident warps)
+	if (b.small) {      // few reads: a warp per read is the short way through (a lane of the state machine walks its read's cells eight at a time)
+		const int smem = (LC_TPB / 32) * lc_warp_smem_bytes(b.lmax);
+		extend_heavy_kernel<<<grid_for((unsigned long long)b.n_reads * 32, LC_TPB, 4), LC_TPB, smem, stream>>>(b, nullptr, (unsigned int)b.n_reads);
+		return 1;
+	}
 	const bool cells8 = lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS");
 	const unsigned hk = (unsigned)ext_gate_mask, rw = (unsigned)ext_row_mask;
 	if (cells8) lc_launch_extend<LcCells8<32>, false>(b, b.n_reads, n_sm, stream, hk, rw);

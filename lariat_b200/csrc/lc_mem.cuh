@@ -18,11 +18,14 @@ struct LcChainOut { int32_t rid, n; int64_t seed_off; uint32_t w; int32_t is_alt
 // Stage 4 on reads with very many chains (repeats): the chains of a read are split into UNITS — clusters of chains whose reference
 // windows overlap (lc_ext_plan) — and every unit is extended on its own.  Per chain: the next chain of its unit, its read, and
 // where the regions it produced went.
+struct LcSortKey { uint64_t lo; uint32_t hi, idx; };      // lc_sort_regs_keyed
 struct LcChainAux { int32_t next, r, n_reg, unit_seeds; int64_t reg_off; };
 struct LcChainRec { int64_t pos; int32_t rid, n, head, tail; uint32_t w; int32_t kept, first, is_alt; };
 #define LC_BT_T 5
 #define LC_BT_MAXK (2 * LC_BT_T - 1)
-struct LcBtNode { int32_t n, internal; int32_t key[LC_BT_MAXK]; int32_t child[LC_BT_MAXK + 1]; };
+// kpos[t] = ch[key[t]].pos (a chain's position never changes once it exists): the descent compares against the node itself instead of
+// hopping to the chain record for every probe (the hops were the top lines of chain_heavy_kernel, profiles/r2g)
+struct LcBtNode { int32_t n, internal; int32_t key[LC_BT_MAXK]; int32_t child[LC_BT_MAXK + 1]; int64_t kpos[LC_BT_MAXK]; };
 
 enum { LC_OVF_INTV = 1, LC_OVF_SEED = 2, LC_OVF_SCRATCH = 4, LC_OVF_CSEED = 8, LC_OVF_REG = 16, LC_OVF_FINAL = 32,
 	   LC_OVF_CIGAR = 64, LC_OVF_Z = 128, LC_OVF_MEMLIST = 256, LC_OVF_CHAIN = 512, LC_OVF_PK = 1024, LC_OVF_MM = 2048 };
@@ -112,6 +115,8 @@ struct LcBatch {
 	uint64_t *ext_hvu_in, *ext_hvu_out;                  // heavy units for the warp-per-unit kernel: weight << 32 | first chain; sorted like wl_in -> wl_out
 	unsigned int *ext_hvu_n;                             // [0] = count, [1] = work counter
 	unsigned long long ext_hvu_cap;
+	LcSortKey *sortk; unsigned long long sortk_cap, *sortk_cur;      // stage 5a: key scratch of the dedup sorts, carved per read
+	int32_t small;                                       // a batch of few reads: the warp-per-read forms of seeding and extension for every read (latency, not throughput)
 };
 
 LC_HD void lc_raise(const LcBatch &b, uint32_t flag)
@@ -335,7 +340,7 @@ struct LcChainer {
 	LcBtNode *nd; int n_nd, root, n_keys;
 	int64_t *s_rbeg; int32_t *s_q, *s_len, *s_next;
 
-	LC_HD int cmp(int64_t pos, int key) const { int64_t kp = ch[key].pos; return (kp < pos) - (pos < kp); }   // chain_cmp (B/bwamem.c:186)
+	static LC_HD int cmp(int64_t pos, int64_t kp) { return (kp < pos) - (pos < kp); }   // chain_cmp (B/bwamem.c:186)
 	LC_HD int new_node(int internal)
 	{
 		LcBtNode &x = nd[n_nd];
@@ -347,9 +352,9 @@ struct LcChainer {
 	{
 		int lo = 0, hi = x.n;
 		if (x.n == 0) return -1;
-		while (lo < hi) { int mid = (lo + hi) >> 1; if (cmp(pos, x.key[mid]) > 0) lo = mid + 1; else hi = mid; }
+		while (lo < hi) { int mid = (lo + hi) >> 1; if (cmp(pos, x.kpos[mid]) > 0) lo = mid + 1; else hi = mid; }
 		if (lo == x.n) { if (r) *r = 1; return x.n - 1; }
-		int rr = cmp(pos, x.key[lo]);
+		int rr = cmp(pos, x.kpos[lo]);
 		if (r) *r = rr;
 		return rr < 0 ? lo - 1 : lo;
 	}
@@ -372,13 +377,13 @@ struct LcChainer {
 		int zi = new_node(nd[yi].internal);
 		LcBtNode &x = nd[xi], &y = nd[yi], &z = nd[zi];
 		z.n = LC_BT_T - 1;
-		for (int t = 0; t < LC_BT_T - 1; ++t) z.key[t] = y.key[t + LC_BT_T];
+		for (int t = 0; t < LC_BT_T - 1; ++t) { z.key[t] = y.key[t + LC_BT_T]; z.kpos[t] = y.kpos[t + LC_BT_T]; }
 		if (y.internal) for (int t = 0; t < LC_BT_T; ++t) z.child[t] = y.child[t + LC_BT_T];
 		y.n = LC_BT_T - 1;
 		for (int t = x.n; t > i; --t) x.child[t + 1] = x.child[t];
 		x.child[i + 1] = zi;
-		for (int t = x.n; t > i; --t) x.key[t] = x.key[t - 1];
-		x.key[i] = y.key[LC_BT_T - 1];
+		for (int t = x.n; t > i; --t) { x.key[t] = x.key[t - 1]; x.kpos[t] = x.kpos[t - 1]; }
+		x.key[i] = y.key[LC_BT_T - 1]; x.kpos[i] = y.kpos[LC_BT_T - 1];
 		++x.n;
 	}
 	// kb_putp / __kb_putp_aux (B/kbtree.h:192-224)
@@ -397,15 +402,15 @@ struct LcChainer {
 			LcBtNode &x = nd[xi];
 			int i = find(x, pos, 0);
 			if (!x.internal) {
-				for (int t = x.n - 1; t > i; --t) x.key[t + 1] = x.key[t];
-				x.key[i + 1] = key;
+				for (int t = x.n - 1; t > i; --t) { x.key[t + 1] = x.key[t]; x.kpos[t + 1] = x.kpos[t]; }
+				x.key[i + 1] = key; x.kpos[i + 1] = pos;
 				++x.n;
 				return;
 			}
 			++i;
 			if (nd[x.child[i]].n == LC_BT_MAXK) {
 				split(xi, i, x.child[i]);
-				if (cmp(pos, x.key[i]) > 0) ++i;
+				if (cmp(pos, x.kpos[i]) > 0) ++i;
 			}
 			xi = x.child[i];
 		}
@@ -458,7 +463,7 @@ LC_HD size_t lc_chain_scratch_bytes(int S)
 }
 
 #define LC_CHAIN_SMALL 12
-#define LC_CHAIN_SMALL_BYTES 1616       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in LcChainJob::init)
+#define LC_CHAIN_SMALL_BYTES 2016       // >= lc_chain_scratch_bytes(LC_CHAIN_SMALL) + 8 (checked in LcChainJob::init)
 
 // Who runs lc_chain_job: one thread (chain_kernel, tests/hostsim) ...
 struct LcChainExec1 {
@@ -1043,11 +1048,39 @@ template <class Lt> LC_HD void lc_sort_regs(lc_alnreg_t *a, int n, Lt lt, int *h
 		}
 	}
 }
-
+// The same two sorts on 16-byte {key, index} entries in a compact scratch array: a comparison reads two adjacent-ish entries instead of
+// hopping through a handle into 88-byte records scattered over the list (hundreds of regions per read in repeats: the sorts of
+// mem_align1_core's dedup were most of pair_prepare_kernel's tail).  which = 1: by `re` (mem_ars2); which = 2: by score (descending), rb, qb
+// (mem_ars).  The keys order exactly as the comparators do, so introsort sees the same outcomes and leaves the same permutation.
+LC_HD void lc_sort_regs_keyed(lc_alnreg_t *a, int n, int which, LcSortKey *ks)
+{
+	for (int i = 0; i < n; ++i) {
+		LcSortKey k;
+		if (which == 1) { k.lo = (uint64_t)a[i].re; k.hi = 0; }
+		else { k.lo = (uint64_t)a[i].rb << 16 | (uint64_t)(uint16_t)a[i].qb; k.hi = (uint32_t)(0x7fffffffll - (int64_t)a[i].score); }
+		k.idx = (uint32_t)i;
+		ks[i] = k;
+	}
+	lc_introsort(ks, (long)n, [](const LcSortKey &x, const LcSortKey &y) { return x.hi < y.hi || (x.hi == y.hi && x.lo < y.lo); });
+	for (int i = 0; i < n; ++i) {                          // the permutation, applied in place (as above)
+		if ((int)ks[i].idx == i) continue;
+		const lc_alnreg_t first = a[i];
+		int j = i;
+		for (;;) {
+			const int k = (int)ks[j].idx;
+			ks[j].idx = (uint32_t)j;
+			if (k == i) { a[j] = first; break; }
+			a[j] = a[k];
+			j = k;
+		}
+	}
+}
 // h/h_cap: scratch for lc_sort_regs (may overlap H and E: the sorts and the patching never run at the same time)
 // *clean (optional) := the call excluded nothing and merged nothing (and saw at least two regions): its output is then a fixed point of the
 // query-less form — sorted by the strict order (score, rb, qb), every n_comp == 1, no redundant pair (see lc_matesw_t)
-LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0, bool *clean = nullptr)
+// ks (optional): n entries of scratch for the keyed sorts (regions with 0 <= qb < 2^16 and 0 <= rb < 2^48: every real one)
+LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0, bool *clean = nullptr,
+							   LcSortKey *ks = nullptr)
 {
 	const lc_opt_t &opt = b.opt;
 	int m, i, j;
@@ -1055,7 +1088,8 @@ LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc
 	if (n <= 1) return n;
 	const int n_in = n;
 	bool merged = false;
-	lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; }, h, h_cap);
+	if (ks && n >= 12) lc_sort_regs_keyed(a, n, 1, ks);
+	else lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; }, h, h_cap);
 	for (i = 0; i < n; ++i) a[i].n_comp = 1;
 	for (i = 1; i < n; ++i) {
 		lc_alnreg_t &p = a[i];
@@ -1087,7 +1121,8 @@ LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc
 	}
 	for (i = 0, m = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
 	n = m;
-	lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
+	if (ks && n >= 12) lc_sort_regs_keyed(a, n, 2, ks);
+	else lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
 		return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb))); }, h, h_cap);
 	for (i = 1; i < n; ++i)
 		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
@@ -1286,7 +1321,12 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 				for (int i = 0; i < ax.n_reg; ++i) dst[m++] = src[i];
 			}
 		}
-		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], n[e], dst, H, E, H, 2 * (b.lmax + 18), &clean[e]);      // tail of mem_align1_core (B/bwamem.c:1070)
+		LcSortKey *ks = nullptr;
+		if (n[e] >= 12 && b.sortk) {                          // (a full pool only means the slower sort)
+			const unsigned long long ko = lc_atomic_add(b.sortk_cur, (unsigned long long)n[e]);
+			if (ko + (unsigned long long)n[e] <= b.sortk_cap) ks = b.sortk + ko;
+		}
+		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], n[e], dst, H, E, H, 2 * (b.lmax + 18), &clean[e], ks);      // tail of mem_align1_core (B/bwamem.c:1070)
 		for (int i = 0; i < n[e]; ++i) {
 			if (dst[i].rid >= 0 && b.ix.anns[dst[i].rid].is_alt) dst[i].is_alt = 1;   // B/bwamem.c:1078-1082
 			best[e] = lc_max(best[e], dst[i].score);                                 // G/gobwa.go:264-283

@@ -218,7 +218,8 @@ public:
 	int memcap = 256;
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
 	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
-	int chain_heavy = 192;                               // chaining: reads with more seeds than this go to the warp-per-read kernel (0 = never)
+	int small_reads = 16384;                             // batches of at most this many reads run in the low-latency form (0 = never)
+	int chain_heavy = 48;                                // chaining: reads with more seeds than this go to the warp-per-read kernel (0 = never)
 	int lst_cap2 = 64, pk_cap2 = 256;     // the second and third pass' capacities; overflow of the third -> the one-thread-per-read redo kernel
 	int lst_cap3 = 0, pk_cap3 = 2048;       // third pass: off by default (0); what outgrows the second goes to the warp-per-read kernel
 	double pk_per_read = 20;            // pool of unsorted seeds between the state machine and lc_seed_finish
@@ -296,7 +297,7 @@ public:
 			unsigned long long *c = (unsigned long long *)d_ctl.p;
 			b.intv_cur = c + 0; b.seed_cur = c + 1; b.scratch_cur = c + 2; b.chain_cur = c + 3; b.cseed_cur = c + 4;
 			b.reg_cur = c + 5; b.fin_cur = c + 6; b.cand_cur = c + 7; b.cigar_cur = c + 8; b.z_cur = c + 9;
-			b.reg_total = c + 10; b.pk_cur = c + 11; b.mm_cur = c + 12;
+			b.reg_total = c + 10; b.pk_cur = c + 11; b.mm_cur = c + 12; b.sortk_cur = c + 13;
 			b.overflow = (uint32_t *)(c + 16);
 			b.work_ctr = (unsigned int *)(c + 20);
 			b.redo_cur = (unsigned int *)(c + 22);
@@ -306,11 +307,13 @@ public:
 			b.chain_heavy_n = (unsigned int *)(c + 29);
 			b.ext_unit_n = (unsigned int *)(c + 30); b.ext_hvu_n = (unsigned int *)(c + 31);      // adjacent: the backend reads both with one copy
 			b.chain_heavy = chain_heavy;
+			b.small = (small_reads > 0 && b.n_reads <= small_reads) ? 1 : 0;
 			b.ext_heavy_seeds = ext_heavy_seeds; b.ext_heavy_chains = ext_heavy_chains;
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);
 		b.n_workers = be.n_workers();
+		b.sortk = nullptr; b.sortk_cap = 0;             // set by stage 5 (run_stages)
 		b.memcap = memcap;
 		{
 			// a forward extension pushes one interval per change of size: ~log4(symbols) entries on unique sequence, more in repeats
@@ -345,11 +348,20 @@ public:
 			b.pk_pool_cap = (unsigned long long)(pk_per_read * R) + 1024;
 			if (!d_intv.ensure(be, sizeof(LcIntvOut) * b.intv_cap) || !d_seed.ensure(be, 8 * b.seed_cap) || !d_pkpool.ensure(be, sizeof(LcPk) * b.pk_pool_cap)) return nomem();
 			b.intv = (LcIntvOut *)d_intv.p; b.seed_row = (uint64_t *)d_seed.p; b.pk_pool = (LcPk *)d_pkpool.p;
+			LcBatch bf = b;                         // the batch as the fallback kernel sees it (its redo list)
+			if (b.small) {
+				// few reads (one barcode group per call, merged or not): a lane of the state machine would take the read's ~700 dependent
+				// extensions one tick at a time; the warp-per-read kernel finishes the read in a fraction of that, and there are warps to spare
+				be.k_iota(b.redo, R);
+				be.dfill(b.r_n_pk, 0xff, 4 * (size_t)R);      // "redone": lc_seed_finish skips the read
+				be.k_seed_redo(bf, R); ++launches;
+				read_ctl();
+				n_redo = n_redo_pass1 = 0;
+			} else {
 			be.k_seed(b, nullptr, R); ++launches;   // the state machine: unsorted seeds per read + the redo list
 			read_ctl();
 			n_redo = (int)(uint32_t)h_ctl[22];
 			n_redo_pass1 = n_redo;
-			LcBatch bf = b;                         // the batch as the fallback kernel sees it (its redo list)
 			// further passes: the reads whose lists outgrew the slots (repeats: many interval sizes, many seeds) run through the same
 			// state machine with longer and longer lists — fewer resident warps each time, but only for the reads that need them.
 			// The overflow lists alternate between two buffers; pass p counts its overflows in control word 23 (low / high half).
@@ -374,6 +386,7 @@ public:
 				be.k_seed_finish(b); ++launches;    // sort + occurrence schedule + positions
 				if (n_redo) { be.k_seed_redo(bf, n_redo); ++launches; }
 				read_ctl();
+			}
 			}
 			if (launch_broken) { err = "a CUDA kernel launch failed in the seeding stage"; return LC_ECUDA; }
 			if (!(h_ctl_ovf & (LC_OVF_INTV | LC_OVF_SEED | LC_OVF_MEMLIST | LC_OVF_PK))) break;
@@ -437,8 +450,8 @@ public:
 		if (rc0) return rc0;
 		const unsigned long long S = h_ctl[1];
 		// ---- stage 2-4 pools, sized exactly from the seed count
-		// chain scratch (<= 101 B/seed + 280 B/read) + extension sort keys (8 B/seed + 16 B/read) + unit planning (40 B/chain + 16 B/read)
-		b.scratch_cap = 152ull * S + 336ull * R + 4096;
+		// chain scratch (<= 120 B/seed + 440 B/read) + extension sort keys (8 B/seed + 16 B/read) + unit planning (40 B/chain + 16 B/read)
+		b.scratch_cap = 172ull * S + 500ull * R + 4096;
 		b.chain_cap = S + 16; b.cseed_cap = S + 16; b.reg_cap = S + 16;
 		{
 			// a heavy unit has more than ext_heavy_seeds seeds or more than ext_heavy_chains chains (each at least one seed)
@@ -468,6 +481,8 @@ public:
 		if (!d_fin.ensure(be, sizeof(lc_alnreg_t) * b.fin_cap) || !d_aln.ensure(be, sizeof(lc_aln_t) * b.fin_cap) ||
 			!d_cand.ensure(be, 8 * b.fin_cap)) return nomem();
 		b.fin = (lc_alnreg_t *)d_fin.p; b.aln = (lc_aln_t *)d_aln.p; b.cand = (uint64_t *)d_cand.p;
+		b.sortk_cap = NREG + 64;
+		b.sortk = d_sortk.ensure(be, sizeof(LcSortKey) * b.sortk_cap) ? (LcSortKey *)d_sortk.p : nullptr;      // optional: without it the sorts go through handles
 		be.k_pair(b, n_pairs); launches += 2;
 		be.ev_record(7);
 		read_ctl();
@@ -584,7 +599,7 @@ public:
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
 							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_redo3, &d_wl,
-							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw, &d_chainaux, &d_units, &d_hvu };
+							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw, &d_chainaux, &d_units, &d_hvu, &d_sortk };
 		for (auto *x : all) x->release(be);
 	}
 
@@ -596,7 +611,7 @@ public:
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
 		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_redo3, d_wl,
-		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw, d_chainaux, d_units, d_hvu;
+		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw, d_chainaux, d_units, d_hvu, d_sortk;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

@@ -4,6 +4,10 @@ import sys
 
 import pytest
 
+# The golden sets are small; without this every test batch would take the low-latency route (a warp per read for seeding and
+# extension, batches of <= 16384 reads) and the state-machine kernels would go untested.  Tests of that route set the variable themselves.
+os.environ.setdefault("LC_SMALL_READS", "0")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -23,6 +23,8 @@ struct HostBackend {
 	void *dmalloc(size_t n) { return malloc(n ? n : 1); }
 	void dfree(void *p) { free(p); }
 	void dzero(void *p, size_t n) { memset(p, 0, n); }
+	void dfill(void *p, int byte, size_t n) { memset(p, byte, n); }
+	void k_iota(int32_t *p, int n) { for (int i = 0; i < n; ++i) p[i] = i; }
 	void dzero_words(unsigned long long *p, size_t n) { memset(p, 0, 8 * n); }
 	void h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
 	void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
@@ -60,7 +62,7 @@ struct HostBackend {
 	bool old_extend = false;
 	int k_extend(const LcBatch &b)
 	{
-		if (old_extend) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, -1, r % workers); return 1; }
+		if (old_extend || b.small) { for (int r = 0; r < b.n_reads; ++r) lc_stage_extend(b, r, -1, r % workers); return 1; }
 		std::vector<uint32_t> he((size_t)lc_ext_he_cols(b.lmax)), qw((size_t)lc_ext_q_words(b.lmax));
 		const bool c8 = lc_ext_cells8_ok(b) && !wide_cells;
 		lc_ext_run_scalar(b, he.data(), qw.data(), c8, idle_ticks);
@@ -114,7 +116,7 @@ int main(int argc, char **argv)
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
 	const char *xpath = 0;
 	int chain_heavy = -1;
-	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0;
+	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0, small_reads = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
 		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
@@ -129,6 +131,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-I") && i + 1 < argc) be.idle_ticks = atoi(argv[++i]);  // idle ticks before every housekeeping step of the state machines
 		else if (!strcmp(argv[i], "-J") && i + 1 < argc) heavy_seeds = atoi(argv[++i]);   // extension: reads above this many chained seeds take the per-read body
 		else if (!strcmp(argv[i], "-Q") && i + 1 < argc) chain_heavy = atoi(argv[++i]);   // chaining: reads above this many seeds take the listed-read body (0 = never)
+		else if (!strcmp(argv[i], "-Z") && i + 1 < argc) small_reads = atoi(argv[++i]);   // batches up to this many reads take the low-latency (per-read) bodies
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
@@ -162,6 +165,7 @@ int main(int argc, char **argv)
 	if (lst_cap2 > 0) { pl.lst_cap2 = lst_cap2; pl.lst_cap3 = lst_cap2 + 2; }      // (third pass: barely larger, so that the last fallback still gets reads)
 	if (heavy_seeds >= 0) pl.ext_heavy_seeds = heavy_seeds;
 	if (chain_heavy >= 0) pl.chain_heavy = chain_heavy;
+	pl.small_reads = small_reads;
 	if (pk_cap2 > 0) { pl.pk_cap2 = pk_cap2; pl.pk_cap3 = pk_cap2 + 2; }
 	pl.force_wide = wide != 0;
 	pl.want_alnx = xpath != 0;

@@ -42,11 +42,13 @@ def test_golden_tiny_bit_exact(tiny_ref):
 
 
 @pytest.mark.parametrize("env", [{"LC_DENSE_SA": "0"}, {"LC_SEED_LST_CAP": "10", "LC_SEED_PK_CAP": "6"}, {"LC_SEED_LST_CAP": "6", "LC_SEED_PK_CAP": "4", "LC_SEED_LST_CAP2": "9", "LC_SEED_PK_CAP2": "7", "LC_SEED_LST_CAP3": "12", "LC_SEED_PK_CAP3": "9"}, {"LC_DENSE_SA": "0", "LC_SEED_LST_CAP": "16"}, {"LC_FORCE_WIDE": "1"}, {"LC_EXT_HEAVY_SEEDS": "2", "LC_EXT_HEAVY_CHAINS": "1"}, {"LC_EXT_HEAVY_SEEDS": "0", "LC_EXT_HEAVY_CHAINS": "0"},
-                                 {"LC_CHAIN_HEAVY": "3"}, {"LC_CHAIN_HEAVY": "40", "LC_FORCE_WIDE": "1"}, {"LC_CHAIN_HEAVY": "0"}])
+                                 {"LC_CHAIN_HEAVY": "3"}, {"LC_CHAIN_HEAVY": "40", "LC_FORCE_WIDE": "1"}, {"LC_CHAIN_HEAVY": "0"},
+                                 {"LC_SMALL_READS": "4096"}, {"LC_SMALL_READS": "4096", "LC_FORCE_WIDE": "1", "LC_DENSE_SA": "0"}])
 def test_golden_tiny_fallback_paths(env, lib_path, monkeypatch):
     """Same golden through the optional paths: sampled suffix array + LF walks instead of the dense array, and the
     one-thread-per-read redo kernel for reads that outgrow the state machine's fixed-size lists; LC_CHAIN_HEAVY: nearly every read
-    through the warp-per-read chaining kernel (32 lanes sharing the filter's kept-chain scan), or none."""
+    through the warp-per-read chaining kernel (32 lanes sharing the filter's kept-chain scan), or none; LC_SMALL_READS: the low-latency
+    route of small batches (warp-per-read seeding and extension for every read), which is the default for calls of <= 16384 reads."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     ref = gobwa.GoBwaLoadReference(os.path.join(GOLDEN, "tiny", "tiny.fa"))
