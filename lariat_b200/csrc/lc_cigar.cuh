@@ -136,7 +136,9 @@ LC_HD void lc_cig_plan(const LcBatch &b, uint64_t cd)
 	}
 	const int w = lc_cig_band_w(b, j), cells = 2 * w + 1;
 	int cls = LC_CIG_FALLBACK;
-	for (int c = LC_CIG_NCLASS - 1; c >= 0; --c) if (cells <= lc_cig_class_cells(c)) cls = c;
+	// (a small batch has warps to spare: the cooperative fill of the warp-per-candidate body is the short way through a band that one
+	// thread would walk cell by cell)
+	if (!b.small) for (int c = LC_CIG_NCLASS - 1; c >= 0; --c) if (cells <= lc_cig_class_cells(c)) cls = c;
 	lc_cig_push_job(b, cls, cd);
 }
 

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(LC_TPB) pair_prepare_kernel(const LcBatch b, i
 	for (int p = worker; p < n_pairs; p += stride) lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
 }
 // Stage 5b: one warp per pair that needs a Smith-Waterman — the two rescue phases with the warp-cooperative local SW
-__global__ void __launch_bounds__(LC_TPB) matesw_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
+__global__ void __launch_bounds__(LC_TPB, 4) matesw_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
 {
 	extern __shared__ int lc_smem[];
 	const int lane = threadIdx.x & 31, per = lc_warp_smem_bytes(b.lmax, 3), rows = lc_warp_row_ints(b.lmax);

@@ -511,7 +511,7 @@ public:
 			}
 			if (NC) {
 				be.k_cigar_plan(b, NC); ++launches;
-				launches += be.k_cigar_band(b, NC);
+				if (!b.small) launches += be.k_cigar_band(b, NC);      // (small batches: every job is on the fallback list)
 				be.k_cigar_fallback(b, NC); ++launches;
 				if (want_alnx) { be.k_alnx(b, NC); ++launches; }      // reads the CIGARs: a no-op if the stage above overflowed
 			}
