@@ -157,14 +157,19 @@ def workload_config(args):
             "sharding": f"barcode groups split over {args.gpus} GPU(s), index replicated per GPU, {args.scaling} scaling"}
 
 
-def kernel_rooflines(stage_ms, counters, clocks, peaks, n_pairs_scale):
+def kernel_rooflines(stage_ms, counters, clocks, peaks, n_pairs_scale, config="c2"):
     """One entry per kernel of the step.  Static part: profiles/kernel_rooflines.json, written by scripts/ncu_kernels.py from an
     `ncu --set full` capture of this workload (warp instructions, DRAM bytes, active threads per launch).  Live part: the CUDA-event
     stage times and work counters of THIS run.  frac_issue = warp-instructions / (time x SMs x 4 schedulers x SM clock): the share of the
     chip's instruction-issue slots the kernel used (the bound of the integer DP kernels); frac_hbm = DRAM bytes / time / HBM peak."""
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "kernel_rooflines.json")))
-    except Exception:
+    prof = None
+    for name in (f"kernel_rooflines_{config}.json", "kernel_rooflines.json"):      # the capture of THIS workload if one is committed
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+            break
+        except Exception:
+            continue
+    if prof is None:
         return None
     out = {"source": prof.get("source"), "workload": prof.get("workload"), "kernels": {}}
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
@@ -431,7 +436,7 @@ def main():
     fm_bytes = 64.0 * counters["occ_blocks"] * res_frac
     ach = fm_bytes / (stage_ms["ms_seed"] * 1e-3) / 1e9 if stage_ms["ms_seed"] > 0 else 0.0
     clocks = sampler.summary()
-    kr = kernel_rooflines(stage_ms, counters, clocks, peaks, res_frac)
+    kr = kernel_rooflines(stage_ms, counters, clocks, peaks, res_frac, "c3" if args.config == "c4" else args.config)
     traffic = None
     limiter = None
     if kr and cfg["config"] == (kr.get("workload") or {}).get("config") and "smem_kernel" in kr["kernels"]:

@@ -187,6 +187,8 @@ lc_ctx *lc_init(const char *idx_prefix, int device, const lc_opt_t *opt)
 		if (o.o_del < 0 || o.o_ins < 0 || o.pen_clip5 < 0 || o.pen_clip3 < 0 || pen > 4096 || (long long)LC_MAX_READ_LEN * o.a + pen > 32767) {
 			fail(LC_EARG, "scoring options out of the supported range: LC_MAX_READ_LEN*a + max penalty must be <= 32767 and penalties <= 4096 (16-bit DP cells)"); return nullptr;
 		}
+		// substitution scores are looked up as bytes (PRMT tables of the extension and CIGAR kernels)
+		if ((long long)o.a + o.b > 127) { fail(LC_EARG, "scoring options out of the supported range: a + b must be <= 127 (byte score tables)"); return nullptr; }
 	}
 	std::shared_ptr<LcSharedIndex> sh(new LcSharedIndex);
 	sh->device = device;

@@ -173,6 +173,21 @@ LC_HD uint32_t lc_cig_qword(const LcCigJob &j, int k)
 	return v;
 }
 
+// four substitution scores at once: byte k of the result = byte ((sel >> 4k) & 7) of the pool {lut_lo, lut_hi} (one PRMT on the device)
+LC_HD uint32_t lc_cig_lut4(uint32_t lut_lo, uint32_t lut_hi, uint32_t sel)
+{
+#ifdef __CUDA_ARCH__
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lut_lo), "r"(lut_hi), "r"(sel));
+	return r;
+#else
+	const uint64_t pool = (uint64_t)lut_hi << 32 | lut_lo;
+	uint32_t r = 0;
+	for (int k = 0; k < 4; ++k) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * k)) & 7u))) & 0xffu) << (8 * k);
+	return r;
+#endif
+}
+
 // ---- one thread per job: ksw_global2 (B/ksw.c:504-606) in diagonal coordinates, NB = band cells of the job's class (multiple of 8)
 template <int NB> LC_HD void lc_cig_band(const LcBatch &b, uint64_t cd)
 {
@@ -183,6 +198,8 @@ template <int NB> LC_HD void lc_cig_band(const LcBatch &b, uint64_t cd)
 	const int w = lc_cig_band_w(b, j), w2x = 2 * w;
 	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_del = sc.e_del, e_ins = sc.e_ins;
 	const int lq = j.lq, rlen = j.rlen;
+	// substitution scores by (query code ^ target code): 0 = match, 1..3 = mismatch, 4..7 = ambiguous query base (-1, B/bwa.c:109-118)
+	const uint32_t lut_lo = ((uint32_t)sc.a & 0xffu) | ((uint32_t)(-sc.b) & 0xffu) * 0x01010100u, lut_hi = 0xffffffffu;
 	// the job's slice of the traceback pool: GS words per row (every carve of this kernel is a multiple of 16 bytes)
 	const unsigned long long zo = lc_carve(b, b.z_cur, b.z_cap, (unsigned long long)rlen * GS * 4, LC_OVF_Z);
 	if (zo == (unsigned long long)-1) return;
@@ -224,16 +241,15 @@ template <int NB> LC_HD void lc_cig_band(const LcBatch &b, uint64_t cd)
 #pragma unroll
 		for (int g = 0; g < G; ++g) {
 			const uint32_t qword = lc_funnel_r(R[g], R[g + 1], ph4);
-			uint32_t y = qword ^ tbm;
-			y |= y >> 1; y |= y >> 2;
-			const uint32_t mb = ~y, nb = qword >> 2;                  // bit 4c: base c matches / base c is ambiguous
+			const uint32_t x = qword ^ tbm;                          // nibble c: 0 = match, 1..3 = mismatch, 4..7 = ambiguous query base
+			const uint32_t sa = lc_cig_lut4(lut_lo, lut_hi, x), sb = lc_cig_lut4(lut_lo, lut_hi, x >> 16);
 			uint32_t zw = 0;
 #pragma unroll
 			for (int c = 0; c < 8; ++c) {
 				const int d = 8 * g + c;
 				const int col = j0 + d;
 				const bool valid = (unsigned)col < (unsigned)lq && d <= w2x;
-				const int s = (mb >> (4 * c) & 1u) ? sc.a : ((nb >> (4 * c) & 1u) ? -1 : -sc.b);
+				const int s = (int)(int8_t)((c < 4 ? sa : sb) >> (8 * (c & 3)));
 				const int M = h[d] + s, ee = e[d + 1];
 				uint32_t dd = M >= ee ? 0u : 1u;
 				int hh = M >= ee ? M : ee;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: ksw_extend2 / SMEM sweep — read length 100-250, band width 100, mismatch+indel rate 0-10 %.
-For every (read length, error rate) the whole path runs on 200 k simulated pairs over a 20 Mb reference; the extension and seeding
+For every (read length, error rate) the whole path runs on 500 k simulated pairs (10^6 reads) over a C2-sized 100 Mb reference; the extension and seeding
 kernels are timed in place (CUDA events of the library's own stages) and divided into the algorithmic work the reference would do,
 counted on the device in a separate pass (lc_set_counting): cells of ksw_extend2 as it iterates them (B/ksw.c:424) -> GCUPS;
 64 B x the occ blocks bwt_2occ4 would touch (B/bwt.c:194) -> FM-index GB/s.  One JSON line per point on stdout.
@@ -12,8 +12,8 @@ sys.path.insert(0, ROOT)
 from lariat_b200 import gobwa, index_build, iofmt, synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--pairs", type=int, default=200_000)
-ap.add_argument("--genome", type=int, default=20_000_000)
+ap.add_argument("--pairs", type=int, default=500_000)
+ap.add_argument("--genome", type=int, default=100_000_000)
 ap.add_argument("--steps", type=int, default=3)
 args = ap.parse_args()
 import torch  # noqa: E402
@@ -29,7 +29,7 @@ with tempfile.TemporaryDirectory() as td:
     assert ref is not None, gobwa.last_error()
     ctx = ref.BWTData
     res = C.POINTER(gobwa.lc_result_t)()
-    for L in (100, 150, 200, 250):
+    for L in (100, 125, 150, 200, 250):
         for err in (0.0, 0.01, 0.02, 0.05, 0.10):
             r = synth.ReadSpec(args.pairs, max(20, args.pairs // 100), read_len=L, sub_rate=err * 0.8, indel_rate=err * 0.2, seed=900 + L)
             sim = synth.simulate_pairs(contigs, loci, r)
