@@ -578,14 +578,14 @@ template <class CELLS, bool UNIT> static inline void lc_ext_run_scalar_t(const L
 	lc_ext_fill_masks(mtab);
 	LcExtLane<1, CELLS, UNIT> ex(b, he, qw + 1, mtab);
 	int next = 0;
-	const int n_items = UNIT ? (int)b.ext_unit_n[0] : b.n_reads;
+	const int n_items = UNIT ? lc_ext_n_units(b) : b.n_reads;
 	for (;;) {
 		while (ex.phase == LC_XP_FETCH) {
 			if (next >= n_items) { ex.phase = LC_XP_DONE; break; }
 			const int it = next++;
-			const int r = UNIT ? b.chain_aux[b.ext_units[it]].r : it;
+			const int r = UNIT ? b.chain_aux[lc_ext_unit_at(b, it)].r : it;
 			lc_ext_load_read<1>(b, r, qw + 1, lc_ext_q_words(b.lmax) - 1);
-			if (UNIT) ex.begin_unit((long long)b.ext_units[it]); else ex.begin_read(r);
+			if (UNIT) ex.begin_unit((long long)lc_ext_unit_at(b, it)); else ex.begin_read(r);
 			ex.resolve();
 		}
 		if (ex.phase == LC_XP_DONE) break;

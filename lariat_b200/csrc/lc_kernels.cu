@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 	if (threadIdx.x == 0) lc_ext_fill_masks(lc_ext_smem);
 	__syncthreads();
 	LcExtLane<32, CELLS, UNIT> ex(b, wbase + lane, qf + lane, lc_ext_smem);
-	const int n_items = UNIT ? (int)b.ext_unit_n[0] : b.n_reads;
+	const int n_items = UNIT ? lc_ext_n_units(b) : b.n_reads;
 	unsigned int *ctr = UNIT ? b.ext_unit_n + 1 : b.work_ctr + 0;
 	for (unsigned it = 0;; ++it) {
 		if ((it & hk_mask) == 0) {                               // warp-uniform
@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 				base = __shfl_sync(LC_FULL, base, 0);
 				int myi = -1, myr = -1;
 				if (need >> lane & 1) { myi = base + __popc(need & ((1u << lane) - 1)); if (myi >= n_items) myi = -1; }
-				if (myi >= 0) myr = UNIT ? b.chain_aux[b.ext_units[myi]].r : myi;
+				const long long myu = (UNIT && myi >= 0) ? (long long)lc_ext_unit_at(b, myi) : -1;
+				if (myi >= 0) myr = UNIT ? b.chain_aux[myu].r : myi;
 				for (unsigned m = need; m; m &= m - 1) {
 					const int L = __ffs(m) - 1;
 					const int rr = __shfl_sync(LC_FULL, myr, L);
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 				__syncwarp();
 				if (need >> lane & 1) {
 					if (myi < 0) ex.phase = LC_XP_DONE;
-					else if (UNIT) ex.begin_unit((long long)b.ext_units[myi]);
+					else if (UNIT) ex.begin_unit(myu);
 					else ex.begin_read(myr);
 				}
 			}
@@ -317,7 +318,25 @@ __global__ void __launch_bounds__(LC_TPB) pair_prepare_kernel(const LcBatch b, i
 {
 	const int worker = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
 	int *wi = b.w_int + (size_t)worker * b.w_int_n;
-	for (int p = worker; p < n_pairs; p += stride) lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
+	for (int p = worker; p < n_pairs; p += stride) if (!lc_pair_prepare_defer(b, p)) lc_pair_prepare(b, p, wi, wi + (b.lmax + 18));
+}
+// ... pairs with very many regions (repeats) were listed instead: a warp each, the same body with the copies and list scans shared out
+__global__ void __launch_bounds__(LC_TPB) pair_prepare_heavy_kernel(const LcBatch b)
+{
+	LcExecWarp ex;
+	ex.H = ex.E = ex.Hmax = nullptr; ex.qs = nullptr; ex.bl = nullptr; ex.cig = nullptr; ex.zloc = nullptr;
+	ex.lane = threadIdx.x & 31;
+	const int worker = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;      // the warp uses the scratch slot of its first thread
+	int *wi = b.w_int + (size_t)worker * b.w_int_n;
+	const unsigned int n = b.prep_heavy_n[0];
+	for (;;) {
+		unsigned int t = 0;
+		if (ex.lane == 0) t = atomicAdd(b.prep_heavy_n + 1, 1u);
+		t = __shfl_sync(LC_FULL, t, 0);
+		if (t >= n) break;
+		lc_pair_prepare_t(b, (int)(uint32_t)b.wl_out[t], wi, wi + (b.lmax + 18), ex);
+		__syncwarp();
+	}
 }
 // Stage 5b: one warp per pair that needs a Smith-Waterman — the two rescue phases with the warp-cooperative local SW
 __global__ void __launch_bounds__(LC_TPB, 4) matesw_kernel(const LcBatch b, const uint64_t *list, const unsigned int n)
@@ -469,7 +488,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
 	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
 	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
-	env_int("LC_SEED_GL_CTAS", seed_gl_ctas, 1, 32); env_int("LC_CHAIN_CTAS", chain_ctas, 1, 16); env_int("LC_CHAIN_HEAVY_CTAS", chain_heavy_ctas, 1, 16);
+	env_int("LC_SEED_GL_CTAS", seed_gl_ctas, 1, 32); env_int("LC_SEED_REDO_CTAS", seed_redo_ctas, 1, 16); env_int("LC_CHAIN_CTAS", chain_ctas, 1, 16); env_int("LC_CHAIN_HEAVY_CTAS", chain_heavy_ctas, 1, 16);
 	env_int("LC_SEED_GATE_MASK", seed_gate_mask, 0, 255); env_int("LC_SEED_GATE_N", seed_gate_n, 1, 33);     // tuning knobs; mask must be 2^k - 1
 	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_ROW_MASK", ext_row_mask, 0, 255);
 }
@@ -587,7 +606,7 @@ int LcCudaBackend::seed_lanes() { return n_sm * 2048; }      // upper bound on r
 void LcCudaBackend::k_seed_redo(const LcBatch &b, int n_redo)
 {
 	cudaMemsetAsync(b.work_ctr + 3, 0, 4, stream);
-	smem_redo_kernel<<<grid_for((unsigned long long)n_redo * 32, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_redo);      // at most n_sm * 16 warps = worker slots
+	smem_redo_kernel<<<grid_for((unsigned long long)n_redo * 32, LC_TPB, seed_redo_ctas), LC_TPB, 0, stream>>>(b, n_redo);      // at most n_sm * 64 warps <= worker slots (n_redo_workers)
 }
 void LcCudaBackend::k_occ_convert(const uint32_t *bwa, uint4 *occ, unsigned long long n_blocks, const LcIndex &ix)
 {
@@ -636,11 +655,13 @@ int LcCudaBackend::k_extend(const LcBatch &b)
 	if (!n) return launches;
 	ext_plan_kernel<<<grid_for(n, LC_TPB, 8), LC_TPB, 0, stream>>>(b, n); ++launches;
 	unsigned int cnt[4] = { 0, 0, 0, 0 };      // ext_unit_n[0..1], ext_hvu_n[0..1] are adjacent control words
+	unsigned int n_back = 0;
 	cudaMemcpyAsync(cnt, b.ext_unit_n, 16, cudaMemcpyDeviceToHost, stream);
+	cudaMemcpyAsync(&n_back, b.ext_unit_back, 4, cudaMemcpyDeviceToHost, stream);
 	cudaStreamSynchronize(stream);
-	if (cnt[0]) {
-		if (cells8) lc_launch_extend<LcCells8<32>, true>(b, cnt[0], n_sm, stream, hk, rw);
-		else lc_launch_extend<LcCells16<32>, true>(b, cnt[0], n_sm, stream, hk, rw);
+	if (cnt[0] + n_back) {
+		if (cells8) lc_launch_extend<LcCells8<32>, true>(b, (long long)cnt[0] + n_back, n_sm, stream, hk, rw);
+		else lc_launch_extend<LcCells16<32>, true>(b, (long long)cnt[0] + n_back, n_sm, stream, hk, rw);
 		++launches;
 	}
 	unsigned int nh = cnt[2] < b.ext_hvu_cap ? cnt[2] : (unsigned int)b.ext_hvu_cap;
@@ -676,6 +697,8 @@ void LcCudaBackend::k_pair(const LcBatch &b, int n_pairs)
 {
 	// at most n_workers threads: the patch scratch (w_int) is indexed by global thread id
 	pair_prepare_kernel<<<grid_for((unsigned long long)n_pairs, LC_TPB, 4), LC_TPB, 0, stream>>>(b, n_pairs);
+	// the listed pairs (count known on the device only: a resident-size grid, warps pull from a counter)
+	if (b.prep_heavy_n) pair_prepare_heavy_kernel<<<grid_for((unsigned long long)n_pairs * 32, LC_TPB, 4), LC_TPB, 0, stream>>>(b);
 	// at most n_workers/32 warps: the sub-optimal-row lists live in the per-worker scratch, indexed by global warp id.
 	unsigned int n = 0;
 	const uint64_t *list = sort_worklist(b, b.resc_n, n);      // pairs that need a Smith-Waterman, heaviest first

@@ -111,10 +111,14 @@ struct LcBatch {
 	unsigned int *ext_heavy_n;                           // stage 4: [0] = reads with very many chains, listed in wl_in for lc_ext_plan
 	int32_t ext_heavy_seeds, ext_heavy_chains;           // a read — and then a unit — is "heavy" above this many chained seeds / chains (0 = never)
 	LcChainAux *chain_aux;                               // parallel to `chain`; filled for the chains of listed reads only
-	uint32_t *ext_units; unsigned int *ext_unit_n;       // units for the lane kernel (first chain of each, index into `chain`): [0] = count, [1] = work counter
+	uint32_t *ext_units; unsigned int *ext_unit_n;       // units for the lane kernel (first chain of each, index into `chain`): [0] = count of the
+	                                                     //   larger units, filled from the front, [1] = work counter
+	unsigned int *ext_unit_back; unsigned long long ext_units_cap;   // count of the small units, filled from the back of the same array: the
+	                                                     //   lanes take the larger units first, so that none of them starts last (lc_ext_unit_at)
 	uint64_t *ext_hvu_in, *ext_hvu_out;                  // heavy units for the warp-per-unit kernel: weight << 32 | first chain; sorted like wl_in -> wl_out
 	unsigned int *ext_hvu_n;                             // [0] = count, [1] = work counter
 	unsigned long long ext_hvu_cap;
+	unsigned int *prep_heavy_n;                          // stage 5a: [0] = pairs listed in wl_out for the warp-per-pair launch, [1] = its work counter; null = never
 	LcSortKey *sortk; unsigned long long sortk_cap, *sortk_cur;      // stage 5a: key scratch of the dedup sorts, carved per read
 	int32_t small;                                       // a batch of few reads: the warp-per-read forms of seeding and extension for every read (latency, not throughput)
 };
@@ -521,6 +525,22 @@ struct LcChainJob {
 		flt = (LcChainFlt *)p;
 		c.s_rbeg = (int64_t *)(b.seed_row + b.r_seed_off[r]);
 	}
+	// what mem_chain needs per seed before it can place it (B/bwamem.c:280-287): query span, and the contig (two binary searches over
+	// the contig table) — independent per seed, so all lanes; srt[] holds the rids until sort_by_weight() takes the array over
+	template <class EX> LC_HD void prep(const EX &ex)
+	{
+		for (int i = 0; i < NI; ++i) {
+			const int slen = (int)(iv[i].qend - iv[i].qbeg), qb = (int)iv[i].qbeg, s0 = (int)iv[i].soff;
+			const int cnt = (i + 1 < NI ? (int)iv[i + 1].soff : S) - s0;
+			for (int t = ex.lane(); t < cnt; t += ex.width()) {
+				const int si = s0 + t;
+				c.s_q[si] = qb; c.s_len[si] = slen; c.s_next[si] = -1;
+				const int64_t rbeg = c.s_rbeg[si];
+				srt[si] = lc_intv2rid(b.ix, rbeg, rbeg + slen);
+			}
+		}
+		ex.sync();
+	}
 	// mem_chain (B/bwamem.c:273-307): every seed joins the chain below it in the tree or opens a new one; then the in-order walk
 	// (__kb_traverse, B/kbtree.h:336-358).  Ordered work: one thread.
 	LC_HD void build()
@@ -528,26 +548,20 @@ struct LcChainJob {
 		const lc_opt_t &opt = b.opt;
 		c.n_ch = 0; c.n_nd = 0; c.n_keys = 0;
 		c.root = c.new_node(0);
-		for (int i = 0; i < NI; ++i) {
-			const int slen = (int)(iv[i].qend - iv[i].qbeg);
-			const int cnt = (i + 1 < NI ? (int)iv[i + 1].soff : S) - (int)iv[i].soff;
-			for (int t = 0; t < cnt; ++t) {
-				const int si = (int)iv[i].soff + t;
-				c.s_q[si] = (int)iv[i].qbeg; c.s_len[si] = slen; c.s_next[si] = -1;
-				const int64_t rbeg = c.s_rbeg[si];
-				const int rid = lc_intv2rid(b.ix, rbeg, rbeg + slen);
-				if (rid < 0) continue;                       // spans contigs or the strand boundary (B/bwamem.c:286-287)
-				bool add = true;
-				if (c.n_keys) {
-					int low = c.lower(rbeg);
-					if (low >= 0 && c.merge(opt, b.ix.l_pac, low, si, rid)) add = false;
-				}
-				if (add) {
-					LcChainRec &nn = c.ch[c.n_ch];
-					nn.pos = rbeg; nn.rid = rid; nn.n = 1; nn.head = nn.tail = si; nn.w = 0; nn.kept = 0; nn.first = -1;
-					nn.is_alt = b.ix.anns[rid].is_alt ? 1 : 0;
-					c.put(c.n_ch++);
-				}
+		for (int si = 0; si < S; ++si) {                     // seeds in interval order, occurrences in schedule order
+			const int rid = srt[si];
+			if (rid < 0) continue;                           // spans contigs or the strand boundary (B/bwamem.c:286-287)
+			const int64_t rbeg = c.s_rbeg[si];
+			bool add = true;
+			if (c.n_keys) {
+				int low = c.lower(rbeg);
+				if (low >= 0 && c.merge(opt, b.ix.l_pac, low, si, rid)) add = false;
+			}
+			if (add) {
+				LcChainRec &nn = c.ch[c.n_ch];
+				nn.pos = rbeg; nn.rid = rid; nn.n = 1; nn.head = nn.tail = si; nn.w = 0; nn.kept = 0; nn.first = -1;
+				nn.is_alt = b.ix.anns[rid].is_alt ? 1 : 0;
+				c.put(c.n_ch++);
 			}
 		}
 		n = 0;
@@ -671,6 +685,7 @@ struct LcChainJob {
 	// the whole of stage 3 for one read
 	template <class EX> LC_HD void run(const EX &ex)
 	{
+		prep(ex);
 		if (ex.leader()) build();
 		ex.sync();
 		n = ex.bcast(n);
@@ -908,6 +923,13 @@ LC_HDN void lc_stage_extend(const LcBatch &b, int r, long long unit, int worker)
 // hundreds of one-chain units: work for many lanes instead of one warp.  The regions come back chain by chain (LcChainAux), so the
 // read's list is rebuilt in the reference's order whatever order the units finished in.
 // Windows are taken before the strand / contig clamps (a superset: merging two units is always safe).
+#define LC_EXT_UNIT_FRONT 4      // units with at least this many seeds are dealt first
+LC_HD int lc_ext_n_units(const LcBatch &b) { return (int)(b.ext_unit_n[0] + b.ext_unit_back[0]); }
+LC_HD uint32_t lc_ext_unit_at(const LcBatch &b, int i)
+{
+	const int nf = (int)b.ext_unit_n[0];
+	return i < nf ? b.ext_units[i] : b.ext_units[b.ext_units_cap - 1 - (unsigned long long)(i - nf)];
+}
 LC_HD unsigned long long lc_ext_plan_scratch_bytes(int NC) { return 40ull * NC + 16; }
 LC_HD void lc_ext_plan(const LcBatch &b, int r)
 {
@@ -961,7 +983,8 @@ LC_HD void lc_ext_plan(const LcBatch &b, int r)
 			const unsigned int at = lc_atomic_add(b.ext_hvu_n, 1u);
 			if (at < b.ext_hvu_cap) b.ext_hvu_in[at] = (uint64_t)(uint32_t)lc_min(tot[u], 0xffff) << 32 | (uint32_t)fc;
 			else lc_raise(b, LC_OVF_CHAIN);
-		} else b.ext_units[lc_atomic_add(b.ext_unit_n, 1u)] = (uint32_t)fc;
+		} else if (tot[u] >= LC_EXT_UNIT_FRONT) b.ext_units[lc_atomic_add(b.ext_unit_n, 1u)] = (uint32_t)fc;
+		else b.ext_units[b.ext_units_cap - 1 - lc_atomic_add(b.ext_unit_back, 1u)] = (uint32_t)fc;
 	}
 }
 
@@ -1294,16 +1317,23 @@ LC_HD int lc_matesw_t(const LcBatch &b, const lc_alnreg_t &a, int l_ms, const ui
 // the final lists carved and filled, and the two rescue phases of GoBwaMemMateSW (G/gobwa.go:264-324) replayed for as long as
 // every mem_matesw call is a no-op (the usual case: a properly paired hit satisfies every anchor).  The first anchor that needs
 // a Smith-Waterman sends the pair to the rescue list; stage 5b (one warp per listed pair) then runs the phases for real.
-LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
+// `ex`: one thread, or — for pairs with very many regions (lc_pair_prepare_defer) — the lanes of a warp: the copies and the list scans are
+// shared out, the sorts and the dedup loop stay with the leader (they are the reference's statements in the reference's order).
+template <class Exec>
+LC_HD void lc_pair_prepare_t(const LcBatch &b, int p, int *H, int *E, const Exec &ex)
 {
 	int n[2], len[2], best[2] = { 0, 0 };
-	bool clean[2];
+	bool clean[2] = { false, false };
 	for (int e = 0; e < 2; ++e) { const int r = 2 * p + e; len[e] = (int)(b.off[r + 1] - b.off[r]); n[e] = b.r_n_reg[r]; }
 	// capacity of the final lists: what stage 4 produced (the dedup can only shrink it) plus one region per rescue call
 	const int cap0 = n[0] + (len[0] > 0 ? lc_min(b.max_anchors, n[1]) : 0);
 	const int cap1 = n[1] + (len[1] > 0 ? lc_min(b.max_anchors, cap0) : 0);
-	b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
-	const unsigned long long fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
+	unsigned long long fo = 0;
+	if (ex.leader()) {
+		b.r_n_fin[2 * p] = b.r_n_fin[2 * p + 1] = 0; b.r_fin_off[2 * p] = b.r_fin_off[2 * p + 1] = 0;
+		fo = lc_carve(b, b.fin_cur, b.fin_cap, (unsigned long long)cap0 + cap1, LC_OVF_FINAL);
+	}
+	fo = ex.bcast(fo);
 	if (fo == (unsigned long long)-1) return;
 	lc_alnreg_t *f0 = b.fin + fo, *f1 = b.fin + fo + cap0;
 	for (int e = 0; e < 2; ++e) {
@@ -1311,46 +1341,78 @@ LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E)
 		lc_alnreg_t *dst = e ? f1 : f0;
 		if (b.r_reg_off[r] >= 0) {                            // one slice of `reg`, in the reference's order
 			const lc_alnreg_t *src = b.reg + b.r_reg_off[r];
-			for (int i = 0; i < n[e]; ++i) dst[i] = src[i];
+			for (int i = ex.lane_id(); i < n[e]; i += ex.n_lanes()) dst[i] = src[i];
 		} else {                                             // extended unit by unit (lc_ext_plan): chain by chain, which IS that order
 			const long long c0 = (long long)b.r_chain_off[r];
 			int m = 0;
 			for (int ci = 0; ci < b.r_n_chain[r]; ++ci) {
 				const LcChainAux &ax = b.chain_aux[c0 + ci];
 				const lc_alnreg_t *src = b.reg + ax.reg_off;
-				for (int i = 0; i < ax.n_reg; ++i) dst[m++] = src[i];
+				for (int i = ex.lane_id(); i < ax.n_reg; i += ex.n_lanes()) dst[m + i] = src[i];
+				m += ax.n_reg;
 			}
 		}
-		LcSortKey *ks = nullptr;
-		if (n[e] >= 12 && b.sortk) {                          // (a full pool only means the slower sort)
-			const unsigned long long ko = lc_atomic_add(b.sortk_cur, (unsigned long long)n[e]);
-			if (ko + (unsigned long long)n[e] <= b.sortk_cap) ks = b.sortk + ko;
+		ex.sync();
+		int ne = n[e];
+		unsigned long long cl = 0;
+		if (ex.leader()) {
+			LcSortKey *ks = nullptr;
+			if (ne >= 12 && b.sortk) {                        // (a full pool only means the slower sort)
+				const unsigned long long ko = lc_atomic_add(b.sortk_cur, (unsigned long long)ne);
+				if (ko + (unsigned long long)ne <= b.sortk_cap) ks = b.sortk + ko;
+			}
+			bool c1 = false;
+			ne = lc_sort_dedup_patch(b, b.seq + b.off[r], ne, dst, H, E, H, 2 * (b.lmax + 18), &c1, ks);      // tail of mem_align1_core (B/bwamem.c:1070)
+			cl = c1 ? 1 : 0;
 		}
-		n[e] = lc_sort_dedup_patch(b, b.seq + b.off[r], n[e], dst, H, E, H, 2 * (b.lmax + 18), &clean[e], ks);      // tail of mem_align1_core (B/bwamem.c:1070)
-		for (int i = 0; i < n[e]; ++i) {
+		ex.sync();
+		n[e] = (int)ex.bcast((unsigned long long)(unsigned)ne); clean[e] = ex.bcast(cl) != 0;
+		int bst = 0;
+		for (int i = ex.lane_id(); i < n[e]; i += ex.n_lanes()) {
 			if (dst[i].rid >= 0 && b.ix.anns[dst[i].rid].is_alt) dst[i].is_alt = 1;   // B/bwamem.c:1078-1082
-			best[e] = lc_max(best[e], dst[i].score);                                 // G/gobwa.go:264-283
+			bst = lc_max(bst, dst[i].score);                                         // G/gobwa.go:264-283
 		}
+		best[e] = ex.max(bst);
+		ex.sync();
 	}
-	b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n[0];
-	b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n[1];
+	if (ex.leader()) {
+		b.r_fin_off[2 * p] = (int64_t)fo; b.r_n_fin[2 * p] = n[0];
+		b.r_fin_off[2 * p + 1] = (int64_t)(fo + cap0); b.r_n_fin[2 * p + 1] = n[1];
+	}
 	bool need = false;
 	int64_t rb, re;
 	int num = 0;
 	for (int i = 0; i < n[1] && num < b.max_anchors && len[0] > 0 && !need; ++i)
-		if (f1[i].score >= best[1] - b.score_delta) { ++num; need = lc_matesw_wants_sw(b, f1[i], len[0], f0, n[0], rb, re); }
+		if (f1[i].score >= best[1] - b.score_delta) { ++num; need = lc_matesw_wants_sw_t(b, f1[i], len[0], f0, n[0], rb, re, ex); }
 	num = 0;
 	for (int i = 0; i < n[0] && num < b.max_anchors && len[1] > 0 && !need; ++i)
-		if (f0[i].score >= best[0] - b.score_delta) { ++num; need = lc_matesw_wants_sw(b, f0[i], len[1], f1, n[1], rb, re); }
+		if (f0[i].score >= best[0] - b.score_delta) { ++num; need = lc_matesw_wants_sw_t(b, f0[i], len[1], f1, n[1], rb, re, ex); }
 	if (need) {                                          // weight = candidates of the pair (anchors to try, lists to scan); bits 48, 49: the lists
 		const int wgt = lc_min(n[0] + n[1], 0xffff);     // are fixed points already (lc_matesw_t) — a clean mem_sort_dedup_patch just made them
-		b.wl_in[lc_atomic_add(b.resc_n, 1u)] = (uint64_t)((clean[0] ? 1 : 0) | (clean[1] ? 2 : 0)) << 48 | (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
+		if (ex.leader()) b.wl_in[lc_atomic_add(b.resc_n, 1u)] = (uint64_t)((clean[0] ? 1 : 0) | (clean[1] ? 2 : 0)) << 48 | (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
 		return;
 	}
-	const unsigned long long co = lc_atomic_add(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
-	for (int i = 0; i < n[0]; ++i) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
-	for (int i = 0; i < n[1]; ++i) b.cand[co + n[0] + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
+	unsigned long long co = 0;
+	if (ex.leader()) co = lc_atomic_add(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
+	co = ex.bcast(co);
+	for (int i = ex.lane_id(); i < n[0]; i += ex.n_lanes()) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
+	for (int i = ex.lane_id(); i < n[1]; i += ex.n_lanes()) b.cand[co + n[0] + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
 }
+struct LcExecOnePair : LcExecOne {      // the thread form
+	LC_HD bool leader() const { return true; }
+	LC_HD void sync() const {}
+	LC_HD unsigned long long bcast(unsigned long long v) const { return v; }
+	LC_HD int max(int v) const { return v; }
+};
+// pairs with more regions than this are listed (wl_out, count in prep_heavy_n[0]) for the warp-per-pair launch of the same body
+#define LC_PREP_HEAVY 96
+LC_HD bool lc_pair_prepare_defer(const LcBatch &b, int p)
+{
+	if (!b.prep_heavy_n || b.r_n_reg[2 * p] + b.r_n_reg[2 * p + 1] <= LC_PREP_HEAVY) return false;
+	b.wl_out[lc_atomic_add(b.prep_heavy_n, 1u)] = (uint64_t)(uint32_t)p;
+	return true;
+}
+LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E) { lc_pair_prepare_t(b, p, H, E, LcExecOnePair()); }
 
 // Stage 5b, one warp (or thread) per listed pair: the two rescue phases on the lists lc_pair_prepare filled
 template <class Exec>

@@ -218,6 +218,7 @@ public:
 	int memcap = 256;
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
 	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
+	bool prep_heavy = true;                              // stage 5a: pairs with very many regions get a warp
 	int small_reads = 16384;                             // batches of at most this many reads run in the low-latency form (0 = never)
 	int chain_heavy = 48;                                // chaining: reads with more seeds than this go to the warp-per-read kernel (0 = never)
 	int lst_cap2 = 64, pk_cap2 = 256;     // the second and third pass' capacities; overflow of the third -> the one-thread-per-read redo kernel
@@ -298,6 +299,8 @@ public:
 			b.intv_cur = c + 0; b.seed_cur = c + 1; b.scratch_cur = c + 2; b.chain_cur = c + 3; b.cseed_cur = c + 4;
 			b.reg_cur = c + 5; b.fin_cur = c + 6; b.cand_cur = c + 7; b.cigar_cur = c + 8; b.z_cur = c + 9;
 			b.reg_total = c + 10; b.pk_cur = c + 11; b.mm_cur = c + 12; b.sortk_cur = c + 13;
+			b.prep_heavy_n = prep_heavy ? (unsigned int *)(c + 14) : nullptr;
+			b.ext_unit_back = (unsigned int *)(c + 15);
 			b.overflow = (uint32_t *)(c + 16);
 			b.work_ctr = (unsigned int *)(c + 20);
 			b.redo_cur = (unsigned int *)(c + 22);
@@ -464,7 +467,7 @@ public:
 			!d_cseed.ensure(be, sizeof(LcSeed) * b.cseed_cap) || !d_reg.ensure(be, sizeof(lc_alnreg_t) * b.reg_cap) ||
 			!d_chainaux.ensure(be, sizeof(LcChainAux) * b.chain_cap) || !d_units.ensure(be, 4 * b.chain_cap) || !d_hvu.ensure(be, 16 * b.ext_hvu_cap)) return nomem();
 		b.scratch = (uint8_t *)d_scratch.p; b.chain = (LcChainOut *)d_chain.p; b.cseed = (LcSeed *)d_cseed.p; b.reg = (lc_alnreg_t *)d_reg.p;
-		b.chain_aux = (LcChainAux *)d_chainaux.p; b.ext_units = (uint32_t *)d_units.p;
+		b.chain_aux = (LcChainAux *)d_chainaux.p; b.ext_units = (uint32_t *)d_units.p; b.ext_units_cap = b.chain_cap;
 		b.ext_hvu_in = (uint64_t *)d_hvu.p; b.ext_hvu_out = b.ext_hvu_in + b.ext_hvu_cap;
 		if (S && !(b.ix.sa32 || b.ix.sa64)) { be.k_sa(b, S); ++launches; }     // with the dense suffix array the seeding kernels wrote positions already
 		be.ev_record(4);
@@ -483,7 +486,7 @@ public:
 		b.fin = (lc_alnreg_t *)d_fin.p; b.aln = (lc_aln_t *)d_aln.p; b.cand = (uint64_t *)d_cand.p;
 		b.sortk_cap = NREG + 64;
 		b.sortk = d_sortk.ensure(be, sizeof(LcSortKey) * b.sortk_cap) ? (LcSortKey *)d_sortk.p : nullptr;      // optional: without it the sorts go through handles
-		be.k_pair(b, n_pairs); launches += 2;
+		be.k_pair(b, n_pairs); launches += b.prep_heavy_n ? 3 : 2;
 		be.ev_record(7);
 		read_ctl();
 		if (launch_broken) { err = "a CUDA kernel launch failed in the pair stage"; return LC_ECUDA; }

@@ -588,6 +588,7 @@ struct LcExecWarp {
 	__device__ __forceinline__ int lane_id() const { return lane; }
 	__device__ __forceinline__ int n_lanes() const { return 32; }
 	__device__ __forceinline__ bool any(bool v) const { return __any_sync(LC_FULL, v) != 0; }
+	__device__ __forceinline__ int max(int v) const { return __reduce_max_sync(LC_FULL, v); }
 	template <class QF, class TF>
 	__device__ __forceinline__ LcSwResult sw_align2(int qlen, QF q, int tlen, TF t, const LcScore &sc, int xtra, LcCounters *cnt) const
 	{

@@ -68,7 +68,7 @@ struct HostBackend {
 		lc_ext_run_scalar(b, he.data(), qw.data(), c8, idle_ticks);
 		if (!*b.ext_heavy_n) return 1;
 		for (unsigned int t = *b.ext_heavy_n; t-- > 0;) lc_ext_plan(b, (int)(uint32_t)b.wl_in[t]);      // reversed: order must not matter
-		n_units += b.ext_unit_n[0]; n_heavy_units += b.ext_hvu_n[0];
+		n_units += lc_ext_n_units(b); n_heavy_units += b.ext_hvu_n[0];
 		lc_ext_run_scalar(b, he.data(), qw.data(), c8, idle_ticks, true);                                // the units' lane kernel
 		for (unsigned int t = b.ext_hvu_n[0]; t-- > 0;) lc_stage_extend(b, -1, (long long)(uint32_t)b.ext_hvu_in[t], (int)(t % workers));   // the large units' kernel
 		return 4;
@@ -77,7 +77,8 @@ struct HostBackend {
 	bool wide_cells = false;     // -H: 16-bit H/E cells even when the batch would fit the byte packing
 	void k_pair(const LcBatch &b, int n_pairs)
 	{
-		for (int p = n_pairs - 1; p >= 0; --p) lc_stage_pair_prepare(b, p, p % workers);   // reversed: order must not matter
+		for (int p = n_pairs - 1; p >= 0; --p) if (!lc_pair_prepare_defer(b, p)) lc_stage_pair_prepare(b, p, p % workers);   // reversed: order must not matter
+		if (b.prep_heavy_n) for (unsigned int t = 0; t < b.prep_heavy_n[0]; ++t) lc_stage_pair_prepare(b, (int)(uint32_t)b.wl_out[t], (int)(t % workers));   // the listed pairs' launch
 		for (unsigned int t = 0; t < *b.resc_n; ++t) lc_stage_pair_rescue(b, (int)(uint32_t)b.wl_in[t], (int)(b.wl_in[t] >> 48) & 3, (int)(t % workers));
 	}
 	void k_cigar(const LcBatch &b, const uint64_t *list, unsigned long long n, const unsigned int *n_dev)
