@@ -119,7 +119,9 @@ struct LcBatch {
 	unsigned int *ext_hvu_n;                             // [0] = count, [1] = work counter
 	unsigned long long ext_hvu_cap;
 	unsigned int *prep_heavy_n;                          // stage 5a: [0] = pairs listed in wl_out for the warp-per-pair launch, [1] = its work counter; null = never
+	lc_alnreg_t *regtmp;                                 // stage 5a: record scratch of the cooperative dedup, carved with sortk (same offsets)
 	LcSortKey *sortk; unsigned long long sortk_cap, *sortk_cur;      // stage 5a: key scratch of the dedup sorts, carved per read
+	int32_t force_coop;                                  // tests: the cooperative dedup of stage 5a even with a one-lane executor
 	int32_t small;                                       // a batch of few reads: the warp-per-read forms of seeding and extension for every read (latency, not throughput)
 };
 
@@ -1101,18 +1103,11 @@ LC_HD void lc_sort_regs_keyed(lc_alnreg_t *a, int n, int which, LcSortKey *ks)
 // h/h_cap: scratch for lc_sort_regs (may overlap H and E: the sorts and the patching never run at the same time)
 // *clean (optional) := the call excluded nothing and merged nothing (and saw at least two regions): its output is then a fixed point of the
 // query-less form — sorted by the strict order (score, rb, qb), every n_comp == 1, no redundant pair (see lc_matesw_t)
-// ks (optional): n entries of scratch for the keyed sorts (regions with 0 <= qb < 2^16 and 0 <= rb < 2^48: every real one)
-LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0, bool *clean = nullptr,
-							   LcSortKey *ks = nullptr)
+// the middle of mem_sort_dedup_patch (B/bwamem.c:441-474): n_comp, the redundancy / patch loop over the list sorted by `re`, compaction
+LC_HDN int lc_dedup_core(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, bool &merged)
 {
 	const lc_opt_t &opt = b.opt;
 	int m, i, j;
-	if (clean) *clean = false;
-	if (n <= 1) return n;
-	const int n_in = n;
-	bool merged = false;
-	if (ks && n >= 12) lc_sort_regs_keyed(a, n, 1, ks);
-	else lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; }, h, h_cap);
 	for (i = 0; i < n; ++i) a[i].n_comp = 1;
 	for (i = 1; i < n; ++i) {
 		lc_alnreg_t &p = a[i];
@@ -1143,14 +1138,73 @@ LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc
 		}
 	}
 	for (i = 0, m = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
-	n = m;
-	if (ks && n >= 12) lc_sort_regs_keyed(a, n, 2, ks);
-	else lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
-		return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb))); }, h, h_cap);
+	return m;
+}
+// its tail (B/bwamem.c:476-487), on the list sorted by (score, rb, qb): identical hits marked and dropped
+LC_HD int lc_dedup_identical(lc_alnreg_t *a, int n)
+{
+	int i, m;
 	for (i = 1; i < n; ++i)
 		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
 	for (i = 1, m = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+	return n < 1 ? n : m;
+}
+
+// ks (optional): n entries of scratch for the keyed sorts (regions with 0 <= qb < 2^16 and 0 <= rb < 2^48: every real one)
+LC_HDN int lc_sort_dedup_patch(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, int *H, int *E, int *h = nullptr, int h_cap = 0, bool *clean = nullptr,
+							   LcSortKey *ks = nullptr)
+{
+	if (clean) *clean = false;
+	if (n <= 1) return n;
+	const int n_in = n;
+	bool merged = false;
+	if (ks && n >= 12) lc_sort_regs_keyed(a, n, 1, ks);
+	else lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) { return x.re < y.re; }, h, h_cap);
+	n = lc_dedup_core(b, query, n, a, H, E, merged);
+	if (ks && n >= 12) lc_sort_regs_keyed(a, n, 2, ks);
+	else lc_sort_regs(a, n, [](const lc_alnreg_t &x, const lc_alnreg_t &y) {
+		return x.score > y.score || (x.score == y.score && (x.rb < y.rb || (x.rb == y.rb && x.qb < y.qb))); }, h, h_cap);
+	const int m = lc_dedup_identical(a, n);
 	if (clean) *clean = !merged && m == n_in;
+	return m;
+}
+
+// The same function run by the lanes of `ex` together, for long lists: the keys are filled and the two permutations applied by all
+// lanes (out of place, through `tmp`: n records of scratch), the introsorts and the dedup loop stay with the leader.  a[] in, a[] out.
+template <class Exec>
+LC_HD int lc_sort_dedup_patch_coop(const LcBatch &b, const uint8_t *query, int n, lc_alnreg_t *a, lc_alnreg_t *tmp, int *H, int *E, bool &clean,
+								   LcSortKey *ks, const Exec &ex)
+{
+	clean = false;
+	if (n <= 1) return n;
+	const int n_in = n;
+	for (int i = ex.lane_id(); i < n; i += ex.n_lanes()) { LcSortKey k; k.lo = (uint64_t)a[i].re; k.hi = 0; k.idx = (uint32_t)i; ks[i] = k; }
+	ex.sync();
+	if (ex.leader()) lc_introsort(ks, (long)n, [](const LcSortKey &x, const LcSortKey &y) { return x.hi < y.hi || (x.hi == y.hi && x.lo < y.lo); });
+	ex.sync();
+	for (int i = ex.lane_id(); i < n; i += ex.n_lanes()) tmp[i] = a[ks[i].idx];
+	ex.sync();
+	unsigned long long mg = 0;
+	int m = n;
+	if (ex.leader()) { bool merged = false; m = lc_dedup_core(b, query, n, tmp, H, E, merged); mg = merged ? 1 : 0; }
+	ex.sync();
+	n = (int)ex.bcast((unsigned long long)(unsigned)m);
+	const bool merged = ex.bcast(mg) != 0;
+	for (int i = ex.lane_id(); i < n; i += ex.n_lanes()) {
+		LcSortKey k;
+		k.lo = (uint64_t)tmp[i].rb << 16 | (uint64_t)(uint16_t)tmp[i].qb; k.hi = (uint32_t)(0x7fffffffll - (int64_t)tmp[i].score); k.idx = (uint32_t)i;
+		ks[i] = k;
+	}
+	ex.sync();
+	if (ex.leader()) lc_introsort(ks, (long)n, [](const LcSortKey &x, const LcSortKey &y) { return x.hi < y.hi || (x.hi == y.hi && x.lo < y.lo); });
+	ex.sync();
+	for (int i = ex.lane_id(); i < n; i += ex.n_lanes()) a[i] = tmp[ks[i].idx];
+	ex.sync();
+	m = n;
+	if (ex.leader()) m = lc_dedup_identical(a, n);
+	ex.sync();
+	m = (int)ex.bcast((unsigned long long)(unsigned)m);
+	clean = !merged && m == n_in;
 	return m;
 }
 
@@ -1354,19 +1408,25 @@ LC_HD void lc_pair_prepare_t(const LcBatch &b, int p, int *H, int *E, const Exec
 		}
 		ex.sync();
 		int ne = n[e];
-		unsigned long long cl = 0;
-		if (ex.leader()) {
-			LcSortKey *ks = nullptr;
-			if (ne >= 12 && b.sortk) {                        // (a full pool only means the slower sort)
-				const unsigned long long ko = lc_atomic_add(b.sortk_cur, (unsigned long long)ne);
-				if (ko + (unsigned long long)ne <= b.sortk_cap) ks = b.sortk + ko;
-			}
-			bool c1 = false;
-			ne = lc_sort_dedup_patch(b, b.seq + b.off[r], ne, dst, H, E, H, 2 * (b.lmax + 18), &c1, ks);      // tail of mem_align1_core (B/bwamem.c:1070)
-			cl = c1 ? 1 : 0;
+		unsigned long long cl = 0, ko = (unsigned long long)-1;
+		if (ex.leader() && ne >= 12 && b.sortk) {            // (a full pool only means the slower sort)
+			ko = lc_atomic_add(b.sortk_cur, (unsigned long long)ne);
+			if (ko + (unsigned long long)ne > b.sortk_cap) ko = (unsigned long long)-1;
 		}
-		ex.sync();
-		n[e] = (int)ex.bcast((unsigned long long)(unsigned)ne); clean[e] = ex.bcast(cl) != 0;
+		ko = ex.bcast(ko);
+		if ((ex.n_lanes() > 1 || b.force_coop) && ko != (unsigned long long)-1 && b.regtmp) {      // tail of mem_align1_core (B/bwamem.c:1070), all lanes
+			bool c1 = false;
+			ne = lc_sort_dedup_patch_coop(b, b.seq + b.off[r], ne, dst, b.regtmp + ko, H, E, c1, b.sortk + ko, ex);
+			clean[e] = c1; n[e] = ne;
+		} else {
+			if (ex.leader()) {
+				bool c1 = false;
+				ne = lc_sort_dedup_patch(b, b.seq + b.off[r], ne, dst, H, E, H, 2 * (b.lmax + 18), &c1, ko != (unsigned long long)-1 ? b.sortk + ko : nullptr);
+				cl = c1 ? 1 : 0;
+			}
+			ex.sync();
+			n[e] = (int)ex.bcast((unsigned long long)(unsigned)ne); clean[e] = ex.bcast(cl) != 0;
+		}
 		int bst = 0;
 		for (int i = ex.lane_id(); i < n[e]; i += ex.n_lanes()) {
 			if (dst[i].rid >= 0 && b.ix.anns[dst[i].rid].is_alt) dst[i].is_alt = 1;   // B/bwamem.c:1078-1082

@@ -218,6 +218,7 @@ public:
 	int memcap = 256;
 	int lst_cap = 0, pk_cap = 64;       // seeding state machine: shared-memory interval list (0 = from the index size) / per-lane seed list; overflow -> second pass
 	int ext_heavy_seeds = 32, ext_heavy_chains = 8;      // extension: reads above either go to the warp-per-read kernel
+	bool force_coop = false;                             // tests (hostsim)
 	bool prep_heavy = true;                              // stage 5a: pairs with very many regions get a warp
 	int small_reads = 16384;                             // batches of at most this many reads run in the low-latency form (0 = never)
 	int chain_heavy = 48;                                // chaining: reads with more seeds than this go to the warp-per-read kernel (0 = never)
@@ -310,13 +311,14 @@ public:
 			b.chain_heavy_n = (unsigned int *)(c + 29);
 			b.ext_unit_n = (unsigned int *)(c + 30); b.ext_hvu_n = (unsigned int *)(c + 31);      // adjacent: the backend reads both with one copy
 			b.chain_heavy = chain_heavy;
+			b.force_coop = force_coop ? 1 : 0;
 			b.small = (small_reads > 0 && b.n_reads <= small_reads) ? 1 : 0;
 			b.ext_heavy_seeds = ext_heavy_seeds; b.ext_heavy_chains = ext_heavy_chains;
 			b.cnt = counting ? (LcCounters *)(c + 32) : nullptr;
 		}
 		be.dzero(d_ctl.p, 4096);
 		b.n_workers = be.n_workers();
-		b.sortk = nullptr; b.sortk_cap = 0;             // set by stage 5 (run_stages)
+		b.sortk = nullptr; b.sortk_cap = 0; b.regtmp = nullptr;            // set by stage 5 (run_stages)
 		b.memcap = memcap;
 		{
 			// a forward extension pushes one interval per change of size: ~log4(symbols) entries on unique sequence, more in repeats
@@ -486,6 +488,7 @@ public:
 		b.fin = (lc_alnreg_t *)d_fin.p; b.aln = (lc_aln_t *)d_aln.p; b.cand = (uint64_t *)d_cand.p;
 		b.sortk_cap = NREG + 64;
 		b.sortk = d_sortk.ensure(be, sizeof(LcSortKey) * b.sortk_cap) ? (LcSortKey *)d_sortk.p : nullptr;      // optional: without it the sorts go through handles
+		b.regtmp = (b.sortk && prep_heavy && d_regtmp.ensure(be, sizeof(lc_alnreg_t) * b.sortk_cap)) ? (lc_alnreg_t *)d_regtmp.p : nullptr;
 		be.k_pair(b, n_pairs); launches += b.prep_heavy_n ? 3 : 2;
 		be.ev_record(7);
 		read_ctl();
@@ -602,7 +605,7 @@ public:
 	{
 		LcBuf<BE> *all[] = { &d_seq, &d_off, &d_perread, &d_ctl, &d_wintv, &d_wint, &d_wu64, &d_wz, &d_intv, &d_seed, &d_scratch, &d_chain,
 							 &d_cseed, &d_reg, &d_fin, &d_aln, &d_cand, &d_cigar, &d_z, &d_outoff, &d_outoff2, &d_outreg, &d_outaln, &d_nfin, &d_wpk, &d_redo, &d_pkpool, &d_cigjobs, &d_wpk2, &d_redo2, &d_redo3, &d_wl,
-							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw, &d_chainaux, &d_units, &d_hvu, &d_sortk };
+							 &d_alnx, &d_mmref, &d_mmread, &d_outalnx, &d_raw, &d_chainaux, &d_units, &d_hvu, &d_sortk, &d_regtmp };
 		for (auto *x : all) x->release(be);
 	}
 
@@ -614,7 +617,7 @@ public:
 private:
 	LcBuf<BE> d_seq, d_off, d_perread, d_ctl, d_wintv, d_wint, d_wu64, d_wz, d_intv, d_seed, d_scratch, d_chain, d_cseed, d_reg, d_fin,
 		d_aln, d_cand, d_cigar, d_z, d_outoff, d_outoff2, d_outreg, d_outaln, d_nfin, d_wpk, d_redo, d_pkpool, d_cigjobs, d_wpk2, d_redo2, d_redo3, d_wl,
-		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw, d_chainaux, d_units, d_hvu, d_sortk;
+		d_alnx, d_mmref, d_mmread, d_outalnx, d_raw, d_chainaux, d_units, d_hvu, d_sortk, d_regtmp;
 	unsigned long long h_ctl[32];
 	uint32_t h_ctl_ovf = 0;
 	LcCounters h_counters;

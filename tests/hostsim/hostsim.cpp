@@ -117,7 +117,7 @@ int main(int argc, char **argv)
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
 	const char *xpath = 0;
 	int chain_heavy = -1;
-	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0, small_reads = 0;
+	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0, small_reads = 0, force_coop = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
 		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
@@ -133,6 +133,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-J") && i + 1 < argc) heavy_seeds = atoi(argv[++i]);   // extension: reads above this many chained seeds take the per-read body
 		else if (!strcmp(argv[i], "-Q") && i + 1 < argc) chain_heavy = atoi(argv[++i]);   // chaining: reads above this many seeds take the listed-read body (0 = never)
 		else if (!strcmp(argv[i], "-Z") && i + 1 < argc) small_reads = atoi(argv[++i]);   // batches up to this many reads take the low-latency (per-read) bodies
+		else if (!strcmp(argv[i], "-P")) force_coop = 1;                                // stage 5a: the cooperative dedup body (one lane here)
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
@@ -166,7 +167,7 @@ int main(int argc, char **argv)
 	if (lst_cap2 > 0) { pl.lst_cap2 = lst_cap2; pl.lst_cap3 = lst_cap2 + 2; }      // (third pass: barely larger, so that the last fallback still gets reads)
 	if (heavy_seeds >= 0) pl.ext_heavy_seeds = heavy_seeds;
 	if (chain_heavy >= 0) pl.chain_heavy = chain_heavy;
-	pl.small_reads = small_reads;
+	pl.small_reads = small_reads; pl.force_coop = force_coop != 0;
 	if (pk_cap2 > 0) { pl.pk_cap2 = pk_cap2; pl.pk_cap3 = pk_cap2 + 2; }
 	pl.force_wide = wide != 0;
 	pl.want_alnx = xpath != 0;

@@ -27,12 +27,12 @@ import pytest
 
 @pytest.mark.parametrize("extra", [["-S"], ["-W"], ["-C", "6"], ["-C", "3", "-M", "4"], ["-S", "-C", "12", "-w", "5", "-W"], ["-I", "3"], ["-I", "2", "-W", "-C", "7"],
                                    ["-C", "6", "-D", "9", "-M", "4", "-E", "7"], ["-C", "3", "-D", "4", "-W"], ["-J", "2"], ["-J", "0"],
-                                   ["-Z", "100000"], ["-Z", "100000", "-W", "-S"]])
+                                   ["-Z", "100000"], ["-Z", "100000", "-W", "-S"], ["-P"], ["-P", "-J", "2"]])
 def test_seeding_state_machine_fallbacks(hostsim_bin, tmp_path, extra):
     """The seeding state machine (lc_seed.cuh) with tiny list capacities (most reads go to the second pass; with -D/-E tiny
     too, on to the one-thread-per-read body), with idle ticks before every housekeeping step (-I), and with the sampled suffix
     array instead of the dense one; -Z: the low-latency route of small batches (per-read seeding and extension bodies for every
-    read): results must not change."""
+    read); -P: the cooperative form of mem_align1_core's dedup (stage 5a, long lists): results must not change."""
     out = tmp_path / "sim.out"
     subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out)] + extra,
                           stderr=subprocess.DEVNULL)
