@@ -376,7 +376,8 @@ def main():
 
     # ---- end-to-end arm: host buffers in, host results out, every step
     all_keys = ("ms_h2d", "ms_seed", "ms_sa", "ms_chain", "ms_extend", "ms_pair", "ms_cigar", "ms_d2h", "ms_total")
-    for cp in [int(x) for x in args.e2e_sweep.split(",") if x]:
+    for ent in [x for x in args.e2e_sweep.split(",") if x]:
+        cp = int(ent)
         check(lib.lc_set_chunk_pairs(ctx, cp))
         for _ in range(2):
             check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
@@ -387,7 +388,9 @@ def main():
             last = {k: round(float(getattr(res.contents, k)), 2) for k in all_keys}
             lib.lc_free_result(ctx, res)
         tw = (time.perf_counter() - tw) / args.steps
-        log(f"[bench] e2e sweep chunk_pairs={cp}: {1e3 * tw:.2f} ms/step wall, {n_pairs / tw:.0f} pairs/s; last call " + json.dumps(last))
+        log(f"[bench] e2e sweep chunk_pairs={ent}: {1e3 * tw:.2f} ms/step wall, {n_pairs / tw:.0f} pairs/s; last call " + json.dumps(last))
+    if args.e2e_sweep:
+        check(lib.lc_set_chunk_pairs(ctx, 500000))      # the library's default
     if args.chunk_pairs >= 0:
         check(lib.lc_set_chunk_pairs(ctx, args.chunk_pairs))
 

@@ -412,10 +412,12 @@ static void set_stage_ms(lc_result_t &r, const float ms[10])
 	r.ms_pair = ms[6]; r.ms_cigar = ms[7]; r.ms_d2h = ms[8]; r.ms_total = ms[9];
 }
 // every read 0 <= len <= LC_MAX_READ_LEN, in int64 (the caller's offsets are not trusted)
-static bool offsets_ok(int n_pairs, const int64_t *off)
+static bool offsets_ok(int n_pairs, const int64_t *off, int *lmax = nullptr)
 {
-	for (size_t r = 0; r < 2 * (size_t)n_pairs; ++r) { const int64_t l = off[r + 1] - off[r]; if (l < 0 || l > LC_MAX_READ_LEN) return false; }
-	return true;
+	int64_t lo, hi;
+	LcPipeline<LcCudaBackend>::length_range(off, 2 * (size_t)n_pairs, lo, hi);
+	if (lmax) *lmax = (int)std::max<int64_t>(1, std::min<int64_t>(hi, LC_MAX_READ_LEN));
+	return lo >= 0 && hi <= LC_MAX_READ_LEN;
 }
 
 // ---- the batched call: upload -> stages -> pack -> D2H into the pinned result arrays; large calls chunked over two lanes -----
@@ -424,7 +426,9 @@ struct LcChunkShared {
 	std::condition_variable cv;
 	std::vector<int64_t> cum_reg;       // [n_chunks + 1] candidates before chunk k, valid once ready[k]
 	std::vector<int64_t> cum_cig, cum_mm;
-	std::vector<char> ready;
+	std::vector<char> ready_reg, ready_cig;
+	int up_next = 0;                    // the chunk whose upload turn it is
+	std::vector<int> bounds;            // [n_chunks + 1] chunk k = pairs bounds[k] .. bounds[k + 1]
 	std::shared_mutex res_mu;           // shared: a D2H into the pinned arrays is in flight; exclusive: the arrays are being regrown
 	int rc = LC_OK;
 	std::string err;
@@ -442,58 +446,93 @@ static void add_counters(LcCounters &a, const LcCounters &b)
 	a.glb_calls += b.glb_calls; a.glb_cells += b.glb_cells;
 }
 
-// chunks first, first + stride, ... of the call on one lane (its own stream, pools and host thread)
+// chunks first, first + stride, ... of the call on one lane (its own stream, pools and host thread).
+// Copies are kept off the critical path in three ways: (1) the chunks' uploads take turns in chunk order — two lanes uploading at once
+// would share the link and both start computing late; (2) the regions are final after the pair stage, so they are packed and copied out
+// on the lane's copy stream while its CIGAR kernels run; (3) one lane's remaining copies sit under the other lane's kernels.
 static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> *pl, LcChunkShared *sh, int first, int stride, int n_chunks, int n_pairs,
 						const uint8_t *bases, const int64_t *off, int score_delta)
 {
 	cudaSetDevice(c->device);
 	LcResultBlock &B = *sh->blk;
 	for (int k = first; k < n_chunks; k += stride) {
-		const int p0 = (int)((int64_t)n_pairs * k / n_chunks), p1 = (int)((int64_t)n_pairs * (k + 1) / n_chunks);
-		int rc = LC_OK;
-		{ std::lock_guard<std::mutex> g(sh->mu); rc = sh->rc; }
-		if (!rc) rc = pl->upload(p1 - p0, bases, off + 2 * (size_t)p0, true);
-		if (!rc) rc = pl->run_stages(score_delta);
-		if (rc) sh->fail_with(rc, pl->err);
-		int64_t reg_base, cig_base, mm_base;
-		{   // chunk k's place in the call's arrays = totals of the chunks before it (known when their CIGAR stage is done)
+		const int p0 = sh->bounds[k], p1 = sh->bounds[k + 1];
+		int rc = LC_OK, lmax = 0;
+		// the chunk's offsets are checked here, while an earlier chunk uploads
+		const bool off_ok = offsets_ok(p1 - p0, off + 2 * (size_t)p0, &lmax);
+		{   // the upload turn of chunk k
 			std::unique_lock<std::mutex> g(sh->mu);
-			sh->cv.wait(g, [&] { return sh->ready[k] != 0; });
-			reg_base = sh->cum_reg[k]; cig_base = sh->cum_cig[k]; mm_base = sh->cum_mm[k];
-			sh->cum_mm[k + 1] = mm_base + (rc ? 0 : (int64_t)pl->n_mm);
+			sh->cv.wait(g, [&] { return sh->up_next == k; });
+			rc = sh->rc;
+		}
+		if (!rc && !off_ok) { rc = LC_EARG; pl->err = "read offsets must be non-decreasing and no read longer than LC_MAX_READ_LEN"; }
+		if (!rc) { rc = pl->upload(p1 - p0, bases, off + 2 * (size_t)p0, true, lmax); be->sync(); }
+		{ std::lock_guard<std::mutex> g(sh->mu); sh->up_next = k + 1; }
+		sh->cv.notify_all();
+		if (!rc) rc = pl->run_front(score_delta);
+		if (rc) sh->fail_with(rc, pl->err);
+		int64_t reg_base;
+		{   // chunk k's place in the call's region arrays = candidates of the chunks before it (known when their pair stage is done)
+			std::unique_lock<std::mutex> g(sh->mu);
+			sh->cv.wait(g, [&] { return sh->ready_reg[k] != 0; });
+			reg_base = sh->cum_reg[k];
 			sh->cum_reg[k + 1] = reg_base + (rc ? 0 : (int64_t)pl->n_cand);
+			sh->ready_reg[k + 1] = 1;
+		}
+		sh->cv.notify_all();
+		const bool ax = pl->want_alnx;
+		const size_t need_reg = (size_t)(reg_base + (rc ? 0 : (int64_t)pl->n_cand));
+		bool regs_in_flight = false;
+		std::shared_lock<std::shared_mutex> rg(sh->res_mu, std::defer_lock);      // held while a D2H into the pinned arrays is in flight
+		if (!rc) rc = pl->run_pack_regs(reg_base);
+		if (!rc) {
+			if (need_reg * sizeof(lc_alnreg_t) > B.p_regs.cap || need_reg * sizeof(lc_aln_t) > B.p_aln.cap || (ax && need_reg * sizeof(lc_alnx_t) > B.p_alnx.cap)) {
+				// regrow (rare: blocks are recycled with their capacities): extrapolate from the chunks seen so far, wait out in-flight copies, keep what is there
+				std::unique_lock<std::shared_mutex> g(sh->res_mu);
+				const size_t want_reg = (size_t)(need_reg * (1.2 * n_pairs / (double)std::max(1, sh->bounds[k + 1]))) + 1024;
+				if (!B.p_regs.ensure(want_reg * sizeof(lc_alnreg_t), B.p_regs.cap) || !B.p_aln.ensure(want_reg * sizeof(lc_aln_t), B.p_aln.cap) ||
+					(ax && !B.p_alnx.ensure(want_reg * sizeof(lc_alnx_t), B.p_alnx.cap))) rc = LC_ENOMEM;
+			}
+			if (rc) sh->fail_with(rc, "cannot allocate pinned host memory for the results");
+			else {
+				rg.lock();
+				const size_t n_off = 2 * (size_t)(p1 - p0) + (k == n_chunks - 1 ? 1 : 0);
+				pl->fetch_regs_into_side((int64_t *)B.p_off.p + 2 * (size_t)p0, n_off, (lc_alnreg_t *)B.p_regs.p + reg_base);
+				regs_in_flight = true;
+			}
+		} else sh->fail_with(rc, pl->err);
+		if (!rc) { rc = pl->run_cigar(); if (rc) sh->fail_with(rc, pl->err); }
+		if (regs_in_flight) { be->copy_sync(); rg.unlock(); }
+		int64_t cig_base, mm_base;
+		{   // ... and in the CIGAR / mismatch-position arrays (known when their CIGAR stage is done)
+			std::unique_lock<std::mutex> g(sh->mu);
+			sh->cv.wait(g, [&] { return sh->ready_cig[k] != 0; });
+			cig_base = sh->cum_cig[k]; mm_base = sh->cum_mm[k];
+			sh->cum_mm[k + 1] = mm_base + (rc ? 0 : (int64_t)pl->n_mm);
 			sh->cum_cig[k + 1] = cig_base + (rc ? 0 : (int64_t)pl->n_cigar_words);
-			sh->ready[k + 1] = 1;
+			sh->ready_cig[k + 1] = 1;
 			if (!rc && sh->cum_cig[k + 1] > 0xffffffffll) { rc = LC_ENOMEM; if (sh->rc == LC_OK) { sh->rc = rc; sh->err = "more than 2^32 CIGAR words in one call"; } }
+			if (!rc && sh->cum_mm[k + 1] > 0xffffffffll) { rc = LC_ENOMEM; if (sh->rc == LC_OK) { sh->rc = rc; sh->err = "more than 2^32 mismatch positions in one call"; } }
 		}
 		sh->cv.notify_all();
 		if (rc) continue;
-		if (sh->cum_mm[k + 1] > 0xffffffffll) { sh->fail_with(LC_ENOMEM, "more than 2^32 mismatch positions in one call"); continue; }
-		rc = pl->run_pack(reg_base, (uint32_t)cig_base, (uint32_t)mm_base);
+		rc = pl->run_pack_aln((uint32_t)cig_base, (uint32_t)mm_base);
 		if (rc) { sh->fail_with(rc, pl->err); continue; }
-		const size_t need_reg = (size_t)(reg_base + (int64_t)pl->n_cand), need_cig = (size_t)(cig_base + (int64_t)pl->n_cigar_words);
-		const bool ax = pl->want_alnx;
+		const size_t need_cig = (size_t)(cig_base + (int64_t)pl->n_cigar_words);
 		const size_t need_mm = ax ? (size_t)(mm_base + (int64_t)pl->n_mm) : 0;
-		if (need_reg * sizeof(lc_alnreg_t) > B.p_regs.cap || need_reg * sizeof(lc_aln_t) > B.p_aln.cap || need_cig * 4 > B.p_cig.cap ||
-			(ax && (need_reg * sizeof(lc_alnx_t) > B.p_alnx.cap || need_mm * 4 > B.p_mmr.cap || need_mm * 4 > B.p_mmd.cap))) {
-			// regrow (rare: blocks are recycled with their capacities): extrapolate from the chunks seen so far, wait out in-flight copies, keep what is there
+		if (need_cig * 4 > B.p_cig.cap || (ax && (need_mm * 4 > B.p_mmr.cap || need_mm * 4 > B.p_mmd.cap))) {
 			std::unique_lock<std::shared_mutex> g(sh->res_mu);
-			const double f = 1.2 * n_chunks / (double)(k + 1);
-			const size_t want_reg = (size_t)(need_reg * f) + 1024, want_cig = (size_t)(need_cig * f) + 1024;
-			if (!B.p_regs.ensure(want_reg * sizeof(lc_alnreg_t), B.p_regs.cap) || !B.p_aln.ensure(want_reg * sizeof(lc_aln_t), B.p_aln.cap) ||
-				!B.p_cig.ensure(want_cig * 4, B.p_cig.cap)) { sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue; }
-			const size_t want_mm = (size_t)(need_mm * f) + 1024;
-			if (ax && (!B.p_alnx.ensure(want_reg * sizeof(lc_alnx_t), B.p_alnx.cap) || !B.p_mmr.ensure(want_mm * 4, B.p_mmr.cap) || !B.p_mmd.ensure(want_mm * 4, B.p_mmd.cap))) {
+			const double f = 1.2 * n_pairs / (double)std::max(1, sh->bounds[k + 1]);
+			const size_t want_cig = (size_t)(need_cig * f) + 1024, want_mm = (size_t)(need_mm * f) + 1024;
+			if (!B.p_cig.ensure(want_cig * 4, B.p_cig.cap) || (ax && (!B.p_mmr.ensure(want_mm * 4, B.p_mmr.cap) || !B.p_mmd.ensure(want_mm * 4, B.p_mmd.cap)))) {
 				sh->fail_with(LC_ENOMEM, "cannot allocate pinned host memory for the results"); continue;
 			}
 		}
 		float ms[10]; LcCounters cn;
 		{
 			std::shared_lock<std::shared_mutex> g(sh->res_mu);
-			const size_t n_off = 2 * (size_t)(p1 - p0) + (k == n_chunks - 1 ? 1 : 0);
-			pl->fetch_into((int64_t *)B.p_off.p + 2 * (size_t)p0, n_off, (lc_alnreg_t *)B.p_regs.p + reg_base, (lc_aln_t *)B.p_aln.p + reg_base,
-						   (uint32_t *)B.p_cig.p + cig_base, ax ? (lc_alnx_t *)B.p_alnx.p + reg_base : nullptr,
-						   ax ? (int32_t *)B.p_mmr.p + mm_base : nullptr, ax ? (int32_t *)B.p_mmd.p + mm_base : nullptr);
+			pl->fetch_aln_into((lc_aln_t *)B.p_aln.p + reg_base, (uint32_t *)B.p_cig.p + cig_base, ax ? (lc_alnx_t *)B.p_alnx.p + reg_base : nullptr,
+							   ax ? (int32_t *)B.p_mmr.p + mm_base : nullptr, ax ? (int32_t *)B.p_mmd.p + mm_base : nullptr);
 			be->sync();
 		}
 		std::string e;
@@ -530,6 +569,10 @@ static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out, int n_chunks)
 {
 	LcSharedIndex &S = *c->sh;
+	// (Tried and dropped: a half-size first and last chunk, so that less of the first upload and the last copy-out is exposed — the
+	// smaller chunks' kernels lose more to their tails than the copies cost: 92 vs 87 ms per 1 M pairs on C2, profiles/r2s_*.)
+	std::vector<int> bounds;
+	for (int k = 0; k <= n_chunks; ++k) bounds.push_back((int)((int64_t)n_pairs * k / n_chunks));
 	const int n_lanes = std::max(1, std::min(n_chunks, c->max_lanes));
 	while ((int)c->lanes.size() < n_lanes - 1) {
 		std::unique_ptr<LcLane> l(new LcLane(c->device));
@@ -542,7 +585,8 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 	if (!blk->p_off.ensure(8 * (2 * (size_t)n_pairs + 1), 0)) { give_block(S, blk); return fail(LC_ENOMEM, "cannot allocate pinned host memory for the results"); }
 	LcChunkShared sh;
 	sh.blk = blk;
-	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.cum_mm.assign(n_chunks + 1, 0); sh.ready.assign(n_chunks + 1, 0); sh.ready[0] = 1;
+	sh.bounds = bounds;
+	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.cum_mm.assign(n_chunks + 1, 0); sh.ready_reg.assign(n_chunks + 1, 0); sh.ready_cig.assign(n_chunks + 1, 0); sh.ready_reg[0] = sh.ready_cig[0] = 1;
 	memset(&sh.cnt, 0, sizeof(sh.cnt));
 	c->be.ev_record(12);
 	{
@@ -746,10 +790,12 @@ void lc_free_result(lc_ctx *c, lc_result_t *res)
 int lc_align_packed(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out)
 {
 	if (!c || n_pairs < 0 || !off || (n_pairs && !bases && off[2 * (size_t)n_pairs] > off[0])) return fail(LC_EARG, "bad arguments");
-	if (!offsets_ok(n_pairs, off)) return fail(LC_EARG, "read offsets must be non-decreasing and no read longer than LC_MAX_READ_LEN");
 	// small calls are merged across threads — unless the work counters are on (they are per call) or the caller asked for chunks this small
-	if (n_pairs > 0 && n_pairs <= c->sh->co_call_max && !c->pl.counting && !(c->chunk_pairs > 0 && (double)n_pairs > 1.5 * c->chunk_pairs))
+	if (n_pairs > 0 && n_pairs <= c->sh->co_call_max && !c->pl.counting && !(c->chunk_pairs > 0 && (double)n_pairs > 1.5 * c->chunk_pairs)) {
+		if (!offsets_ok(n_pairs, off)) return fail(LC_EARG, "read offsets must be non-decreasing and no read longer than LC_MAX_READ_LEN");
 		return coalesced_align(c, n_pairs, bases, off, score_delta, out);
+	}
+	// (larger calls: every chunk's offsets are checked by its lane before anything of the chunk is read)
 	std::lock_guard<std::mutex> g(c->mu);
 	return do_align(c, n_pairs, bases, off, score_delta, out);
 }

@@ -21,6 +21,7 @@ struct LcCudaBackend {
 	cudaEvent_t ev[LC_N_EVENTS];
 	cudaStream_t aux[LC_CIG_NCLASS] = {};      // side streams: the band classes of the CIGAR stage run concurrently (fork/join on events)
 	cudaEvent_t ev_fork = 0, ev_join[LC_CIG_NCLASS] = {};
+	cudaStream_t cpy = 0; cudaEvent_t ev_cpy = 0;      // copy stream: the regions' D2H runs under the CIGAR kernels (LcPipeline::fetch_regs_into_side)
 	void *scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
 	void *seed_glists = nullptr; size_t seed_glists_bytes = 0;      // interval lists of the later seeding passes (smem_kernel<.., GL>)
 	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
@@ -41,6 +42,9 @@ struct LcCudaBackend {
 	void d2h(void *d, const void *s, size_t n);
 	void d2d(void *d, const void *s, size_t n);
 	void sync();
+	void copy_fork();                                  // what is enqueued on the copy stream from here on waits for the main stream's work so far
+	void d2h_copy(void *d, const void *s, size_t n);
+	void copy_sync();
 	void ev_record(int i);
 	float ev_ms(int a, int b);
 	int grid_for(unsigned long long items, int tpb, int ctas_per_sm) const;

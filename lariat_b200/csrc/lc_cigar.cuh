@@ -75,7 +75,7 @@ LC_HD int lc_cig_band_w(const LcBatch &b, const LcCigJob &j)
 
 LC_HD void lc_cig_push_job(const LcBatch &b, int list, uint64_t cd)
 {
-	const unsigned int at = lc_atomic_add(b.cig_n + list, 1u);
+	const unsigned int at = lc_atomic_add_agg(b.cig_n + list, 1u);
 	b.cig_jobs[(size_t)list * b.cig_jobs_cap + at] = cd;
 }
 

@@ -446,8 +446,8 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE>, bool UNIT = false> struct
 				if (UNIT) {
 					const int TU = b.chain_aux[cg].unit_seeds;
 					n_av0 = 0;
-					ro = lc_carve(b, b.reg_cur, b.reg_cap, (unsigned long long)TU, LC_OVF_REG);
-					const unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * TU + 8, LC_OVF_SCRATCH);
+					ro = lc_carve_plain(b, b.reg_cur, b.reg_cap, (unsigned long long)TU, LC_OVF_REG);
+					const unsigned long long so = lc_carve_plain(b, b.scratch_cur, b.scratch_cap, 8ull * TU + 8, LC_OVF_SCRATCH);
 					if (ro == (unsigned long long)-1 || so == (unsigned long long)-1) phase = LC_XP_FETCH;
 					else { av = b.reg + ro; srt = (uint64_t *)lc_align8((size_t)(b.scratch + so)); }
 				}
@@ -458,8 +458,8 @@ template <int STRIDE, class CELLS = LcCells16<STRIDE>, bool UNIT = false> struct
 					b.wl_in[lc_atomic_add(b.ext_heavy_n, 1u)] = (uint64_t)(uint32_t)lc_min(T, 0xffff) << 32 | (uint32_t)r;
 					phase = LC_XP_FETCH;
 				} else {
-					ro = lc_carve(b, b.reg_cur, b.reg_cap, (unsigned long long)T, LC_OVF_REG);
-					const unsigned long long so = lc_carve(b, b.scratch_cur, b.scratch_cap, 8ull * T + 8, LC_OVF_SCRATCH);
+					ro = lc_carve_plain(b, b.reg_cur, b.reg_cap, (unsigned long long)T, LC_OVF_REG);
+					const unsigned long long so = lc_carve_plain(b, b.scratch_cur, b.scratch_cap, 8ull * T + 8, LC_OVF_SCRATCH);
 					if (ro == (unsigned long long)-1 || so == (unsigned long long)-1) phase = LC_XP_FETCH;
 					else { av = b.reg + ro; srt = (uint64_t *)lc_align8((size_t)(b.scratch + so)); }
 				}

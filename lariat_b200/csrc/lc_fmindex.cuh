@@ -48,6 +48,33 @@ template <typename T> LC_HD T lc_atomic_add(T *p, T v)
 	T o = *p; *p += v; return o;   // hostsim runs the "threads" one after another
 #endif
 }
+// Bump pools and work lists hang off a handful of counters: one atomic per read on the SAME word serialises in the L2 (~1 ns each,
+// 2-6 M per step: it was half of seed_finish_kernel, chain_kernel, cigar_plan_kernel and pair_prepare_kernel).  In this form the
+// lanes of a warp that arrive together with the same counter send ONE atomic for their sum and share the range out by lane order.
+// For the thread-per-item kernels; the lane state machines keep the plain form (measured: the extension kernel loses 4 ms of 31
+// to the extra instructions, its atomics are spread over the whole kernel anyway).
+template <typename T> LC_HD T lc_atomic_add_agg(T *p, T v)
+{
+#ifdef __CUDA_ARCH__
+	const unsigned act = __activemask();
+	const unsigned grp = __match_any_sync(act, (unsigned long long)(uintptr_t)p);
+	const int lane = threadIdx.x & 31;
+	if (grp == (1u << lane)) return atomicAdd(p, v);
+	T pre = 0, tot = 0;
+	for (unsigned m = grp; m; m &= m - 1) {
+		const int L = __ffs(m) - 1;
+		const T o = __shfl_sync(grp, v, L);
+		if (L < lane) pre += o;
+		tot += o;
+	}
+	const int leader = __ffs(grp) - 1;
+	T base = 0;
+	if (lane == leader) base = atomicAdd(p, tot);
+	return __shfl_sync(grp, base, leader) + pre;
+#else
+	return lc_atomic_add(p, v);
+#endif
+}
 template <typename T> LC_HD T lc_max(T a, T b) { return a > b ? a : b; }
 template <typename T> LC_HD T lc_min(T a, T b) { return a < b ? a : b; }
 

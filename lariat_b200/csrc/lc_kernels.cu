@@ -485,6 +485,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventCreate(&ev[i]);
 	cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+	cudaStreamCreateWithFlags(&cpy, cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_cpy, cudaEventDisableTiming);
 	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
 	workers = n_sm * 4 * LC_TPB;     // 4 resident CTAs of 128 threads per SM
 	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
@@ -500,6 +501,7 @@ LcCudaBackend::~LcCudaBackend()
 	for (int i = 0; i < LC_N_EVENTS; ++i) cudaEventDestroy(ev[i]);
 	for (int i = 0; i < LC_CIG_NCLASS; ++i) { cudaEventDestroy(ev_join[i]); cudaStreamDestroy(aux[i]); }
 	cudaEventDestroy(ev_fork);
+	cudaEventDestroy(ev_cpy); cudaStreamDestroy(cpy);
 	cudaStreamDestroy(stream);
 }
 void *LcCudaBackend::dmalloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
@@ -513,6 +515,9 @@ void LcCudaBackend::h2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s
 void LcCudaBackend::d2h(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); }
 void LcCudaBackend::d2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream); }
 void LcCudaBackend::sync() { cudaStreamSynchronize(stream); }
+void LcCudaBackend::copy_fork() { cudaEventRecord(ev_cpy, stream); cudaStreamWaitEvent(cpy, ev_cpy, 0); }
+void LcCudaBackend::d2h_copy(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, cpy); }
+void LcCudaBackend::copy_sync() { cudaStreamSynchronize(cpy); }
 void LcCudaBackend::ev_record(int i) { cudaEventRecord(ev[i], stream); }
 float LcCudaBackend::ev_ms(int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0; } return ms; }
 int LcCudaBackend::grid_for(unsigned long long items, int tpb, int ctas_per_sm) const

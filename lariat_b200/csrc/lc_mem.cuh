@@ -134,7 +134,14 @@ LC_HD void lc_raise(const LcBatch &b, uint32_t flag)
 #endif
 }
 // carve `n` elements from a bump pool; returns the offset, or (u64)-1 after raising `flag`
+// (warp-aggregated atomic: lc_fmindex.cuh; lc_carve_plain for the lane state machines)
 LC_HD unsigned long long lc_carve(const LcBatch &b, unsigned long long *cur, unsigned long long cap, unsigned long long n, uint32_t flag)
+{
+	unsigned long long o = lc_atomic_add_agg(cur, n);
+	if (o + n > cap) { lc_raise(b, flag); return (unsigned long long)-1; }
+	return o;
+}
+LC_HD unsigned long long lc_carve_plain(const LcBatch &b, unsigned long long *cur, unsigned long long cap, unsigned long long n, uint32_t flag)
 {
 	unsigned long long o = lc_atomic_add(cur, n);
 	if (o + n > cap) { lc_raise(b, flag); return (unsigned long long)-1; }
@@ -709,7 +716,7 @@ LC_HDN void lc_stage_chain(const LcBatch &b, int r)
 	LcChainJob job(b, r);
 	if (!job.prologue()) return;
 	const int S = job.S;
-	if (b.chain_heavy > 0 && S > b.chain_heavy) { b.chain_list[lc_atomic_add(b.chain_heavy_n, 1u)] = r; return; }
+	if (b.chain_heavy > 0 && S > b.chain_heavy) { b.chain_list[lc_atomic_add_agg(b.chain_heavy_n, 1u)] = r; return; }
 	// A read with a handful of seeds (the usual case outside repeats) keeps the chainer's arrays in thread-local memory: the pool is
 	// cold global memory, and chaining is a string of dependent accesses to it (ncu: the kernel is latency, not work).
 	uint64_t small[LC_CHAIN_SMALL_BYTES / 8];
@@ -1410,7 +1417,7 @@ LC_HD void lc_pair_prepare_t(const LcBatch &b, int p, int *H, int *E, const Exec
 		int ne = n[e];
 		unsigned long long cl = 0, ko = (unsigned long long)-1;
 		if (ex.leader() && ne >= 12 && b.sortk) {            // (a full pool only means the slower sort)
-			ko = lc_atomic_add(b.sortk_cur, (unsigned long long)ne);
+			ko = lc_atomic_add_agg(b.sortk_cur, (unsigned long long)ne);
 			if (ko + (unsigned long long)ne > b.sortk_cap) ko = (unsigned long long)-1;
 		}
 		ko = ex.bcast(ko);
@@ -1449,11 +1456,11 @@ LC_HD void lc_pair_prepare_t(const LcBatch &b, int p, int *H, int *E, const Exec
 		if (f0[i].score >= best[0] - b.score_delta) { ++num; need = lc_matesw_wants_sw_t(b, f0[i], len[1], f1, n[1], rb, re, ex); }
 	if (need) {                                          // weight = candidates of the pair (anchors to try, lists to scan); bits 48, 49: the lists
 		const int wgt = lc_min(n[0] + n[1], 0xffff);     // are fixed points already (lc_matesw_t) — a clean mem_sort_dedup_patch just made them
-		if (ex.leader()) b.wl_in[lc_atomic_add(b.resc_n, 1u)] = (uint64_t)((clean[0] ? 1 : 0) | (clean[1] ? 2 : 0)) << 48 | (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
+		if (ex.leader()) b.wl_in[lc_atomic_add_agg(b.resc_n, 1u)] = (uint64_t)((clean[0] ? 1 : 0) | (clean[1] ? 2 : 0)) << 48 | (uint64_t)(uint32_t)wgt << 32 | (uint32_t)p;
 		return;
 	}
 	unsigned long long co = 0;
-	if (ex.leader()) co = lc_atomic_add(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
+	if (ex.leader()) co = lc_atomic_add_agg(b.cand_cur, (unsigned long long)(n[0] + n[1]));   // candidate list for stage 6 (sized like fin)
 	co = ex.bcast(co);
 	for (int i = ex.lane_id(); i < n[0]; i += ex.n_lanes()) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;
 	for (int i = ex.lane_id(); i < n[1]; i += ex.n_lanes()) b.cand[co + n[0] + i] = (uint64_t)(2 * p + 1) << 32 | (uint32_t)i;
@@ -1469,7 +1476,7 @@ struct LcExecOnePair : LcExecOne {      // the thread form
 LC_HD bool lc_pair_prepare_defer(const LcBatch &b, int p)
 {
 	if (!b.prep_heavy_n || b.r_n_reg[2 * p] + b.r_n_reg[2 * p + 1] <= LC_PREP_HEAVY) return false;
-	b.wl_out[lc_atomic_add(b.prep_heavy_n, 1u)] = (uint64_t)(uint32_t)p;
+	b.wl_out[lc_atomic_add_agg(b.prep_heavy_n, 1u)] = (uint64_t)(uint32_t)p;
 	return true;
 }
 LC_HD void lc_pair_prepare(const LcBatch &b, int p, int *H, int *E) { lc_pair_prepare_t(b, p, H, E, LcExecOnePair()); }
@@ -1497,7 +1504,7 @@ LC_HD void lc_pair_rescue_t(const LcBatch &b, int p, int fixed_bits, const Exec 
 	unsigned long long co = 0;
 	if (ex.leader()) {
 		b.r_n_fin[2 * p] = n0; b.r_n_fin[2 * p + 1] = n1;
-		co = lc_atomic_add(b.cand_cur, (unsigned long long)(n0 + n1));
+		co = lc_atomic_add_agg(b.cand_cur, (unsigned long long)(n0 + n1));
 	}
 	co = ex.bcast(co);
 	for (int i = ex.lane_id(); i < n0; i += ex.n_lanes()) b.cand[co + i] = (uint64_t)(2 * p) << 32 | (uint32_t)i;

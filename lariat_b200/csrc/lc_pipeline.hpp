@@ -159,18 +159,22 @@ struct LcPackArgs {            // stage 7: dense result arrays
 };
 
 // r in [0, n_reads]: entry n_reads only carries the total
+// The regions (out_reg, off_final) are final after the pair stage, the alignments (out_aln, out_alnx) after the CIGAR stage: the
+// pipeline packs them in two launches (null = not in this launch) so that the regions' D2H runs under the CIGAR kernels.
 LC_HD void lc_stage_pack(const LcBatch &b, const LcPackArgs &pa, int r)
 {
 	const int64_t dst = pa.out_off[r];
-	pa.off_final[r] = dst + pa.reg_base;
+	if (pa.off_final) pa.off_final[r] = dst + pa.reg_base;
 	if (r >= b.n_reads) return;
 	const int n = b.r_n_fin[r];
 	const int64_t src = b.r_fin_off[r];
 	for (int i = 0; i < n; ++i) {
-		pa.out_reg[dst + i] = b.fin[src + i];
-		lc_aln_t a = b.aln[src + i];
-		a.cigar_off += pa.cig_base;
-		pa.out_aln[dst + i] = a;
+		if (pa.out_reg) pa.out_reg[dst + i] = b.fin[src + i];
+		if (pa.out_aln) {
+			lc_aln_t a = b.aln[src + i];
+			a.cigar_off += pa.cig_base;
+			pa.out_aln[dst + i] = a;
+		}
 		if (pa.out_alnx) { lc_alnx_t x = b.alnx[src + i]; x.mm_off += pa.mm_base; pa.out_alnx[dst + i] = x; }
 	}
 }
@@ -241,17 +245,26 @@ public:
 	}
 
 	// ---- upload: bases are ASCII or codes (is_ascii), off[2*n_pairs+1]
-	int upload(int n_pairs_, const uint8_t *bases, const int64_t *off, bool is_ascii)
+	// shortest / longest read of off[0..R]: the caller's offsets are not trusted (lengths in int64).  Branch-free, so it vectorises.
+	static void length_range(const int64_t *off, size_t R, int64_t &lo, int64_t &hi)
+	{
+		int64_t mn = 0, mx = 0;
+		for (size_t r = 0; r < R; ++r) { const int64_t len = off[r + 1] - off[r]; mn = len < mn ? len : mn; mx = len > mx ? len : mx; }
+		lo = mn; hi = mx;
+	}
+	// known_lmax > 0: the caller has validated the offsets (length_range) and passes the longest read
+	int upload(int n_pairs_, const uint8_t *bases, const int64_t *off, bool is_ascii, int known_lmax = 0)
 	{
 		n_pairs = n_pairs_;
 		const int R = 2 * n_pairs;
 		const int64_t off0 = off[0], total = off[R] - off0;     // off0 != 0: the batch is a slice of a larger packed array
-		int lmax = 1;
-		for (int r = 0; r < R; ++r) {      // the caller's offsets are not trusted: lengths in int64, 0 <= len <= LC_MAX_READ_LEN
-			const int64_t len = off[r + 1] - off[r];
-			if (len < 0) { err = "read offsets must be non-decreasing"; return LC_EARG; }
-			if (len > LC_MAX_READ_LEN) { err = "read longer than LC_MAX_READ_LEN"; return LC_EARG; }
-			lmax = std::max<int>(lmax, (int)len);
+		int lmax = known_lmax;
+		if (lmax <= 0) {                   // 0 <= len <= LC_MAX_READ_LEN for every read
+			int64_t lo, hi;
+			length_range(off, (size_t)R, lo, hi);
+			if (lo < 0) { err = "read offsets must be non-decreasing"; return LC_EARG; }
+			if (hi > LC_MAX_READ_LEN) { err = "read longer than LC_MAX_READ_LEN"; return LC_EARG; }
+			lmax = std::max<int>(1, (int)hi);
 		}
 		be.ev_record(0);
 		if (!d_seq.ensure(be, (size_t)total + 16) || !d_off.ensure(be, sizeof(int64_t) * (R + 1))) return nomem();
@@ -447,6 +460,14 @@ public:
 	// stages 1-6; afterwards n_cand / n_cigar_words are known on the host
 	int run_stages(int score_delta)
 	{
+		int rc = run_front(score_delta);
+		if (!rc) rc = run_cigar();
+		return rc;
+	}
+
+	// stages 1-5 (seeding ... mate rescue); afterwards the regions are final and n_cand is known on the host
+	int run_front(int score_delta)
+	{
 		const int R = b.n_reads;
 		b.score_delta = score_delta;
 		int rc0 = setup();
@@ -494,9 +515,15 @@ public:
 		read_ctl();
 		if (launch_broken) { err = "a CUDA kernel launch failed in the pair stage"; return LC_ECUDA; }
 		if (h_ctl_ovf) { err = "internal pool overflow in pair stage"; return LC_ENOMEM; }
-		const unsigned long long NC = h_ctl[7];
+		n_cand = h_ctl[7];
 		n_rescue_pairs = (unsigned long long)(uint32_t)h_ctl[27];
-		// ---- stage 6: CIGARs (lc_cigar.cuh: plan -> register-band kernels -> warp fallback; regrow + rerun on overflow)
+		return LC_OK;
+	}
+
+	// stage 6: CIGARs (lc_cigar.cuh: plan -> register-band kernels -> warp fallback; regrow + rerun on overflow).  Reads the regions, does not change them.
+	int run_cigar()
+	{
+		const unsigned long long NC = n_cand;
 		b.cig_jobs_cap = NC + 1;
 		if (!d_cigjobs.ensure(be, 8 * (size_t)LC_CIG_NLIST * b.cig_jobs_cap)) return nomem();
 		b.cig_jobs = (uint64_t *)d_cigjobs.p;
@@ -534,21 +561,36 @@ public:
 			be.dzero(b.cig_n, 4 * LC_CIG_NLIST);
 		}
 		be.ev_record(8);
-		n_cand = NC; n_cigar_words = h_ctl[8]; n_mm = want_alnx ? h_ctl[12] : 0;
+		n_cigar_words = h_ctl[8]; n_mm = want_alnx ? h_ctl[12] : 0;
 		return LC_OK;
 	}
 
 	// ---- stage 7: pack into dense arrays (candidate indices offset by reg_base, CIGAR indices by cig_base)
 	int run_pack(int64_t reg_base, uint32_t cig_base, uint32_t mm_base = 0)
 	{
+		int rc = run_pack_regs(reg_base);
+		if (!rc) rc = run_pack_aln(cig_base, mm_base);
+		return rc;
+	}
+	// the regions and the per-read offsets: any time after run_front()
+	int run_pack_regs(int64_t reg_base)
+	{
 		const int R = b.n_reads;
 		const unsigned long long NC = n_cand;
-		if (!d_outoff.ensure(be, 8 * ((size_t)R + 1)) || !d_outoff2.ensure(be, 8 * ((size_t)R + 1)) || !d_outreg.ensure(be, sizeof(lc_alnreg_t) * (NC + 1)) ||
-			!d_outaln.ensure(be, sizeof(lc_aln_t) * (NC + 1))) return nomem();
+		if (!d_outoff.ensure(be, 8 * ((size_t)R + 1)) || !d_outoff2.ensure(be, 8 * ((size_t)R + 1)) || !d_outreg.ensure(be, sizeof(lc_alnreg_t) * (NC + 1))) return nomem();
 		be.scan_exclusive(b.r_n_fin, (int64_t *)d_outoff.p, R + 1); ++launches;   // r_n_fin[R] == 0, so out[R] = total
-		LcPackArgs pa; pa.out_off = (const int64_t *)d_outoff.p; pa.out_reg = (lc_alnreg_t *)d_outreg.p; pa.out_aln = (lc_aln_t *)d_outaln.p;
-		pa.off_final = (int64_t *)d_outoff2.p; pa.reg_base = reg_base; pa.cig_base = cig_base;
-		pa.out_alnx = nullptr; pa.mm_base = mm_base;
+		LcPackArgs pa; memset(&pa, 0, sizeof(pa));
+		pa.out_off = (const int64_t *)d_outoff.p; pa.out_reg = (lc_alnreg_t *)d_outreg.p; pa.off_final = (int64_t *)d_outoff2.p; pa.reg_base = reg_base;
+		be.k_pack(b, pa); ++launches;
+		return LC_OK;
+	}
+	// the alignments (and stage 6b's records): after run_cigar()
+	int run_pack_aln(uint32_t cig_base, uint32_t mm_base = 0)
+	{
+		const unsigned long long NC = n_cand;
+		if (!d_outaln.ensure(be, sizeof(lc_aln_t) * (NC + 1))) return nomem();
+		LcPackArgs pa; memset(&pa, 0, sizeof(pa));
+		pa.out_off = (const int64_t *)d_outoff.p; pa.out_aln = (lc_aln_t *)d_outaln.p; pa.cig_base = cig_base; pa.mm_base = mm_base;
 		if (b.alnx) { if (!d_outalnx.ensure(be, sizeof(lc_alnx_t) * (NC + 1))) return nomem(); pa.out_alnx = (lc_alnx_t *)d_outalnx.p; }
 		be.k_pack(b, pa); ++launches;
 		be.ev_record(9);
@@ -560,12 +602,25 @@ public:
 	void fetch_into(int64_t *h_off, size_t n_off, lc_alnreg_t *h_regs, lc_aln_t *h_aln, uint32_t *h_cig,
 					lc_alnx_t *h_alnx = nullptr, int32_t *h_mmref = nullptr, int32_t *h_mmread = nullptr)
 	{
+		be.d2h(h_off, d_outoff2.p, 8 * n_off);
+		if (n_cand) be.d2h(h_regs, d_outreg.p, sizeof(lc_alnreg_t) * n_cand);
+		fetch_aln_into(h_aln, h_cig, h_alnx, h_mmref, h_mmread);
+	}
+	// The two halves of fetch_into for a caller that packs in two steps.  The regions' copy goes to the backend's copy stream, ordered
+	// after run_pack_regs(): it runs under the CIGAR kernels.  be.copy_sync() before the host reads them.
+	void fetch_regs_into_side(int64_t *h_off, size_t n_off, lc_alnreg_t *h_regs)
+	{
+		be.copy_fork();
+		be.d2h_copy(h_off, d_outoff2.p, 8 * n_off);
+		if (n_cand) be.d2h_copy(h_regs, d_outreg.p, sizeof(lc_alnreg_t) * n_cand);
+	}
+	void fetch_aln_into(lc_aln_t *h_aln, uint32_t *h_cig, lc_alnx_t *h_alnx = nullptr, int32_t *h_mmref = nullptr, int32_t *h_mmread = nullptr)
+	{
 		if (b.alnx && h_alnx) {
 			if (n_cand) be.d2h(h_alnx, d_outalnx.p, sizeof(lc_alnx_t) * n_cand);
 			if (n_mm) { be.d2h(h_mmref, d_mmref.p, 4 * n_mm); be.d2h(h_mmread, d_mmread.p, 4 * n_mm); }
 		}
-		be.d2h(h_off, d_outoff2.p, 8 * n_off);
-		if (n_cand) { be.d2h(h_regs, d_outreg.p, sizeof(lc_alnreg_t) * n_cand); be.d2h(h_aln, d_outaln.p, sizeof(lc_aln_t) * n_cand); }
+		if (n_cand) be.d2h(h_aln, d_outaln.p, sizeof(lc_aln_t) * n_cand);
 		if (n_cigar_words) be.d2h(h_cig, d_cigar.p, 4 * n_cigar_words);
 		if (counting) be.d2h(&h_counters, (uint8_t *)d_ctl.p + 32 * 8, sizeof(LcCounters));
 		be.ev_record(10);

@@ -317,7 +317,7 @@ template <typename U, bool COUNT = true, int STRIDE = 1> struct LcSeedLane {    
 #if defined(LC_STATS) && !defined(__CUDA_ARCH__)
 				if (COUNT && b.cnt) fprintf(stderr, "SEEDEXT %d %u %d\n", r, cnt_ext, n_mem);
 #endif
-				unsigned long long po = n_mem ? lc_carve(b, b.pk_cur, b.pk_pool_cap, (unsigned long long)n_mem, LC_OVF_PK) : 0ull;
+				unsigned long long po = n_mem ? lc_carve_plain(b, b.pk_cur, b.pk_pool_cap, (unsigned long long)n_mem, LC_OVF_PK) : 0ull;
 				if (po == (unsigned long long)-1) { po = 0; n_mem = 0; }
 				for (int t = 0; t < n_mem; ++t) b.pk_pool[po + t] = memv[t];
 				b.r_pk_off[r] = (int64_t)po; b.r_n_pk[r] = n_mem;

@@ -30,6 +30,9 @@ struct HostBackend {
 	void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
 	void d2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
 	void sync() {}
+	void copy_fork() {}
+	void d2h_copy(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+	void copy_sync() {}
 	void ev_record(int) {}
 	float ev_ms(int, int) { return 0.f; }
 	void k_convert(uint8_t *p, unsigned long long n, bool ascii) { for (unsigned long long i = 0; i < n; ++i) p[i] = lc_nt4(p[i], ascii); }
@@ -182,12 +185,18 @@ int main(int argc, char **argv)
 		for (int p0 = 0; p0 < n && !rc; p0 += chunk) {
 			const int np = std::min(chunk, n - p0);
 			rc = pl.upload(np, raw.data(), off.data() + 2 * (size_t)p0, true);
-			if (!rc) rc = pl.run_stages(delta);
-			if (!rc) rc = pl.run_pack(reg_base, cig_base, mm_base);
+			// the order of lc_api.cu's lane_worker: the regions are packed and fetched before the CIGAR stage runs
+			if (!rc) rc = pl.run_front(delta);
+			if (!rc) rc = pl.run_pack_regs(reg_base);
 			if (rc) break;
-			res.regs.resize((size_t)reg_base + pl.n_cand); res.aln.resize((size_t)reg_base + pl.n_cand); res.cigars.resize((size_t)cig_base + pl.n_cigar_words);
+			res.regs.resize((size_t)reg_base + pl.n_cand); res.aln.resize((size_t)reg_base + pl.n_cand);
+			pl.fetch_regs_into_side(res.reg_off.data() + 2 * (size_t)p0, 2 * (size_t)np + 1, res.regs.data() + reg_base);
+			rc = pl.run_cigar();
+			if (!rc) rc = pl.run_pack_aln(cig_base, mm_base);
+			if (rc) break;
+			res.cigars.resize((size_t)cig_base + pl.n_cigar_words);
 			if (xpath) { res.alnx.resize((size_t)reg_base + pl.n_cand); res.mm_ref.resize((size_t)mm_base + pl.n_mm + 1); res.mm_read.resize((size_t)mm_base + pl.n_mm + 1); }
-			pl.fetch_into(res.reg_off.data() + 2 * (size_t)p0, 2 * (size_t)np + 1, res.regs.data() + reg_base, res.aln.data() + reg_base, res.cigars.data() + cig_base,
+			pl.fetch_aln_into(res.aln.data() + reg_base, res.cigars.data() + cig_base,
 						  xpath ? res.alnx.data() + reg_base : nullptr, xpath ? res.mm_ref.data() + mm_base : nullptr, xpath ? res.mm_read.data() + mm_base : nullptr);
 			mm_base += (uint32_t)pl.n_mm;
 			float ms[10]; LcCounters cn; pl.fetch_done(ms, cn);
