@@ -45,13 +45,14 @@ def run(args, lib, ref, bases, off, n_pairs, cfg, metric, ncores, fa, pairs, cpu
         cpu = {"value": j["pairs_per_s"], "unit": "read-pairs/s", "cores": ncores, "kind": kind,
                "sample": f"first {sample} pairs of the workload, index preloaded, {ncores} threads, wall clock {j['seconds']:.2f}s"}
     sweep = []
+    devices = int(os.environ.get("LC_PERCALL_DEVICES", "1"))      # > 1: ONE driver process over that many GPUs (the driver's -G), as a Go binary would
     for t in [int(x) for x in str(args.threads).split(",") if x]:
         # enough work per point for a stable rate: at least ~2 s at 1 M pairs/s, bounded by the workload
-        j = run_driver(fa, pairs, "-", t, args.call_pairs, n_pairs, repeat=max(1, args.steps // 2), device=device)
+        j = run_driver(fa, pairs, "-", t, args.call_pairs, n_pairs, repeat=max(1, args.steps // 2), device=device, devices=devices)
         sweep.append(j)
     best = max(sweep, key=lambda x: x["pairs_per_s"])
     first = sweep[0]
-    return {"metric": metric, "mode": "percall", "value": first["pairs_per_s"], "unit": "read-pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    return {"metric": metric, "mode": "percall", "value": first["pairs_per_s"], "unit": "read-pairs/s", "n_gpus": devices, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": first["call_ms_p50"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": cfg,
             "what": f"{args.call_pairs}-pair calls (one barcode group each) from T host threads through lc_align_packed, pageable input, results held "
