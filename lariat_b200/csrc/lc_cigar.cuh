@@ -17,10 +17,11 @@
 //   * everything unusual — bands wider than 80 cells, the rare band-doubling retry of mem_reg2aln (B/bwamem.c:1111-1119),
 //     CIGARs with more than LC_CIG_MAXOPS merged ops, degenerate regions — goes to a fallback list that the warp-per-candidate
 //     body (lc_stage_cigar_t) processes from scratch.
-// Values are plain int32 with the reference's own NEG_INF, so every comparison is the reference's comparison.
+// Band values are 16-bit, two per register, with -16384 for the reference's MINUS_INF: exact under the range check lc_cig_fits16 (below).
 // All bodies are LC_HD: tests/hostsim runs them serially on the CPU against the oracle.
 #pragma once
 #include "lc_mem.cuh"
+#include "lc_extsm.cuh"      // the two-halves-per-register helpers (lc_p2_*, lc_prmt)
 
 #define LC_CIG_NCLASS 5
 #define LC_CIG_FALLBACK LC_CIG_NCLASS      // index of the fallback list
@@ -119,6 +120,24 @@ LC_HD bool lc_cig_emit(const LcBatch &b, const LcCigJob &j, const uint32_t *cig,
 	return true;
 }
 
+// ---- 16-bit cells.  The band kernel keeps two band slots per register (s16x2: VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / PRMT on
+// sm_100a, the portable forms of lc_extsm.cuh in tests/hostsim) and uses -16384 for the reference's MINUS_INF (-2^30).  That is exact, not
+// approximate: every value of the recurrence is either FINITE (the score of a real partial alignment, or H(i,-1)) or DERIVED FROM
+// MINUS_INF (MINUS_INF plus a few scores/penalties).  Sums keep the category, a maximum of two values of one category compares them
+// the same way under any constant shift, and between the categories the finite value wins in both arithmetics as long as
+//     finite values  >  -16384 + a * rlen  (the highest a derived value can climb)      and      derived values  >=  -32768.
+// lc_cig_fits16 checks exactly that for the job; jobs that fail (not reachable with Lariat's scoring and reads <= 700 bp) take the fallback.
+#define LC_CIG_NEG16 (-16384)
+LC_HD bool lc_cig_fits16(const LcBatch &b, const LcCigJob &j)
+{
+	const LcScore &sc = b.sc;
+	const int oe_max = lc_max(sc.o_del + sc.e_del, sc.o_ins + sc.e_ins);
+	const int pmax = lc_max(lc_max(sc.b, oe_max), 1);                 // the most one step of a path can cost
+	const long long fin_lo = -((long long)(j.rlen + j.lq + 2) * pmax + 2LL * oe_max);      // paths are <= rlen + lq steps; + the t = M - oe intermediates
+	const long long der_hi = (long long)LC_CIG_NEG16 + (long long)lc_max(sc.a, 0) * j.rlen;
+	const long long der_lo = (long long)LC_CIG_NEG16 - (long long)(j.rlen + 2 + 96) * pmax - 2LL * oe_max;      // (+ F decaying across a whole row of slots that are not live)
+	return fin_lo > der_hi + 64 && der_lo >= -32768 + 64 && (long long)j.lq * lc_max(sc.a, 0) < 32000;
+}
 // ---- one thread per candidate: finish the gap-free ones, bin the rest
 LC_HD void lc_cig_plan(const LcBatch &b, uint64_t cd)
 {
@@ -138,7 +157,7 @@ LC_HD void lc_cig_plan(const LcBatch &b, uint64_t cd)
 	int cls = LC_CIG_FALLBACK;
 	// (a small batch has warps to spare: the cooperative fill of the warp-per-candidate body is the short way through a band that one
 	// thread would walk cell by cell)
-	if (!b.small) for (int c = LC_CIG_NCLASS - 1; c >= 0; --c) if (cells <= lc_cig_class_cells(c)) cls = c;
+	if (!b.small && lc_cig_fits16(b, j)) for (int c = LC_CIG_NCLASS - 1; c >= 0; --c) if (cells <= lc_cig_class_cells(c)) cls = c;
 	lc_cig_push_job(b, cls, cd);
 }
 
@@ -188,27 +207,53 @@ LC_HD uint32_t lc_cig_lut4(uint32_t lut_lo, uint32_t lut_hi, uint32_t sel)
 #endif
 }
 
-// ---- one thread per job: ksw_global2 (B/ksw.c:504-606) in diagonal coordinates, NB = band cells of the job's class (multiple of 8)
+LC_HD int lc_bitrev3(int c) { return ((c & 1) << 2) | (c & 2) | ((c >> 2) & 1); }
+// bits [lo, hi) of a bitmap, the 32 of them that start at `base`
+LC_HD uint32_t lc_range_word(int lo, int hi, int base)
+{
+	const int l = lo - base, h = hi - base;
+	const uint32_t mh = h <= 0 ? 0u : (h >= 32 ? 0xffffffffu : (1u << h) - 1u);
+	const uint32_t ml = l <= 0 ? 0u : (l >= 32 ? 0xffffffffu : (1u << l) - 1u);
+	return mh & ~ml;
+}
+
+// ---- one thread per job: ksw_global2 (B/ksw.c:504-606) in diagonal coordinates, NB = band cells of the job's class (multiple of 8).
+// Slot d of row i is column j0 + d (j0 = i - w); pair p holds slots 2p (low half) and 2p + 1.  A slot is LIVE in a row when its column
+// is inside the query and d <= 2w; the reference computes no other cell.  One bitmap per row, expanded to half-word masks by a multiply
+// and a sign-replicating PRMT, keeps the others out: their M is forced to "minus infinity" and their H to H(i,-1).  F runs left to right
+// through the pairs (one VIADDMNMX and one PRMT per pair on the dependent chain); E and H are elementwise.  The four direction bits of a cell come from "maximum != operand" tests, one nibble per cell, eight
+// cells per traceback word in bit-reversed nibble order (the order the packed halves fall into).
 template <int NB> LC_HD void lc_cig_band(const LcBatch &b, uint64_t cd)
 {
-	constexpr int G = NB / 8, GS = (G + 3) & ~3;      // words per traceback row, padded to whole 16-byte stores
+	constexpr int G = NB / 8, GS = (G + 3) & ~3, NP = NB / 2;      // GS: words per traceback row, padded to whole 16-byte stores
 	LcCigJob j;
 	lc_cig_decode(b, cd, j);
 	const LcScore &sc = b.sc;
 	const int w = lc_cig_band_w(b, j), w2x = 2 * w;
-	const int oe_del = sc.o_del + sc.e_del, oe_ins = sc.o_ins + sc.e_ins, e_del = sc.e_del, e_ins = sc.e_ins;
 	const int lq = j.lq, rlen = j.rlen;
 	// substitution scores by (query code ^ target code): 0 = match, 1..3 = mismatch, 4..7 = ambiguous query base (-1, B/bwa.c:109-118)
 	const uint32_t lut_lo = ((uint32_t)sc.a & 0xffu) | ((uint32_t)(-sc.b) & 0xffu) * 0x01010100u, lut_hi = 0xffffffffu;
+	const uint32_t n_oe_del = lc_p2_dup(-(sc.o_del + sc.e_del)), n_e_del = lc_p2_dup(-sc.e_del), n_oe_ins = lc_p2_dup(-(sc.o_ins + sc.e_ins)), n_e_ins = lc_p2_dup(-sc.e_ins);
+	const uint32_t n_e12 = ((uint32_t)(-sc.e_ins) & 0xffffu) | ((uint32_t)(-2 * sc.e_ins) & 0xffffu) << 16;
+	const uint32_t NEG2 = lc_p2_dup(LC_CIG_NEG16), ONE2 = 0x00010001u;
 	// the job's slice of the traceback pool: GS words per row (every carve of this kernel is a multiple of 16 bytes)
 	const unsigned long long zo = lc_carve(b, b.z_cur, b.z_cap, (unsigned long long)rlen * GS * 4, LC_OVF_Z);
 	if (zo == (unsigned long long)-1) return;
 	uint32_t *z = (uint32_t *)(b.zpool + zo);
-	int h[NB], e[NB + 1];
+	uint32_t H[NP], E[NP + 1];
 	// row -1 (B/ksw.c:520-523): slot d holds H(-1, d - w - 1), the diagonal of cell (0, d - w)
 #pragma unroll
-	for (int d = 0; d < NB; ++d) { h[d] = d == w ? 0 : (d > w && d <= w2x ? -(sc.o_ins + sc.e_ins * (d - w)) : LC_NEG_INF); e[d] = LC_NEG_INF; }
-	e[NB] = LC_NEG_INF;
+	for (int p = 0; p < NP; ++p) {
+		uint32_t v = 0;
+#pragma unroll
+		for (int hf = 0; hf < 2; ++hf) {
+			const int d = 2 * p + hf;
+			const int x = d == w ? 0 : (d > w && d <= w2x ? -(sc.o_ins + sc.e_ins * (d - w)) : LC_CIG_NEG16);
+			v |= ((uint32_t)x & 0xffffu) << (16 * hf);
+		}
+		H[p] = v; E[p] = NEG2;
+	}
+	E[NP] = NEG2;
 	// the query window: R[g] = oriented bases 8(kb+g) .. +7
 	uint32_t R[G + 1];
 	int kb = (-w) >> 3;
@@ -233,47 +278,68 @@ template <int NB> LC_HD void lc_cig_band(const LcBatch &b, uint64_t cd)
 		const uint32_t tb = ((pw >> ((((int)(fp >> 2) & 3) << 3) + ((~(int)fp & 3) << 1))) & 3u) ^ comp;
 		const uint32_t tbm = tb * 0x11111111u;
 		const int ph4 = (j0 & 7) << 2;
-		const int hvirt = -(sc.o_del + sc.e_del * (i + 1));           // H(i, -1): the left boundary while the band touches column 0
-		int f = LC_NEG_INF;
-		uint32_t zrow[GS];
+		// H(i, -1), the left boundary while the band touches column 0: every slot that is not live takes it (only the slot of column -1
+		// is ever read with it: slots further left are rewritten row after row until they are that slot, slots right of the live
+		// range never feed a live one)
+		const uint32_t HV = lc_p2_dup(-(sc.o_del + sc.e_del * (i + 1)));
+		// live slots of the row: [s_lo, s_hi)
+		const int s_lo = j0 < 0 ? -j0 : 0, s_hi = lc_min(w2x + 1, lq - j0);
+		uint32_t vb[(NB + 31) / 32];
 #pragma unroll
-		for (int g = G; g < GS; ++g) zrow[g] = 0;
+		for (int k = 0; k < (NB + 31) / 32; ++k) vb[k] = lc_range_word(s_lo, s_hi, 32 * k);
+		uint32_t fb = NEG2;                                           // F entering the next slot, in both halves
+		uint32_t zrow[4];
 #pragma unroll
 		for (int g = 0; g < G; ++g) {
 			const uint32_t qword = lc_funnel_r(R[g], R[g + 1], ph4);
 			const uint32_t x = qword ^ tbm;                          // nibble c: 0 = match, 1..3 = mismatch, 4..7 = ambiguous query base
 			const uint32_t sa = lc_cig_lut4(lut_lo, lut_hi, x), sb = lc_cig_lut4(lut_lo, lut_hi, x >> 16);
-			uint32_t zw = 0;
+			// half-word masks of the eight slots: bit 2k of the byte to the sign of byte k of ye, bit 2k + 1 likewise of yo
+			const uint32_t b8 = (vb[g >> 2] >> (8 * (g & 3))) & 0xffu;
+			const uint32_t ye = (b8 & 0x55u) * 0x02082080u, yo = ((b8 >> 1) & 0x55u) * 0x02082080u;
+			uint32_t rr[4];
 #pragma unroll
-			for (int c = 0; c < 8; ++c) {
-				const int d = 8 * g + c;
-				const int col = j0 + d;
-				const bool valid = (unsigned)col < (unsigned)lq && d <= w2x;
-				const int s = (int)(int8_t)((c < 4 ? sa : sb) >> (8 * (c & 3)));
-				const int M = h[d] + s, ee = e[d + 1];
-				uint32_t dd = M >= ee ? 0u : 1u;
-				int hh = M >= ee ? M : ee;
-				dd = hh >= f ? dd : 2u;
-				hh = hh >= f ? hh : f;
-				int t = M - oe_del, en = ee - e_del;
-				if (en > t) dd |= 4u; else en = t;
-				t = M - oe_ins;
-				int fn = f - e_ins;
-				if (fn > t) dd |= 8u; else fn = t;
-				if (valid) { h[d] = hh; e[d] = en; f = fn; zw |= dd << (4 * c); }
-				else if (col == -1) h[d] = hvirt;
+			for (int k = 0; k < 4; ++k) {
+				const int p = 4 * g + k;
+				const uint32_t S = lc_prmt(k < 2 ? sa : sb, 0u, (k & 1) ? 0xb3a2u : 0x9180u);       // two scores, sign-extended to 16 bits
+				const uint32_t mk = lc_prmt(ye, yo, 0xcc88u + 0x1111u * (uint32_t)k);      // halves = sign of byte k of ye / of yo
+				// a slot that is not live computes with M = "minus infinity": whatever it then derives stays in that category and
+				// cannot reach a live slot as a finite value (F flows through it, E is only read by the slot on its left, one row on)
+				const uint32_t Mr = lc_p2_add(H[p], S);
+				const uint32_t M = (Mr & mk) | (NEG2 & ~mk);
+				const uint32_t eo = lc_prmt(E[p], E[p + 1], 0x5432u);                                // E(i, column) of the two slots
+				const uint32_t mx = lc_p2_max(M, eo);
+				const uint32_t A = lc_p2_add(M, n_oe_ins);
+				// F(j+1) = max(F(j) - e, A(j)): for the pair {f1, f2} = max({f0 - e, f0 - 2e}, {a0, max(a0 - e, a1)}); only one VIADDMNMX
+				// and the PRMT that spreads f2 are on the chain from pair to pair
+				const uint32_t pp = lc_p2_addmax(lc_prmt(NEG2, A, 0x5410u), n_e_ins, A);
+				const uint32_t fn = lc_p2_addmax(fb, n_e12, pp);                                     // F leaving the two slots
+				const uint32_t fe = lc_prmt(fb, fn, 0x5410u);                                        // F entering them
+				fb = lc_prmt(fn, fn, 0x3232u);
+				const uint32_t hh = lc_p2_max(mx, fe);
+				const uint32_t t1 = lc_p2_add(M, n_oe_del);
+				const uint32_t en = lc_p2_addmax(eo, n_e_del, t1);
+				H[p] = (hh & mk) | (HV & ~mk);
+				E[p] = en;
+				// direction bits (B/ksw.c:560-575): 1 = E beats M, 2 = F beats both, 4 = E extends, 8 = F extends
+				const uint32_t c1 = lc_p2_minu(mx ^ M, ONE2), c2 = lc_p2_minu(hh ^ mx, ONE2), c4 = lc_p2_minu(en ^ t1, ONE2), c8 = lc_p2_minu(fn ^ A, ONE2);
+				rr[k] = c1 + 2u * c2 + 4u * c4 + 8u * c8;
 			}
-			zrow[g] = zw;
-		}
+			// nibble of slot c of the group at bit 4 * lc_bitrev3(c)
+			zrow[g & 3] = (rr[0] | rr[1] << 8) | (rr[2] | rr[3] << 8) << 4;
+			if ((g & 3) == 3 || g == G - 1) {
 #pragma unroll
-		for (int g = 0; g < GS; g += 4) lc_st16(z + (size_t)i * GS + g, zrow[g], zrow[g + 1], zrow[g + 2], zrow[g + 3]);
+				for (int q = (g & 3) + 1; q < 4; ++q) zrow[q] = 0;
+				lc_st16(z + (size_t)i * GS + (g & ~3), zrow[0], zrow[1], zrow[2], zrow[3]);
+			}
+		}
 	}
 	// H[qlen] of the reference = H(rlen-1, lq-1): slot lq - rlen + w
 	int score = LC_NEG_INF;
 	{
 		const int dq = lq - rlen + w;
 #pragma unroll
-		for (int d = 0; d < NB; ++d) if (d == dq) score = h[d];
+		for (int p = 0; p < NP; ++p) if (p == (dq >> 1)) score = (int)(int16_t)((dq & 1) ? H[p] >> 16 : H[p] & 0xffffu);
 	}
 	if (b.cnt) {
 		unsigned long long cells = 0;
@@ -289,8 +355,8 @@ template <int NB> LC_HD void lc_cig_band(const LcBatch &b, uint64_t cd)
 	while (i >= 0 && k >= 0) {
 		int d = k - i + w;
 		d = d < 0 ? 0 : (d >= NB ? NB - 1 : d);
-		const uint32_t nib = z[(size_t)i * GS + (d >> 3)] >> ((d & 7) << 2) & 15u;
-		state = state == 0 ? (int)(nib & 3u) : state == 1 ? (int)(nib >> 2 & 1u) : (int)(nib >> 3 & 1u) * 2;
+		const uint32_t nib = z[(size_t)i * GS + (d >> 3)] >> (lc_bitrev3(d & 7) << 2) & 15u;
+		state = state == 0 ? ((nib & 2u) ? 2 : (int)(nib & 1u)) : state == 1 ? (int)(nib >> 2 & 1u) : (int)(nib >> 3 & 1u) * 2;
 		int op;
 		if (state == 0) { op = 0; n_mm += lc_cig_q(j, k) != lc_cig_t(b, j, i); --i; --k; }
 		else if (state == 1) { op = 2; --i; }
