@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 	LcExtLane<32, CELLS, UNIT> ex(b, wbase + lane, qf + lane, lc_ext_smem);
 	const int n_items = UNIT ? lc_ext_n_units(b) : b.n_reads;
 	unsigned int *ctr = UNIT ? b.ext_unit_n + 1 : b.work_ctr + 0;
+	const unsigned rmask = row_mask & 255u, row_n = row_mask >> 8;
 	for (unsigned it = 0;; ++it) {
 		if ((it & hk_mask) == 0) {                               // warp-uniform
 			const unsigned need = __ballot_sync(LC_FULL, ex.phase == LC_XP_FETCH);
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(LC_EXT_TPB, 8) extend_kernel(const LcBatch b, 
 			if (!__ballot_sync(LC_FULL, ex.phase != LC_XP_DONE)) break;
 			if (__any_sync(LC_FULL, ex.phase < LC_XP_DP && ex.phase != LC_XP_FETCH)) ex.resolve();
 		}
-		ex.tick((it & row_mask) == 0);
+		// the end-of-row gate: every (mask + 1) ticks, or as soon as row_n lanes wait (row_n > 32: never) — warp-uniform either way
+		ex.tick((it & rmask) == 0 || (row_n <= 32 && __popc(__ballot_sync(LC_FULL, ex.phase == LC_XP_ROWEND)) >= (int)row_n));
 	}
 }
 
@@ -491,7 +493,7 @@ LcCudaBackend::LcCudaBackend(int device_) : device(device_)
 	auto env_int = [](const char *name, int &v, int lo, int hi) { if (const char *e = getenv(name)) { const int x = atoi(e); if (x >= lo && x <= hi) v = x; } };
 	env_int("LC_SEED_GL_CTAS", seed_gl_ctas, 1, 32); env_int("LC_SEED_REDO_CTAS", seed_redo_ctas, 1, 16); env_int("LC_CHAIN_CTAS", chain_ctas, 1, 16); env_int("LC_CHAIN_HEAVY_CTAS", chain_heavy_ctas, 1, 16);
 	env_int("LC_SEED_GATE_MASK", seed_gate_mask, 0, 255); env_int("LC_SEED_GATE_N", seed_gate_n, 1, 33);     // tuning knobs; mask must be 2^k - 1
-	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_ROW_MASK", ext_row_mask, 0, 255);
+	env_int("LC_EXT_GATE_MASK", ext_gate_mask, 0, 255); env_int("LC_EXT_ROW_MASK", ext_row_mask, 0, 255); env_int("LC_EXT_ROW_N", ext_row_n, 1, 33);
 }
 LcCudaBackend::~LcCudaBackend()
 {
@@ -649,7 +651,7 @@ int LcCudaBackend::k_extend(const LcBatch &b)
 		return 1;
 	}
 	const bool cells8 = lc_ext_cells8_ok(b) && !getenv("LC_EXT_WIDE_CELLS");
-	const unsigned hk = (unsigned)ext_gate_mask, rw = (unsigned)ext_row_mask;
+	const unsigned hk = (unsigned)ext_gate_mask, rw = (unsigned)ext_row_mask | (unsigned)ext_row_n << 8;
 	if (cells8) lc_launch_extend<LcCells8<32>, false>(b, b.n_reads, n_sm, stream, hk, rw);
 	else lc_launch_extend<LcCells16<32>, false>(b, b.n_reads, n_sm, stream, hk, rw);
 	int launches = 1;

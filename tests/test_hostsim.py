@@ -72,6 +72,33 @@ def test_stage_bodies_on_fresh_repeat_rich_data(hostsim_bin, oracle_port, tmp_pa
     assert got.read_bytes() == want.read_bytes()
 
 
+@pytest.mark.parametrize("read_len,sub_rate", [(100, 0.03), (250, 0.02)])
+def test_cigar_bands_on_indel_rich_reads(hostsim_bin, oracle_port, tmp_path, read_len, sub_rate):
+    """The 16-bit band kernels of the CIGAR stage (lc_cig_band: live-slot masks, F chain, direction bits, traceback) on reads where
+    most candidates need a real banded alignment: an indel in most reads, 2-3 % substitutions (wide bands), short and long reads."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from lariat_b200 import index_build, iofmt, synth
+    g = synth.GenomeSpec(400_000, 3, 911 + read_len, segdup_frac=0.05, segdup_len=(500, 3000), families=[(300, 60, 0.05, 0.12)], n_tandem=8, name="ichr")
+    r = synth.ReadSpec(700, 10, read_len=read_len, mol_len=40_000, mols_per_barcode=8, sub_rate=sub_rate, indel_rate=0.9 / read_len,
+                       degraded_frac=0.10, insert_mean=2.2 * read_len + 50, insert_clip=(read_len + 20, 4 * read_len + 100), seed=913 + read_len)
+    contigs, loci = synth.make_genome(g)
+    fa = str(tmp_path / "i.fa")
+    synth.write_fasta(fa, contigs)
+    index_build.build_index_torch(fa, contigs)
+    sim = synth.simulate_pairs(contigs, loci, r)
+    pairs = str(tmp_path / "i.pairs")
+    iofmt.write_pairs(pairs, sim["r1"], sim["r2"])
+    want, got = tmp_path / "want.out", tmp_path / "got.out"
+    subprocess.check_call([os.path.join(oracle_port, "replay_port"), fa, pairs, str(want), "-t", "4"], stderr=subprocess.DEVNULL)
+    out = subprocess.run([hostsim_bin, fa, pairs, str(got)], stderr=subprocess.PIPE, text=True, check=True).stderr
+    assert got.read_bytes() == want.read_bytes()
+    import re
+    m = re.search(r"band class (\d+)/(\d+)/(\d+)/(\d+)/(\d+), fallback (\d+)", out)
+    bands = [int(x) for x in m.groups()[:5]]
+    assert sum(bands) > 500 and sum(1 for x in bands if x > 0) >= 3, out      # the band kernels did the work, in several classes
+
+
 @pytest.mark.parametrize("extra", [["-W"], ["-W", "-S"], ["-W", "-C", "6", "-M", "4", "-D", "9", "-E", "7"], ["-W", "-I", "2", "-K", "101"]])
 def test_multi_superblock_and_high_interval_bits(hostsim_sb_bin, tmp_path, extra):
     """What an index of >= 2^32 symbols exercises and a small one never does: superblock index >= 1 in every occ lookup and LF step,
