@@ -376,8 +376,15 @@ def main():
 
     # ---- end-to-end arm: host buffers in, host results out, every step
     all_keys = ("ms_h2d", "ms_seed", "ms_sa", "ms_chain", "ms_extend", "ms_pair", "ms_cigar", "ms_d2h", "ms_total")
-    for ent in [x for x in args.e2e_sweep.split(",") if x]:
-        cp = int(ent)
+    swept_env = set()
+    for ent in [x for x in args.e2e_sweep.split(",") if x]:      # "N" or "N:KEY=VAL+KEY=VAL" (chunk-plan knobs of lc_api.cu, read per call)
+        cp = int(ent.split(":")[0])
+        for k in swept_env:
+            os.environ.pop(k, None)
+        for kv in (ent.split(":")[1].split("+") if ":" in ent else []):
+            k, v = kv.split("=")
+            os.environ[k] = v
+            swept_env.add(k)
         check(lib.lc_set_chunk_pairs(ctx, cp))
         for _ in range(2):
             check(lib.lc_align_packed(ctx, n_pairs, hb.data_ptr(), ho.data_ptr(), 25, C.byref(res)))
@@ -390,6 +397,8 @@ def main():
         tw = (time.perf_counter() - tw) / args.steps
         log(f"[bench] e2e sweep chunk_pairs={ent}: {1e3 * tw:.2f} ms/step wall, {n_pairs / tw:.0f} pairs/s; last call " + json.dumps(last))
     if args.e2e_sweep:
+        for k in swept_env:
+            os.environ.pop(k, None)
         check(lib.lc_set_chunk_pairs(ctx, 500000))      # the library's default
     if args.chunk_pairs >= 0:
         check(lib.lc_set_chunk_pairs(ctx, args.chunk_pairs))

@@ -130,6 +130,7 @@ struct lc_ctx {
 	std::vector<std::unique_ptr<LcLane> > lanes;      // lanes 2..n of chunked calls (lane 1 is be/pl above): own stream, pools and host thread
 	int max_lanes = 2;              // LC_LANES
 	int chunk_pairs = 500000;       // LC_CHUNK_PAIRS; calls of more than 1.5 chunks run chunked over two lanes, 0 = never
+	int chunk_first_pct = 50;       // size of a call's first chunk, in % of an equal share (do_align_chunks; swept on C2: 100 / 60 / 50 / 40 / 30 -> 79.8 / 77.8 / 77.3 / 77.3 / 78.3 ms)
 	explicit lc_ctx(int dev) : device(dev), be(dev), pl(be) { memset(&res, 0, sizeof(res)); }
 };
 
@@ -429,6 +430,7 @@ struct LcChunkShared {
 	std::vector<char> ready_reg, ready_cig;
 	int up_next = 0;                    // the chunk whose upload turn it is
 	std::vector<int> bounds;            // [n_chunks + 1] chunk k = pairs bounds[k] .. bounds[k + 1]
+	bool late_regs = false;             // LC_LATE_REGS=1 (tests): every chunk takes the "CIGAR stage first, regions' copy after" order
 	std::shared_mutex res_mu;           // shared: a D2H into the pinned arrays is in flight; exclusive: the arrays are being regrown
 	int rc = LC_OK;
 	std::string err;
@@ -472,12 +474,17 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 		if (!rc) rc = pl->run_front(score_delta);
 		if (rc) sh->fail_with(rc, pl->err);
 		int64_t reg_base;
-		{   // chunk k's place in the call's region arrays = candidates of the chunks before it (known when their pair stage is done)
-			std::unique_lock<std::mutex> g(sh->mu);
-			sh->cv.wait(g, [&] { return sh->ready_reg[k] != 0; });
-			reg_base = sh->cum_reg[k];
-			sh->cum_reg[k + 1] = reg_base + (rc ? 0 : (int64_t)pl->n_cand);
-			sh->ready_reg[k + 1] = 1;
+		bool cigar_done = false;
+		for (;;) {   // chunk k's place in the call's region arrays = candidates of the chunks before it (known when their pair stage is done)
+			{
+				std::unique_lock<std::mutex> g(sh->mu);
+				if ((!sh->ready_reg[k] || sh->late_regs) && !cigar_done && !rc) { g.unlock(); rc = pl->run_cigar(); cigar_done = true; if (rc) sh->fail_with(rc, pl->err); continue; }   // (the chunk before is not that far yet: the CIGAR stage first, the regions' copy after it)
+				sh->cv.wait(g, [&] { return sh->ready_reg[k] != 0; });
+				reg_base = sh->cum_reg[k];
+				sh->cum_reg[k + 1] = reg_base + (rc ? 0 : (int64_t)pl->n_cand);
+				sh->ready_reg[k + 1] = 1;
+			}
+			break;
 		}
 		sh->cv.notify_all();
 		const bool ax = pl->want_alnx;
@@ -501,7 +508,7 @@ static void lane_worker(lc_ctx *c, LcCudaBackend *be, LcPipeline<LcCudaBackend> 
 				regs_in_flight = true;
 			}
 		} else sh->fail_with(rc, pl->err);
-		if (!rc) { rc = pl->run_cigar(); if (rc) sh->fail_with(rc, pl->err); }
+		if (!rc && !cigar_done) { rc = pl->run_cigar(); if (rc) sh->fail_with(rc, pl->err); }
 		if (regs_in_flight) { be->copy_sync(); rg.unlock(); }
 		int64_t cig_base, mm_base;
 		{   // ... and in the CIGAR / mismatch-position arrays (known when their CIGAR stage is done)
@@ -569,10 +576,26 @@ static int do_align(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t 
 static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const int64_t *off, int score_delta, lc_result_t **out, int n_chunks)
 {
 	LcSharedIndex &S = *c->sh;
-	// (Tried and dropped: a half-size first and last chunk, so that less of the first upload and the last copy-out is exposed — the
-	// smaller chunks' kernels lose more to their tails than the copies cost: 92 vs 87 ms per 1 M pairs on C2, profiles/r2s_*.)
+	// The first chunk's upload has nothing to hide under, so the first chunk is made smaller than the others (first_pct % of an
+	// equal share, LC_CHUNK_FIRST; the rest is split evenly).  (A small LAST chunk as well — LC_CHUNK_TAPER=1 — was measured and is
+	// off: a small batch running alone at the end loses more to its kernels' tails than its copy-out costs.)
 	std::vector<int> bounds;
-	for (int k = 0; k <= n_chunks; ++k) bounds.push_back((int)((int64_t)n_pairs * k / n_chunks));
+	{
+		const char *e = getenv("LC_CHUNK_TAPER");
+		const char *f = getenv("LC_CHUNK_FIRST");
+		const int first_pct = f ? std::max(5, std::min(100, atoi(f))) : c->chunk_first_pct;
+		if (n_chunks >= 2 && n_pairs >= 2 * n_chunks && e && atoi(e) == 1) {
+			const int U = n_chunks;
+			bounds.push_back(0);
+			for (int j = 1; j <= U; ++j) bounds.push_back((int)((int64_t)n_pairs * (2 * j - 1) / (2 * U)));
+			bounds.push_back(n_pairs);
+			n_chunks = U + 1;
+		} else if (n_chunks >= 2 && n_pairs >= 100 * n_chunks && first_pct < 100) {
+			const int first = (int)((int64_t)n_pairs * first_pct / (100LL * n_chunks));
+			bounds.push_back(0);
+			for (int k = 0; k < n_chunks; ++k) bounds.push_back(first + (int)((int64_t)(n_pairs - first) * k / (n_chunks - 1)));
+		} else for (int k = 0; k <= n_chunks; ++k) bounds.push_back((int)((int64_t)n_pairs * k / n_chunks));
+	}
 	const int n_lanes = std::max(1, std::min(n_chunks, c->max_lanes));
 	while ((int)c->lanes.size() < n_lanes - 1) {
 		std::unique_ptr<LcLane> l(new LcLane(c->device));
@@ -586,6 +609,7 @@ static int do_align_chunks(lc_ctx *c, int n_pairs, const uint8_t *bases, const i
 	LcChunkShared sh;
 	sh.blk = blk;
 	sh.bounds = bounds;
+	{ const char *e = getenv("LC_LATE_REGS"); sh.late_regs = e && atoi(e) == 1; }
 	sh.cum_reg.assign(n_chunks + 1, 0); sh.cum_cig.assign(n_chunks + 1, 0); sh.cum_mm.assign(n_chunks + 1, 0); sh.ready_reg.assign(n_chunks + 1, 0); sh.ready_cig.assign(n_chunks + 1, 0); sh.ready_reg[0] = sh.ready_cig[0] = 1;
 	memset(&sh.cnt, 0, sizeof(sh.cnt));
 	c->be.ev_record(12);

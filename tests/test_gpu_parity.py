@@ -77,6 +77,24 @@ def test_golden_tiny_chunked_two_lanes(chunk, lanes, lib_path, monkeypatch):
     ref.close()
 
 
+@pytest.mark.parametrize("env", [{"LC_CHUNK_TAPER": "1"}, {"LC_LATE_REGS": "1"}, {"LC_CHUNK_TAPER": "1", "LC_LATE_REGS": "1", "LC_LANES": "3"},
+                                 {"LC_CHUNK_FIRST": "40"}, {"LC_CHUNK_FIRST": "100"}])
+def test_golden_tiny_chunk_plans(env, lib_path, monkeypatch):
+    """The other orders a chunked call can take: a smaller first chunk (LC_CHUNK_FIRST), a half-size first and last chunk (LC_CHUNK_TAPER), and a chunk whose predecessor is not
+    through its pair stage yet, so that its CIGAR stage runs before its regions are packed and copied out (forced by LC_LATE_REGS)."""
+    monkeypatch.setenv("LC_CHUNK_PAIRS", "70")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ref = gobwa.GoBwaLoadReference(os.path.join(GOLDEN, "tiny", "tiny.fa"))
+    assert ref is not None, gobwa.last_error()
+    bases, off = _load_pairs(os.path.join(GOLDEN, "tiny", "tiny.pairs"))
+    want = open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
+    for _ in range(3):
+        br = ref.align_packed(bases, off, 25)
+        assert br.dump() == want
+    ref.close()
+
+
 def test_batch_split_invariance(tiny_ref):
     """Barcode groups are independent: aligning a sub-batch gives the same per-pair results as the big batch."""
     bases, off = _load_pairs(os.path.join(GOLDEN, "tiny", "tiny.pairs"))
