@@ -26,7 +26,7 @@ struct LcCudaBackend {
 	void *seed_glists = nullptr; size_t seed_glists_bytes = 0;      // interval lists of the later seeding passes (smem_kernel<.., GL>)
 	// housekeeping gates of the state-machine kernels (lc_kernels.cu): serve waiting lanes every (mask + 1) ticks or when n lanes wait
 	int seed_gate_mask = 3, seed_gate_n = 12, ext_gate_mask = 15, ext_row_mask = 1, ext_row_n = 33;
-	int seed_gl_ctas = 8, seed_redo_ctas = 4, chain_ctas = 4, chain_heavy_ctas = 12;      // resident CTAs per SM of the latency-bound kernels (tuning knobs)
+	int seed_gl_ctas = 8, seed_redo_ctas = 4, chain_ctas = 7, chain_heavy_ctas = 12;      // resident CTAs per SM of the latency-bound kernels (tuning knobs)
 
 	explicit LcCudaBackend(int device_);
 	~LcCudaBackend();
