@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(256) rebase_kernel(int64_t *off, int n, int64_
 }
 
 // ---- microbenchmark kernels (BASELINE.json configs[4]) -------------------------------------------------------
-// ksw_extend2 on independent jobs: the same warp-cooperative routine extend_kernel uses, one warp per job
+// ksw_extend2 on independent jobs, one warp per job: the warp-cooperative routine (lc_extend2_warp) that extend_heavy_kernel and the
+// low-latency route use — NOT the per-lane state machine of extend_kernel, which tests/hostsim and the end-to-end dumps cover
 __global__ void __launch_bounds__(LC_TPB) ksw_extend_kernel(const LcExtJobs j)
 {
 	extern __shared__ int lc_smem[];
