@@ -120,7 +120,7 @@ int main(int argc, char **argv)
 	if (argc < 4) { fprintf(stderr, "usage: hostsim <idx> <pairs.bin> <out.bin> [-d delta] [-w workers] [-n max_pairs] [-c]\n"); return 2; }
 	const char *xpath = 0;
 	int chain_heavy = -1;
-	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0, small_reads = 0, force_coop = 0;
+	int delta = 25, maxp = -1, count = 0, lst_cap = -1, pk_cap = -1, lst_cap2 = -1, pk_cap2 = -1, heavy_seeds = -1, dense = 1, wide = 0, chunk = 0, small_reads = 0, force_coop = 0, late_regs = 0;
 	HostBackend be;
 	for (int i = 4; i < argc; ++i) {
 		if (!strcmp(argv[i], "-d") && i + 1 < argc) delta = atoi(argv[++i]);
@@ -140,6 +140,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[i], "-X")) be.old_extend = true;
 		else if (!strcmp(argv[i], "-G")) be.old_cigar = true;
 		else if (!strcmp(argv[i], "-H")) be.wide_cells = true;
+		else if (!strcmp(argv[i], "-L")) late_regs = 1;                                 // with -K: every second chunk takes the "CIGAR stage first" order
 		else if (!strcmp(argv[i], "-K") && i + 1 < argc) chunk = atoi(argv[++i]);       // run the batch as chunks of this many pairs (the way lc_align_packed splits large calls)
 		else if (!strcmp(argv[i], "-x") && i + 1 < argc) xpath = argv[++i];             // stage 6b on: write the GetAlignments records (LRX1) here
 		else if (!strcmp(argv[i], "-S")) dense = 0;                                     // sampled suffix array + LF walks instead of the dense one
@@ -185,13 +186,16 @@ int main(int argc, char **argv)
 		for (int p0 = 0; p0 < n && !rc; p0 += chunk) {
 			const int np = std::min(chunk, n - p0);
 			rc = pl.upload(np, raw.data(), off.data() + 2 * (size_t)p0, true);
-			// the order of lc_api.cu's lane_worker: the regions are packed and fetched before the CIGAR stage runs
+			// the orders of lc_api.cu's lane_worker: the regions are packed and fetched before the CIGAR stage runs, or — when the chunk
+			// before is not through its pair stage yet (-L: every second chunk here) — after it
+			const bool late = late_regs && ((p0 / chunk) & 1);
 			if (!rc) rc = pl.run_front(delta);
+			if (!rc && late) rc = pl.run_cigar();
 			if (!rc) rc = pl.run_pack_regs(reg_base);
 			if (rc) break;
 			res.regs.resize((size_t)reg_base + pl.n_cand); res.aln.resize((size_t)reg_base + pl.n_cand);
 			pl.fetch_regs_into_side(res.reg_off.data() + 2 * (size_t)p0, 2 * (size_t)np + 1, res.regs.data() + reg_base);
-			rc = pl.run_cigar();
+			if (!late) rc = pl.run_cigar();
 			if (!rc) rc = pl.run_pack_aln(cig_base, mm_base);
 			if (rc) break;
 			res.cigars.resize((size_t)cig_base + pl.n_cigar_words);

@@ -39,12 +39,16 @@ def test_seeding_state_machine_fallbacks(hostsim_bin, tmp_path, extra):
     assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
 
 
-@pytest.mark.parametrize("chunk", ["64", "101", "600"])
-def test_chunked_call_equals_one_batch(hostsim_bin, tmp_path, chunk):
+@pytest.mark.parametrize("chunk,extra", [("64", []), ("101", []), ("600", []), ("64", ["-L"]), ("97", ["-L", "-x"])])
+def test_chunked_call_equals_one_batch(hostsim_bin, tmp_path, chunk, extra):
     """lc_align_packed cuts large calls into chunks of pairs (slices of the packed arrays; candidate and CIGAR indices offset by the
-    totals of the chunks before): the pipeline pieces it uses for that (rebased upload, run_stages, run_pack, fetch_into)."""
+    totals of the chunks before): the pipeline pieces it uses for that (rebased upload, run_front, run_pack_regs, the regions' fetch,
+    run_cigar, run_pack_aln, the alignments' fetch), in both orders a lane can take (-L: every second chunk runs its CIGAR stage
+    before its regions are packed)."""
     out = tmp_path / "sim.out"
-    subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out), "-K", chunk],
+    if "-x" in extra:
+        extra = ["-L", "-x", str(tmp_path / "sim.x")]
+    subprocess.check_call([hostsim_bin, os.path.join(GOLDEN, "tiny", "tiny.fa"), os.path.join(GOLDEN, "tiny", "tiny.pairs"), str(out), "-K", chunk] + extra,
                           stderr=subprocess.DEVNULL)
     assert out.read_bytes() == open(os.path.join(GOLDEN, "tiny", "tiny.ref.out"), "rb").read()
 
